@@ -1,0 +1,171 @@
+/*
+ * obia_b200.h -- C ABI of the B200-native SLIC + zonal-statistics hot path.
+ *
+ * The reference (iosefa/obia) is pure Python and has no FFI of its own; the
+ * native work on this path is done by third-party wheels it calls.  Each entry
+ * point below names the reference call site (file:line under /root/reference)
+ * and the third-party routine it replaces.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`
+ *   - the caller allocates and owns all buffers (sizes given per function;
+ *     `obia_b200_*_workspace_bytes` for scratch); the library never allocates
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), no
+ *     hidden synchronisation unless stated
+ *   - return 0 on success, negative on error; `obia_b200_last_error()` gives a
+ *     thread-local message.  Nothing throws across the ABI.
+ *   - rasters are row-major; `raw` is pixel-interleaved (H, W, C) float32
+ *     exactly like `Image.img_data` (obia/handlers/geotif.py:100); SLIC
+ *     features are band-planar [Cf][H][pitch] float32; labels are (H, W) int32.
+ */
+#ifndef OBIA_B200_H
+#define OBIA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OBIA_B200_OK 0
+#define OBIA_B200_ERR_ARG (-1)
+#define OBIA_B200_ERR_CUDA (-2)
+#define OBIA_B200_ERR_UNSUPPORTED (-3)
+
+#define OBIA_B200_MAX_BANDS 64 /* selected bands per call (kernel-parameter table) */
+
+const char *obia_b200_last_error(void);
+int obia_b200_version(void);
+
+/* ---------------------------------------------------------------- K1 ----
+ * Per-band min / max over a pixel-interleaved raster, plus the same over the
+ * masked pixels only, plus a non-finite flag per band.
+ * Replaces numpy's `np.min/np.max` in `normalize_band`
+ * (obia/segmentation/segment_boundaries.py:11-16, applied to every band at
+ * :31-33) and the `image_values.min()/max()` of skimage.segmentation.slic
+ * reached from segment_boundaries.py:51.
+ *   raw        [n_pixels][C] float32
+ *   mask       [n_pixels] uint8 or NULL
+ *   out        [C][4] float32 : min, max, masked min, masked max
+ *   nonfinite  [C] int32      : bit0 = NaN seen, bit1 = +-inf seen
+ */
+int obia_b200_band_minmax(const float *raw, int64_t n_pixels, int32_t C,
+                          const uint8_t *mask, float *out, int32_t *nonfinite,
+                          void *stream);
+
+/* In-place per-band min-max normalisation of the caller's raster: the side
+ * effect of segment_boundaries.py:31-33 (`img_data[:,:,i] = normalize_band`).
+ *   minmax : the [C][4] device array written by obia_b200_band_minmax
+ */
+int obia_b200_normalize_inplace(float *raw, int64_t n_pixels, int32_t C,
+                                const float *minmax, void *stream);
+
+/* Fused band select + obia min-max normalise + skimage global rescale +
+ * optional RGB->CIELAB + multiply by 1/compactness, written band-planar.
+ * Replaces segment_boundaries.py:35-43 and, inside skimage.segmentation.slic
+ * (segment_boundaries.py:51): `image -= imin; image /= (imax-imin)`,
+ * `rgb2lab`, `image * ratio`.
+ *   bands_host  [Cs] selected band indices; Cs <= OBIA_B200_MAX_BANDS
+ *   features    [Cf][H][pitch] float32, Cf = 3 if to_lab else Cs
+ *   pitch       elements per feature row, multiple of 4, >= W
+ *   ratio       float32(1/compactness); pass 1.0f when a Gaussian pass follows
+ */
+int obia_b200_slic_features(const float *raw, int64_t H, int64_t W, int32_t C,
+                            const int32_t *bands_host, int32_t Cs,
+                            const float *band_min_host,
+                            const float *band_max_host, float imin, float imax,
+                            int32_t to_lab, float ratio, float *features,
+                            int64_t pitch, void *stream);
+
+/* Separable Gaussian pre-smoothing of planar features (skimage's `sigma>0`
+ * branch: skimage.filters.gaussian -> scipy.ndimage.gaussian_filter,
+ * mode='reflect', truncate=4; float64 accumulation, float32 storage between
+ * the row and column passes, like scipy).  Output is multiplied by `ratio`.
+ *   weights_host [2*radius+1] float64 normalised kernel (host)
+ *   tmp, out     [Cf][H][pitch] float32 (out may alias in; tmp may not)
+ */
+int obia_b200_gaussian_planar(const float *in, float *tmp, float *out,
+                              int64_t H, int64_t W, int64_t pitch, int32_t Cf,
+                              const double *weights_y_host, int32_t radius_y,
+                              const double *weights_x_host, int32_t radius_x,
+                              float ratio, void *stream);
+
+/* ---------------------------------------------------------------- K2 ----
+ * SLIC iterations: replaces Cython `_slic_cython`
+ * (skimage/segmentation/_slic.pyx) reached from segment_boundaries.py:51.
+ * Semantics kept: +-2*step scatter window per centre with C truncation,
+ * float32 distance in the reference's operation order (no FMA contraction),
+ * strict-less update with the lowest centre index winning exact ties, exactly
+ * `max_num_iter` iterations, empty centre -> NaN centre that never wins.
+ * Centre sums are accumulated in 64-bit fixed point so the result does not
+ * depend on thread scheduling.
+ *
+ *   features  [Cf][H][pitch] float32
+ *   mask      [H][W] uint8 or NULL
+ *   centres   [n][2+Cf] float32 rows (cy, cx, colour...) in/out
+ *   labels    [H][W] int32 out (pre-filled by the call with start_label-1)
+ *   workspace obia_b200_slic_workspace_bytes(...) bytes
+ *   step      float: max of the init steps (spatial weight 1/step^2)
+ *   step_y/x  integer window half sizes (regular_grid steps)
+ *   fix_scale power-of-two scale of the fixed-point colour sums
+ *   status    [4] int32 device words (zeroed by the call): [0] != 0 when a
+ *             tile's candidate list overflowed (result invalid)
+ */
+int64_t obia_b200_slic_workspace_bytes(int64_t H, int64_t W, int32_t Cf,
+                                       int64_t n, int32_t step_y,
+                                       int32_t step_x);
+int obia_b200_slic_iterate(const float *features, const uint8_t *mask,
+                           float *centres, int32_t *labels, void *workspace,
+                           int64_t H, int64_t W, int64_t pitch, int32_t Cf,
+                           int64_t n, float step, int32_t step_y,
+                           int32_t step_x, int32_t max_num_iter,
+                           int32_t start_label, int32_t ignore_color,
+                           double fix_scale, int32_t *status, void *stream);
+
+/* ---------------------------------------------------------------- K3 ----
+ * Enforce connectivity: replaces Cython `_enforce_label_connectivity_cython`
+ * (sequential raster-scan BFS) reached from segment_boundaries.py:51.
+ * Union-find connected components + exact data-parallel replay of the
+ * reference's small-segment merge, BFS size cap and raster-order numbering
+ * (see DESIGN.md, K3).  Synchronises the stream internally (a few 4-byte
+ * read-backs drive the fixed-point loop).
+ *   labels_in  [H][W] int32 (values start_label-1 = masked)
+ *   labels_out [H][W] int32
+ *   n_labels_host  out: number of kept segments (labels are
+ *                  start_label .. start_label+n-1, plus possibly 0)
+ */
+int64_t obia_b200_connectivity_workspace_bytes(int64_t H, int64_t W);
+int obia_b200_enforce_connectivity(const int32_t *labels_in,
+                                   int32_t *labels_out, void *workspace,
+                                   int64_t H, int64_t W, int64_t min_size,
+                                   int64_t max_size, int32_t start_label,
+                                   int64_t *n_labels_host, void *stream);
+
+/* ---------------------------------------------------------------- K4 ----
+ * Per-segment, per-band zonal statistics in one pass over the raster:
+ * replaces the per-segment loop of `create_objects`
+ * (obia/segmentation/segment_statistics.py:475-508): crop_image_to_bbox +
+ * mask_image_with_polygon (obia/utils/utils.py:37-67) +
+ * calculate_spectral_stats (segment_statistics.py:113-176: np.mean, np.var,
+ * np.min, np.max, scipy.stats.skew, scipy.stats.kurtosis).
+ *   labels     [H][W] int32; pixels with label < 0 or > max_label are skipped
+ *   raw        [H][W][C] float32
+ *   bands_host [Cz] band indices
+ *   resolution np.finfo(dtype).resolution of the dtype the reference would
+ *              compute in (1e-6 float32 rasters, 1e-15 integer rasters):
+ *              scipy returns NaN skew/kurtosis when m2 <= (resolution*mean)^2
+ *   stats      [max_label+1][Cz][8] float64 out:
+ *              count, mean, variance, min, max, skewness, kurtosis, sum
+ *              (count==0 -> NaN statistics)
+ */
+int64_t obia_b200_zonal_workspace_bytes(int64_t max_label, int32_t Cz);
+int obia_b200_zonal_stats(const int32_t *labels, const float *raw, int64_t H,
+                          int64_t W, int32_t C, const int32_t *bands_host,
+                          int32_t Cz, int64_t max_label, double resolution,
+                          double *stats, void *workspace, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBIA_B200_H */

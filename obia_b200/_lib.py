@@ -1,0 +1,69 @@
+"""ctypes binding of libobia_b200.so (the C ABI declared in include/obia_b200.h).
+
+The library is built in-tree by `obia_b200/csrc/build.sh` (or
+`__graft_entry__.build()`); there is NO CPU fallback: if the shared object is
+missing or a call fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libobia_b200.so")
+
+_i32, _i64 = ctypes.c_int32, ctypes.c_int64
+_f32, _f64 = ctypes.c_float, ctypes.c_double
+_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/obia_b200.h one to one
+SIGNATURES = {
+    "obia_b200_last_error": (ctypes.c_char_p, []),
+    "obia_b200_version": (ctypes.c_int, []),
+    "obia_b200_band_minmax": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "obia_b200_normalize_inplace": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "obia_b200_slic_features": (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _i32, _vp, _vp, _f32, _f32,
+                                               _i32, _f32, _vp, _i64, _vp]),
+    "obia_b200_gaussian_planar": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _i32, _vp,
+                                                 _i32, _f32, _vp]),
+    "obia_b200_slic_workspace_bytes": (_i64, [_i64, _i64, _i32, _i64, _i32, _i32]),
+    "obia_b200_slic_iterate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i64, _f32,
+                                              _i32, _i32, _i32, _i32, _i32, _f64, _vp, _vp]),
+    "obia_b200_connectivity_workspace_bytes": (_i64, [_i64, _i64]),
+    "obia_b200_enforce_connectivity": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp,
+                                                      _vp]),
+    "obia_b200_zonal_workspace_bytes": (_i64, [_i64, _i32]),
+    "obia_b200_zonal_stats": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _i64, _f64, _vp, _vp,
+                                             _vp]),
+}
+
+_LIB = None
+
+
+class ObiaB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first "
+            "(`python -c 'import __graft_entry__ as g; g.build()'` or obia_b200/csrc/build.sh). "
+            "obia_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the build disagree
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().obia_b200_last_error()
+        raise ObiaB200Error(f"{what} failed ({rc}): {msg.decode() if msg else ''}")

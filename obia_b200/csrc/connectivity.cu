@@ -1,0 +1,543 @@
+// K3: enforce connectivity (replaces skimage
+// `_enforce_label_connectivity_cython`, reached from
+// obia/segmentation/segment_boundaries.py:51).
+//
+// The reference is one sequential raster scan with a BFS per component.  The
+// same result is produced here by data-parallel phases (host model with the
+// proof-by-test of equivalence: tests/cc_parallel_model.py):
+//   1. union-find connected components (4-connectivity, equal label) with
+//      min-index roots: T[p] = first raster pixel of p's component;
+//   2. components larger than max_size: one thread per component replays the
+//      capped BFS and splits it into pieces (T[p] = piece start);
+//   3. pieces smaller than min_size: one thread per piece replays the BFS of
+//      the reference to find `adjacent` = last-seen neighbour that was already
+//      labelled when the scan reached the piece (T[q] < t), iterated to a
+//      fixed point for the start_label=1 corner case (label 0 == mask label);
+//   4. kept pieces are numbered by the rank of their start pixel (prefix sum),
+//      merged pieces follow their adjacent chain.
+#include "common.cuh"
+
+namespace obia {
+
+constexpr int kScanChunk = 2048;
+constexpr int32_t kTInf = 0x7fffffff;
+
+struct CcWs {
+    int32_t *parent, *T, *psize, *adj, *aux, *queue, *list, *blocksum, *ctr;
+    uint8_t *visit;
+    int64_t nblocks;
+    int64_t bytes;
+};
+// ctr words
+enum { CTR_NSMALL = 0, CTR_NOVER = 1, CTR_CURSOR = 2, CTR_CHANGED = 3, CTR_NKEPT = 4, CTR_ERR = 5, CTR_WORDS = 8 };
+
+static CcWs cc_ws_layout(void *base, int64_t N)
+{
+    CcWs w;
+    char *p = (char *)base;
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) {
+        char *r = p + off;
+        off += round_up(bytes, 256);
+        return r;
+    };
+    w.parent = (int32_t *)take(N * 4);
+    w.T = (int32_t *)take(N * 4);
+    w.psize = (int32_t *)take(N * 4);
+    w.adj = (int32_t *)take(N * 4);
+    w.aux = (int32_t *)take(N * 4);
+    w.queue = (int32_t *)take(2 * N * 4);
+    w.list = (int32_t *)take(N * 4);
+    w.nblocks = ceil_div(N, kScanChunk);
+    w.blocksum = (int32_t *)take((w.nblocks + 1) * 4);
+    w.ctr = (int32_t *)take(CTR_WORDS * 4);
+    w.visit = (uint8_t *)take(N);
+    w.bytes = off;
+    return w;
+}
+
+__device__ __forceinline__ int32_t uf_find(const int32_t *parent, int32_t x)
+{
+    int32_t p = __ldcg(parent + x);
+    while (p != x) {
+        x = p;
+        p = __ldcg(parent + x);
+    }
+    return x;
+}
+
+__device__ __forceinline__ void uf_union(int32_t *parent, int32_t a, int32_t b)
+{
+    bool done;
+    do {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a < b) {
+            const int32_t old = atomicMin(parent + b, a);
+            done = (old == b);
+            b = old;
+        } else if (b < a) {
+            const int32_t old = atomicMin(parent + a, b);
+            done = (old == a);
+            a = old;
+        } else {
+            done = true;
+        }
+    } while (!done);
+}
+
+// phase 1a: link every pixel to its upper neighbour when labels agree
+__global__ void __launch_bounds__(256)
+cc_init_kernel(const int32_t *__restrict__ lab, int32_t *__restrict__ parent, int32_t *__restrict__ psize,
+               uint8_t *__restrict__ visit, int64_t N, int W, int32_t mask_label)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int32_t l = lab[i];
+    int32_t p = (int32_t)i;
+    if (l != mask_label && i >= W && lab[i - W] == l) p = (int32_t)(i - W);
+    parent[i] = p;
+    psize[i] = 0;
+    visit[i] = 0;
+}
+
+// phase 1b: merge with the left neighbour (skipped when the row above already
+// connects the two pixels)
+__global__ void __launch_bounds__(256)
+cc_merge_kernel(const int32_t *__restrict__ lab, int32_t *parent, int64_t N, int W, int32_t mask_label)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int x = (int)(i % W);
+    if (x == 0) return;
+    const int32_t l = lab[i];
+    if (l == mask_label || lab[i - 1] != l) return;
+    if (i >= W && lab[i - W] == l && lab[i - W - 1] == l) return;
+    uf_union(parent, (int32_t)i, (int32_t)(i - 1));
+}
+
+// phase 1c: flatten, T = root, component sizes (one atomic per run of equal
+// roots inside a warp)
+__global__ void __launch_bounds__(256)
+cc_flatten_kernel(const int32_t *__restrict__ lab, int32_t *parent, int32_t *__restrict__ T,
+                  int32_t *psize, int64_t N, int32_t mask_label)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int32_t root = -1;
+    if (i < N && lab[i] != mask_label) {
+        root = uf_find(parent, (int32_t)i);
+        parent[i] = root;
+        T[i] = root;
+    } else if (i < N) {
+        T[i] = -1;
+    }
+    const int32_t prev = __shfl_up_sync(0xffffffffu, root, 1);
+    const bool is_head = (lane == 0) || (prev != root);
+    const unsigned heads = __ballot_sync(0xffffffffu, is_head);
+    if (is_head && root >= 0) {
+        const unsigned later = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+        const int end = later ? (__ffs(later) - 1) : 32;
+        atomicAdd(psize + root, end - lane);
+    }
+}
+
+// phase 2 list: roots of components larger than max_size
+__global__ void __launch_bounds__(256)
+cc_list_over_kernel(const int32_t *__restrict__ T, const int32_t *__restrict__ psize, int32_t *list,
+                    int32_t *ctr, int64_t N, int64_t max_size)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    if (T[i] == (int32_t)i && (int64_t)psize[i] > max_size) {
+        const int e = atomicAdd(ctr + CTR_NOVER, 1);
+        list[N - 1 - e] = (int32_t)i;  // oversized list grows from the end of `list`
+    }
+}
+
+__device__ __forceinline__ bool nbr(int dir, int py, int px, int H, int W, int32_t &q)
+{
+    // reference neighbour order: x+1, x-1, y+1, y-1
+    int yy = py, xx = px;
+    if (dir == 0) xx += 1;
+    else if (dir == 1) xx -= 1;
+    else if (dir == 2) yy += 1;
+    else yy -= 1;
+    if (xx < 0 || xx >= W || yy < 0 || yy >= H) return false;
+    q = yy * W + xx;
+    return true;
+}
+
+// phase 2: replay the BFS cap on oversized components, one thread each
+__global__ void __launch_bounds__(128)
+cc_split_kernel(const int32_t *__restrict__ lab, const int32_t *__restrict__ parent, int32_t *T,
+                int32_t *psize, int32_t *queue, const int32_t *__restrict__ list, int32_t *ctr,
+                uint8_t *visit, int64_t N, int H, int W, int64_t max_size)
+{
+    const int n_over = ctr[CTR_NOVER];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_over; e += gridDim.x * blockDim.x) {
+        const int32_t r = list[N - 1 - e];
+        const int32_t L = lab[r];
+        const int32_t n = psize[r];
+        int32_t *qu = queue + atomicAdd(ctr + CTR_CURSOR, n);
+        // uncapped BFS: mark members (visit = 2), bounding box
+        int cnt = 1, head = 0;
+        qu[0] = r;
+        visit[r] = 2;
+        int ymin = r / W, ymax = ymin, xmin = r % W, xmax = xmin;
+        while (head < cnt) {
+            const int32_t p = qu[head++];
+            const int py = p / W, px = p % W;
+            for (int d = 0; d < 4; ++d) {
+                int32_t q;
+                if (!nbr(d, py, px, H, W, q)) continue;
+                if (lab[q] == L && visit[q] == 0) {
+                    visit[q] = 2;
+                    qu[cnt++] = q;
+                    const int qy = q / W, qx = q % W;
+                    ymin = min(ymin, qy); ymax = max(ymax, qy);
+                    xmin = min(xmin, qx); xmax = max(xmax, qx);
+                }
+            }
+        }
+        // pieces in raster order of their first unassigned member
+        for (int y = ymin; y <= ymax; ++y) {
+            for (int x = xmin; x <= xmax; ++x) {
+                const int32_t s = y * W + x;
+                if (parent[s] != r || visit[s] != 2) continue;
+                int pc = 1, ph = 0;
+                qu[0] = s;
+                visit[s] = 1;
+                while (ph < pc && (int64_t)pc < max_size) {
+                    const int32_t p = qu[ph];
+                    const int py = p / W, px = p % W;
+                    for (int d = 0; d < 4; ++d) {
+                        int32_t q;
+                        if (!nbr(d, py, px, H, W, q)) continue;
+                        if (lab[q] == L && visit[q] == 2) {
+                            visit[q] = 1;
+                            qu[pc++] = q;
+                            if ((int64_t)pc >= max_size) break;
+                        }
+                    }
+                    ++ph;
+                }
+                for (int i = 0; i < pc; ++i) {
+                    T[qu[i]] = s;
+                    visit[qu[i]] = 0;
+                }
+                psize[s] = pc;
+            }
+        }
+    }
+}
+
+// phase 3 list: starts of pieces smaller than min_size
+__global__ void __launch_bounds__(256)
+cc_list_small_kernel(const int32_t *__restrict__ T, const int32_t *__restrict__ psize, int32_t *list,
+                     int32_t *adj, int32_t *aux, int32_t *ctr, int64_t N, int64_t min_size)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    if (T[i] == (int32_t)i && (int64_t)psize[i] < min_size) {
+        const int e = atomicAdd(ctr + CTR_NSMALL, 1);
+        list[e] = (int32_t)i;
+        adj[i] = -1;
+        aux[i] = (int32_t)i;  // tfix: optimistic "labelled at its own time"
+    }
+}
+
+struct CcParams {
+    int H, W;
+    int64_t min_size, max_size;
+    int32_t mask_label, start_label;
+};
+
+__device__ __forceinline__ bool labelled_at(const int32_t *lab, const int32_t *T, const int32_t *psize,
+                                            const int32_t *aux, const CcParams &P, int32_t q, int32_t t,
+                                            int32_t now)
+{
+    if (lab[q] == P.mask_label) return false;
+    const int32_t tq = T[q];
+    if (tq == t || tq > now) return false;
+    if ((int64_t)psize[tq] >= P.min_size) return true;  // kept piece processed earlier
+    if (P.start_label == 0) return true;                // merged pieces carry a label >= 0
+    return __ldcg(aux + tq) < now;                      // start_label 1: label 0 == mask label until tfix
+}
+
+// replay of the reference BFS restricted to piece t, started at pixel s
+__device__ int bfs_piece(const int32_t *lab, const int32_t *T, const int32_t *psize, const int32_t *aux,
+                         uint8_t *visit, int32_t *qu, const CcParams &P, int32_t t, int32_t s,
+                         int32_t L, int32_t &adj_out)
+{
+    int cnt = 1, head = 0;
+    int32_t adjq = -1;
+    qu[0] = s;
+    visit[s] = 1;
+    while (head < cnt && (int64_t)cnt < P.max_size) {
+        const int32_t p = qu[head];
+        const int py = p / P.W, px = p % P.W;
+        for (int d = 0; d < 4; ++d) {
+            int32_t q;
+            if (!nbr(d, py, px, P.H, P.W, q)) continue;
+            const bool same = (lab[q] == L) && (T[q] == t);
+            if (same) {
+                if (!visit[q]) {
+                    visit[q] = 1;
+                    qu[cnt++] = q;
+                    if ((int64_t)cnt >= P.max_size) break;
+                }
+            } else if (labelled_at(lab, T, psize, aux, P, q, t, s)) {
+                adjq = q;
+            }
+        }
+        ++head;
+    }
+    adj_out = adjq;
+    return cnt;
+}
+
+__global__ void __launch_bounds__(128)
+cc_small_adjacent_kernel(const int32_t *__restrict__ lab, const int32_t *__restrict__ T,
+                         const int32_t *__restrict__ psize, int32_t *adj, int32_t *aux, int32_t *queue,
+                         const int32_t *__restrict__ list, int32_t *ctr, uint8_t *visit, CcParams P)
+{
+    const int n_small = ctr[CTR_NSMALL];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_small; e += gridDim.x * blockDim.x) {
+        const int32_t t = list[e];
+        const int32_t L = lab[t];
+        const int32_t n = psize[t];
+        int32_t *qu = queue + atomicAdd(ctr + CTR_CURSOR, n);
+        int32_t a;
+        int cnt = bfs_piece(lab, T, psize, aux, visit, qu, P, t, t, L, a);
+        for (int i = 0; i < cnt; ++i) visit[qu[i]] = 0;
+        int32_t fix = t;
+        if (a < 0 && P.start_label == 1) {
+            // merged to 0 == mask label: the raster scan re-enters the piece at each
+            // later pixel of the first BFS (ascending) until a labelled neighbour shows
+            fix = kTInf;
+            // (total queue demand stays <= 2N: n per piece + one copy per cascading piece)
+            int32_t *cand = queue + atomicAdd(ctr + CTR_CURSOR, cnt);
+            int32_t *qu2 = qu;
+            for (int i = 0; i < cnt; ++i) cand[i] = qu[i];
+            int32_t last = t;
+            while (true) {
+                int32_t s = kTInf;
+                for (int i = 0; i < cnt; ++i)
+                    if (cand[i] > last && cand[i] < s) s = cand[i];
+                if (s == kTInf) break;
+                last = s;
+                int32_t a2;
+                const int c2 = bfs_piece(lab, T, psize, aux, visit, qu2, P, t, s, L, a2);
+                for (int i = 0; i < c2; ++i) visit[qu2[i]] = 0;
+                if (a2 >= 0) {
+                    a = a2;
+                    fix = s;
+                    break;
+                }
+            }
+        }
+        adj[t] = a;
+        if (aux[t] != fix) {
+            aux[t] = fix;
+            atomicExch(ctr + CTR_CHANGED, 1);
+        }
+    }
+}
+
+// phase 4a/b/c: rank of kept piece starts (chunked prefix sum)
+__device__ __forceinline__ bool is_kept_start(const int32_t *T, const int32_t *psize, int64_t i,
+                                              int64_t min_size)
+{
+    return T[i] == (int32_t)i && (int64_t)psize[i] >= min_size;
+}
+
+__global__ void __launch_bounds__(256)
+cc_count_kernel(const int32_t *__restrict__ T, const int32_t *__restrict__ psize, int32_t *blocksum,
+                int64_t N, int64_t min_size)
+{
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kScanChunk;
+    int c = 0;
+    for (int j = threadIdx.x; j < kScanChunk; j += 256) {
+        const int64_t i = base + j;
+        if (i < N && is_kept_start(T, psize, i, min_size)) ++c;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) blocksum[blockIdx.x] = s_cnt;
+}
+
+__global__ void __launch_bounds__(1024)
+cc_scan_blocks_kernel(int32_t *blocksum, int64_t nblocks, int32_t *ctr)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t b0 = 0; b0 < nblocks; b0 += 1024) {
+        const int64_t i = b0 + threadIdx.x;
+        const int v = (i < nblocks) ? blocksum[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int excl = carry + (warp ? s_warp[warp - 1] : 0) + incl - v;
+        if (i < nblocks) blocksum[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ctr[CTR_NKEPT] = s_carry;
+}
+
+__global__ void __launch_bounds__(256)
+cc_number_kernel(const int32_t *__restrict__ T, const int32_t *__restrict__ psize,
+                 const int32_t *__restrict__ blocksum, int32_t *aux, int64_t N, int64_t min_size,
+                 int32_t start_label)
+{
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = blocksum[blockIdx.x];
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kScanChunk;
+    for (int j0 = 0; j0 < kScanChunk; j0 += 256) {
+        const int64_t i = base + j0 + threadIdx.x;
+        const bool k = (i < N) && is_kept_start(T, psize, i, min_size);
+        const unsigned m = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (k) aux[i] = start_label + before + __popc(m & ((1u << lane) - 1u));
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) tot += s_warp[w];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+}
+
+// phase 4d: final labels
+__global__ void __launch_bounds__(256)
+cc_resolve_kernel(const int32_t *__restrict__ lab, const int32_t *__restrict__ T,
+                  const int32_t *__restrict__ psize, const int32_t *__restrict__ adj,
+                  const int32_t *__restrict__ aux, int32_t *__restrict__ out, int64_t N, int64_t min_size,
+                  int32_t mask_label)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    if (lab[i] == mask_label) {
+        out[i] = mask_label;
+        return;
+    }
+    int32_t t = T[i];
+    int32_t r;
+    while (true) {
+        if ((int64_t)psize[t] >= min_size) {
+            r = aux[t];
+            break;
+        }
+        const int32_t a = adj[t];
+        if (a < 0) {
+            r = 0;  // `adjacent` initial value
+            break;
+        }
+        t = T[a];
+    }
+    out[i] = r;
+}
+
+}  // namespace obia
+
+using namespace obia;
+
+extern "C" int64_t obia_b200_connectivity_workspace_bytes(int64_t H, int64_t W)
+{
+    if (H <= 0 || W <= 0) return -1;
+    return cc_ws_layout(nullptr, H * W).bytes;
+}
+
+extern "C" int obia_b200_enforce_connectivity(const int32_t *labels_in, int32_t *labels_out,
+                                              void *workspace, int64_t H, int64_t W, int64_t min_size,
+                                              int64_t max_size, int32_t start_label,
+                                              int64_t *n_labels_host, void *stream)
+{
+    if (!labels_in || !labels_out || !workspace || H <= 0 || W <= 0)
+        return set_err(OBIA_B200_ERR_ARG, "enforce_connectivity: bad argument");
+    if (max_size < 1) return set_err(OBIA_B200_ERR_ARG, "enforce_connectivity: max_size must be >= 1");
+    if (start_label != 0 && start_label != 1) return set_err(OBIA_B200_ERR_ARG, "start_label should be 0 or 1.");
+    const int64_t N = H * W;
+    if (N >= 0x7fffffffLL) return set_err(OBIA_B200_ERR_UNSUPPORTED, "enforce_connectivity: H*W exceeds int32");
+    cudaStream_t st = (cudaStream_t)stream;
+    CcWs w = cc_ws_layout(workspace, N);
+    const int32_t mask_label = start_label - 1;
+    const unsigned gridN = (unsigned)ceil_div(N, 256);
+
+    OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr, 0, CTR_WORDS * 4, st));
+    cc_init_kernel<<<gridN, 256, 0, st>>>(labels_in, w.parent, w.psize, w.visit, N, (int)W, mask_label);
+    OBIA_LAUNCH_CHECK();
+    cc_merge_kernel<<<gridN, 256, 0, st>>>(labels_in, w.parent, N, (int)W, mask_label);
+    OBIA_LAUNCH_CHECK();
+    cc_flatten_kernel<<<gridN, 256, 0, st>>>(labels_in, w.parent, w.T, w.psize, N, mask_label);
+    OBIA_LAUNCH_CHECK();
+    cc_list_over_kernel<<<gridN, 256, 0, st>>>(w.T, w.psize, w.list, w.ctr, N, max_size);
+    OBIA_LAUNCH_CHECK();
+    cc_split_kernel<<<kNumSMs * 2, 128, 0, st>>>(labels_in, w.parent, w.T, w.psize, w.queue, w.list, w.ctr,
+                                                 w.visit, N, (int)H, (int)W, max_size);
+    OBIA_LAUNCH_CHECK();
+    cc_list_small_kernel<<<gridN, 256, 0, st>>>(w.T, w.psize, w.list, w.adj, w.aux, w.ctr, N, min_size);
+    OBIA_LAUNCH_CHECK();
+
+    CcParams P;
+    P.H = (int)H; P.W = (int)W; P.min_size = min_size; P.max_size = max_size;
+    P.mask_label = mask_label; P.start_label = start_label;
+    int32_t hctr[CTR_WORDS];
+    for (int round = 0; round < 100000; ++round) {
+        OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + CTR_CURSOR, 0, 2 * 4, st));  // cursor + changed
+        cc_small_adjacent_kernel<<<kNumSMs * 8, 128, 0, st>>>(labels_in, w.T, w.psize, w.adj, w.aux, w.queue,
+                                                              w.list, w.ctr, w.visit, P);
+        OBIA_LAUNCH_CHECK();
+        if (start_label == 0) break;  // no label-0 ambiguity: one round is exact
+        OBIA_CUDA_CHECK(cudaMemcpyAsync(hctr, w.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, st));
+        OBIA_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (!hctr[CTR_CHANGED]) break;
+    }
+
+    cc_count_kernel<<<(unsigned)w.nblocks, 256, 0, st>>>(w.T, w.psize, w.blocksum, N, min_size);
+    OBIA_LAUNCH_CHECK();
+    cc_scan_blocks_kernel<<<1, 1024, 0, st>>>(w.blocksum, w.nblocks, w.ctr);
+    OBIA_LAUNCH_CHECK();
+    cc_number_kernel<<<(unsigned)w.nblocks, 256, 0, st>>>(w.T, w.psize, w.blocksum, w.aux, N, min_size,
+                                                          start_label);
+    OBIA_LAUNCH_CHECK();
+    cc_resolve_kernel<<<gridN, 256, 0, st>>>(labels_in, w.T, w.psize, w.adj, w.aux, labels_out, N, min_size,
+                                             mask_label);
+    OBIA_LAUNCH_CHECK();
+    OBIA_CUDA_CHECK(cudaMemcpyAsync(hctr, w.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, st));
+    OBIA_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (n_labels_host) *n_labels_host = hctr[CTR_NKEPT];
+    return OBIA_B200_OK;
+}

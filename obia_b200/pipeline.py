@@ -1,0 +1,305 @@
+"""Device pipeline: raw raster (H, W, C) float32 in HBM -> SLIC label raster ->
+per-segment zonal statistics, all through the C ABI of libobia_b200.so.
+
+PyTorch is used for device memory, streams and (elsewhere) torch.distributed
+only; every per-pixel operation is a hand-written sm_100a kernel.  There is no
+CPU path here: a missing library or a non-CUDA tensor raises.
+
+Reference path being replaced (file:line under /root/reference):
+  obia/segmentation/segment_boundaries.py:31-57  (normalise, select, slic, mask)
+  obia/segmentation/segment_statistics.py:113-176, 475-508 (spectral statistics)
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib, slic_host
+
+STAT_FIELDS = ("count", "mean", "variance", "min", "max", "skewness", "kurtosis", "sum")
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (obia_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _i32_array(values):
+    arr = (ctypes.c_int32 * len(values))(*[int(v) for v in values])
+    return arr
+
+
+# ------------------------------------------------------------------ K1 ------
+def band_minmax(raw, mask=None):
+    """Per-band (min, max, masked min, masked max) and non-finite flags, on the host.
+
+    One pass over the raster; the tiny result is copied back (one stream sync)
+    because the host needs it to validate the input the way numpy/skimage do.
+    """
+    lib = _lib.load()
+    _require_cuda(raw, "raw", torch.float32)
+    H, W, C = raw.shape
+    out = torch.empty((C, 4), dtype=torch.float32, device=raw.device)
+    flags = torch.empty((C,), dtype=torch.int32, device=raw.device)
+    if mask is not None:
+        _require_cuda(mask, "mask", torch.uint8)
+    _lib.check(lib.obia_b200_band_minmax(_p(raw), H * W, C, _p(mask), _p(out), _p(flags), _stream_ptr()),
+               "band_minmax")
+    return out, flags
+
+
+def normalize_inplace(raw, minmax_dev):
+    """`img_data[:, :, i] = normalize_band(...)` for every band (segment_boundaries.py:31-33)."""
+    lib = _lib.load()
+    _require_cuda(raw, "raw", torch.float32)
+    H, W, C = raw.shape
+    _lib.check(lib.obia_b200_normalize_inplace(_p(raw), H * W, C, _p(minmax_dev), _stream_ptr()),
+               "normalize_inplace")
+
+
+@dataclass
+class SlicResult:
+    labels: torch.Tensor            # (H, W) int32; masked pixels = -1 when a mask was given
+    n_labels: int                   # number of kept segments after connectivity (or centres)
+    start_label: int
+    n_centres: int
+    step: float
+    step_yx: tuple
+    minmax: torch.Tensor            # (C, 4) device
+    minmax_host: np.ndarray
+    centres: torch.Tensor           # (n, 2 + Cf) device, final means
+    pre_connectivity: torch.Tensor | None = None
+    features: torch.Tensor | None = None
+    timings: dict = field(default_factory=dict)
+
+
+def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.0, max_num_iter=10,
+                sigma=0, spacing=None, convert2lab=None, enforce_connectivity=True,
+                min_size_factor=0.5, max_size_factor=3, slic_zero=False, start_label=1, mask=None,
+                channel_axis=-1, keep_intermediates=False, init_centroids=None):
+    """SLIC label raster of `raw[:, :, segmentation_bands]` with obia's wrapper semantics.
+
+    Equivalent of segment_boundaries.py:31-57 up to the label raster: every band
+    is min-max normalised (on the fly; `raw` itself is NOT modified here), the
+    selected bands go through skimage's slic() semantics, masked pixels get -1.
+
+    kwargs are skimage.segmentation.slic's (obia forwards **kwargs verbatim).
+    """
+    lib = _lib.load()
+    _require_cuda(raw, "raw", torch.float32)
+    if raw.dim() != 3:
+        raise ValueError("raw must be (H, W, C)")
+    if channel_axis not in (-1, 2):
+        raise NotImplementedError("only channel_axis=-1 (obia always passes H, W, C)")
+    if slic_zero:
+        raise NotImplementedError("slic_zero=True (SLICO) is not implemented on the B200 path yet")
+    if spacing is not None and tuple(float(s) for s in np.ravel(spacing)) not in ((1.0, 1.0), (1.0, 1.0, 1.0)):
+        raise NotImplementedError("anisotropic `spacing` is not implemented on the B200 path")
+    if start_label not in (0, 1):
+        raise ValueError("start_label should be 0 or 1.")
+    H, W, C = (int(s) for s in raw.shape)
+    dev = raw.device
+    if segmentation_bands is None:
+        segmentation_bands = list(range(C))
+    segmentation_bands = [int(b) for b in segmentation_bands]
+    for band in segmentation_bands:
+        if band >= C or band < 0:
+            raise IndexError(f"Band index {band} out of range. Available bands indices: 0 to {C - 1}.")
+    Cs = len(segmentation_bands)
+
+    mask_dev = None
+    if mask is not None:
+        if isinstance(mask, torch.Tensor):
+            mask_dev = (mask != 0).to(device=dev, dtype=torch.uint8).contiguous()
+        else:
+            mask_dev = torch.from_numpy(np.ascontiguousarray(np.asarray(mask) != 0).astype(np.uint8)).to(dev)
+        if tuple(mask_dev.shape) != (H, W):
+            raise ValueError("image and mask should have the same shape.")
+
+    # ---- K1a: band ranges (needed on the host for validation, like numpy does) ----
+    minmax, flags = band_minmax(raw, mask_dev)
+    mm = minmax.cpu().numpy()
+    fl = flags.cpu().numpy()
+    f32 = np.float32
+    with np.errstate(invalid="ignore", divide="ignore"):
+        nmin, nmax = [], []
+        for b in segmentation_bands:
+            mn, mx, mmn, mmx = (f32(v) for v in mm[b])
+            if fl[b] or not np.isfinite(mn) or not np.isfinite(mx) or mx == mn:
+                # NaN/inf in the band, or a constant band (0/0 after obia's normalise)
+                raise ValueError("unmasked NaN values in image are not supported")
+            if mask_dev is not None and np.isnan(mmn):
+                raise ValueError("zero-size array to reduction operation minimum which has no identity")
+            d = f32(mx - mn)
+            nmin.append(f32(f32(mmn - mn) / d))
+            nmax.append(f32(f32(mmx - mn) / d))
+        imin, imax = f32(min(nmin)), f32(max(nmax))
+
+    multichannel = True
+    to_lab = False
+    if multichannel and (convert2lab or convert2lab is None):
+        if Cs != 3 and convert2lab:
+            raise ValueError("Lab colorspace conversion requires a RGB image.")
+        to_lab = Cs == 3
+    Cf = 3 if to_lab else Cs
+
+    # ---- centres --------------------------------------------------------------
+    if init_centroids is not None:
+        yx, steps = init_centroids
+    elif mask_dev is not None:
+        yx, steps = slic_host.mask_centroids(mask_dev.cpu().numpy(), int(n_segments))
+    else:
+        yx, steps = slic_host.grid_centroids(H, W, n_segments)
+    n = int(yx.shape[0])
+    step = float(max(steps))
+    step_y, step_x = slic_host.window_steps(H, W, n)
+    if not step > 0:
+        raise ValueError("degenerate SLIC initialisation (step == 0)")
+    centres_np = np.zeros((n, 2 + Cf), dtype=np.float32)
+    centres_np[:, :2] = yx.astype(np.float32)
+    centres = torch.from_numpy(centres_np).to(dev)
+
+    # ---- K1b: features ----------------------------------------------------------
+    ratio = f32(1.0 / compactness)
+    sig = f32(sigma) if np.ndim(sigma) == 0 else None
+    if sig is None:
+        sig_y, sig_x = (f32(s) for s in np.ravel(sigma)[-2:])
+    else:
+        sig_y = sig_x = sig
+    smooth = bool(sig_y > 0 or sig_x > 0)
+    pitch = (W + 31) // 32 * 32
+    feats = torch.empty((Cf, H, pitch), dtype=torch.float32, device=dev)
+    bands_arr = _i32_array(segmentation_bands)
+    bmin = np.ascontiguousarray(mm[:, 0], dtype=np.float32)
+    bmax = np.ascontiguousarray(mm[:, 1], dtype=np.float32)
+    _lib.check(lib.obia_b200_slic_features(
+        _p(raw), H, W, C, bands_arr, Cs, bmin.ctypes.data_as(ctypes.c_void_p),
+        bmax.ctypes.data_as(ctypes.c_void_p), float(imin), float(imax), int(to_lab),
+        float(1.0 if smooth else ratio), _p(feats), pitch, _stream_ptr()), "slic_features")
+    if smooth:
+        wy, ry = slic_host.gaussian_taps(sig_y) if sig_y > 0 else (np.ones(1), 0)
+        wx, rx = slic_host.gaussian_taps(sig_x) if sig_x > 0 else (np.ones(1), 0)
+        tmp = torch.empty_like(feats)
+        _lib.check(lib.obia_b200_gaussian_planar(
+            _p(feats), _p(tmp), _p(feats), H, W, pitch, Cf, wy.ctypes.data_as(ctypes.c_void_p), ry,
+            wx.ctypes.data_as(ctypes.c_void_p), rx, float(ratio), _stream_ptr()), "gaussian_planar")
+        del tmp
+
+    # ---- K2: iterations -----------------------------------------------------------
+    max_abs = float(ratio) * (256.0 if to_lab else 4.0)
+    fix_scale = slic_host.fixed_point_scale(max_abs, H, W, step_y, step_x)
+    ws_bytes = lib.obia_b200_slic_workspace_bytes(H, W, Cf, n, step_y, step_x)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    labels = torch.empty((H, W), dtype=torch.int32, device=dev)
+    status = torch.zeros((4,), dtype=torch.int32, device=dev)
+
+    def run(ignore_color):
+        _lib.check(lib.obia_b200_slic_iterate(
+            _p(feats), _p(mask_dev), _p(centres), _p(labels), _p(ws), H, W, pitch, Cf, n, step,
+            step_y, step_x, int(max_num_iter), int(start_label), int(ignore_color), fix_scale,
+            _p(status), _stream_ptr()), "slic_iterate")
+        if int(status[0].item()) != 0:
+            raise _lib.ObiaB200Error("slic_iterate: a tile collected more than 4096 candidate centres "
+                                     "(degenerate centre distribution)")
+
+    if mask_dev is not None:
+        run(True)   # maskSLIC step 2: spatial-only k-means moves the centres first
+    run(False)
+    del ws
+
+    pre_cc = labels.clone() if keep_intermediates else None
+    n_labels = n
+    if enforce_connectivity:
+        if mask_dev is not None:
+            segment_size = float(mask_dev.sum().item()) / n
+        else:
+            segment_size = float(H * W) / n
+        min_size = int(min_size_factor * segment_size)
+        max_size = int(max_size_factor * segment_size)
+        if max_size < 1:
+            raise ValueError("max_size_factor too small: connectivity needs max_size >= 1")
+        cc_bytes = lib.obia_b200_connectivity_workspace_bytes(H, W)
+        cc_ws = torch.empty((cc_bytes,), dtype=torch.uint8, device=dev)
+        out = torch.empty_like(labels)
+        nl = ctypes.c_int64(0)
+        _lib.check(lib.obia_b200_enforce_connectivity(
+            _p(labels), _p(out), _p(cc_ws), H, W, min_size, max_size, int(start_label),
+            ctypes.byref(nl), _stream_ptr()), "enforce_connectivity")
+        labels = out
+        n_labels = int(nl.value)
+        del cc_ws
+
+    if mask_dev is not None:
+        labels.masked_fill_(mask_dev == 0, -1)   # segment_boundaries.py:55-57
+
+    return SlicResult(labels=labels, n_labels=n_labels, start_label=int(start_label), n_centres=n,
+                      step=step, step_yx=(step_y, step_x), minmax=minmax, minmax_host=mm, centres=centres,
+                      pre_connectivity=pre_cc, features=feats if keep_intermediates else None)
+
+
+def enforce_connectivity(labels, min_size, max_size, start_label=1):
+    """K3 on its own: (labels_out int32 (H, W), number of kept segments)."""
+    lib = _lib.load()
+    _require_cuda(labels, "labels", torch.int32)
+    H, W = (int(s) for s in labels.shape)
+    ws = torch.empty((lib.obia_b200_connectivity_workspace_bytes(H, W),), dtype=torch.uint8,
+                     device=labels.device)
+    out = torch.empty_like(labels)
+    nl = ctypes.c_int64(0)
+    _lib.check(lib.obia_b200_enforce_connectivity(_p(labels), _p(out), _p(ws), H, W, int(min_size),
+                                                  int(max_size), int(start_label), ctypes.byref(nl),
+                                                  _stream_ptr()), "enforce_connectivity")
+    return out, int(nl.value)
+
+
+# ------------------------------------------------------------------ K4 ------
+def zonal_stats(labels, raw, bands=None, max_label=None, resolution=1e-6):
+    """Per-label, per-band statistics table, float64 (max_label+1, Cz, 8) on the device.
+
+    Fields: STAT_FIELDS.  Labels < 0 (obia's -1 = masked) are ignored.
+    """
+    lib = _lib.load()
+    _require_cuda(labels, "labels", torch.int32)
+    _require_cuda(raw, "raw", torch.float32)
+    H, W, C = (int(s) for s in raw.shape)
+    if tuple(labels.shape) != (H, W):
+        raise ValueError("labels and raster shapes differ")
+    if bands is None:
+        bands = list(range(C))
+    bands = [int(b) for b in bands]
+    if max_label is None:
+        max_label = int(labels.max().item())
+    max_label = max(int(max_label), 0)
+    Cz = len(bands)
+    stats = torch.empty((max_label + 1, Cz, 8), dtype=torch.float64, device=raw.device)
+    ws = torch.empty((lib.obia_b200_zonal_workspace_bytes(max_label, 8),), dtype=torch.uint8,
+                     device=raw.device)
+    for c0 in range(0, Cz, 64):   # kernel-parameter table holds 64 bands per call
+        sub = bands[c0:c0 + 64]
+        if Cz <= 64:
+            view = stats
+        else:
+            view = torch.empty((max_label + 1, len(sub), 8), dtype=torch.float64, device=raw.device)
+        _lib.check(lib.obia_b200_zonal_stats(_p(labels), _p(raw), H, W, C, _i32_array(sub), len(sub),
+                                             max_label, float(resolution), _p(view), _p(ws),
+                                             _stream_ptr()), "zonal_stats")
+        if Cz > 64:
+            stats[:, c0:c0 + len(sub)] = view
+    return stats

@@ -1,0 +1,64 @@
+"""Drop-in for obia/segmentation/segment.py (`segment`, `Segments`).
+
+Same signature and return object as the reference
+(/root/reference/obia/segmentation/segment.py:10-93): `segment()` =
+`create_segments` (SLIC on the GPU) followed by `create_objects` (zonal
+statistics on the GPU); `calc_min` / `calc_max` are not forwarded, exactly like
+the reference (:87-91), so they are always on.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .segment_boundaries import create_segments
+from .segment_statistics import create_objects
+
+
+class Segments:
+    _segments = None
+    segments = None
+    method = None
+    params = {}   # class-level shared dict, as in the reference (:33)
+
+    def __init__(self, _segments, segments, method, **kwargs):
+        self._segments = _segments
+        self.segments = segments
+        self.method = method
+        self.params.update(kwargs)
+
+    def to_segmented_image(self, image):
+        """Overlay segment boundaries (yellow) on a PIL image (segment.py:41-53)."""
+        from PIL.Image import Image as PILImage
+        from PIL.Image import fromarray
+        if not isinstance(image, PILImage):
+            raise TypeError('Input must be a PIL Image')
+        img = np.array(image).astype(np.float64) / 255.0
+        if img.ndim == 2:
+            img = np.stack([img] * 3, axis=-1)
+        lab = self._segments.label_raster.cpu().numpy()
+        edge = np.zeros(lab.shape, dtype=bool)
+        edge[:, :-1] |= lab[:, :-1] != lab[:, 1:]
+        edge[:-1, :] |= lab[:-1, :] != lab[1:, :]
+        img[edge, :3] = (1.0, 1.0, 0.0)
+        return fromarray((img * 255).astype(np.uint8))
+
+    def write_segments(self, file_path):
+        if hasattr(self.segments, "to_file"):
+            self.segments.to_file(file_path)
+        else:
+            raise NotImplementedError("writing a GeoPackage needs geopandas (host step outside the GPU path)")
+
+
+def segment(image, segmentation_bands=None, statistics_bands=None,
+            method="slic", calc_mean=True, calc_variance=True,
+            calc_skewness=True, calc_kurtosis=True, calc_contrast=True,
+            calc_dissimilarity=True, calc_homogeneity=True, calc_ASM=True,
+            calc_energy=True, calc_correlation=True, **kwargs):
+    segments_gdf = create_segments(image, segmentation_bands=segmentation_bands, method=method, **kwargs)
+    slic_kwargs = {k: v for k, v in kwargs.items() if k not in ("mutate_image", "polygonize")}
+    objects_gdf = create_objects(segments_gdf, image, spectral_bands=statistics_bands, calc_mean=calc_mean,
+                                 calc_variance=calc_variance, calc_skewness=calc_skewness, calc_kurtosis=calc_kurtosis,
+                                 calc_contrast=calc_contrast, calc_dissimilarity=calc_dissimilarity,
+                                 calc_homogeneity=calc_homogeneity, calc_ASM=calc_ASM, calc_energy=calc_energy,
+                                 calc_correlation=calc_correlation)
+    return Segments(segments_gdf, objects_gdf, method, **slic_kwargs)

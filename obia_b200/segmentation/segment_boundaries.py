@@ -1,0 +1,180 @@
+"""Drop-in for obia/segmentation/segment_boundaries.py (`create_segments`).
+
+Same call: `create_segments(image, segmentation_bands=None, method="slic", **kwargs)`
+with kwargs = skimage.segmentation.slic's (`n_segments`, `compactness`,
+`max_num_iter`, `sigma`, `convert2lab`, `enforce_connectivity`,
+`min_size_factor`, `max_size_factor`, `start_label`, `mask`, ...), same
+IndexError / ValueError / Exception behaviour
+(/root/reference/obia/segmentation/segment_boundaries.py:18-78).
+
+What differs, on purpose (DESIGN.md "boundary"):
+  * the work is done on the GPU in label-raster space; the returned table has
+    the reference's columns (`geometry`, `segment_id`) and row order (ascending
+    label, one row per 4-connected region, `segment_id = 1..N`) and carries the
+    label raster as `.label_raster`.  Polygon geometries are materialised on
+    the host only on request (`polygonize=True`, needs shapely) -- the
+    reference's per-label full-raster `rasterio.features.shapes` loop
+    (:62-70) is O(n_segments * H * W) and is not on the GPU path.
+  * the reference prints the shape of the band stack (:46); this does not.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+
+
+class SegmentsFrame(pd.DataFrame):
+    """pandas DataFrame [`geometry`, `segment_id`] + the label raster it describes.
+
+    Extra attributes (kept through pandas operations where possible):
+      label_raster    (H, W) int32 CUDA tensor; -1 = masked out
+      segment_labels  int64 numpy array: label value of each row (row i <-> segment_id i+1)
+      crs, transform  copied from the Image
+    """
+    _metadata = ["label_raster", "segment_labels", "crs", "transform", "slic_result"]
+
+    @property
+    def _constructor(self):
+        return SegmentsFrame
+
+
+def normalize_band(band):
+    """segment_boundaries.py:11-16 (host helper kept for API parity)."""
+    return (band - np.min(band)) / (np.max(band) - np.min(band))
+
+
+def _epsg_string(crs):
+    try:
+        import pyproj
+        return f"EPSG:{pyproj.CRS(crs).to_epsg()}"
+    except Exception:
+        return crs
+
+
+def _apply_image_mutation(image, raw, minmax_dev):
+    """Side effect of segment_boundaries.py:31-33: every band of `img_data` normalised in place."""
+    import torch
+
+    from .. import pipeline
+
+    data = image.img_data
+    if isinstance(data, torch.Tensor) and data.is_cuda and data.dtype == torch.float32 and data.is_contiguous():
+        pipeline.normalize_inplace(data, minmax_dev)
+        return
+    tmp = raw.clone()
+    pipeline.normalize_inplace(tmp, minmax_dev)
+    if isinstance(data, torch.Tensor):
+        data.copy_(tmp.to(data.device, dtype=data.dtype))
+    else:
+        arr = np.asarray(data)
+        if arr.dtype == np.float32 and arr.flags.c_contiguous and arr.flags.writeable:
+            torch.from_numpy(arr).copy_(tmp, non_blocking=False)
+        else:
+            arr[...] = tmp.cpu().numpy()
+
+
+def frame_from_labels(labels, start_label, n_labels, connected, image=None, polygonize=False):
+    """Build the `[geometry, segment_id]` table from a label raster.
+
+    Row order = ascending label value, then raster order of the region's first
+    pixel (what `np.unique` + `rasterio.features.shapes` give at :59-70).
+    """
+    import torch
+
+    if connected:
+        # consecutive labels, one 4-connected region each: no search needed.  Label 0
+        # can exist besides start_label=1 (SURVEY.md defect 7): found by one reduction.
+        lo = int(start_label)
+        has_zero = False
+        if start_label == 1:
+            has_zero = bool((labels == 0).any().item())
+        seg_labels = np.arange(lo, lo + n_labels, dtype=np.int64)
+        if has_zero:
+            # label 0 regions may be several: number them by component
+            seg_labels = None
+    else:
+        seg_labels = None
+    if seg_labels is None:
+        # general case: one row per 4-connected region of equal label
+        from .. import pipeline
+        lab_cc = torch.where(labels < 0, torch.full_like(labels, -1), labels + 1).contiguous()
+        comp, _ = pipeline.enforce_connectivity(lab_cc, 0, 2 ** 31 - 2, start_label=0)
+        # comp numbers regions by first pixel; order rows by (label, first pixel)
+        valid = labels >= 0
+        comp_v = comp[valid].to(torch.int64)
+        lab_v = labels[valid].to(torch.int64)
+        ncomp = int(comp_v.max().item()) + 1 if comp_v.numel() else 0
+        comp_label = torch.zeros((ncomp,), dtype=torch.int64, device=labels.device)
+        comp_label[comp_v] = lab_v
+        order = torch.argsort(comp_label, stable=True)   # comp ids are already in first-pixel order
+        seg_labels = comp_label[order].cpu().numpy()
+        # rows index regions, not labels: remap the raster to region ids (1..N)
+        rank = torch.empty_like(order)
+        rank[order] = torch.arange(ncomp, device=labels.device)
+        region = torch.full_like(labels, -1)
+        region[valid] = (rank[comp_v] + 1).to(torch.int32)
+        raster, ids = region, np.arange(1, ncomp + 1, dtype=np.int64)
+    else:
+        raster, ids = labels, np.arange(1, len(seg_labels) + 1, dtype=np.int64)
+
+    geometry = [None] * len(ids)
+    if polygonize:
+        from ..utils.polygonize import polygons_from_labels
+        geometry = polygons_from_labels(raster.cpu().numpy(), seg_labels if raster is labels else ids,
+                                        None if image is None else image.affine_transformation)
+    gdf = SegmentsFrame({"geometry": geometry, "segment_id": ids})
+    gdf.label_raster = raster
+    gdf.segment_labels = seg_labels if raster is labels else ids
+    gdf.crs = None if image is None else _epsg_string(image.crs)
+    gdf.transform = None if image is None else image.transform
+    return gdf
+
+
+def create_segments(image, segmentation_bands=None, method="slic", *, mutate_image=True,
+                    polygonize=False, **kwargs):
+    """
+    :param image: Image (obia_b200.handlers.geotif.Image) -- `img_data` (H, W, C) float32.
+    :param segmentation_bands: band indices used for segmentation (None = all).
+    :param method: 'slic' (the GPU hot path).  'quickshift' is not implemented.
+    :param mutate_image: reproduce the reference's in-place normalisation of `image.img_data`.
+    :param polygonize: also build shapely polygons on the host (slow, optional).
+    :param kwargs: skimage.segmentation.slic keyword arguments.
+    :return: SegmentsFrame with columns `geometry`, `segment_id`.
+    """
+    from .. import pipeline
+
+    if method == "quickshift":
+        raise NotImplementedError("method='quickshift' is not part of the B200 hot path")
+    if method != "slic":
+        raise Exception('An unknown segmentation method was requested.')
+
+    raw = image.device_raw()
+    num_bands = int(raw.shape[2])
+    if segmentation_bands is None:
+        segmentation_bands = list(range(num_bands))
+    # same validation and message as :38-40; note the reference normalises (mutates)
+    # every band BEFORE validating the indices (:31-33)
+    bad = [b for b in segmentation_bands if b >= num_bands or b < 0]
+
+    if bad and mutate_image:
+        minmax, _ = pipeline.band_minmax(raw)
+        _apply_image_mutation(image, raw, minmax)
+    for band in bad:
+        raise IndexError(f"Band index {band} out of range. Available bands indices: 0 to {num_bands - 1}.")
+
+    try:
+        res = pipeline.slic_labels(raw, segmentation_bands, **kwargs)
+    except Exception:
+        # the reference has already normalised img_data when slic() raises (:31-33 run first)
+        if mutate_image:
+            minmax, _ = pipeline.band_minmax(raw)
+            _apply_image_mutation(image, raw, minmax)
+        raise
+    if mutate_image:
+        _apply_image_mutation(image, raw, res.minmax)
+
+    connected = bool(kwargs.get("enforce_connectivity", True))
+    gdf = frame_from_labels(res.labels, res.start_label, res.n_labels, connected, image=image,
+                            polygonize=polygonize)
+    gdf.slic_result = res
+    return gdf

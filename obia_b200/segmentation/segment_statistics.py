@@ -1,0 +1,119 @@
+"""Drop-in for obia/segmentation/segment_statistics.py (`create_objects`).
+
+Same signature, guards and column contract as the reference
+(/root/reference/obia/segmentation/segment_statistics.py:392-511, columns from
+`_create_empty_stats_columns` :12-110): `segment_id`, then per spectral band
+`b{i}_mean, _variance, _min, _max, _skewness, _kurtosis`, then per textural band
+`b{i}_contrast, _dissimilarity, _homogeneity, _ASM, _energy, _correlation`, then
+`pai, fhd, ch, mean_intensity, variance_intensity`, then `geometry`.
+
+The per-segment loop (crop -> polygon mask -> numpy/scipy statistics, :475-508)
+is replaced by ONE fused pass of the CUDA zonal-statistics kernel over the label
+raster.  Statistics are taken over the RAW raster values, like the reference
+(which re-reads the file, obia/utils/utils.py:45-48).
+
+Not on the GPU path yet: GLCM texture columns are emitted as NaN
+(`calculate_textural` keeps the reference's default so the column set is the one
+`classify` expects); the point-cloud columns are NaN in the reference too.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+
+
+def _create_empty_stats_columns(spectral_bands, textural_bands, calc_mean, calc_variance, calc_min, calc_max,
+                                calc_skewness, calc_kurtosis,
+                                calc_contrast, calc_dissimilarity, calc_homogeneity, calc_ASM, calc_energy,
+                                calc_correlation,
+                                calc_pai, calc_fhd, calc_ch, calc_mean_intensity, calc_variance_intensity):
+    """Column list in the reference's order (segment_statistics.py:64-110)."""
+    columns = ['segment_id']
+    spectral = [("mean", calc_mean), ("variance", calc_variance), ("min", calc_min), ("max", calc_max),
+                ("skewness", calc_skewness), ("kurtosis", calc_kurtosis)]
+    textural = [("contrast", calc_contrast), ("dissimilarity", calc_dissimilarity),
+                ("homogeneity", calc_homogeneity), ("ASM", calc_ASM), ("energy", calc_energy),
+                ("correlation", calc_correlation)]
+    for b in spectral_bands:
+        columns += [f"b{b}_{name}" for name, on in spectral if on]
+    for b in textural_bands:
+        columns += [f"b{b}_{name}" for name, on in textural if on]
+    cloud = [("pai", calc_pai), ("fhd", calc_fhd), ("ch", calc_ch), ("mean_intensity", calc_mean_intensity),
+             ("variance_intensity", calc_variance_intensity)]
+    columns += [name for name, on in cloud if on]
+    columns.append('geometry')
+    return columns
+
+
+def _labels_of(segments):
+    """(label raster CUDA int32, label value per row) of a segments table."""
+    raster = getattr(segments, "label_raster", None)
+    if raster is None:
+        raise TypeError(
+            "create_objects needs the table returned by obia_b200 create_segments (it carries the label "
+            "raster); rasterising arbitrary polygon GeoDataFrames is a host step outside the GPU path")
+    return raster, np.asarray(segments.segment_labels, dtype=np.int64)
+
+
+def create_objects(
+        segments, image, ept=None, ept_srs=None, spectral_bands=None, textural_bands=None, voxel_resolution=None,
+        calculate_spectral=True, calculate_textural=True, calculate_structural=False, calculate_radiometric=False,
+        calc_mean=True, calc_variance=True, calc_min=True, calc_max=True, calc_skewness=True, calc_kurtosis=True,
+        calc_contrast=True, calc_dissimilarity=True, calc_homogeneity=True, calc_ASM=True, calc_energy=True,
+        calc_correlation=True,
+        calc_pai=True, calc_fhd=True, calc_ch=True, calc_mean_intensity=True, calc_variance_intensity=True
+):
+    """Per-segment feature table (see module docstring for the column contract)."""
+    from .. import pipeline
+
+    if not (calculate_spectral or calculate_textural or calculate_structural or calculate_radiometric):
+        raise ValueError(
+            "At least one of 'calculate_spectral', 'calculate_textural', 'calculate_structural', or 'calculate_radiometric' must be True."
+        )
+    if ept is not None or calculate_structural or calculate_radiometric:
+        raise NotImplementedError(
+            "Point-cloud workflows are temporarily disabled. "
+            "Use spectral/textural statistics only for now."
+        )
+
+    raw = image.device_raw()
+    n_bands = int(raw.shape[2])
+    if spectral_bands is None:
+        spectral_bands = list(range(n_bands))
+    if textural_bands is None:
+        textural_bands = list(range(n_bands))
+
+    columns = _create_empty_stats_columns(
+        spectral_bands, textural_bands,
+        calc_mean, calc_variance, calc_min, calc_max, calc_skewness, calc_kurtosis,
+        calc_contrast, calc_dissimilarity, calc_homogeneity, calc_ASM, calc_energy, calc_correlation,
+        calc_pai, calc_fhd, calc_ch, calc_mean_intensity, calc_variance_intensity
+    )
+
+    raster, row_labels = _labels_of(segments)
+    data = {"segment_id": np.asarray(segments["segment_id"]), "geometry": list(segments["geometry"])}
+    if len(spectral_bands) > 0 and len(row_labels) > 0:
+        for b in spectral_bands:
+            if b < 0 or b >= n_bands:
+                # the reference indexes the (C, h, w) crop with the band number (:144)
+                raise IndexError(f"index {b} is out of bounds for axis 0 with size {n_bands}")
+        max_label = int(row_labels.max())
+        # the reference computes in float32 for float32 rasters (np.where keeps float32):
+        # scipy's "nearly constant" NaN rule uses that dtype's resolution
+        stats = pipeline.zonal_stats(raster, raw, spectral_bands, max_label=max_label, resolution=1e-6)
+        table = stats[row_labels].cpu().numpy()      # (rows, Cz, 8)
+        names = pipeline.STAT_FIELDS
+        want = [("mean", calc_mean), ("variance", calc_variance), ("min", calc_min), ("max", calc_max),
+                ("skewness", calc_skewness), ("kurtosis", calc_kurtosis)]
+        for j, b in enumerate(spectral_bands):
+            for name, on in want:
+                if on:
+                    data[f"b{b}_{name}"] = table[:, j, names.index(name)]
+    out = pd.DataFrame(data, columns=columns)   # missing columns (texture, point cloud) -> NaN
+    from .segment_boundaries import SegmentsFrame
+    out = SegmentsFrame(out)
+    out.label_raster = raster
+    out.segment_labels = row_labels
+    out.crs = getattr(segments, "crs", None)
+    out.transform = getattr(segments, "transform", None)
+    return out

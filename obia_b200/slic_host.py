@@ -1,0 +1,119 @@
+"""Host-side set-up of a SLIC run: grid geometry, centre initialisation and the
+Gaussian taps.  O(n_segments) work that scikit-image also does in Python
+before entering its Cython loop (reached from
+/root/reference/obia/segmentation/segment_boundaries.py:51); the per-pixel work
+is all in the CUDA library.
+
+Restated from scikit-image (`skimage/util/_regular_grid.py::regular_grid`,
+`skimage/segmentation/slic_superpixels.py::_get_grid_centroids`,
+`::_get_mask_centroids`), see SURVEY.md section 3.4 step 4.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def regular_grid_steps(shape_zyx, n_points):
+    """(starts, steps) of skimage's `regular_grid`; step None -> every index.
+
+    skimage sorts the dimensions, spreads `n_points` over the volume with a
+    cubic-root step, then clamps dimensions that are thinner than the step
+    (always the depth-1 axis for obia's 2-D rasters).
+    """
+    shape = np.asarray(shape_zyx)
+    ndim = len(shape)
+    order = np.argsort(shape)
+    unsort = np.argsort(order)
+    dims = shape[order]
+    space = float(np.prod(shape))
+    if space <= n_points:
+        return [0] * ndim, [None] * ndim
+    steps = np.full(ndim, (space / n_points) ** (1.0 / ndim), dtype=np.float64)
+    if (dims < steps).any():
+        for d in range(ndim):
+            steps[d] = dims[d]
+            space = float(np.prod(dims[d + 1:]))
+            steps[d + 1:] = (space / n_points) ** (1.0 / (ndim - d - 1))
+            if (dims >= steps).all():
+                break
+    starts = (steps // 2).astype(int)
+    isteps = np.round(steps).astype(int)  # numpy rounds half to even, like skimage
+    return [int(starts[i]) for i in unsort], [int(isteps[i]) for i in unsort]
+
+
+def window_steps(H, W, n_centres):
+    """Integer (step_y, step_x) that `_slic_cython` recomputes for its +-2*step windows."""
+    _, steps = regular_grid_steps((1, H, W), n_centres)
+    sy = 1 if steps[1] is None else steps[1]
+    sx = 1 if steps[2] is None else steps[2]
+    return int(sy), int(sx)
+
+
+def grid_centroids(H, W, n_segments):
+    """Unmasked initial centres: all grid points, y-major.  Returns (yx float64 (n,2), steps (3,))."""
+    starts, steps = regular_grid_steps((1, H, W), n_segments)
+    ys = np.arange(H)[slice(starts[1], None, steps[1])]
+    xs = np.arange(W)[slice(starts[2], None, steps[2])]
+    gy, gx = np.meshgrid(ys, xs, indexing="ij")
+    yx = np.stack([gy.ravel(), gx.ravel()], axis=-1).astype(np.float64)
+    fsteps = np.asarray([1.0 if s is None else float(s) for s in steps])
+    return yx, fsteps
+
+
+def mask_centroids(mask_hw, n_segments):
+    """maskSLIC initial centres (RandomState(123) sampling + 5 k-means sweeps).
+
+    Same scipy routines scikit-image calls (`kmeans2`, `pdist`).
+    Returns (yx float64 (n,2), steps (3,) = mean |centroid - nearest centroid| per axis).
+    """
+    from scipy.cluster.vq import kmeans2
+    from scipy.spatial import cKDTree
+
+    mask3 = np.ascontiguousarray(mask_hw, dtype=bool)[np.newaxis]
+    coord = np.array(np.nonzero(mask3), dtype=float).T
+    if len(coord) == 0:
+        # scikit-image fails on `image[mask].min()` of an empty selection
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    rng = np.random.RandomState(123)
+    idx_full = np.arange(len(coord), dtype=int)
+    idx = np.sort(rng.choice(idx_full, min(n_segments, len(coord)), replace=False))
+    n_dense = int((10 ** 2) * n_segments)
+    idx_dense = np.sort(rng.choice(idx_full, min(n_dense, len(coord)), replace=False))
+    centroids, _ = kmeans2(coord[idx_dense], coord[idx], iter=5)
+    # nearest other centroid: scikit-image builds the full O(n^2) pdist matrix and
+    # takes argmin; a k-d tree gives the same neighbour for distinct distances
+    if len(centroids) > 1:
+        if len(centroids) <= 2048:
+            from scipy.spatial.distance import pdist, squareform
+            dist = squareform(pdist(centroids))
+            np.fill_diagonal(dist, np.inf)
+            closest = dist.argmin(-1)
+        else:
+            _, nn = cKDTree(centroids).query(centroids, k=2)
+            closest = nn[:, 1]
+        steps = np.abs(centroids - centroids[closest, :]).mean(0)
+    else:
+        # pdist of one point is empty; argmin of the 1x1 [[inf]] matrix is 0
+        steps = np.abs(centroids - centroids[[0], :]).mean(0)
+    return centroids[:, 1:3].copy(), steps
+
+
+def gaussian_taps(sigma):
+    """scipy.ndimage `_gaussian_kernel1d(sigma, 0, int(4*sigma+0.5))` (symmetric, float64)."""
+    sd = float(sigma)
+    radius = int(4.0 * sd + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sd * sd) * x ** 2)
+    phi = phi / phi.sum()
+    return np.ascontiguousarray(phi, dtype=np.float64), radius
+
+
+def fixed_point_scale(max_abs_value, H, W, step_y, step_x):
+    """Power-of-two scale so that per-centre colour sums fit 62 bits."""
+    reach = min(H * W, (4 * step_y + 1) * (4 * step_x + 1))
+    bits_px = max(1, math.ceil(math.log2(reach + 1)))
+    bits_val = math.ceil(math.log2(max(max_abs_value, 1e-30))) + 1
+    shift = 62 - bits_px - bits_val
+    return float(2.0 ** min(shift, 60))

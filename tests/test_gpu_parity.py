@@ -1,0 +1,336 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star): integer / index work bit-exact (connectivity,
+assignment given identical centres, counts); float statistics within 1e-5
+relative; full-SLIC labels >= 99.5 % per-pixel agreement.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------ K1 ------
+@pytest.mark.parametrize("H,W,C,masked", [(37, 53, 3, False), (64, 64, 8, True), (19, 21, 5, True),
+                                          (128, 96, 64, False), (7, 9, 1, False)])
+def test_band_minmax(H, W, C, masked):
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    raw = synth_raster(H, W, C, seed=H + C) * 100 - 20
+    mask = None
+    if masked:
+        mask = (np.random.RandomState(1).rand(H, W) < 0.4).astype(np.uint8)
+    mm, fl = pipeline.band_minmax(_cuda(raw), None if mask is None else _cuda(mask))
+    mm = mm.cpu().numpy()
+    assert not fl.cpu().numpy().any()
+    np.testing.assert_array_equal(mm[:, 0], raw.reshape(-1, C).min(0))
+    np.testing.assert_array_equal(mm[:, 1], raw.reshape(-1, C).max(0))
+    if masked:
+        sel = raw[mask != 0]
+        np.testing.assert_array_equal(mm[:, 2], sel.min(0))
+        np.testing.assert_array_equal(mm[:, 3], sel.max(0))
+
+
+def test_band_minmax_nonfinite_flags():
+    from obia_b200 import pipeline
+    raw = np.random.RandomState(0).rand(16, 16, 4).astype(np.float32)
+    raw[3, 4, 1] = np.nan
+    raw[5, 6, 2] = np.inf
+    _, fl = pipeline.band_minmax(_cuda(raw))
+    assert fl.cpu().numpy().tolist() == [0, 1, 2, 0]
+
+
+def test_normalize_inplace_bitexact():
+    from obia_b200 import pipeline
+    import slic_oracle as so
+    from gpu_helpers import synth_raster
+    raw = synth_raster(45, 67, 5, seed=3) * 1000
+    t = _cuda(raw)
+    mm, _ = pipeline.band_minmax(t)
+    pipeline.normalize_inplace(t, mm)
+    want = raw.copy()
+    for i in range(5):
+        want[:, :, i] = so.normalize_band(want[:, :, i])
+    np.testing.assert_array_equal(t.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("C,bands,compactness", [(8, None, 0.1), (5, [4, 0, 2, 3], 10.0), (64, None, 1.0)])
+def test_features_bitexact_multiband(C, bands, compactness):
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster, oracle_features
+    raw = synth_raster(50, 70, C, seed=C) * 300 + 5
+    bands = list(range(C)) if bands is None else bands
+    want = oracle_features(raw, bands, compactness, convert2lab=False)
+    res = pipeline.slic_labels(_cuda(raw), bands, n_segments=20, compactness=compactness, max_num_iter=1,
+                               convert2lab=False, keep_intermediates=True)
+    got = res.features.cpu().numpy()[:, :, :70]
+    np.testing.assert_array_equal(np.moveaxis(got, 0, -1), want)
+
+
+def test_features_lab_close():
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster, oracle_features
+    raw = synth_raster(60, 80, 3, seed=9, quantize=True)
+    want = oracle_features(raw, [0, 1, 2], 10.0)
+    res = pipeline.slic_labels(_cuda(raw), [0, 1, 2], n_segments=20, compactness=10.0, max_num_iter=1,
+                               keep_intermediates=True)
+    got = np.moveaxis(res.features.cpu().numpy()[:, :, :80], 0, -1)
+    # powf/cbrtf differ by a few ulp between libm and CUDA: not bit-exact by construction
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
+
+
+def test_gaussian_matches_scipy():
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster, oracle_features
+    raw = synth_raster(41, 59, 4, seed=2)
+    want = oracle_features(raw, [0, 1, 2, 3], 0.5, convert2lab=False, sigma=1.3)
+    res = pipeline.slic_labels(_cuda(raw), None, n_segments=20, compactness=0.5, max_num_iter=1,
+                               convert2lab=False, sigma=1.3, keep_intermediates=True)
+    got = np.moveaxis(res.features.cpu().numpy()[:, :, :59], 0, -1)
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
+    print("gaussian exact fraction", float((got == want).mean()))
+
+
+# ------------------------------------------------------------------ K2 ------
+@pytest.mark.parametrize("H,W,C,n,compactness,masked", [
+    (64, 96, 3, 40, 0.2, False), (90, 70, 8, 60, 0.05, False), (50, 50, 4, 30, 1.0, True),
+    (33, 130, 16, 25, 0.3, False), (40, 40, 64, 16, 0.5, False), (71, 45, 1, 50, 0.1, False)])
+def test_assign_bitexact_given_centres(H, W, C, n, compactness, masked):
+    """One assignment sweep from identical centres must reproduce the oracle's labels exactly."""
+    import slic_oracle as so
+    from gpu_helpers import synth_raster, run_slic_iterate
+    feats = (synth_raster(H, W, C, seed=H * W + C) / compactness).astype(np.float32)
+    mask = None
+    if masked:
+        mask = np.ones((H, W), np.uint8)
+        mask[:10, :15] = 0
+        mask[30:, 40:] = 0
+    # centres after two oracle iterations (drifted, non-grid)
+    centroids, steps = so._get_grid_centroids((1, H, W), n)
+    seg = np.ascontiguousarray(np.concatenate([centroids, np.zeros((len(centroids), C))], -1), dtype=np.float32)
+    so.slic_core(feats, mask, seg, max(steps), 2, np.ones(3, np.float32), False, 1, False)
+    want, dist = so.slic_assign_once(feats, mask, seg, max(steps), 1, False)
+    got, _ = run_slic_iterate(feats, mask, seg[:, 1:], max(steps), 1, start_label=1)
+    np.testing.assert_array_equal(got, want)
+
+
+def test_centre_update_close():
+    import slic_oracle as so
+    from gpu_helpers import synth_raster, run_slic_iterate
+    H, W, C, n = 80, 100, 5, 50
+    feats = (synth_raster(H, W, C, seed=5) / 0.3).astype(np.float32)
+    centroids, steps = so._get_grid_centroids((1, H, W), n)
+    seg = np.ascontiguousarray(np.concatenate([centroids, np.zeros((len(centroids), C))], -1), dtype=np.float32)
+    seg0 = seg.copy()
+    so.slic_core(feats, None, seg, max(steps), 1, np.ones(3, np.float32), False, 1, False)
+    _, got = run_slic_iterate(feats, None, seg0[:, 1:], max(steps), 1)
+    np.testing.assert_allclose(got, seg[:, 1:], rtol=2e-5, atol=1e-5)
+
+
+def _agreement(a, b):
+    return float((a == b).mean())
+
+
+@pytest.mark.parametrize("H,W,C,n,compactness,kw", [
+    (200, 300, 4, 150, 0.1, {}),
+    (256, 256, 3, 100, 10.0, {}),                       # RGB -> Lab path (README quickstart shape)
+    (180, 220, 8, 120, 0.05, dict(max_num_iter=5)),
+    (150, 150, 6, 80, 0.2, dict(start_label=0, min_size_factor=0.3)),
+    (120, 160, 3, 60, 5.0, dict(sigma=1.0)),
+])
+def test_slic_full_agreement(H, W, C, n, compactness, kw):
+    """Whole create_segments path vs the oracle: >= 99.5 % identical labels."""
+    import slic_oracle as so
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    raw = synth_raster(H, W, C, seed=n, quantize=(C == 3))
+    want = so.create_segments_labels(raw.copy(), None, n_segments=n, compactness=compactness, **kw)
+    res = pipeline.slic_labels(_cuda(raw), None, n_segments=n, compactness=compactness, **kw)
+    got = res.labels.cpu().numpy()
+    agree = _agreement(got, want)
+    print(f"agreement {agree:.5f} labels gpu={res.n_labels} oracle={want.max()}")
+    assert agree >= 0.995
+
+
+def test_slic_masked_agreement():
+    import slic_oracle as so
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    H, W, C, n = 160, 200, 4, 60
+    raw = synth_raster(H, W, C, seed=77)
+    yy, xx = np.mgrid[:H, :W]
+    mask = ((yy - 80) ** 2 / 70 ** 2 + (xx - 100) ** 2 / 90 ** 2) < 1.0
+    want = so.create_segments_labels(raw.copy(), None, n_segments=n, compactness=0.2, mask=mask)
+    res = pipeline.slic_labels(_cuda(raw), None, n_segments=n, compactness=0.2, mask=mask)
+    got = res.labels.cpu().numpy()
+    assert (got[~mask] == -1).all()
+    agree = _agreement(got, want)
+    print(f"masked agreement {agree:.5f}")
+    assert agree >= 0.995
+
+
+# ------------------------------------------------------------------ K3 ------
+def _random_label_cases():
+    rng = np.random.RandomState(11)
+    cases = []
+    for trial in range(40):
+        H, W = int(rng.randint(3, 70)), int(rng.randint(3, 70))
+        start_label = int(rng.randint(0, 2))
+        by, bx = int(rng.randint(2, 12)), int(rng.randint(2, 12))
+        yy, xx = np.mgrid[:H, :W]
+        lab = (yy // by) * ((W + bx - 1) // bx) + xx // bx
+        p = rng.choice([0.0, 0.05, 0.3])
+        noise = rng.rand(H, W) < p
+        lab = np.where(noise, rng.randint(0, lab.max() + 1, size=(H, W)), lab) + start_label
+        if rng.rand() < 0.3:
+            lab = np.where(rng.rand(H, W) < 0.15, start_label - 1, lab)
+        if rng.rand() < 0.6:
+            min_size = int(rng.randint(1, by * bx)); max_size = int(min_size * 6)
+        else:
+            min_size = int(rng.randint(0, 15)); max_size = int(rng.randint(1, 50))
+        cases.append((lab.astype(np.int32), min_size, max_size, start_label))
+    return cases
+
+
+def test_connectivity_exact_random():
+    """Exact equality with the sequential reference algorithm on adversarial label rasters."""
+    import slic_oracle as so
+    from obia_b200 import pipeline
+    for lab, min_size, max_size, start_label in _random_label_cases():
+        want = so.enforce_connectivity(lab, min_size, max_size, start_label)
+        got, nlab = pipeline.enforce_connectivity(_cuda(lab), min_size, max_size, start_label)
+        np.testing.assert_array_equal(got.cpu().numpy(), want,
+                                      err_msg=f"{lab.shape} min={min_size} max={max_size} sl={start_label}")
+
+
+@pytest.mark.parametrize("compactness", [0.03, 0.3])
+def test_connectivity_exact_on_slic_output(compactness):
+    import slic_oracle as so
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    H, W, C, n = 300, 400, 4, 300
+    raw = synth_raster(H, W, C, seed=4, noise=0.08)
+    _, st = so.slic(np.stack([so.normalize_band(raw[:, :, i]) for i in range(C)], -1), n_segments=n,
+                    compactness=compactness, return_state=True)
+    pre = st["pre_connectivity"].astype(np.int32)
+    seg_size = H * W / st["n_centroids"]
+    min_size, max_size = int(0.5 * seg_size), int(3 * seg_size)
+    want = so.enforce_connectivity(pre, min_size, max_size, 1)
+    got, nlab = pipeline.enforce_connectivity(_cuda(pre), min_size, max_size, 1)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    assert nlab == want.max()
+
+
+# ------------------------------------------------------------------ K4 ------
+@pytest.mark.parametrize("C,bands,quantize", [(3, None, True), (8, [7, 0, 3], False), (20, None, False)])
+def test_zonal_stats(C, bands, quantize):
+    import slic_oracle as so
+    import stats_oracle
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    H, W, n = 150, 210, 90
+    raw = synth_raster(H, W, C, seed=C, quantize=quantize)
+    if not quantize:
+        raw = raw * 1000 + 50
+    labels = so.create_segments_labels(raw.copy(), None, n_segments=n, compactness=0.5 if C != 3 else 10)
+    labels = labels.astype(np.int32)
+    labels[:5, :7] = -1
+    bands = list(range(C)) if bands is None else bands
+    ids = np.unique(labels[labels >= 0])
+    want, counts = stats_oracle.zonal_stats(labels, raw, bands, ids, compute_dtype=np.float64)
+    got = pipeline.zonal_stats(_cuda(labels), _cuda(raw), bands, resolution=1e-15).cpu().numpy()[ids]
+    np.testing.assert_array_equal(got[:, :, 0], np.repeat(counts[:, None], len(bands), 1))   # counts bit-exact
+    np.testing.assert_allclose(got[:, :, 1], want[:, :, 0], rtol=1e-5)    # mean
+    np.testing.assert_allclose(got[:, :, 2], want[:, :, 1], rtol=1e-5, atol=1e-12)    # variance
+    np.testing.assert_array_equal(got[:, :, 3], want[:, :, 2])            # min exact
+    np.testing.assert_array_equal(got[:, :, 4], want[:, :, 3])            # max exact
+    np.testing.assert_allclose(got[:, :, 5], want[:, :, 4], rtol=1e-4, atol=1e-6, equal_nan=True)   # skewness
+    np.testing.assert_allclose(got[:, :, 6], want[:, :, 5], rtol=1e-4, atol=1e-6, equal_nan=True)   # kurtosis
+
+
+def test_zonal_stats_edge_cases():
+    """single-pixel and constant segments (NaN skew/kurtosis), missing labels, ragged sizes."""
+    import stats_oracle
+    from obia_b200 import pipeline
+    H, W = 23, 31
+    labels = np.full((H, W), 2, np.int32)
+    labels[0, 0] = 0            # single pixel
+    labels[5:9, 5:9] = 5        # constant-valued block
+    labels[10:, 20:] = -1       # masked
+    labels[22, 30] = 9          # label 9 (3,4,6,7,8 missing)
+    raw = np.random.RandomState(0).rand(H, W, 2).astype(np.float32) * 10
+    raw[5:9, 5:9] = 3.25
+    ids = np.array([0, 2, 5, 9])
+    want, counts = stats_oracle.zonal_stats(labels, raw, [0, 1], ids)
+    got = pipeline.zonal_stats(_cuda(labels), _cuda(raw), [0, 1], resolution=1e-6).cpu().numpy()
+    assert got.shape == (10, 2, 8)
+    np.testing.assert_array_equal(got[ids, 0, 0], counts)
+    assert (got[[1, 3, 4, 6, 7, 8], :, 0] == 0).all() and np.isnan(got[[1, 3, 4], :, 1]).all()
+    np.testing.assert_allclose(got[ids][:, :, 1], want[:, :, 0], rtol=1e-5)
+    np.testing.assert_allclose(got[ids][:, :, 2], want[:, :, 1], rtol=1e-5, atol=1e-9)
+    assert np.isnan(got[0, :, 5]).all() and np.isnan(got[5, :, 6]).all()     # n=1 / constant -> NaN
+    assert np.isnan(want[[0, 2], :, 4]).all()
+
+
+# ------------------------------------------------------------- end to end ---
+def test_segment_end_to_end_columns_and_values():
+    import slic_oracle as so
+    import stats_oracle
+    from obia_b200.handlers.geotif import Image
+    from obia_b200.segmentation.segment import segment
+    from gpu_helpers import synth_raster
+    raw = synth_raster(128, 128, 3, seed=42, quantize=True)
+    img = Image(raw.copy(), "EPSG:32702", [1, 0, 0, -1, 0, 0], None, None)
+    seg = segment(img, segmentation_bands=[0, 1, 2], method="slic", n_segments=200, compactness=8, start_label=1)
+    cols = list(seg.segments.columns)
+    assert cols[0] == "segment_id" and cols[-1] == "geometry"
+    assert cols[1:7] == ["b0_mean", "b0_variance", "b0_min", "b0_max", "b0_skewness", "b0_kurtosis"]
+    assert cols[19:25] == ["b0_contrast", "b0_dissimilarity", "b0_homogeneity", "b0_ASM", "b0_energy", "b0_correlation"]
+    assert cols[-6:-1] == ["pai", "fhd", "ch", "mean_intensity", "variance_intensity"]
+    assert len(cols) == 1 + 18 + 18 + 5 + 1
+    # side effect parity: img_data normalised in place, per band
+    want_img = raw.copy()
+    ref_labels = so.create_segments_labels(want_img, [0, 1, 2], n_segments=200, compactness=8, start_label=1)
+    np.testing.assert_array_equal(img.img_data, want_img)
+    labels = seg._segments.label_raster.cpu().numpy()
+    assert (labels == ref_labels).mean() >= 0.995
+    assert list(seg._segments["segment_id"]) == list(range(1, len(seg._segments) + 1))
+    # statistics over the RAW values, per segment row
+    rows = np.asarray(seg.segments.segment_labels)
+    want, _ = stats_oracle.zonal_stats(labels, raw, [0, 1, 2], rows)
+    for j in range(3):
+        np.testing.assert_allclose(seg.segments[f"b{j}_mean"].to_numpy(), want[:, j, 0], rtol=1e-5)
+        np.testing.assert_allclose(seg.segments[f"b{j}_variance"].to_numpy(), want[:, j, 1], rtol=2e-5, atol=1e-9)
+        np.testing.assert_array_equal(seg.segments[f"b{j}_max"].to_numpy(), want[:, j, 3])
+
+
+def test_create_segments_errors():
+    from obia_b200.handlers.geotif import Image
+    from obia_b200.segmentation.segment_boundaries import create_segments
+    from obia_b200.segmentation.segment_statistics import create_objects
+    raw = np.random.RandomState(0).rand(32, 32, 4).astype(np.float32)
+    img = Image(raw.copy(), None, None, None, None)
+    with pytest.raises(IndexError):
+        create_segments(img, segmentation_bands=[0, 4], n_segments=10)
+    with pytest.raises(Exception, match="unknown segmentation method"):
+        create_segments(img, method="watershed")
+    with pytest.raises(ValueError, match="RGB"):
+        create_segments(Image(raw.copy(), None, None, None, None), convert2lab=True, n_segments=10)
+    with pytest.raises(ValueError, match="start_label"):
+        create_segments(Image(raw.copy(), None, None, None, None), start_label=2, n_segments=10)
+    const = raw.copy(); const[:, :, 2] = 7.0
+    with pytest.raises(ValueError, match="NaN"):
+        create_segments(Image(const, None, None, None, None), n_segments=10)
+    segs = create_segments(Image(raw.copy(), None, None, None, None), n_segments=10, compactness=0.5)
+    with pytest.raises(ValueError):
+        create_objects(segs, img, calculate_spectral=False, calculate_textural=False)
+    with pytest.raises(NotImplementedError):
+        create_objects(segs, img, calculate_structural=True)
