@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- megapixels/s of the obia hot path (SLIC + per-segment zonal statistics) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1, one rank per GPU)
+
+A "step" is one pass of the hot path over one synthetic raster: raw (H, W, C) float32 resident in
+HBM -> SLIC label raster -> per-segment per-band statistics table in HBM.  Workload =
+BASELINE.json configs[1]: 8-band float32 10000x10000, n_segments=200000 (3.2 GB, far larger
+than the 126 MB L2, so no L2 flush is needed between steps).
+
+One JSON line is printed by rank 0 (see the task contract): `value` = whole-job MP/s with inputs
+resident in HBM; `e2e` = the same metric through the public API `segment()` with pinned HOST
+buffers (H2D of the raster and D2H of the results inside the timed region); `roofline` for the
+dominant kernel (SLIC assign+update) timed with CUDA events on its launch stream;
+`cpu_baseline` = the CPU oracle (a port of the reference's scikit-image/numpy/scipy path) on a
+bounded crop of the same workload.
+
+`--impl reference` times the reference's own CPU implementation of the path.  The reference is
+pure Python over scikit-image, which is not installable here, so (as the task allows) the arm runs
+the oracle port on the host cores on bounded crops of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(H=10000, W=10000, C=8, n_segments=200000, compactness=0.1, max_num_iter=10)
+METRIC = "megapixels_per_s_slic_plus_zonal_stats"
+
+
+# ------------------------------------------------------------------ helpers ---
+def synth_raster_np(H, W, C, seed):
+    """CPU twin of the device generator (same formula, numpy RNG): low-frequency surface + N(0, 0.05)."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[:H, :W].astype(np.float32)
+    out = np.empty((H, W, C), dtype=np.float32)
+    for c in range(C):
+        fy, fx = 0.004 * (c + 1), 0.003 * (c + 2)
+        surf = 0.5 + 0.25 * np.sin(yy * fy + c) + 0.25 * np.cos(xx * fx - c)
+        out[:, :, c] = (0.6 + 0.05 * c) * surf + rng.normal(0, 0.05, (H, W)).astype(np.float32)
+    return out
+
+
+def synth_raster_cuda(H, W, C, seed, device):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    yy = torch.arange(H, device=device, dtype=torch.float32)[:, None]
+    xx = torch.arange(W, device=device, dtype=torch.float32)[None, :]
+    out = torch.empty((H, W, C), dtype=torch.float32, device=device)
+    for c in range(C):
+        fy, fx = 0.004 * (c + 1), 0.003 * (c + 2)
+        surf = 0.5 + 0.25 * torch.sin(yy * fy + c) + 0.25 * torch.cos(xx * fx - c)
+        noise = torch.randn((H, W), generator=g, device=device, dtype=torch.float32) * 0.05
+        out[:, :, c] = (0.6 + 0.05 * c) * surf + noise
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            while not self._halt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: report what we could not measure
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def load_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------ CPU oracle leg ---
+def cpu_oracle_step(size, seed=2):
+    """One pass of the CPU port (oracle) over a size x size crop of the workload. Returns seconds."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import slic_oracle as so
+    import stats_oracle
+    wl = WORKLOAD
+    raw = synth_raster_np(size, size, wl["C"], seed)
+    n = max(1, int(round(wl["n_segments"] * (size / wl["H"]) * (size / wl["W"]))))  # same grid step
+    t0 = time.perf_counter()
+    labels = so.create_segments_labels(raw.copy(), None, n_segments=n, compactness=wl["compactness"],
+                                       max_num_iter=wl["max_num_iter"])
+    t1 = time.perf_counter()
+    ids = np.unique(labels[labels >= 0])
+    stats_oracle.zonal_stats(labels, raw, list(range(wl["C"])), ids)
+    t2 = time.perf_counter()
+    return t2 - t0, t1 - t0, t2 - t1, len(ids)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    size = 512
+    for _ in range(args.warmup):
+        cpu_oracle_step(size)
+    t = []
+    for _ in range(args.steps):
+        t.append(cpu_oracle_step(size)[0])
+    total = sum(t)
+    mpx = size * size / 1e6
+    value = mpx * args.steps / total
+    sample = (f"{size}x{size}x{WORKLOAD['C']} crop of the workload per step, n_segments scaled by area "
+              f"(same grid step 22), single thread (scikit-image's SLIC and obia's per-segment numpy/scipy "
+              f"loop are single-threaded); CPU cost is linear in pixels at fixed step")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "c2: 8-band float32 10000x10000, slic n_segments=200000 + zonal stats",
+                   "sample": sample, **{k: WORKLOAD[k] for k in ("n_segments", "compactness", "max_num_iter")}},
+        "cpu_baseline": {"value": value, "unit": "MP/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ our arm ---
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from obia_b200 import _lib, pipeline
+    from obia_b200.handlers.geotif import Image
+    from obia_b200.segmentation.segment import segment
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    wl = dict(WORKLOAD)
+    if args.size:
+        wl["H"] = wl["W"] = args.size
+        wl["n_segments"] = max(1, int(round(WORKLOAD["n_segments"] * (args.size / WORKLOAD["H"]) ** 2)))
+    H, W, C = wl["H"], wl["W"], wl["C"]
+    slic_kw = dict(n_segments=wl["n_segments"], compactness=wl["compactness"], max_num_iter=wl["max_num_iter"])
+    # weak scaling: every rank owns one raster of the workload shape (independent units, no
+    # data-path collective); seeds differ per rank
+    raw = synth_raster_cuda(H, W, C, seed=2 + rank, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        res = pipeline.slic_labels(raw, None, **slic_kw)
+        stats = pipeline.zonal_stats(res.labels, raw, None, max_label=res.n_labels)
+        return res, stats
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        res, stats = step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.obia_b200_profile_enable(1)
+    launches0 = lib.obia_b200_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        res, stats = step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = lib.obia_b200_launch_count() - launches0
+    lib.obia_b200_profile_enable(0)
+    import ctypes
+    k_ms, k_n = ctypes.c_double(0), ctypes.c_int64(0)
+    lib.obia_b200_profile_read(ctypes.byref(k_ms), ctypes.byref(k_n))
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    mpx = H * W / 1e6
+    value = world * mpx * args.steps / (ms_total / 1e3)
+
+    # ---- e2e through the public API with pinned host buffers -------------------
+    e2e = None
+    if not args.no_e2e:
+        pristine = torch.empty((H, W, C), dtype=torch.float32, pin_memory=True)
+        pristine.copy_(raw)
+        work = torch.empty((H, W, C), dtype=torch.float32, pin_memory=True)
+        e2e_steps = min(args.steps, args.e2e_steps)
+        t_e2e, d2h = 0.0, 0
+        for i in range(1 + e2e_steps):     # first one is a warm-up
+            work.copy_(pristine)            # restore the input buffer (not part of the path)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            img = Image(work.numpy(), "EPSG:32702", [1, 0, 0, -1, 0, 0], None, None)
+            seg = segment(img, None, None, "slic", **slic_kw)   # H2D upload + kernels + D2H table
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if i > 0:
+                t_e2e += dt
+            n_rows = len(seg.segments)
+            d2h = work.numel() * 4 + n_rows * C * 8 * 8     # normalised img_data write-back + stats rows
+            del img, seg
+        t2 = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * mpx * e2e_steps / float(t2.item()), "unit": "MP/s",
+               "h2d_bytes_per_step": H * W * C * 4, "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "api": "obia_b200.segmentation.segment.segment(Image(host ndarray), method='slic', ...)"}
+        del pristine, work
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -----------------------------------------
+    peak, peak_kind = load_peak_hbm()
+    Cf = C
+    I = wl["max_num_iter"]
+    alg_bytes = (4.0 * Cf + 4.0 / I) * H * W          # SURVEY.md 8(d) stage B per launch
+    k_avg_ms = k_ms.value / max(1, k_n.value)
+    achieved = alg_bytes / (k_avg_ms / 1e3) / 1e9 if k_avg_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "slic_assign_update_kernel", "achieved": achieved, "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": None, "avg_launch_ms": k_avg_ms, "launches_timed": int(k_n.value),
+                "kernel_share_of_step": (k_ms.value / ms_total) if ms_total else None,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "pipeline_bytes_per_px": 2 * 4 * C + 4 * Cf * (1 + I) + 16 + 4 * C,
+                "pipeline_frac_of_hbm_roofline": ((2 * 4 * C + 4 * Cf * (1 + I) + 16 + 4 * C) * H * W
+                                                  / (ms_total / args.steps / 1e3) / 1e9 / peak)}
+
+    # ---- CPU baseline (bounded sample) ---------------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        size = args.cpu_size
+        tot, t_slic, t_stats, nseg = cpu_oracle_step(size)
+        cpu = {"value": size * size / 1e6 / tot, "unit": "MP/s", "cores": 1, "kind": "port",
+               "sample": (f"{size}x{size}x{C} crop, n_segments scaled by area (same grid step), one pass: "
+                          f"slic {t_slic:.1f}s + per-segment numpy/scipy stats {t_stats:.1f}s over {nseg} segments"),
+               "host_cores_available": os.cpu_count()}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"c2: {C}-band float32 {H}x{W}, slic n_segments={wl['n_segments']} + zonal stats "
+                               f"on all bands, one raster per GPU",
+                   "compactness": wl["compactness"], "max_num_iter": I,
+                   "l2": "inputs (3.2 GB/step) are larger than the 126 MB L2; no flush between steps",
+                   "segments_out": int(res.n_labels)},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=0, help="debug: square raster side instead of 10000")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-size", type=int, default=768)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

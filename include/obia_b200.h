@@ -38,6 +38,14 @@ extern "C" {
 const char *obia_b200_last_error(void);
 int obia_b200_version(void);
 
+/* Measurement hooks (bench.py): number of kernels this library has launched in
+ * the process, and CUDA-event timing of the dominant kernel (SLIC
+ * assign+update) on the stream it is launched on.  `profile_read` waits for the
+ * recorded events, returns their summed duration and count, and clears them. */
+int64_t obia_b200_launch_count(void);
+int obia_b200_profile_enable(int on);
+int obia_b200_profile_read(double *total_ms, int64_t *launches);
+
 /* ---------------------------------------------------------------- K1 ----
  * Per-band min / max over a pixel-interleaved raster, plus the same over the
  * masked pixels only, plus a non-finite flag per band.

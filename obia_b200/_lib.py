@@ -20,6 +20,9 @@ _vp = ctypes.c_void_p
 SIGNATURES = {
     "obia_b200_last_error": (ctypes.c_char_p, []),
     "obia_b200_version": (ctypes.c_int, []),
+    "obia_b200_launch_count": (_i64, []),
+    "obia_b200_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "obia_b200_profile_read": (ctypes.c_int, [_vp, _vp]),
     "obia_b200_band_minmax": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "obia_b200_normalize_inplace": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "obia_b200_slic_features": (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _i32, _vp, _vp, _f32, _f32,

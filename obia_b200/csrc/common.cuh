@@ -21,13 +21,22 @@ int set_err(int code, const char *fmt, ...);
                                  cudaGetErrorString(_e), __FILE__, __LINE__);        \
     } while (0)
 
+// every kernel launch of the library goes through OBIA_LAUNCH_CHECK, which also
+// counts it (obia_b200_launch_count: the "gpu_launches" figure of bench.py)
+void count_launch();
+
 #define OBIA_LAUNCH_CHECK()                                                          \
     do {                                                                             \
+        obia::count_launch();                                                        \
         cudaError_t _e = cudaGetLastError();                                         \
         if (_e != cudaSuccess)                                                       \
             return obia::set_err(OBIA_B200_ERR_CUDA, "kernel launch failed: %s (%s:%d)", \
                                  cudaGetErrorString(_e), __FILE__, __LINE__);        \
     } while (0)
+
+// optional CUDA-event timing of one kernel class (the SLIC assign+update kernel)
+void prof_begin(cudaStream_t st);
+void prof_end(cudaStream_t st);
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 

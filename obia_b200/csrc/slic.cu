@@ -331,9 +331,11 @@ static int launch_assign(const float *feat, const uint8_t *mask, const float *ce
                          int32_t *status, cudaStream_t st)
 {
     dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, kWarps * PX));
+    prof_begin(st);
     slic_assign_update_kernel<CP, PX><<<grid, kWarps * 32, 0, st>>>(
         feat, mask, centres, w.head, w.next, labels, w.acc, (int)H, (int)W, pitch, Cf, sw, step_y, step_x,
         (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, status);
+    prof_end(st);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
 }
