@@ -21,7 +21,7 @@
 
 namespace obia {
 
-constexpr int kIdCap = 4096;  // centre ids a tile can collect
+constexpr int kIdCap = 2048;  // centre ids a tile can collect
 constexpr int kChunk = 64;    // centre records resident in shared memory at once
 constexpr int kWarps = 8;
 
@@ -98,6 +98,100 @@ __device__ __forceinline__ int floordiv_i(int a, int b)
 // C cast float -> integer as the Cython code does (`<Py_ssize_t>`): truncation
 __device__ __forceinline__ int trunc_i(float v) { return (int)v; }
 
+// ---- packed fp32x2 arithmetic (sm_100a FADD2 / FFMA2): two pixels per instruction ------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 pack2(float lo, float hi)
+{
+    u64 d;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// Per-candidate record in shared memory.
+struct __align__(16) CandHead {
+    float cy, cx;
+    int k, pad;
+};
+
+// Distance of the PX pixels of this lane to one candidate centre, in the reference's
+// operation order:  d = ((dy + dx) * w) + sum_c fma(t_c, t_c, .)   (t_c = pixel_c - centre_c).
+// Everything except the colour FMA is separately rounded (scalar FMUL feeding FADD2 is never
+// contracted).  CHECK = per-pixel window test (skipped when the whole warp strip is inside).
+template <int CP, int PX, bool CHECK>
+__device__ __forceinline__ void eval_candidate(const u64 (&px2)[(PX + 1) / 2][CP], const float (&px1)[CP],
+                                               const u64 (&nx2)[(PX + 1) / 2], float nx1, float fy,
+                                               const CandHead h, const int4 w, const float *__restrict__ nf,
+                                               float spatial_weight, int ignore_color, int y, int xb,
+                                               float (&best)[PX], int (&bestk)[PX])
+{
+    int lo = 0, span = PX;
+    if (CHECK) {
+        lo = w.z - xb;
+        span = (y >= w.x && y < w.y) ? (w.w - w.z) : 0;  // row outside the window: nothing valid
+    }
+    const float ty = __fsub_rn(h.cy, fy);
+    const float dy = __fmul_rn(ty, ty);
+    if constexpr (PX >= 2) {
+#pragma unroll
+        for (int p = 0; p < PX / 2; ++p) {
+            const u64 tx2 = add2(nx2[p], pack2(h.cx, h.cx));  // cx - x  ==  cx + (-x)
+            float tx0, tx1;
+            unpack2(tx2, tx0, tx1);
+            const u64 s2 = add2(pack2(dy, dy), pack2(__fmul_rn(tx0, tx0), __fmul_rn(tx1, tx1)));
+            float s0, s1;
+            unpack2(s2, s0, s1);
+            u64 d2 = pack2(__fmul_rn(s0, spatial_weight), __fmul_rn(s1, spatial_weight));
+            if (!ignore_color) {
+                u64 acc = 0ull;
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+                    const float m = nf[c];  // negated centre colour, broadcast to both halves
+                    const u64 t2 = add2(px2[p][c], pack2(m, m));
+                    acc = fma2(t2, t2, acc);
+                }
+                d2 = add2(d2, acc);
+            }
+            float d0, d1;
+            unpack2(d2, d0, d1);
+            const int j0 = 2 * p, j1 = 2 * p + 1;
+            const bool v0 = !CHECK || (unsigned)(j0 - lo) < (unsigned)span;
+            const bool v1 = !CHECK || (unsigned)(j1 - lo) < (unsigned)span;
+            if (v0 && d0 < best[j0]) { best[j0] = d0; bestk[j0] = h.k; }
+            if (v1 && d1 < best[j1]) { best[j1] = d1; bestk[j1] = h.k; }
+        }
+    } else {
+        const float tx = __fadd_rn(h.cx, nx1);
+        float d = __fmul_rn(__fadd_rn(dy, __fmul_rn(tx, tx)), spatial_weight);
+        if (!ignore_color) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                const float t = __fadd_rn(px1[c], nf[c]);
+                acc = __fmaf_rn(t, t, acc);
+            }
+            d = __fadd_rn(d, acc);
+        }
+        const bool v0 = !CHECK || (unsigned)(0 - lo) < (unsigned)span;
+        if (v0 && d < best[0]) { best[0] = d; bestk[0] = h.k; }
+    }
+}
+
 template <int CP, int PX>
 __global__ void __launch_bounds__(kWarps * 32)
 slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restrict__ mask,
@@ -109,12 +203,13 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
 {
     constexpr int LX = 32 / PX;  // lanes along x
     constexpr int TH = kWarps * PX;
+    constexpr int NP = (PX + 1) / 2;
     __shared__ int s_ids[kIdCap];
+    __shared__ int s_sorted[kIdCap];
     __shared__ int s_nids;
     __shared__ int4 s_win[kChunk];
-    __shared__ int s_k[kChunk];
-    __shared__ float s_cy[kChunk], s_cx[kChunk];
-    __shared__ __align__(16) float s_f[kChunk][CP];
+    __shared__ CandHead s_head[kChunk];
+    __shared__ __align__(16) float s_nf[kChunk][CP];  // negated centre colours
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * TH;
@@ -148,12 +243,21 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
         if (tid == 0) atomicExch(&status[0], 1);
         nids = kIdCap;
     }
+    // ascending centre index: "first strict improvement" then equals the reference's
+    // lowest-k-wins tie rule (ids are unique, so the rank is a permutation)
+    for (int i = tid; i < nids; i += kWarps * 32) {
+        const int k = s_ids[i];
+        int r = 0;
+        for (int j = 0; j < nids; ++j) r += (s_ids[j] < k);
+        s_sorted[r] = k;
+    }
 
     // ---- this lane's pixels ----------------------------------------------
     const int y = ty0 + warp * PX + lane / LX;
     const int xb = tx0 + (lane % LX) * PX;
     const bool row_ok = y < H;
-    float px[PX][CP];
+    u64 px2[NP][CP];
+    float px1[CP];
     bool valid[PX];
 #pragma unroll
     for (int j = 0; j < PX; ++j) {
@@ -164,22 +268,26 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     // spatial-only (ignore_color) pass of masked SLIC
 #pragma unroll
     for (int c = 0; c < CP; ++c) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c < Cf && row_ok && xb < W) {
             const float *src = feat + (int64_t)c * H * pitch + (int64_t)y * pitch + xb;
             if constexpr (PX == 4) {
-                const float4 v = *reinterpret_cast<const float4 *>(src);
-                px[0][c] = v.x; px[1][c] = v.y; px[2][c] = v.z; px[3][c] = v.w;
+                v = *reinterpret_cast<const float4 *>(src);
             } else if constexpr (PX == 2) {
-                const float2 v = *reinterpret_cast<const float2 *>(src);
-                px[0][c] = v.x; px[1][c] = v.y;
+                const float2 t = *reinterpret_cast<const float2 *>(src);
+                v.x = t.x; v.y = t.y;
             } else {
-                px[0][c] = *src;
+                v.x = *src;
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < PX; ++j) px[j][c] = 0.0f;
         }
+        px1[c] = v.x;
+        px2[0][c] = pack2(v.x, v.y);
+        if constexpr (PX == 4) px2[NP - 1][c] = pack2(v.z, v.w);
     }
+    u64 nx2[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) nx2[p] = pack2(-(float)(xb + 2 * p), -(float)(xb + 2 * p + 1));
+    const float nx1 = -(float)xb;
 
     const float INF = __int_as_float(0x7f800000);
     float best[PX];
@@ -189,23 +297,23 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
         best[j] = INF;
         bestk[j] = -1;
     }
-    // warp footprint (inclusive), clipped to the image
+    // warp strip (inclusive), clipped to the image
     const int wy0 = ty0 + warp * PX, wy1 = min(wy0 + PX, H) - 1;
     const float fy = (float)y;
 
-    // ---- evaluate candidates chunk by chunk -------------------------------
+    // ---- evaluate candidates chunk by chunk (ascending k) ---------------------
     for (int c0 = 0; c0 < nids; c0 += kChunk) {
         const int nc = min(kChunk, nids - c0);
-        __syncthreads();  // previous chunk fully consumed
+        __syncthreads();  // previous chunk fully consumed (and s_sorted complete)
         for (int i = tid; i < nc * (2 + CP); i += kWarps * 32) {
             const int s = i / (2 + CP), f = i % (2 + CP);
-            const int k = s_ids[c0 + s];
+            const int k = s_sorted[c0 + s];
             const float *rec = centres + (int64_t)k * (2 + Cf);
             if (f == 0) {
                 const float cy = rec[0], cx = rec[1];
-                s_cy[s] = cy;
-                s_cx[s] = cx;
-                s_k[s] = k;
+                CandHead h;
+                h.cy = cy; h.cx = cx; h.k = k; h.pad = 0;
+                s_head[s] = h;
                 // windows exactly as the reference computes them (float32, then C cast)
                 const float ylo = __fsub_rn(cy, (float)(2 * step_y));
                 const float yhi = __fadd_rn(__fadd_rn(cy, (float)(2 * step_y)), 1.0f);
@@ -219,58 +327,65 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
                 s_win[s] = w;
             } else if (f >= 2) {
                 const int c = f - 2;
-                s_f[s][c] = (c < Cf) ? rec[2 + c] : 0.0f;
+                s_nf[s][c] = (c < Cf) ? -rec[2 + c] : 0.0f;
             }
         }
         __syncthreads();
 
-        for (int s = 0; s < nc; ++s) {
-            const int4 w = s_win[s];
-            // warp-uniform rejection: window does not touch this warp's 32 x PX strip
-            if (w.x > wy1 || w.y <= wy0 || w.z > tx1 || w.w <= tx0) continue;
-            if (!(y >= w.x && y < w.y)) continue;
-            const float cy = s_cy[s], cx = s_cx[s];
-            const int k = s_k[s];
-            const float ty = __fsub_rn(cy, fy);
-            const float dy = __fmul_rn(ty, ty);
+        // every lane tests two candidates against the warp strip; the warp then walks
+        // the surviving ones in ascending order
 #pragma unroll
-            for (int j = 0; j < PX; ++j) {
-                const int x = xb + j;
-                if (!valid[j] || x < w.z || x >= w.w) continue;
-                const float tx = __fsub_rn(cx, (float)x);
-                const float dx = __fmul_rn(tx, tx);
-                float d = __fmul_rn(__fadd_rn(dy, dx), spatial_weight);
-                if (!ignore_color) {
-                    float dc = 0.0f;
-#pragma unroll
-                    for (int c = 0; c < CP; ++c) {
-                        const float t = __fsub_rn(px[j][c], s_f[s][c]);
-                        dc = __fadd_rn(dc, __fmul_rn(t, t));
-                    }
-                    d = __fadd_rn(d, dc);
-                }
-                if (d < best[j] || (d == best[j] && k < bestk[j])) {
-                    best[j] = d;
-                    bestk[j] = k;
-                }
+        for (int half = 0; half < kChunk / 32; ++half) {
+            const int sc = half * 32 + lane;
+            bool hit = false, full = false;
+            if (sc < nc) {
+                const int4 w = s_win[sc];
+                hit = !(w.x > wy1 || w.y <= wy0 || w.z > tx1 || w.w <= tx0);
+                full = w.x <= wy0 && w.y > wy1 && w.z <= tx0 && w.w > tx1;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            const unsigned mfull = __ballot_sync(0xffffffffu, full);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int s = half * 32 + b;
+                const CandHead h = s_head[s];
+                const int4 w = s_win[s];
+                if (mfull & (1u << b))
+                    eval_candidate<CP, PX, false>(px2, px1, nx2, nx1, fy, h, w, s_nf[s], spatial_weight,
+                                                  ignore_color, y, xb, best, bestk);
+                else
+                    eval_candidate<CP, PX, true>(px2, px1, nx2, nx1, fy, h, w, s_nf[s], spatial_weight,
+                                                 ignore_color, y, xb, best, bestk);
             }
         }
     }
 
     // ---- labels ------------------------------------------------------------
     int kk[PX];
+    bool all_found = true;
 #pragma unroll
     for (int j = 0; j < PX; ++j) {
         kk[j] = -1;
         if (valid[j]) {
-            const int64_t o = (int64_t)y * W + xb + j;
             if (bestk[j] >= 0) {
                 kk[j] = bestk[j];
-                labels[o] = bestk[j] + start_label;
             } else {
-                kk[j] = labels[o] - start_label;  // no window reached the pixel: keep
+                kk[j] = labels[(int64_t)y * W + xb + j] - start_label;  // no window reached the pixel: keep
+                all_found = false;
             }
+        } else {
+            all_found = false;
         }
+    }
+    if (PX == 4 && all_found && (W & 3) == 0) {
+        *reinterpret_cast<int4 *>(labels + (int64_t)y * W + xb) =
+            make_int4(kk[0] + start_label, kk[1 % PX] + start_label, kk[2 % PX] + start_label,
+                      kk[3 % PX] + start_label);
+    } else {
+#pragma unroll
+        for (int j = 0; j < PX; ++j)
+            if (valid[j] && bestk[j] >= 0) labels[(int64_t)y * W + xb + j] = bestk[j] + start_label;
     }
 
     // ---- fused centre update: group by winner inside the warp ---------------
@@ -298,7 +413,11 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
                 sy += y - ty0;  // tile-local, re-based below
                 sx += xb + j - tx0;
 #pragma unroll
-                for (int c = 0; c < CP; ++c) fs[c] = __fadd_rn(fs[c], px[j][c]);
+                for (int c = 0; c < CP; ++c) {
+                    float lo, hi;
+                    unpack2(px2[(j / 2) % NP][c], lo, hi);
+                    fs[c] = __fadd_rn(fs[c], (PX == 1) ? px1[c] : ((j & 1) ? hi : lo));
+                }
             }
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);

@@ -32,7 +32,11 @@ def build(force: bool = False) -> str:
     # tests use float64 images); connectivity is type-independent.
     subprocess.run(["gcc", *flags, "-DREAL=double", "-DSUFFIX(n)=n##_f64",
                     "-DOBIA_ORACLE_NO_CC", "-c", SRC, "-o", o64], check=True)
-    subprocess.run(["gcc", "-shared", "-o", OUT, o32, o64, "-lm"], check=True)
+    # float32 twin with the colour accumulation contracted to FMA (see slic_core.c)
+    ofma = os.path.join(OUT_DIR, "slic_core_f32_fma.o")
+    subprocess.run(["gcc", *flags, "-DORACLE_FMA", "-DREAL=float", "-DSUFFIX(n)=n##_fma",
+                    "-DOBIA_ORACLE_NO_CC", "-c", SRC, "-o", ofma], check=True)
+    subprocess.run(["gcc", "-shared", "-o", OUT, o32, o64, ofma, "-lm"], check=True)
     return OUT
 
 

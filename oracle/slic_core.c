@@ -39,6 +39,19 @@
 #define SUFFIX(n) n
 #endif
 
+/* Colour accumulation `dist_color += t * t`.
+ * Default: separate multiply and add (x86-64 scikit-image wheels: baseline ISA,
+ * no FMA).  With -DORACLE_FMA the statement is contracted to one fused
+ * multiply-add, which is what compilers emit for it on targets whose baseline
+ * has FMA (arm64 wheels: clang -ffp-contract=on / gcc -ffp-contract=fast).  The
+ * CUDA kernel uses the fused form (packed FFMA2), so the `_fma` build is the
+ * bit-exact twin of the GPU assignment; the default build is the x86-64 twin. */
+#ifdef ORACLE_FMA
+#define COLOR_ACC(acc, t) fmaf((t), (t), (acc))
+#else
+#define COLOR_ACC(acc, t) ((acc) + (t) * (t))
+#endif
+
 /* Cython's max()/min() lower to a ternary; NaN therefore propagates the way
  * `(b > a) ? b : a` does.  Keep that shape. */
 static inline REAL cy_maxf(REAL a, REAL b) { return (b > a) ? b : a; }
@@ -117,7 +130,7 @@ int64_t SUFFIX(obia_oracle_slic_core)(const REAL *image, const uint8_t *mask,
                         const REAL *px = image + (y * W + x) * C;
                         for (int64_t c = 0; c < C; ++c) {
                             const REAL t = px[c] - seg[3 + c];
-                            dist_color += t * t;
+                            dist_color = COLOR_ACC(dist_color, t);
                         }
                         if (slic_zero) dist_color /= max_dist_color[k];
                         dist_center += dist_color;
@@ -165,7 +178,7 @@ int64_t SUFFIX(obia_oracle_slic_core)(const REAL *image, const uint8_t *mask,
                     REAL dist_color = (REAL)0;
                     for (int64_t c = 0; c < C; ++c) {
                         const REAL t = px[c] - seg[3 + c];
-                        dist_color += t * t;
+                        dist_color = COLOR_ACC(dist_color, t);
                     }
                     if (max_dist_color[k] < dist_color) max_dist_color[k] = dist_color;
                 }
@@ -215,7 +228,7 @@ void SUFFIX(obia_oracle_slic_assign_once)(const REAL *image, const uint8_t *mask
                     const REAL *px = image + (y * W + x) * C;
                     for (int64_t c = 0; c < C; ++c) {
                         const REAL t = px[c] - seg[3 + c];
-                        dist_color += t * t;
+                        dist_color = COLOR_ACC(dist_color, t);
                     }
                     dist_center += dist_color;
                 }

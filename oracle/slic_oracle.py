@@ -54,10 +54,14 @@ def _lib():
                                               ctypes.c_int, i64, i64, vp]
         lib.obia_oracle_slic_core_f64.restype = i64
         lib.obia_oracle_slic_core_f64.argtypes = lib.obia_oracle_slic_core.argtypes
+        lib.obia_oracle_slic_core_fma.restype = i64
+        lib.obia_oracle_slic_core_fma.argtypes = lib.obia_oracle_slic_core.argtypes
+        lib.obia_oracle_slic_assign_once_fma.restype = None
         lib.obia_oracle_slic_assign_once.restype = None
         lib.obia_oracle_slic_assign_once.argtypes = [vp, vp, vp, i64, i64, i64, i64,
                                                      f32, i64, ctypes.c_int, i64,
                                                      i64, vp, vp]
+        lib.obia_oracle_slic_assign_once_fma.argtypes = lib.obia_oracle_slic_assign_once.argtypes
         lib.obia_oracle_enforce_connectivity.restype = ctypes.c_int
         lib.obia_oracle_enforce_connectivity.argtypes = [vp, i64, i64, i64, i64, i64, vp]
         _LIB = lib
@@ -163,9 +167,16 @@ def rgb2lab(rgb):
 # --------------------------------------------------------------------------
 # the two Cython loops (C core)
 # --------------------------------------------------------------------------
+# Which float32 build of the C core the module uses: False = separate multiply/add in the
+# colour term (x86-64 scikit-image wheels), True = fused multiply-add (arm64 wheels and the
+# CUDA kernel).  Tests flip it to check the GPU bit-for-bit (fma) and statistically (both).
+USE_FMA = False
+
+
 def slic_core(image_hwc, mask_hw, segments, step, max_num_iter, spacing,
-              slic_zero, start_label, ignore_color):
+              slic_zero, start_label, ignore_color, fma=None):
     """`_slic_cython` for depth 1.  `segments` (n, 3+C) float32 is updated in place."""
+    fma = USE_FMA if fma is None else fma
     H, W, C = image_hwc.shape
     n = segments.shape[0]
     _, step_y, step_x = grid_steps((1, H, W), n)
@@ -175,7 +186,10 @@ def slic_core(image_hwc, mask_hw, segments, step, max_num_iter, spacing,
     image_hwc = np.ascontiguousarray(image_hwc, dtype=dt)
     spacing = np.ascontiguousarray(spacing, dtype=dt)
     mask_u8 = None if mask_hw is None else np.ascontiguousarray(mask_hw, dtype=np.uint8)
-    fn = _lib().obia_oracle_slic_core if dt == np.float32 else _lib().obia_oracle_slic_core_f64
+    if dt == np.float32:
+        fn = _lib().obia_oracle_slic_core_fma if fma else _lib().obia_oracle_slic_core
+    else:
+        fn = _lib().obia_oracle_slic_core_f64
     rc = fn(_ptr(image_hwc), _ptr(mask_u8), _ptr(segments),
                                       H, W, C, n, float(step), int(max_num_iter),
                                       _ptr(spacing), int(bool(slic_zero)),
@@ -186,8 +200,9 @@ def slic_core(image_hwc, mask_hw, segments, step, max_num_iter, spacing,
     return nearest
 
 
-def slic_assign_once(image_hwc, mask_hw, segments, step, start_label, ignore_color):
+def slic_assign_once(image_hwc, mask_hw, segments, step, start_label, ignore_color, fma=None):
     """One assignment sweep (no update) -> (labels int64, distance float32)."""
+    fma = USE_FMA if fma is None else fma
     H, W, C = image_hwc.shape
     n = segments.shape[0]
     _, step_y, step_x = grid_steps((1, H, W), n)
@@ -196,7 +211,8 @@ def slic_assign_once(image_hwc, mask_hw, segments, step, start_label, ignore_col
     image_hwc = np.ascontiguousarray(image_hwc, dtype=np.float32)
     segments = np.ascontiguousarray(segments, dtype=np.float32)
     mask_u8 = None if mask_hw is None else np.ascontiguousarray(mask_hw, dtype=np.uint8)
-    _lib().obia_oracle_slic_assign_once(_ptr(image_hwc), _ptr(mask_u8), _ptr(segments),
+    fn = _lib().obia_oracle_slic_assign_once_fma if fma else _lib().obia_oracle_slic_assign_once
+    fn(_ptr(image_hwc), _ptr(mask_u8), _ptr(segments),
                                         H, W, C, n, float(step), int(start_label),
                                         int(bool(ignore_color)), step_y, step_x,
                                         _ptr(nearest), _ptr(distance))
