@@ -116,7 +116,8 @@ int obia_b200_gaussian_planar(const float *in, float *tmp, float *out,
  *   workspace obia_b200_slic_workspace_bytes(...) bytes
  *   step      float: max of the init steps (spatial weight 1/step^2)
  *   step_y/x  integer window half sizes (regular_grid steps)
- *   fix_scale power-of-two scale of the fixed-point colour sums
+ *   fix_scale power-of-two scale of the fixed-point colour sums; must satisfy
+ *             max|feature| * fix_scale * min(H*W, (4*step_y+1)*(4*step_x+1)) <= 2^62
  *   status    [4] int32 device words (zeroed by the call): [0] != 0 when a
  *             tile's candidate list overflowed (result invalid)
  */

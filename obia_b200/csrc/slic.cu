@@ -21,8 +21,6 @@
 
 namespace obia {
 
-constexpr int kIdCap = 2048;  // centre ids a tile can collect
-constexpr int kChunk = 64;    // centre records resident in shared memory at once
 constexpr int kWarps = 8;
 
 // workspace layout (all 16-byte aligned)
@@ -123,34 +121,32 @@ __device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
     asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
 
-// Per-candidate record in shared memory.
-struct __align__(16) CandHead {
-    float cy, cx;
-    int k, pad;
-};
 
 // Distance of the PX pixels of this lane to one candidate centre, in the reference's
 // operation order:  d = ((dy + dx) * w) + sum_c fma(t_c, t_c, .)   (t_c = pixel_c - centre_c).
 // Everything except the colour FMA is separately rounded (scalar FMUL feeding FADD2 is never
 // contracted).  CHECK = per-pixel window test (skipped when the whole warp strip is inside).
+// Candidate slots are sorted by centre index and visited in ascending order, so a strict
+// "less than" update is exactly the reference's rule (lowest k wins exact ties).
 template <int CP, int PX, bool CHECK>
 __device__ __forceinline__ void eval_candidate(const u64 (&px2)[(PX + 1) / 2][CP], const float (&px1)[CP],
                                                const u64 (&nx2)[(PX + 1) / 2], float nx1, float fy,
-                                               const CandHead h, const int4 w, const float *__restrict__ nf,
-                                               float spatial_weight, int ignore_color, int y, int xb,
-                                               float (&best)[PX], int (&bestk)[PX])
+                                               float cy, float cx, const int4 w,
+                                               const float *__restrict__ nf, float spatial_weight,
+                                               int ignore_color, int y, int xb, int slot,
+                                               float (&best)[PX], int (&bests)[PX])
 {
     int lo = 0, span = PX;
     if (CHECK) {
         lo = w.z - xb;
         span = (y >= w.x && y < w.y) ? (w.w - w.z) : 0;  // row outside the window: nothing valid
     }
-    const float ty = __fsub_rn(h.cy, fy);
+    const float ty = __fsub_rn(cy, fy);
     const float dy = __fmul_rn(ty, ty);
     if constexpr (PX >= 2) {
 #pragma unroll
         for (int p = 0; p < PX / 2; ++p) {
-            const u64 tx2 = add2(nx2[p], pack2(h.cx, h.cx));  // cx - x  ==  cx + (-x)
+            const u64 tx2 = add2(nx2[p], pack2(cx, cx));  // cx - x  ==  cx + (-x)
             float tx0, tx1;
             unpack2(tx2, tx0, tx1);
             const u64 s2 = add2(pack2(dy, dy), pack2(__fmul_rn(tx0, tx0), __fmul_rn(tx1, tx1)));
@@ -167,16 +163,20 @@ __device__ __forceinline__ void eval_candidate(const u64 (&px2)[(PX + 1) / 2][CP
                 }
                 d2 = add2(d2, acc);
             }
-            float d0, d1;
-            unpack2(d2, d0, d1);
-            const int j0 = 2 * p, j1 = 2 * p + 1;
-            const bool v0 = !CHECK || (unsigned)(j0 - lo) < (unsigned)span;
-            const bool v1 = !CHECK || (unsigned)(j1 - lo) < (unsigned)span;
-            if (v0 && d0 < best[j0]) { best[j0] = d0; bestk[j0] = h.k; }
-            if (v1 && d1 < best[j1]) { best[j1] = d1; bestk[j1] = h.k; }
+            float d[2];
+            unpack2(d2, d[0], d[1]);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int j = 2 * p + q;
+                const bool v = !CHECK || (unsigned)(j - lo) < (unsigned)span;
+                if (v && d[q] < best[j]) {
+                    best[j] = d[q];
+                    bests[j] = slot;
+                }
+            }
         }
     } else {
-        const float tx = __fadd_rn(h.cx, nx1);
+        const float tx = __fadd_rn(cx, nx1);
         float d = __fmul_rn(__fadd_rn(dy, __fmul_rn(tx, tx)), spatial_weight);
         if (!ignore_color) {
             float acc = 0.0f;
@@ -187,36 +187,60 @@ __device__ __forceinline__ void eval_candidate(const u64 (&px2)[(PX + 1) / 2][CP
             }
             d = __fadd_rn(d, acc);
         }
-        const bool v0 = !CHECK || (unsigned)(0 - lo) < (unsigned)span;
-        if (v0 && d < best[0]) { best[0] = d; bestk[0] = h.k; }
+        const bool v = !CHECK || (unsigned)(0 - lo) < (unsigned)span;
+        if (v && d < best[0]) {
+            best[0] = d;
+            bests[0] = slot;
+        }
     }
 }
 
+// shared-memory sizing per channel count (everything static, < 48 KB)
+template <int CP> struct Traits {
+    static constexpr int kIds = 1024;   // centre ids a tile can collect
+    static constexpr int kChk = (CP <= 32) ? 64 : 32;       // centre records resident at once
+    static constexpr int kAcc = (CP <= 16) ? 128 : 32;      // slots with a tile accumulator row
+    static constexpr int kRec = (CP <= 4) ? 512 : (CP == 8) ? 384 : (CP == 16) ? 192 : (CP == 32) ? 128 : 64;
+};
+
+// Warp strip: 16 pixels wide x (32 / (16/PX)) rows; a CTA tile is 2 x 4 strips (32 px wide).
 template <int CP, int PX>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, (CP <= 16) ? 3 : 1)
 slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restrict__ mask,
                           const float *__restrict__ centres, const int32_t *__restrict__ head,
                           const int32_t *__restrict__ next, int32_t *__restrict__ labels,
                           unsigned long long *__restrict__ acc, int H, int W, int64_t pitch, int Cf,
                           float spatial_weight, int step_y, int step_x, int ncy, int ncx,
-                          int start_label, int ignore_color, double fix_scale, int32_t *status)
+                          int start_label, int ignore_color, double fix_scale, float fix_scale32,
+                          long long fix_ratio, int32_t *status)
 {
-    constexpr int LX = 32 / PX;  // lanes along x
-    constexpr int TH = kWarps * PX;
+    constexpr int LPR = 16 / PX;   // lanes per strip row
+    constexpr int RW = 32 / LPR;   // rows per warp strip
+    constexpr int TH = 4 * RW;     // tile rows (tile is 32 wide)
     constexpr int NP = (PX + 1) / 2;
-    __shared__ int s_ids[kIdCap];
-    __shared__ int s_sorted[kIdCap];
-    __shared__ int s_nids;
-    __shared__ int4 s_win[kChunk];
-    __shared__ CandHead s_head[kChunk];
-    __shared__ __align__(16) float s_nf[kChunk][CP];  // negated centre colours
+    constexpr int NF = 3 + CP;     // accumulator fields per slot (count, sum y, sum x, colours)
+    constexpr int kIds = Traits<CP>::kIds, kChk = Traits<CP>::kChk, kAcc = Traits<CP>::kAcc,
+                  kRec = Traits<CP>::kRec;
+    constexpr int NT = kWarps * 32;
+    __shared__ int s_ids[kIds];      // as collected
+    __shared__ int s_sorted[kIds];   // ascending centre index
+    __shared__ int s_nids, s_nrec;
+    __shared__ int4 s_win[kChk];
+    __shared__ float2 s_cyx[kChk];
+    __shared__ __align__(16) float s_nf[kChk][CP];  // negated centre colours
+    __shared__ int s_acc[kAcc][NF];
+    __shared__ __align__(16) int s_rec[kRec][NF + 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * TH;
     const int tx1 = min(tx0 + 32, W) - 1, ty1 = min(ty0 + TH, H) - 1;  // inclusive
 
     // ---- collect candidate centre ids -----------------------------------
-    if (tid == 0) s_nids = 0;
+    if (tid == 0) {
+        s_nids = 0;
+        s_nrec = 0;
+    }
+    for (int i = tid; i < kAcc * NF; i += NT) (&s_acc[0][0])[i] = 0;
     __syncthreads();
     {
         // a centre at cy reaches rows y with  y - 2s <= cy < y + 1 + 2s; two pixels
@@ -227,25 +251,24 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
         const int gx_lo = max(0, floordiv_i(tx0 - 2 * step_x - 2, step_x));
         const int gx_hi = min(ncx - 1, floordiv_i(tx1 + 2 * step_x + 2, step_x));
         const int ny = gy_hi - gy_lo + 1, nx = gx_hi - gx_lo + 1;
-        for (int i = tid; i < ny * nx; i += kWarps * 32) {
+        for (int i = tid; i < ny * nx; i += NT) {
             const int gy = gy_lo + i / nx, gx = gx_lo + i % nx;
             int k = head[(int64_t)gy * ncx + gx];
             while (k >= 0) {
                 const int slot = atomicAdd(&s_nids, 1);
-                if (slot < kIdCap) s_ids[slot] = k;
+                if (slot < kIds) s_ids[slot] = k;
                 k = next[k];
             }
         }
     }
     __syncthreads();
     int nids = s_nids;
-    if (nids > kIdCap) {
+    if (nids > kIds) {
         if (tid == 0) atomicExch(&status[0], 1);
-        nids = kIdCap;
+        nids = kIds;
     }
-    // ascending centre index: "first strict improvement" then equals the reference's
-    // lowest-k-wins tie rule (ids are unique, so the rank is a permutation)
-    for (int i = tid; i < nids; i += kWarps * 32) {
+    // rank sort (ids are unique): slot order == centre-index order
+    for (int i = tid; i < nids; i += NT) {
         const int k = s_ids[i];
         int r = 0;
         for (int j = 0; j < nids; ++j) r += (s_ids[j] < k);
@@ -253,16 +276,18 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     }
 
     // ---- this lane's pixels ----------------------------------------------
-    const int y = ty0 + warp * PX + lane / LX;
-    const int xb = tx0 + (lane % LX) * PX;
+    const int sx0 = tx0 + (warp & 1) * 16, sy0 = ty0 + (warp >> 1) * RW;   // strip origin
+    const int y = sy0 + lane / LPR;
+    const int xb = sx0 + (lane % LPR) * PX;
     const bool row_ok = y < H;
     u64 px2[NP][CP];
     float px1[CP];
-    bool valid[PX];
+    unsigned vmask = 0;   // bit j: pixel j is inside the raster and the mask
 #pragma unroll
     for (int j = 0; j < PX; ++j) {
-        valid[j] = row_ok && (xb + j) < W;
-        if (valid[j] && mask) valid[j] = mask[(int64_t)y * W + xb + j] != 0;
+        bool v = row_ok && (xb + j) < W;
+        if (v && mask) v = mask[(int64_t)y * W + xb + j] != 0;
+        vmask |= (v ? 1u : 0u) << j;
     }
     // features are always loaded: the centre update sums colours even in the
     // spatial-only (ignore_color) pass of masked SLIC
@@ -291,29 +316,29 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
 
     const float INF = __int_as_float(0x7f800000);
     float best[PX];
-    int bestk[PX];
+    int bests[PX];
 #pragma unroll
     for (int j = 0; j < PX; ++j) {
         best[j] = INF;
-        bestk[j] = -1;
+        bests[j] = -1;
     }
     // warp strip (inclusive), clipped to the image
-    const int wy0 = ty0 + warp * PX, wy1 = min(wy0 + PX, H) - 1;
+    const int wx0 = sx0, wx1 = min(sx0 + 16, W) - 1;
+    const int wy0 = sy0, wy1 = min(sy0 + RW, H) - 1;
     const float fy = (float)y;
+    float wbound = INF;  // upper bound of every strip pixel's final distance (pruning bound)
 
-    // ---- evaluate candidates chunk by chunk (ascending k) ---------------------
-    for (int c0 = 0; c0 < nids; c0 += kChunk) {
-        const int nc = min(kChunk, nids - c0);
-        __syncthreads();  // previous chunk fully consumed (and s_sorted complete)
-        for (int i = tid; i < nc * (2 + CP); i += kWarps * 32) {
+    // ---- evaluate candidates chunk by chunk ------------------------------------
+    for (int c0 = 0; c0 < nids; c0 += kChk) {
+        const int nc = min(kChk, nids - c0);
+        __syncthreads();  // previous chunk fully consumed; s_sorted complete
+        for (int i = tid; i < nc * (2 + CP); i += NT) {
             const int s = i / (2 + CP), f = i % (2 + CP);
             const int k = s_sorted[c0 + s];
             const float *rec = centres + (int64_t)k * (2 + Cf);
             if (f == 0) {
                 const float cy = rec[0], cx = rec[1];
-                CandHead h;
-                h.cy = cy; h.cx = cx; h.k = k; h.pad = 0;
-                s_head[s] = h;
+                s_cyx[s] = make_float2(cy, cx);
                 // windows exactly as the reference computes them (float32, then C cast)
                 const float ylo = __fsub_rn(cy, (float)(2 * step_y));
                 const float yhi = __fadd_rn(__fadd_rn(cy, (float)(2 * step_y)), 1.0f);
@@ -332,31 +357,68 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
         }
         __syncthreads();
 
-        // every lane tests two candidates against the warp strip; the warp then walks
-        // the surviving ones in ascending order
+        // Each lane owns kChk/32 candidates: does the window touch the strip, and what is a
+        // lower bound of the spatial term over the strip (deflated so rounding can never lift
+        // it above a true per-pixel value).
+        bool hit[kChk / 32];
+        float lb[kChk / 32];
+        unsigned seedkey = 0xffffffffu;
 #pragma unroll
-        for (int half = 0; half < kChunk / 32; ++half) {
+        for (int half = 0; half < kChk / 32; ++half) {
             const int sc = half * 32 + lane;
-            bool hit = false, full = false;
+            hit[half] = false;
+            lb[half] = INF;
             if (sc < nc) {
                 const int4 w = s_win[sc];
-                hit = !(w.x > wy1 || w.y <= wy0 || w.z > tx1 || w.w <= tx0);
-                full = w.x <= wy0 && w.y > wy1 && w.z <= tx0 && w.w > tx1;
+                if (!(w.x > wy1 || w.y <= wy0 || w.z > wx1 || w.w <= wx0)) {
+                    const float2 c = s_cyx[sc];
+                    const float ddy = fmaxf(0.0f, fmaxf((float)wy0 - c.x, c.x - (float)wy1));
+                    const float ddx = fmaxf(0.0f, fmaxf((float)wx0 - c.y, c.y - (float)wx1));
+                    hit[half] = true;
+                    lb[half] = (ddy * ddy + ddx * ddx) * spatial_weight * 0.9999f;
+                    seedkey = min(seedkey, (__float_as_uint(lb[half]) & ~63u) | (unsigned)sc);
+                }
             }
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            const unsigned mfull = __ballot_sync(0xffffffffu, full);
+        }
+        // Seed the pruning bound with the nearest candidate: its distances bound every pixel's
+        // final minimum from above.  (It is evaluated again at its own position below, so the
+        // ascending-order tie rule is untouched.)
+        seedkey = __reduce_min_sync(0xffffffffu, seedkey);
+        if (seedkey != 0xffffffffu && __uint_as_float(seedkey & ~63u) < wbound) {
+            const int s = (int)(seedkey & 63u);
+            float tb[PX];
+            int ts[PX];
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                tb[j] = ((vmask >> j) & 1u) ? INF : 0.0f;   // pixels outside raster/mask never bound
+                ts[j] = -1;
+            }
+            const float2 c = s_cyx[s];
+            eval_candidate<CP, PX, true>(px2, px1, nx2, nx1, fy, c.x, c.y, s_win[s], s_nf[s], spatial_weight,
+                                         ignore_color, y, xb, 0, tb, ts);
+            float m = tb[0];
+#pragma unroll
+            for (int j = 1; j < PX; ++j) m = fmaxf(m, tb[j]);
+            wbound = fminf(wbound, __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m))));
+        }
+        // Candidates whose bound exceeds wbound cannot beat any pixel's current or final best
+        // (d >= spatial term >= bound > best): skip them.  Survivors go in ascending slot order.
+#pragma unroll
+        for (int half = 0; half < kChk / 32; ++half) {
+            unsigned m = __ballot_sync(0xffffffffu, hit[half] && lb[half] <= wbound);
             while (m) {
                 const int b = __ffs(m) - 1;
                 m &= m - 1;
                 const int s = half * 32 + b;
-                const CandHead h = s_head[s];
+                const float2 c = s_cyx[s];
                 const int4 w = s_win[s];
-                if (mfull & (1u << b))
-                    eval_candidate<CP, PX, false>(px2, px1, nx2, nx1, fy, h, w, s_nf[s], spatial_weight,
-                                                  ignore_color, y, xb, best, bestk);
+                const bool full = w.x <= wy0 && w.y > wy1 && w.z <= wx0 && w.w > wx1;
+                if (full)
+                    eval_candidate<CP, PX, false>(px2, px1, nx2, nx1, fy, c.x, c.y, w, s_nf[s], spatial_weight,
+                                                  ignore_color, y, xb, c0 + s, best, bests);
                 else
-                    eval_candidate<CP, PX, true>(px2, px1, nx2, nx1, fy, h, w, s_nf[s], spatial_weight,
-                                                 ignore_color, y, xb, best, bestk);
+                    eval_candidate<CP, PX, true>(px2, px1, nx2, nx1, fy, c.x, c.y, w, s_nf[s], spatial_weight,
+                                                 ignore_color, y, xb, c0 + s, best, bests);
             }
         }
     }
@@ -366,17 +428,9 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     bool all_found = true;
 #pragma unroll
     for (int j = 0; j < PX; ++j) {
-        kk[j] = -1;
-        if (valid[j]) {
-            if (bestk[j] >= 0) {
-                kk[j] = bestk[j];
-            } else {
-                kk[j] = labels[(int64_t)y * W + xb + j] - start_label;  // no window reached the pixel: keep
-                all_found = false;
-            }
-        } else {
-            all_found = false;
-        }
+        const bool v = (vmask >> j) & 1u;
+        kk[j] = (v && bests[j] >= 0) ? s_sorted[bests[j]] : -1;
+        all_found = all_found && v && bests[j] >= 0;
     }
     if (PX == 4 && all_found && (W & 3) == 0) {
         *reinterpret_cast<int4 *>(labels + (int64_t)y * W + xb) =
@@ -385,61 +439,88 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     } else {
 #pragma unroll
         for (int j = 0; j < PX; ++j)
-            if (valid[j] && bestk[j] >= 0) labels[(int64_t)y * W + xb + j] = bestk[j] + start_label;
+            if (kk[j] >= 0) labels[(int64_t)y * W + xb + j] = kk[j] + start_label;
     }
 
-    // ---- fused centre update: group by winner inside the warp ---------------
-    unsigned pending = 0;
+    // ---- fused centre update ---------------------------------------------------
+    // Per lane, pixels with the same winner are summed in registers (fixed order) and written as
+    // one 32-bit fixed-point record to shared memory; the tile then folds the records into its
+    // per-slot accumulators field-parallel (integer adds: independent of scheduling) and issues
+    // one RED.64 per touched (centre, field).
 #pragma unroll
-    for (int j = 0; j < PX; ++j)
-        if (kk[j] >= 0) pending |= 1u << j;
-    while (true) {
-        int mine = -1;
+    for (int j = 0; j < PX; ++j) {
+        const bool v = (vmask >> j) & 1u;
+        bool first = v;
 #pragma unroll
-        for (int j = PX - 1; j >= 0; --j)
-            if (pending & (1u << j)) mine = kk[j];
-        const unsigned vote = __ballot_sync(0xffffffffu, mine >= 0);
-        if (!vote) break;
-        const int L = __shfl_sync(0xffffffffu, mine, __ffs(vote) - 1);
-        int cnt = 0, sy = 0, sx = 0;
+        for (int jj = 0; jj < j; ++jj)
+            first = first && !(((vmask >> jj) & 1u) && bests[j] >= 0 && bests[jj] == bests[j]);
+        int kcur = kk[j];
+        if (first && kcur < 0) kcur = labels[(int64_t)y * W + xb + j] - start_label;  // kept its previous centre
+        first = first && kcur >= 0;
+        int cnt = 0, sxl = 0;
         float fs[CP];
 #pragma unroll
         for (int c = 0; c < CP; ++c) fs[c] = 0.0f;
+        if (first) {
 #pragma unroll
-        for (int j = 0; j < PX; ++j) {
-            if ((pending & (1u << j)) && kk[j] == L) {
-                pending &= ~(1u << j);
-                cnt += 1;
-                sy += y - ty0;  // tile-local, re-based below
-                sx += xb + j - tx0;
+            for (int jj = j; jj < PX; ++jj) {
+                if (jj == j || (((vmask >> jj) & 1u) && bests[j] >= 0 && bests[jj] == bests[j])) {
+                    cnt += 1;
+                    sxl += xb + jj - tx0;
 #pragma unroll
-                for (int c = 0; c < CP; ++c) {
-                    float lo, hi;
-                    unpack2(px2[(j / 2) % NP][c], lo, hi);
-                    fs[c] = __fadd_rn(fs[c], (PX == 1) ? px1[c] : ((j & 1) ? hi : lo));
+                    for (int c = 0; c < CP; ++c) {
+                        float lo, hi;
+                        unpack2(px2[(jj / 2) % NP][c], lo, hi);
+                        fs[c] = __fadd_rn(fs[c], (PX == 1) ? px1[c] : ((jj & 1) ? hi : lo));
+                    }
                 }
             }
         }
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        sy = __reduce_add_sync(0xffffffffu, sy);
-        sx = __reduce_add_sync(0xffffffffu, sx);
+        const int slot = bests[j];
+        const bool to_rec = first && slot >= 0 && slot < kAcc;
+        int ridx = -1;
+        if (to_rec) ridx = atomicAdd(&s_nrec, 1);
+        if (to_rec && ridx < kRec) {
+            int *r = s_rec[ridx];
+            r[0] = slot;
+            r[1] = cnt;
+            r[2] = cnt * (y - ty0);
+            r[3] = sxl;
 #pragma unroll
-        for (int c = 0; c < CP; ++c) {
+            for (int c = 0; c < CP; ++c) r[4 + c] = __float2int_rn(fs[c] * fix_scale32);
+        } else if (first) {
+            // no tile accumulator for this centre (or record pool full): add to HBM directly
+            unsigned long long *a = acc + (int64_t)kcur * (3 + Cf);
+            atomicAdd(&a[0], (unsigned long long)cnt);
+            atomicAdd(&a[1], (unsigned long long)((long long)cnt * y));
+            atomicAdd(&a[2], (unsigned long long)((long long)sxl + (long long)cnt * tx0));
 #pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) fs[c] = __fadd_rn(fs[c], __shfl_xor_sync(0xffffffffu, fs[c], o));
+            for (int c = 0; c < CP; ++c)
+                if (c < Cf) atomicAdd(&a[3 + c], (unsigned long long)__double2ll_rn((double)fs[c] * fix_scale));
         }
-        // lane f adds field f (coalesced 64-bit reductions)
-        unsigned long long *a = acc + (int64_t)L * (3 + Cf);
-        if (lane == 0) atomicAdd(&a[0], (unsigned long long)cnt);
-        if (lane == 1) atomicAdd(&a[1], (unsigned long long)((long long)sy + (long long)cnt * ty0));
-        if (lane == 2) atomicAdd(&a[2], (unsigned long long)((long long)sx + (long long)cnt * tx0));
-#pragma unroll
-        for (int c = 0; c < CP; ++c) {
-            if (c < Cf && lane == ((3 + c) & 31)) {
-                const long long q = __double2ll_rn((double)fs[c] * fix_scale);
-                atomicAdd(&a[3 + c], (unsigned long long)q);
-            }
+    }
+    __syncthreads();
+    {
+        const int nrec = min(s_nrec, kRec);
+        for (int e = tid; e < nrec * NF; e += NT) {
+            const int r = e / NF, f = e - r * NF;
+            const int v = s_rec[r][1 + f];
+            if (v != 0) atomicAdd(&s_acc[s_rec[r][0]][f], v);
         }
+    }
+    __syncthreads();
+    const int nslots = min(nids, kAcc);
+    for (int i = tid; i < nslots * (3 + Cf); i += NT) {
+        const int slot = i / (3 + Cf), f = i % (3 + Cf);
+        const int cnt = s_acc[slot][0];
+        if (cnt == 0) continue;
+        const long long v = s_acc[slot][f];
+        long long g;
+        if (f == 0) g = v;
+        else if (f == 1) g = v + (long long)cnt * ty0;
+        else if (f == 2) g = v + (long long)cnt * tx0;
+        else g = v * fix_ratio;
+        if (g != 0) atomicAdd(&acc[(int64_t)s_sorted[slot] * (3 + Cf) + f], (unsigned long long)g);
     }
 }
 
@@ -449,11 +530,20 @@ static int launch_assign(const float *feat, const uint8_t *mask, const float *ce
                          int step_y, int step_x, int start_label, int ignore_color, double fix_scale,
                          int32_t *status, cudaStream_t st)
 {
-    dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, kWarps * PX));
+    // 32-bit fixed point for the per-tile shared-memory sums.  fix_scale obeys
+    //   max|feature| * fix_scale * reach <= 2^62,  reach = min(H*W, (4*step_y+1)*(4*step_x+1)),
+    // so with bits_px = ceil(log2(reach+1)):  max|feature| * (fix_scale * 2^(bits_px-42)) <= 2^20,
+    // and a tile of <= 1024 pixels stays below 2^30.
+    const int64_t reach = std::min<int64_t>(H * W, (int64_t)(4 * step_y + 1) * (4 * step_x + 1));
+    int bits_px = 1;
+    while ((1LL << bits_px) < reach + 1) ++bits_px;
+    const float fix_scale32 = (float)ldexp(fix_scale, bits_px - 42);
+    const long long fix_ratio = 1LL << (42 - bits_px);
+    dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 4 * (32 / (16 / PX))));
     prof_begin(st);
     slic_assign_update_kernel<CP, PX><<<grid, kWarps * 32, 0, st>>>(
         feat, mask, centres, w.head, w.next, labels, w.acc, (int)H, (int)W, pitch, Cf, sw, step_y, step_x,
-        (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, status);
+        (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, fix_scale32, fix_ratio, status);
     prof_end(st);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;

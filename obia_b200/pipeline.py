@@ -216,7 +216,7 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
             step_y, step_x, int(max_num_iter), int(start_label), int(ignore_color), fix_scale,
             _p(status), _stream_ptr()), "slic_iterate")
         if int(status[0].item()) != 0:
-            raise _lib.ObiaB200Error("slic_iterate: a tile collected more than 2048 candidate centres "
+            raise _lib.ObiaB200Error("slic_iterate: a tile collected more than 1024 candidate centres "
                                      "(degenerate centre distribution)")
 
     if mask_dev is not None:

@@ -116,4 +116,4 @@ def fixed_point_scale(max_abs_value, H, W, step_y, step_x):
     bits_px = max(1, math.ceil(math.log2(reach + 1)))
     bits_val = math.ceil(math.log2(max(max_abs_value, 1e-30))) + 1
     shift = 62 - bits_px - bits_val
-    return float(2.0 ** min(shift, 60))
+    return float(2.0 ** shift)
