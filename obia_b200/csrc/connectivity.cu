@@ -303,37 +303,69 @@ cc_small_adjacent_kernel(const int32_t *__restrict__ lab, const int32_t *__restr
                          const int32_t *__restrict__ list, int32_t *ctr, uint8_t *visit, CcParams P)
 {
     const int n_small = ctr[CTR_NSMALL];
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_small; e += gridDim.x * blockDim.x) {
-        const int32_t t = list[e];
-        const int32_t L = lab[t];
-        const int32_t n = psize[t];
-        int32_t *qu = queue + atomicAdd(ctr + CTR_CURSOR, n);
-        int32_t a;
-        int cnt = bfs_piece(lab, T, psize, aux, visit, qu, P, t, t, L, a);
-        for (int i = 0; i < cnt; ++i) visit[qu[i]] = 0;
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * blockDim.x;
+    // warp-uniform trip count: the queue space of a warp's pieces is claimed with one atomic
+    for (int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); e0 < n_small; e0 += stride) {
+        const int e = e0 + lane;
+        const bool active = e < n_small;
+        int32_t t = 0, L = 0, n = 0;
+        if (active) {
+            t = list[e];
+            L = lab[t];
+            n = psize[t];
+        }
+        // single-pixel pieces (the bulk when labels are noisy) need no queue
+        const int need = (active && n > 1) ? n : 0;
+        int incl = need;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 0 && total > 0) base = atomicAdd(ctr + CTR_CURSOR, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (!active) continue;
+        int32_t a = -1;
         int32_t fix = t;
-        if (a < 0 && P.start_label == 1) {
-            // merged to 0 == mask label: the raster scan re-enters the piece at each
-            // later pixel of the first BFS (ascending) until a labelled neighbour shows
-            fix = kTInf;
-            // (total queue demand stays <= 2N: n per piece + one copy per cascading piece)
-            int32_t *cand = queue + atomicAdd(ctr + CTR_CURSOR, cnt);
-            int32_t *qu2 = qu;
-            for (int i = 0; i < cnt; ++i) cand[i] = qu[i];
-            int32_t last = t;
-            while (true) {
-                int32_t s = kTInf;
-                for (int i = 0; i < cnt; ++i)
-                    if (cand[i] > last && cand[i] < s) s = cand[i];
-                if (s == kTInf) break;
-                last = s;
-                int32_t a2;
-                const int c2 = bfs_piece(lab, T, psize, aux, visit, qu2, P, t, s, L, a2);
-                for (int i = 0; i < c2; ++i) visit[qu2[i]] = 0;
-                if (a2 >= 0) {
-                    a = a2;
-                    fix = s;
-                    break;
+        if (n == 1) {
+            const int py = t / P.W, px = t % P.W;
+            // (with max_size <= 1 the reference's BFS loop never runs: no neighbour is looked at)
+            for (int d = 0; d < 4 && P.max_size > 1; ++d) {
+                int32_t q;
+                if (!nbr(d, py, px, P.H, P.W, q)) continue;
+                if (labelled_at(lab, T, psize, aux, P, q, t, t)) a = q;
+            }
+            if (a < 0 && P.start_label == 1) fix = kTInf;  // stays label 0: no later pixel to re-enter at
+        } else {
+            int32_t *qu = queue + base + incl - need;
+            const int cnt = bfs_piece(lab, T, psize, aux, visit, qu, P, t, t, L, a);
+            for (int i = 0; i < cnt; ++i) visit[qu[i]] = 0;
+            if (a < 0 && P.start_label == 1) {
+                // merged to 0 == mask label: the raster scan re-enters the piece at each
+                // later pixel of the first BFS (ascending) until a labelled neighbour shows
+                fix = kTInf;
+                // (total queue demand stays <= 2N: n per piece + one copy per cascading piece)
+                int32_t *cand = queue + atomicAdd(ctr + CTR_CURSOR, cnt);
+                int32_t *qu2 = qu;
+                for (int i = 0; i < cnt; ++i) cand[i] = qu[i];
+                int32_t last = t;
+                while (true) {
+                    int32_t s = kTInf;
+                    for (int i = 0; i < cnt; ++i)
+                        if (cand[i] > last && cand[i] < s) s = cand[i];
+                    if (s == kTInf) break;
+                    last = s;
+                    int32_t a2;
+                    const int c2 = bfs_piece(lab, T, psize, aux, visit, qu2, P, t, s, L, a2);
+                    for (int i = 0; i < c2; ++i) visit[qu2[i]] = 0;
+                    if (a2 >= 0) {
+                        a = a2;
+                        fix = s;
+                        break;
+                    }
                 }
             }
         }

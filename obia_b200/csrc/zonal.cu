@@ -91,11 +91,18 @@ __device__ __forceinline__ double warp_sum_d(double v)
 }
 
 // stats layout per (label, band): count, mean, variance, min, max, skewness, kurtosis, sum
-__global__ void __launch_bounds__(256)
+//
+// VEC: the 8 bands of this pass are contiguous and 16-byte aligned in the pixel record, so a
+// pixel is fetched with two 128-bit loads.  Rows are processed four at a time so that a warp
+// has four label loads and then up to eight raster loads in flight instead of a chain of
+// dependent round trips per row.
+template <bool VEC>
+__global__ void __launch_bounds__(256, 2)
 zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw, ZonalWs w, int W,
                     int C, ZBands zb, int Cz, int64_t max_label, double resolution,
                     double *__restrict__ stats)
 {
+    constexpr int R = 4;
     const int lane = threadIdx.x & 31;
     const int64_t L = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (L > max_label) return;
@@ -113,6 +120,19 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
 #pragma unroll
     for (int b = 0; b < kZB; ++b) bidx[b] = zb.band[min(b0 + b, Cz - 1)];
 
+    auto load_px = [&](int64_t pix, float (&v)[kZB]) {
+        const float *p = raw + pix * C;
+        if (VEC) {
+            const float4 a = *reinterpret_cast<const float4 *>(p + bidx[0]);
+            const float4 c = *reinterpret_cast<const float4 *>(p + bidx[0] + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+        } else {
+#pragma unroll
+            for (int b = 0; b < kZB; ++b) v[b] = p[bidx[b]];
+        }
+    };
+
     // pivot = the segment's first pixel in its first row (row y0 holds one by construction)
     float pivot[kZB];
     {
@@ -123,71 +143,133 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (m) xr = xs + __ffs(m) - 1;
         }
-        const float *p = raw + ((int64_t)y0 * W + xr) * C;
-#pragma unroll
-        for (int b = 0; b < kZB; ++b) pivot[b] = p[bidx[b]];
+        load_px((int64_t)y0 * W + xr, pivot);
     }
 
     const float INF = __int_as_float(0x7f800000);
-    float s1[kZB], s2[kZB], s3[kZB], s4[kZB], mn[kZB], mx[kZB];
-    double d1[kZB], d2[kZB], d3[kZB], d4[kZB];
+    // ps[m*8 + b] = float32 partial of the (m+1)-th pivot-shifted power sum of band b (this lane's
+    // pixels since the last fold); `tot` = float64 running total of ps[lane] over the whole warp.
+    float ps[4 * kZB], mn[kZB], mx[kZB];
+    double tot = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4 * kZB; ++i) ps[i] = 0.0f;
 #pragma unroll
     for (int b = 0; b < kZB; ++b) {
-        s1[b] = s2[b] = s3[b] = s4[b] = 0.0f;
-        d1[b] = d2[b] = d3[b] = d4[b] = 0.0;
         mn[b] = INF;
         mx[b] = -INF;
     }
-    int pending = 0;
-    for (int y = y0; y <= y1; ++y) {
-        const int64_t row = (int64_t)y * W;
+    // Fold: transposed butterfly.  At each step a lane keeps the half of the vector selected by
+    // its lane bit and adds the partner's copy of that half, so after 5 steps lane l holds the
+    // warp total of element l (31 shuffles instead of 32 x 5).  Sums continue in float64.
+    auto fold = [&]() {
+        double h16[16];
+        {
+            const bool up = lane & 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float send = up ? ps[i] : ps[i + 16];
+                const float keep = up ? ps[i + 16] : ps[i];
+                h16[i] = (double)keep + (double)__shfl_xor_sync(0xffffffffu, send, 16);
+            }
+        }
+        double h8[8];
+        {
+            const bool up = lane & 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const double send = up ? h16[i] : h16[i + 8];
+                const double keep = up ? h16[i + 8] : h16[i];
+                h8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+        }
+        double h4[4];
+        {
+            const bool up = lane & 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double send = up ? h8[i] : h8[i + 4];
+                const double keep = up ? h8[i + 4] : h8[i];
+                h4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+        }
+        double h2[2];
+        {
+            const bool up = lane & 2;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double send = up ? h4[i] : h4[i + 2];
+                const double keep = up ? h4[i + 2] : h4[i];
+                h2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+        }
+        {
+            const bool up = lane & 1;
+            const double send = up ? h2[0] : h2[1];
+            const double keep = up ? h2[1] : h2[0];
+            tot += keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+#pragma unroll
+        for (int i = 0; i < 4 * kZB; ++i) ps[i] = 0.0f;
+    };
+
+    int since_fold = 0;
+    for (int yb = y0; yb <= y1; yb += R) {
         for (int xs = x0; xs <= x1; xs += 32) {
             const int x = xs + lane;
-            if (x <= x1 && labels[row + x] == (int32_t)L) {
-                const float *p = raw + (row + x) * C;
+            bool hit[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int y = yb + r;
+                hit[r] = (x <= x1) && (y <= y1) && (labels[(int64_t)y * W + x] == (int32_t)L);
+            }
+            float v[R][kZB];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (hit[r]) load_px((int64_t)(yb + r) * W + x, v[r]);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (!hit[r]) continue;
 #pragma unroll
                 for (int b = 0; b < kZB; ++b) {
-                    const float v = p[bidx[b]];
-                    const float d = v - pivot[b];
+                    const float d = v[r][b] - pivot[b];
                     const float dd = d * d;
-                    s1[b] += d;
-                    s2[b] += dd;
-                    s3[b] = fmaf(dd, d, s3[b]);
-                    s4[b] = fmaf(dd, dd, s4[b]);
-                    mn[b] = fminf(mn[b], v);
-                    mx[b] = fmaxf(mx[b], v);
+                    ps[b] += d;
+                    ps[kZB + b] += dd;
+                    ps[2 * kZB + b] = fmaf(dd, d, ps[2 * kZB + b]);
+                    ps[3 * kZB + b] = fmaf(dd, dd, ps[3 * kZB + b]);
+                    mn[b] = fminf(mn[b], v[r][b]);
+                    mx[b] = fmaxf(mx[b], v[r][b]);
                 }
-                if (++pending == 16) {
-                    pending = 0;
-#pragma unroll
-                    for (int b = 0; b < kZB; ++b) {
-                        d1[b] += (double)s1[b]; d2[b] += (double)s2[b];
-                        d3[b] += (double)s3[b]; d4[b] += (double)s4[b];
-                        s1[b] = s2[b] = s3[b] = s4[b] = 0.0f;
-                    }
-                }
+            }
+            // warp-uniform: at most R pixels per lane per iteration -> <= 32 float32 terms per fold
+            if (++since_fold == 8) {
+                since_fold = 0;
+                fold();
             }
         }
     }
+    fold();
 #pragma unroll
     for (int b = 0; b < kZB; ++b) {
-        d1[b] = warp_sum_d(d1[b] + (double)s1[b]);
-        d2[b] = warp_sum_d(d2[b] + (double)s2[b]);
-        d3[b] = warp_sum_d(d3[b] + (double)s3[b]);
-        d4[b] = warp_sum_d(d4[b] + (double)s4[b]);
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
             mn[b] = fminf(mn[b], __shfl_xor_sync(0xffffffffu, mn[b], o));
             mx[b] = fmaxf(mx[b], __shfl_xor_sync(0xffffffffu, mx[b], o));
         }
     }
+    // lane m*8 + b holds the m-th power sum of band b: hand the four sums of band b to lane b
+    const int bsel = lane & (kZB - 1);
+    const double S1 = __shfl_sync(0xffffffffu, tot, bsel);
+    const double S2 = __shfl_sync(0xffffffffu, tot, kZB + bsel);
+    const double S3 = __shfl_sync(0xffffffffu, tot, 2 * kZB + bsel);
+    const double S4 = __shfl_sync(0xffffffffu, tot, 3 * kZB + bsel);
     // lane b finishes band b
 #pragma unroll
     for (int b = 0; b < kZB; ++b) {
         if (lane == b && b < nb) {
             const double n = (double)cnt_total;
-            const double md = d1[b] / n;
-            const double e2 = d2[b] / n, e3 = d3[b] / n, e4 = d4[b] / n;
+            const double md = S1 / n;
+            const double e2 = S2 / n, e3 = S3 / n, e4 = S4 / n;
             const double mean = (double)pivot[b] + md;
             double m2 = e2 - md * md;
             if (m2 < 0.0) m2 = 0.0;
@@ -247,8 +329,16 @@ extern "C" int obia_b200_zonal_stats(const int32_t *labels, const float *raw, in
     zonal_bbox_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(labels, w, N, (int)W, max_label);
     OBIA_LAUNCH_CHECK();
     dim3 grid((unsigned)ceil_div(n, 8), (unsigned)ceil_div(Cz, kZB));
-    zonal_gather_kernel<<<grid, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label, resolution,
-                                              stats);
+    // vector path: every 8-band pass reads 8 contiguous, 16-byte aligned floats of the pixel record
+    bool vec = (C % 4 == 0) && (Cz % kZB == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
+    for (int b = 0; b < Cz && vec; ++b)
+        vec = (b % kZB == 0) ? (zb.band[b] % 4 == 0) : (zb.band[b] == zb.band[b - 1] + 1);
+    if (vec)
+        zonal_gather_kernel<true><<<grid, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label,
+                                                        resolution, stats);
+    else
+        zonal_gather_kernel<false><<<grid, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label,
+                                                         resolution, stats);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
 }
