@@ -1,0 +1,79 @@
+"""CPU: host-side logic of the product (grid geometry, centre initialisation, Gaussian taps,
+fixed-point scale, feature-column contract) against the oracle / the real scipy."""
+import numpy as np
+import pytest
+
+import slic_oracle as so
+from obia_b200 import slic_host
+
+
+@pytest.mark.parametrize("H,W,n", [(2048, 2048, 3000), (10000, 10000, 200000), (200, 200, 100), (37, 911, 50),
+                                   (64, 64, 5000), (8, 8, 100), (300, 20, 7), (1, 50, 5)])
+def test_grid_matches_oracle(H, W, n):
+    yx, steps = slic_host.grid_centroids(H, W, n)
+    c, s = so._get_grid_centroids((1, H, W), n)
+    np.testing.assert_array_equal(yx, c[:, 1:])
+    np.testing.assert_array_equal(steps, s)
+    assert slic_host.window_steps(H, W, len(yx)) == so.grid_steps((1, H, W), len(c))[1:]
+
+
+def test_mask_centroids_match_oracle():
+    yy, xx = np.mgrid[:90, :120]
+    mask = ((yy - 40) ** 2 + (xx - 70) ** 2) < 35 ** 2
+    yx, steps = slic_host.mask_centroids(mask, 25)
+    c, s = so._get_mask_centroids(mask[np.newaxis].astype(np.uint8), 25, True)
+    np.testing.assert_allclose(yx, c[:, 1:], rtol=0, atol=0)
+    np.testing.assert_allclose(steps, s)
+    with pytest.raises(ValueError):
+        slic_host.mask_centroids(np.zeros((5, 5), bool), 3)
+
+
+@pytest.mark.parametrize("sigma", [0.5, 1.0, 1.3, 2.7])
+def test_gaussian_taps_reproduce_scipy(sigma):
+    from scipy import ndimage
+    w, r = slic_host.gaussian_taps(np.float32(sigma))
+    assert r == int(4.0 * float(np.float32(sigma)) + 0.5) and len(w) == 2 * r + 1
+    x = np.random.RandomState(0).rand(64).astype(np.float32)
+    want = ndimage.gaussian_filter1d(x, float(np.float32(sigma)), mode="reflect", truncate=4.0)
+    pad = np.concatenate([x[::-1], x, x[::-1]]).astype(np.float64)      # half-sample symmetric
+    got = np.array([np.dot(w, pad[64 + i - r:64 + i + r + 1]) for i in range(64)]).astype(np.float32)
+    np.testing.assert_allclose(got, want, rtol=2e-6)
+
+
+def test_fixed_point_scale_leaves_headroom():
+    for (H, W, sy, sx, mx) in [(10000, 10000, 22, 22, 40.0), (200, 200, 20, 20, 0.1), (64, 64, 1, 1, 1e4),
+                               (40000, 40000, 2000, 2000, 2560.0)]:
+        s = slic_host.fixed_point_scale(mx, H, W, sy, sx)
+        reach = min(H * W, (4 * sy + 1) * (4 * sx + 1))
+        assert mx * s * reach <= 2.0 ** 62 and s == 2.0 ** round(np.log2(s))
+
+
+def test_feature_column_contract():
+    """Column names / order consumed by `classify` (obia/classification/classify.py:83)."""
+    from obia_b200.segmentation.segment_statistics import _create_empty_stats_columns
+    cols = _create_empty_stats_columns([0, 2], [0, 2], True, True, True, True, True, True,
+                                       True, True, True, True, True, True, True, True, True, True, True)
+    assert cols == (["segment_id"]
+                    + [f"b{b}_{s}" for b in (0, 2) for s in ("mean", "variance", "min", "max", "skewness", "kurtosis")]
+                    + [f"b{b}_{s}" for b in (0, 2) for s in ("contrast", "dissimilarity", "homogeneity", "ASM", "energy", "correlation")]
+                    + ["pai", "fhd", "ch", "mean_intensity", "variance_intensity", "geometry"])
+    cols = _create_empty_stats_columns([1], [], True, False, True, False, False, True,
+                                       True, True, True, True, True, True, False, False, False, False, False)
+    assert cols == ["segment_id", "b1_mean", "b1_min", "b1_kurtosis", "geometry"]
+
+
+def test_stats_oracle_is_numpy_scipy():
+    """The statistics oracle is literally np.mean/np.var/scipy.stats on the segment's pixels."""
+    import stats_oracle
+    from scipy.stats import kurtosis, skew
+    rng = np.random.RandomState(0)
+    labels = rng.randint(0, 5, size=(30, 40)).astype(np.int32)
+    raw = rng.rand(30, 40, 3).astype(np.float32) * 100
+    out, counts = stats_oracle.zonal_stats(labels, raw, [0, 2], np.arange(5))
+    for i in range(5):
+        px = raw[labels == i]
+        assert counts[i] == len(px)
+        np.testing.assert_allclose(out[i, 1, 0], np.mean(px[:, 2]), rtol=1e-6)
+        np.testing.assert_allclose(out[i, 1, 1], np.var(px[:, 2]), rtol=1e-5)
+        np.testing.assert_allclose(out[i, 0, 4], skew(px[:, 0].astype(np.float64)), rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(out[i, 0, 5], kurtosis(px[:, 0].astype(np.float64)), rtol=1e-3, atol=1e-3)
