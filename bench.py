@@ -278,9 +278,17 @@ def run_ours(args):
     alg_bytes = (4.0 * Cf + 4.0 / I) * H * W          # SURVEY.md 8(d) stage B per launch
     k_avg_ms = k_ms.value / max(1, k_n.value)
     achieved = alg_bytes / (k_avg_ms / 1e3) / 1e9 if k_avg_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj["workload"] == {"H": H, "W": W, "C": C}:
+            k = tj["slic_assign_update_kernel"]
+            traffic = k["dram_bytes_read"] + k["dram_bytes_write"]     # per launch, from the ncu capture
     roofline = {"bound": "hbm", "kernel": "slic_assign_update_kernel", "achieved": achieved, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "avg_launch_ms": k_avg_ms, "launches_timed": int(k_n.value),
+                "traffic": traffic, "avg_launch_ms": k_avg_ms, "launches_timed": int(k_n.value),
                 "kernel_share_of_step": (k_ms.value / ms_total) if ms_total else None,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "pipeline_bytes_per_px": 2 * 4 * C + 4 * Cf * (1 + I) + 16 + 4 * C,
