@@ -86,34 +86,111 @@ __device__ __forceinline__ void uf_union(int32_t *parent, int32_t a, int32_t b)
     } while (!done);
 }
 
-// phase 1a: link every pixel to its upper neighbour when labels agree
-__global__ void __launch_bounds__(256)
-cc_init_kernel(const int32_t *__restrict__ lab, int32_t *__restrict__ parent, int32_t *__restrict__ psize,
-               uint8_t *__restrict__ visit, int64_t N, int W, int32_t mask_label)
+// phase 1a: union-find inside a 32 x 32 tile, entirely in shared memory (short chains, no global
+// atomics); every pixel then points at the global index of its tile-local root.  Local and
+// global raster order agree inside a tile, so the local min-index root is the tile's first pixel
+// of the component.
+constexpr int kTile = 32;
+
+__device__ __forceinline__ int uf_find_s(const volatile int *parent, int x)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const int32_t l = lab[i];
-    int32_t p = (int32_t)i;
-    if (l != mask_label && i >= W && lab[i - W] == l) p = (int32_t)(i - W);
-    parent[i] = p;
-    psize[i] = 0;
-    visit[i] = 0;
+    int p = parent[x];
+    while (p != x) {
+        x = p;
+        p = parent[x];
+    }
+    return x;
 }
 
-// phase 1b: merge with the left neighbour (skipped when the row above already
-// connects the two pixels)
-__global__ void __launch_bounds__(256)
-cc_merge_kernel(const int32_t *__restrict__ lab, int32_t *parent, int64_t N, int W, int32_t mask_label)
+__device__ __forceinline__ void uf_union_s(int *parent, int a, int b)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const int x = (int)(i % W);
-    if (x == 0) return;
+    bool done;
+    do {
+        a = uf_find_s(parent, a);
+        b = uf_find_s(parent, b);
+        if (a < b) {
+            const int old = atomicMin(parent + b, a);
+            done = (old == b);
+            b = old;
+        } else if (b < a) {
+            const int old = atomicMin(parent + a, b);
+            done = (old == a);
+            a = old;
+        } else {
+            done = true;
+        }
+    } while (!done);
+}
+
+__global__ void __launch_bounds__(256)
+cc_local_kernel(const int32_t *__restrict__ lab, int32_t *__restrict__ parent, int32_t *__restrict__ psize,
+                uint8_t *__restrict__ visit, int H, int W, int32_t mask_label)
+{
+    __shared__ int32_t s_lab[kTile * kTile];
+    __shared__ int s_par[kTile * kTile];
+    const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+    for (int i = threadIdx.x; i < kTile * kTile; i += 256) {
+        const int ly = i / kTile, lx = i % kTile;
+        const int y = y0 + ly, x = x0 + lx;
+        s_lab[i] = (y < H && x < W) ? lab[(int64_t)y * W + x] : mask_label;
+        s_par[i] = i;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kTile * kTile; i += 256) {
+        const int32_t l = s_lab[i];
+        if (l == mask_label) continue;
+        const int ly = i / kTile, lx = i % kTile;
+        const bool up = ly > 0 && s_lab[i - kTile] == l;
+        const bool left = lx > 0 && s_lab[i - 1] == l;
+        if (up) uf_union_s(s_par, i, i - kTile);
+        // the row above already joins the two pixels when both upper neighbours match
+        if (left && !(up && s_lab[i - kTile - 1] == l)) uf_union_s(s_par, i, i - 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kTile * kTile; i += 256) {
+        const int ly = i / kTile, lx = i % kTile;
+        const int y = y0 + ly, x = x0 + lx;
+        if (y >= H || x >= W) continue;
+        const int64_t g = (int64_t)y * W + x;
+        const int r = uf_find_s(s_par, i);
+        parent[g] = (int32_t)((int64_t)(y0 + r / kTile) * W + x0 + r % kTile);
+        psize[g] = 0;
+        visit[g] = 0;
+    }
+}
+
+// phase 1b: join components across tile borders (global union-find with atomicMin)
+__global__ void __launch_bounds__(256)
+cc_border_kernel(const int32_t *__restrict__ lab, int32_t *parent, int H, int W, int32_t mask_label)
+{
+    // one thread per border pixel: left columns of tiles (x % 32 == 0, x > 0), then top rows
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ncolb = (W - 1) / kTile;          // number of vertical borders
+    const int nrowb = (H - 1) / kTile;          // number of horizontal borders
+    const int64_t nv = (int64_t)ncolb * H;
+    const int64_t nh = (int64_t)nrowb * W;
+    int y, x;
+    bool vertical;
+    if (t < nv) {
+        vertical = true;
+        y = (int)(t / ncolb);
+        x = (int)(t % ncolb + 1) * kTile;
+    } else if (t < nv + nh) {
+        vertical = false;
+        const int64_t u = t - nv;
+        y = (int)(u / W + 1) * kTile;
+        x = (int)(u % W);
+    } else {
+        return;
+    }
+    const int64_t i = (int64_t)y * W + x;
     const int32_t l = lab[i];
-    if (l == mask_label || lab[i - 1] != l) return;
-    if (i >= W && lab[i - W] == l && lab[i - W - 1] == l) return;
-    uf_union(parent, (int32_t)i, (int32_t)(i - 1));
+    if (l == mask_label) return;
+    if (vertical) {
+        if (lab[i - 1] == l) uf_union(parent, (int32_t)i, (int32_t)(i - 1));
+    } else {
+        if (lab[i - W] == l) uf_union(parent, (int32_t)i, (int32_t)(i - W));
+    }
 }
 
 // phase 1c: flatten, T = root, component sizes (one atomic per run of equal
@@ -232,15 +309,31 @@ cc_split_kernel(const int32_t *__restrict__ lab, const int32_t *__restrict__ par
     }
 }
 
-// phase 3 list: starts of pieces smaller than min_size
+// phase 3 list: starts of pieces smaller than min_size (one global atomic per CTA)
 __global__ void __launch_bounds__(256)
 cc_list_small_kernel(const int32_t *__restrict__ T, const int32_t *__restrict__ psize, int32_t *list,
                      int32_t *adj, int32_t *aux, int32_t *ctr, int64_t N, int64_t min_size)
 {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    if (T[i] == (int32_t)i && (int64_t)psize[i] < min_size) {
-        const int e = atomicAdd(ctr + CTR_NSMALL, 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool is_small = (i < N) && T[i] == (int32_t)i && (int64_t)psize[i] < min_size;
+    const unsigned m = __ballot_sync(0xffffffffu, is_small);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) {
+            const int c = s_warp[w];
+            s_warp[w] = tot;
+            tot += c;
+        }
+        s_base = tot ? atomicAdd(ctr + CTR_NSMALL, tot) : 0;
+    }
+    __syncthreads();
+    if (is_small) {
+        const int e = s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u));
         list[e] = (int32_t)i;
         adj[i] = -1;
         aux[i] = (int32_t)i;  // tfix: optimistic "labelled at its own time"
@@ -529,10 +622,17 @@ extern "C" int obia_b200_enforce_connectivity(const int32_t *labels_in, int32_t 
     const unsigned gridN = (unsigned)ceil_div(N, 256);
 
     OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr, 0, CTR_WORDS * 4, st));
-    cc_init_kernel<<<gridN, 256, 0, st>>>(labels_in, w.parent, w.psize, w.visit, N, (int)W, mask_label);
-    OBIA_LAUNCH_CHECK();
-    cc_merge_kernel<<<gridN, 256, 0, st>>>(labels_in, w.parent, N, (int)W, mask_label);
-    OBIA_LAUNCH_CHECK();
+    {
+        dim3 tiles((unsigned)ceil_div(W, kTile), (unsigned)ceil_div(H, kTile));
+        cc_local_kernel<<<tiles, 256, 0, st>>>(labels_in, w.parent, w.psize, w.visit, (int)H, (int)W, mask_label);
+        OBIA_LAUNCH_CHECK();
+        const int64_t nborder = ((W - 1) / kTile) * H + ((H - 1) / kTile) * W;
+        if (nborder > 0) {
+            cc_border_kernel<<<(unsigned)ceil_div(nborder, 256), 256, 0, st>>>(labels_in, w.parent, (int)H, (int)W,
+                                                                              mask_label);
+            OBIA_LAUNCH_CHECK();
+        }
+    }
     cc_flatten_kernel<<<gridN, 256, 0, st>>>(labels_in, w.parent, w.T, w.psize, N, mask_label);
     OBIA_LAUNCH_CHECK();
     cc_list_over_kernel<<<gridN, 256, 0, st>>>(w.T, w.psize, w.list, w.ctr, N, max_size);

@@ -200,7 +200,7 @@ template <int CP> struct Traits {
     static constexpr int kIds = 1024;   // centre ids a tile can collect
     static constexpr int kChk = (CP <= 32) ? 64 : 32;       // centre records resident at once
     static constexpr int kAcc = (CP <= 16) ? 128 : 32;      // slots with a tile accumulator row
-    static constexpr int kRec = (CP <= 4) ? 512 : (CP == 8) ? 384 : (CP == 16) ? 192 : (CP == 32) ? 128 : 64;
+    static constexpr int kRec = (CP <= 4) ? 768 : (CP == 8) ? 640 : (CP == 16) ? 288 : (CP == 32) ? 128 : 64;
 };
 
 // Warp strip: 16 pixels wide x (32 / (16/PX)) rows; a CTA tile is 2 x 4 strips (32 px wide).
@@ -443,44 +443,15 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     }
 
     // ---- fused centre update ---------------------------------------------------
-    // Per lane, pixels with the same winner are summed in registers (fixed order) and written as
-    // one 32-bit fixed-point record to shared memory; the tile then folds the records into its
-    // per-slot accumulators field-parallel (integer adds: independent of scheduling) and issues
-    // one RED.64 per touched (centre, field).
-#pragma unroll
-    for (int j = 0; j < PX; ++j) {
-        const bool v = (vmask >> j) & 1u;
-        bool first = v;
-#pragma unroll
-        for (int jj = 0; jj < j; ++jj)
-            first = first && !(((vmask >> jj) & 1u) && bests[j] >= 0 && bests[jj] == bests[j]);
-        int kcur = kk[j];
-        if (first && kcur < 0) kcur = labels[(int64_t)y * W + xb + j] - start_label;  // kept its previous centre
-        first = first && kcur >= 0;
-        int cnt = 0, sxl = 0;
-        float fs[CP];
-#pragma unroll
-        for (int c = 0; c < CP; ++c) fs[c] = 0.0f;
-        if (first) {
-#pragma unroll
-            for (int jj = j; jj < PX; ++jj) {
-                if (jj == j || (((vmask >> jj) & 1u) && bests[j] >= 0 && bests[jj] == bests[j])) {
-                    cnt += 1;
-                    sxl += xb + jj - tx0;
-#pragma unroll
-                    for (int c = 0; c < CP; ++c) {
-                        float lo, hi;
-                        unpack2(px2[(jj / 2) % NP][c], lo, hi);
-                        fs[c] = __fadd_rn(fs[c], (PX == 1) ? px1[c] : ((jj & 1) ? hi : lo));
-                    }
-                }
-            }
-        }
-        const int slot = bests[j];
-        const bool to_rec = first && slot >= 0 && slot < kAcc;
-        int ridx = -1;
-        if (to_rec) ridx = atomicAdd(&s_nrec, 1);
-        if (to_rec && ridx < kRec) {
+    // Per lane: the pixels that share the lane's leading winner are summed in registers (fixed
+    // order) into one record, every other pixel becomes its own record.  Records are 32-bit
+    // fixed point in shared memory; the tile then folds them into its per-slot accumulators
+    // field-parallel (integer adds: independent of scheduling) and issues one RED.64 per touched
+    // (centre, field).
+    auto emit = [&](int slot, int kcur, int cnt, int sxl, const float (&fs)[CP]) {
+        int ridx = kRec;
+        if (slot >= 0 && slot < kAcc) ridx = atomicAdd(&s_nrec, 1);
+        if (ridx < kRec) {
             int *r = s_rec[ridx];
             r[0] = slot;
             r[1] = cnt;
@@ -488,7 +459,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
             r[3] = sxl;
 #pragma unroll
             for (int c = 0; c < CP; ++c) r[4 + c] = __float2int_rn(fs[c] * fix_scale32);
-        } else if (first) {
+        } else {
             // no tile accumulator for this centre (or record pool full): add to HBM directly
             unsigned long long *a = acc + (int64_t)kcur * (3 + Cf);
             atomicAdd(&a[0], (unsigned long long)cnt);
@@ -498,6 +469,46 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
             for (int c = 0; c < CP; ++c)
                 if (c < Cf) atomicAdd(&a[3 + c], (unsigned long long)__double2ll_rn((double)fs[c] * fix_scale));
         }
+    };
+    auto px_val = [&](int j, int c) -> float {
+        if constexpr (PX == 1) {
+            return px1[c];
+        } else {
+            float lo, hi;
+            unpack2(px2[(j / 2) % NP][c], lo, hi);
+            return (j & 1) ? hi : lo;
+        }
+    };
+    int lead = -1;   // leading winner slot of this lane
+#pragma unroll
+    for (int j = PX - 1; j >= 0; --j)
+        if (((vmask >> j) & 1u) && bests[j] >= 0) lead = bests[j];
+    if (lead >= 0) {
+        int cnt = 0, sxl = 0;
+        float fs[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) fs[c] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            if (((vmask >> j) & 1u) && bests[j] == lead) {
+                cnt += 1;
+                sxl += xb + j - tx0;
+#pragma unroll
+                for (int c = 0; c < CP; ++c) fs[c] = __fadd_rn(fs[c], px_val(j, c));
+            }
+        }
+        emit(lead, s_sorted[lead], cnt, sxl, fs);
+    }
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+        if (!((vmask >> j) & 1u) || bests[j] == lead) continue;
+        int kcur = kk[j];
+        if (kcur < 0) kcur = labels[(int64_t)y * W + xb + j] - start_label;   // kept its previous centre
+        if (kcur < 0) continue;
+        float fs[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) fs[c] = px_val(j, c);
+        emit(bests[j], kcur, 1, xb + j - tx0, fs);
     }
     __syncthreads();
     {
