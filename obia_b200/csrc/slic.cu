@@ -329,6 +329,9 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     float wbound = INF;  // upper bound of every strip pixel's final distance (pruning bound)
 
     // ---- evaluate candidates chunk by chunk ------------------------------------
+#ifdef OBIA_EXP_SKIP_EVAL
+    nids = 0;
+#endif
     for (int c0 = 0; c0 < nids; c0 += kChk) {
         const int nc = min(kChk, nids - c0);
         __syncthreads();  // previous chunk fully consumed; s_sorted complete
@@ -483,6 +486,10 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
 #pragma unroll
     for (int j = PX - 1; j >= 0; --j)
         if (((vmask >> j) & 1u) && bests[j] >= 0) lead = bests[j];
+#ifdef OBIA_EXP_SKIP_UPDATE
+    lead = -1;
+    vmask = 0;
+#endif
     if (lead >= 0) {
         int cnt = 0, sxl = 0;
         float fs[CP];
@@ -511,6 +518,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
         emit(bests[j], kcur, 1, xb + j - tx0, fs);
     }
     __syncthreads();
+#ifndef OBIA_EXP_SKIP_REDUCE
     {
         const int nrec = min(s_nrec, kRec);
         for (int e = tid; e < nrec * NF; e += NT) {
@@ -519,7 +527,11 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
             if (v != 0) atomicAdd(&s_acc[s_rec[r][0]][f], v);
         }
     }
+#endif
     __syncthreads();
+#ifdef OBIA_EXP_SKIP_FLUSH
+    return;
+#endif
     const int nslots = min(nids, kAcc);
     for (int i = tid; i < nslots * (3 + Cf); i += NT) {
         const int slot = i / (3 + Cf), f = i % (3 + Cf);
