@@ -93,7 +93,7 @@ class SlicResult:
 def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.0, max_num_iter=10,
                 sigma=0, spacing=None, convert2lab=None, enforce_connectivity=True,
                 min_size_factor=0.5, max_size_factor=3, slic_zero=False, start_label=1, mask=None,
-                channel_axis=-1, keep_intermediates=False, init_centroids=None):
+                channel_axis=-1, keep_intermediates=False, init_centroids=None, minmax=None):
     """SLIC label raster of `raw[:, :, segmentation_bands]` with obia's wrapper semantics.
 
     Equivalent of segment_boundaries.py:31-57 up to the label raster: every band
@@ -134,7 +134,10 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
             raise ValueError("image and mask should have the same shape.")
 
     # ---- K1a: band ranges (needed on the host for validation, like numpy does) ----
-    minmax, flags = band_minmax(raw, mask_dev)
+    if minmax is not None and mask_dev is None:
+        minmax, flags = minmax           # already computed by the caller (same raster, no mask)
+    else:
+        minmax, flags = band_minmax(raw, mask_dev)
     mm = minmax.cpu().numpy()
     fl = flags.cpu().numpy()
     f32 = np.float32

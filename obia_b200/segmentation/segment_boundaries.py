@@ -51,8 +51,15 @@ def _epsg_string(crs):
         return crs
 
 
-def _apply_image_mutation(image, raw, minmax_dev):
-    """Side effect of segment_boundaries.py:31-33: every band of `img_data` normalised in place."""
+def _apply_image_mutation(image, raw, minmax_dev, stream=None, after=None):
+    """Side effect of segment_boundaries.py:31-33: every band of `img_data` normalised in place.
+
+    With `stream` the normalise + device-to-host copy is enqueued on that side stream once the
+    work already queued on `after` (the main stream) is done, so it overlaps the SLIC kernels;
+    the caller synchronises `stream` before returning to the user.
+    """
+    import contextlib
+
     import torch
 
     from .. import pipeline
@@ -61,16 +68,20 @@ def _apply_image_mutation(image, raw, minmax_dev):
     if isinstance(data, torch.Tensor) and data.is_cuda and data.dtype == torch.float32 and data.is_contiguous():
         pipeline.normalize_inplace(data, minmax_dev)
         return
-    tmp = raw.clone()
-    pipeline.normalize_inplace(tmp, minmax_dev)
-    if isinstance(data, torch.Tensor):
-        data.copy_(tmp.to(data.device, dtype=data.dtype))
-    else:
-        arr = np.asarray(data)
-        if arr.dtype == np.float32 and arr.flags.c_contiguous and arr.flags.writeable:
-            torch.from_numpy(arr).copy_(tmp, non_blocking=False)
+    with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+        if stream is not None and after is not None:
+            stream.wait_stream(after)
+        tmp = raw.clone()
+        pipeline.normalize_inplace(tmp, minmax_dev)
+        if isinstance(data, torch.Tensor):
+            data.copy_(tmp.to(data.device, dtype=data.dtype))
         else:
-            arr[...] = tmp.cpu().numpy()
+            arr = np.asarray(data)
+            if arr.dtype == np.float32 and arr.flags.c_contiguous and arr.flags.writeable:
+                host = torch.from_numpy(arr)
+                host.copy_(tmp, non_blocking=stream is not None and host.is_pinned())
+            else:
+                arr[...] = tmp.cpu().numpy()
 
 
 def frame_from_labels(labels, start_label, n_labels, connected, image=None, polygonize=False):
@@ -117,12 +128,12 @@ def frame_from_labels(labels, start_label, n_labels, connected, image=None, poly
     else:
         raster, ids = labels, np.arange(1, len(seg_labels) + 1, dtype=np.int64)
 
-    geometry = [None] * len(ids)
+    geometry = None
     if polygonize:
         from ..utils.polygonize import polygons_from_labels
         geometry = polygons_from_labels(raster.cpu().numpy(), seg_labels if raster is labels else ids,
                                         None if image is None else image.affine_transformation)
-    gdf = SegmentsFrame({"geometry": geometry, "segment_id": ids})
+    gdf = SegmentsFrame({"geometry": geometry, "segment_id": ids}, index=pd.RangeIndex(len(ids)))
     gdf.label_raster = raster
     gdf.segment_labels = seg_labels if raster is labels else ids
     gdf.crs = None if image is None else _epsg_string(image.crs)
@@ -162,15 +173,30 @@ def create_segments(image, segmentation_bands=None, method="slic", *, mutate_ima
     for band in bad:
         raise IndexError(f"Band index {band} out of range. Available bands indices: 0 to {num_bands - 1}.")
 
+    import torch
+    side = None
     try:
-        res = pipeline.slic_labels(raw, segmentation_bands, **kwargs)
+        pre = None
+        if mutate_image and kwargs.get("mask", None) is None:
+            # the band ranges are known after one pass: start writing the normalised raster back
+            # on a side stream while SLIC runs (the reference mutates img_data first, :31-33)
+            pre = pipeline.band_minmax(raw)
+            if not (isinstance(image.img_data, torch.Tensor) and image.img_data.is_cuda):
+                side = torch.cuda.Stream(device=raw.device)
+                _apply_image_mutation(image, raw, pre[0], stream=side,
+                                      after=torch.cuda.current_stream(raw.device))
+        res = pipeline.slic_labels(raw, segmentation_bands, minmax=pre, **kwargs)
     except Exception:
         # the reference has already normalised img_data when slic() raises (:31-33 run first)
-        if mutate_image:
+        if mutate_image and side is None:
             minmax, _ = pipeline.band_minmax(raw)
             _apply_image_mutation(image, raw, minmax)
+        if side is not None:
+            side.synchronize()
         raise
-    if mutate_image:
+    if side is not None:
+        side.synchronize()
+    elif mutate_image:
         _apply_image_mutation(image, raw, res.minmax)
 
     connected = bool(kwargs.get("enforce_connectivity", True))

@@ -91,8 +91,14 @@ def create_objects(
     )
 
     raster, row_labels = _labels_of(segments)
-    data = {"segment_id": np.asarray(segments["segment_id"]), "geometry": list(segments["geometry"])}
-    if len(spectral_bands) > 0 and len(row_labels) > 0:
+    n_rows = len(row_labels)
+    float_cols = columns[1:-1]
+    # one (n_columns, n_rows) float64 block, column-major for pandas (zero-copy): the statistics
+    # are the leading columns in the reference's order; texture / point-cloud columns stay NaN
+    import torch
+    block = np.empty((len(float_cols), n_rows), dtype=np.float64)
+    n_stat = 0
+    if len(spectral_bands) > 0 and n_rows > 0:
         for b in spectral_bands:
             if b < 0 or b >= n_bands:
                 # the reference indexes the (C, h, w) crop with the band number (:144)
@@ -101,15 +107,21 @@ def create_objects(
         # the reference computes in float32 for float32 rasters (np.where keeps float32):
         # scipy's "nearly constant" NaN rule uses that dtype's resolution
         stats = pipeline.zonal_stats(raster, raw, spectral_bands, max_label=max_label, resolution=1e-6)
-        table = stats[row_labels].cpu().numpy()      # (rows, Cz, 8)
         names = pipeline.STAT_FIELDS
         want = [("mean", calc_mean), ("variance", calc_variance), ("min", calc_min), ("max", calc_max),
                 ("skewness", calc_skewness), ("kurtosis", calc_kurtosis)]
-        for j, b in enumerate(spectral_bands):
-            for name, on in want:
-                if on:
-                    data[f"b{b}_{name}"] = table[:, j, names.index(name)]
-    out = pd.DataFrame(data, columns=columns)   # missing columns (texture, point cloud) -> NaN
+        fields = [names.index(name) for name, on in want if on]
+        if fields:
+            rows = torch.from_numpy(row_labels).to(stats.device)
+            sel = stats.index_select(0, rows)[:, :, fields]                  # (rows, Cz, nstat)
+            sel = sel.permute(1, 2, 0).reshape(len(spectral_bands) * len(fields), n_rows).contiguous()
+            n_stat = sel.shape[0]
+            assert float_cols[:n_stat] == [f"b{b}_{name}" for b in spectral_bands for name, on in want if on]
+            torch.from_numpy(block[:n_stat]).copy_(sel)
+    block[n_stat:] = np.nan
+    out = pd.DataFrame(block.T, columns=float_cols, copy=False)
+    out.insert(0, "segment_id", np.asarray(segments["segment_id"]))
+    out["geometry"] = segments["geometry"].to_numpy() if len(segments) else None
     from .segment_boundaries import SegmentsFrame
     out = SegmentsFrame(out)
     out.label_raster = raster
