@@ -15,6 +15,8 @@
 //      fixed point for the start_label=1 corner case (label 0 == mask label);
 //   4. kept pieces are numbered by the rank of their start pixel (prefix sum),
 //      merged pieces follow their adjacent chain.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace obia {
@@ -23,13 +25,14 @@ constexpr int kScanChunk = 2048;
 constexpr int32_t kTInf = 0x7fffffff;
 
 struct CcWs {
-    int32_t *parent, *T, *psize, *adj, *aux, *queue, *list, *blocksum, *ctr;
+    int32_t *parent, *T, *psize, *adj, *aux, *queue, *list, *blocksum, *ctr, *stamp, *dirty0, *dirty1;
     uint8_t *visit;
     int64_t nblocks;
     int64_t bytes;
 };
 // ctr words
-enum { CTR_NSMALL = 0, CTR_NOVER = 1, CTR_CURSOR = 2, CTR_CHANGED = 3, CTR_NKEPT = 4, CTR_ERR = 5, CTR_WORDS = 8 };
+enum { CTR_NSMALL = 0, CTR_NOVER = 1, CTR_CURSOR = 2, CTR_CHANGED = 3, CTR_NKEPT = 4, CTR_ERR = 5, CTR_NDIRTY0 = 6,
+       CTR_NDIRTY1 = 7, CTR_ROUNDS = 8, CTR_WORDS = 12 };
 
 static CcWs cc_ws_layout(void *base, int64_t N)
 {
@@ -52,6 +55,9 @@ static CcWs cc_ws_layout(void *base, int64_t N)
     w.blocksum = (int32_t *)take((w.nblocks + 1) * 4);
     w.ctr = (int32_t *)take(CTR_WORDS * 4);
     w.visit = (uint8_t *)take(N);
+    w.stamp = (int32_t *)take(N * 4);    // round in which a piece was last queued for re-evaluation
+    w.dirty0 = (int32_t *)take(N * 4);   // ping-pong lists of pieces to re-evaluate
+    w.dirty1 = (int32_t *)take(N * 4);
     w.bytes = off;
     return w;
 }
@@ -124,7 +130,7 @@ __device__ __forceinline__ void uf_union_s(int *parent, int a, int b)
 
 __global__ void __launch_bounds__(256)
 cc_local_kernel(const int32_t *__restrict__ lab, int32_t *__restrict__ parent, int32_t *__restrict__ psize,
-                uint8_t *__restrict__ visit, int H, int W, int32_t mask_label)
+                uint8_t *__restrict__ visit, int32_t *__restrict__ stamp, int H, int W, int32_t mask_label)
 {
     __shared__ int32_t s_lab[kTile * kTile];
     __shared__ int s_par[kTile * kTile];
@@ -156,6 +162,7 @@ cc_local_kernel(const int32_t *__restrict__ lab, int32_t *__restrict__ parent, i
         parent[g] = (int32_t)((int64_t)(y0 + r / kTile) * W + x0 + r % kTile);
         psize[g] = 0;
         visit[g] = 0;
+        stamp[g] = 0;
     }
 }
 
@@ -346,25 +353,35 @@ struct CcParams {
     int32_t mask_label, start_label;
 };
 
+// Scan position at which pixel q (not in piece t) receives a label > mask label, kTInf if never:
+// kept pieces at their start; merged pieces at their start for start_label 0 (they always carry
+// a label >= 0), at `tfix` for start_label 1 (label 0 == mask label until a later re-scan).
+__device__ __forceinline__ int32_t label_time(const int32_t *lab, const int32_t *T, const int32_t *psize,
+                                              const int32_t *aux, const CcParams &P, int32_t q, int32_t t)
+{
+    if (lab[q] == P.mask_label) return kTInf;
+    const int32_t tq = T[q];
+    if (tq == t) return kTInf;
+    if ((int64_t)psize[tq] >= P.min_size) return tq;
+    if (P.start_label == 0) return tq;
+    return __ldcg(aux + tq);
+}
+
 __device__ __forceinline__ bool labelled_at(const int32_t *lab, const int32_t *T, const int32_t *psize,
                                             const int32_t *aux, const CcParams &P, int32_t q, int32_t t,
                                             int32_t now)
 {
-    if (lab[q] == P.mask_label) return false;
-    const int32_t tq = T[q];
-    if (tq == t || tq > now) return false;
-    if ((int64_t)psize[tq] >= P.min_size) return true;  // kept piece processed earlier
-    if (P.start_label == 0) return true;                // merged pieces carry a label >= 0
-    return __ldcg(aux + tq) < now;                      // start_label 1: label 0 == mask label until tfix
+    return label_time(lab, T, psize, aux, P, q, t) < now;
 }
 
 // replay of the reference BFS restricted to piece t, started at pixel s
 __device__ int bfs_piece(const int32_t *lab, const int32_t *T, const int32_t *psize, const int32_t *aux,
                          uint8_t *visit, int32_t *qu, const CcParams &P, int32_t t, int32_t s,
-                         int32_t L, int32_t &adj_out)
+                         int32_t L, int32_t &adj_out, int32_t &first_time)
 {
     int cnt = 1, head = 0;
     int32_t adjq = -1;
+    int32_t tmin = kTInf;   // earliest scan position at which any examined neighbour is labelled
     qu[0] = s;
     visit[s] = 1;
     while (head < cnt && (int64_t)cnt < P.max_size) {
@@ -380,70 +397,94 @@ __device__ int bfs_piece(const int32_t *lab, const int32_t *T, const int32_t *ps
                     qu[cnt++] = q;
                     if ((int64_t)cnt >= P.max_size) break;
                 }
-            } else if (labelled_at(lab, T, psize, aux, P, q, t, s)) {
-                adjq = q;
+            } else {
+                const int32_t lt = label_time(lab, T, psize, aux, P, q, t);
+                tmin = min(tmin, lt);
+                if (lt < s) adjq = q;
             }
         }
         ++head;
     }
     adj_out = adjq;
+    first_time = tmin;
     return cnt;
 }
 
-__global__ void __launch_bounds__(128)
-cc_small_adjacent_kernel(const int32_t *__restrict__ lab, const int32_t *__restrict__ T,
-                         const int32_t *__restrict__ psize, int32_t *adj, int32_t *aux, int32_t *queue,
-                         const int32_t *__restrict__ list, int32_t *ctr, uint8_t *visit, CcParams P)
+struct CcArrays {
+    const int32_t *lab, *T, *psize, *list;
+    int32_t *adj, *aux, *queue, *ctr, *stamp;
+    uint8_t *visit;
+};
+
+// A small piece that touches pixel p of a piece whose `tfix` just changed may have relied on the
+// old value -- later pieces at their start, EARLIER pieces at one of their re-scan times -- so
+// every small neighbour is queued for re-evaluation (once per round).
+__device__ __forceinline__ void push_dependents(const CcArrays &A, const CcParams &P, int32_t p, int32_t t,
+                                                int round_id, int32_t *dirty_next, int32_t *n_next)
 {
-    const int n_small = ctr[CTR_NSMALL];
-    const int lane = threadIdx.x & 31;
-    const int stride = gridDim.x * blockDim.x;
-    // warp-uniform trip count: the queue space of a warp's pieces is claimed with one atomic
-    for (int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); e0 < n_small; e0 += stride) {
-        const int e = e0 + lane;
-        const bool active = e < n_small;
-        int32_t t = 0, L = 0, n = 0;
-        if (active) {
-            t = list[e];
-            L = lab[t];
-            n = psize[t];
+    const int py = p / P.W, px = p % P.W;
+    for (int d = 0; d < 4; ++d) {
+        int32_t q;
+        if (!nbr(d, py, px, P.H, P.W, q)) continue;
+        if (A.lab[q] == P.mask_label) continue;
+        const int32_t tq = A.T[q];
+        if (tq == t || (int64_t)A.psize[tq] >= P.min_size) continue;
+        if (atomicExch(A.stamp + tq, round_id) != round_id) dirty_next[atomicAdd(n_next, 1)] = tq;
+    }
+}
+
+// `adjacent` of one small piece (start pixel t) under the current knowledge of its earlier
+// neighbours; `qu` = queue space for max(psize[t], 1) pixels (+ psize[t] more for the re-scan copy,
+// claimed from the global cursor on demand).  Returns true when the piece's tfix changed.
+__device__ bool small_piece_adjacent(const CcArrays &A, const CcParams &P, int32_t t, int32_t *qu,
+                                     int round_id, int32_t *dirty_next, int32_t *n_next)
+{
+    const int32_t L = A.lab[t];
+    const int32_t n = A.psize[t];
+    int32_t a = -1;
+    int32_t fix = t;
+    int cnt = 1;
+    const int32_t *members = qu;   // pixels of the first BFS
+    if (n == 1) {
+        const int py = t / P.W, px = t % P.W;
+        // (with max_size <= 1 the reference's BFS loop never runs: no neighbour is looked at)
+        for (int d = 0; d < 4 && P.max_size > 1; ++d) {
+            int32_t q;
+            if (!nbr(d, py, px, P.H, P.W, q)) continue;
+            if (labelled_at(A.lab, A.T, A.psize, A.aux, P, q, t, t)) a = q;
         }
-        // single-pixel pieces (the bulk when labels are noisy) need no queue
-        const int need = (active && n > 1) ? n : 0;
-        int incl = need;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        int base = 0;
-        if (lane == 0 && total > 0) base = atomicAdd(ctr + CTR_CURSOR, total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (!active) continue;
-        int32_t a = -1;
-        int32_t fix = t;
-        if (n == 1) {
-            const int py = t / P.W, px = t % P.W;
-            // (with max_size <= 1 the reference's BFS loop never runs: no neighbour is looked at)
-            for (int d = 0; d < 4 && P.max_size > 1; ++d) {
-                int32_t q;
-                if (!nbr(d, py, px, P.H, P.W, q)) continue;
-                if (labelled_at(lab, T, psize, aux, P, q, t, t)) a = q;
-            }
-            if (a < 0 && P.start_label == 1) fix = kTInf;  // stays label 0: no later pixel to re-enter at
-        } else {
-            int32_t *qu = queue + base + incl - need;
-            const int cnt = bfs_piece(lab, T, psize, aux, visit, qu, P, t, t, L, a);
-            for (int i = 0; i < cnt; ++i) visit[qu[i]] = 0;
-            if (a < 0 && P.start_label == 1) {
-                // merged to 0 == mask label: the raster scan re-enters the piece at each
-                // later pixel of the first BFS (ascending) until a labelled neighbour shows
-                fix = kTInf;
-                // (total queue demand stays <= 2N: n per piece + one copy per cascading piece)
-                int32_t *cand = queue + atomicAdd(ctr + CTR_CURSOR, cnt);
-                int32_t *qu2 = qu;
-                for (int i = 0; i < cnt; ++i) cand[i] = qu[i];
+        if (a < 0 && P.start_label == 1) fix = kTInf;  // stays label 0: no later pixel to re-enter at
+        qu[0] = t;
+    } else {
+        int32_t tmin;
+        cnt = bfs_piece(A.lab, A.T, A.psize, A.aux, A.visit, qu, P, t, t, L, a, tmin);
+        for (int i = 0; i < cnt; ++i) A.visit[qu[i]] = 0;
+        if (a < 0 && P.start_label == 1) {
+            // Merged to 0 == mask label: the raster scan re-enters the piece at each of its later
+            // pixels (ascending) until the BFS from there sees a labelled neighbour.
+            fix = kTInf;
+            // (queue demand stays <= 2N: psize per piece + one copy per re-scanned piece)
+            int32_t *cand = A.queue + atomicAdd(A.ctr + CTR_CURSOR, cnt);
+            int32_t *qu2 = qu;
+            for (int i = 0; i < cnt; ++i) cand[i] = qu[i];
+            members = cand;
+            if ((int64_t)n < P.max_size) {
+                // The BFS is not cut by the size cap, so from ANY start it examines every
+                // neighbour of the piece: the first successful re-scan is at the first member
+                // pixel after the earliest labelling time among those neighbours.
+                int32_t s = kTInf;
+                if (tmin != kTInf)
+                    for (int i = 0; i < cnt; ++i)
+                        if (cand[i] > tmin && cand[i] < s) s = cand[i];
+                if (s != kTInf) {
+                    int32_t a2, tm2;
+                    const int c2 = bfs_piece(A.lab, A.T, A.psize, A.aux, A.visit, qu2, P, t, s, L, a2, tm2);
+                    for (int i = 0; i < c2; ++i) A.visit[qu2[i]] = 0;
+                    a = a2;
+                    fix = (a2 >= 0) ? s : kTInf;
+                }
+            } else {
+                // size cap can truncate the BFS (min_size > max_size): replay every re-scan
                 int32_t last = t;
                 while (true) {
                     int32_t s = kTInf;
@@ -451,9 +492,9 @@ cc_small_adjacent_kernel(const int32_t *__restrict__ lab, const int32_t *__restr
                         if (cand[i] > last && cand[i] < s) s = cand[i];
                     if (s == kTInf) break;
                     last = s;
-                    int32_t a2;
-                    const int c2 = bfs_piece(lab, T, psize, aux, visit, qu2, P, t, s, L, a2);
-                    for (int i = 0; i < c2; ++i) visit[qu2[i]] = 0;
+                    int32_t a2, tm2;
+                    const int c2 = bfs_piece(A.lab, A.T, A.psize, A.aux, A.visit, qu2, P, t, s, L, a2, tm2);
+                    for (int i = 0; i < c2; ++i) A.visit[qu2[i]] = 0;
                     if (a2 >= 0) {
                         a = a2;
                         fix = s;
@@ -462,11 +503,79 @@ cc_small_adjacent_kernel(const int32_t *__restrict__ lab, const int32_t *__restr
                 }
             }
         }
-        adj[t] = a;
-        if (aux[t] != fix) {
-            aux[t] = fix;
-            atomicExch(ctr + CTR_CHANGED, 1);
+    }
+    A.adj[t] = a;
+    if (A.aux[t] == fix) return false;
+    A.aux[t] = fix;
+    if (P.start_label == 0) return true;   // no label-0 ambiguity: nobody depends on tfix
+    // tell later small neighbours of the piece to look again
+    for (int i = 0; i < cnt; ++i) push_dependents(A, P, members[i], t, round_id, dirty_next, n_next);
+    return true;
+}
+
+// round 1: every small piece, in parallel (optimistic: every merged neighbour counts as labelled
+// from its own start time).  Pieces whose tfix turns out different queue their dependents.
+__global__ void __launch_bounds__(128)
+cc_small_adjacent_kernel(CcArrays A, CcParams P, int32_t *dirty_next)
+{
+    const int n_small = A.ctr[CTR_NSMALL];
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * blockDim.x;
+    // warp-uniform trip count: the queue space of a warp's pieces is claimed with one atomic
+    for (int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); e0 < n_small; e0 += stride) {
+        const int e = e0 + lane;
+        const bool active = e < n_small;
+        int32_t t = 0, n = 0;
+        if (active) {
+            t = A.list[e];
+            n = A.psize[t];
         }
+        const int need = active ? n : 0;
+        int incl = need;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 0 && total > 0) base = atomicAdd(A.ctr + CTR_CURSOR, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (!active) continue;
+        small_piece_adjacent(A, P, t, A.queue + base + incl - need, 1, dirty_next, A.ctr + CTR_NDIRTY0);
+    }
+}
+
+// rounds 2..: re-evaluate only the queued pieces (the start_label = 1 "label 0 == mask label"
+// chains; usually there are none).  One launch per round; the lists ping-pong.  The fixed point
+// is unique: a decision at a scan position depends only on earlier scan positions.
+__global__ void __launch_bounds__(128)
+cc_small_round_kernel(CcArrays A, CcParams P, const int32_t *__restrict__ cur, int32_t *nxt, int cur_ctr,
+                      int nxt_ctr, int round_id)
+{
+    const int n = A.ctr[cur_ctr];
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * blockDim.x;
+    for (int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); e0 < n; e0 += stride) {
+        const int e = e0 + lane;
+        const bool active = e < n;
+        int32_t t = 0, need = 0;
+        if (active) {
+            t = cur[e];
+            need = A.psize[t];
+        }
+        int incl = need;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 0 && total > 0) base = atomicAdd(A.ctr + CTR_CURSOR, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (!active) continue;
+        small_piece_adjacent(A, P, t, A.queue + base + incl - need, round_id, nxt, A.ctr + nxt_ctr);
     }
 }
 
@@ -569,8 +678,8 @@ cc_number_kernel(const int32_t *__restrict__ T, const int32_t *__restrict__ psiz
 __global__ void __launch_bounds__(256)
 cc_resolve_kernel(const int32_t *__restrict__ lab, const int32_t *__restrict__ T,
                   const int32_t *__restrict__ psize, const int32_t *__restrict__ adj,
-                  const int32_t *__restrict__ aux, int32_t *__restrict__ out, int64_t N, int64_t min_size,
-                  int32_t mask_label)
+                  const int32_t *__restrict__ aux, int32_t *__restrict__ out, int32_t *ctr, int64_t N,
+                  int64_t min_size, int32_t mask_label)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -579,19 +688,23 @@ cc_resolve_kernel(const int32_t *__restrict__ lab, const int32_t *__restrict__ T
         return;
     }
     int32_t t = T[i];
-    int32_t r;
-    while (true) {
+    int32_t r = mask_label;
+    bool done = false;
+    for (int hop = 0; hop < (1 << 24) && !done; ++hop) {   // chains are short; never spin
         if ((int64_t)psize[t] >= min_size) {
             r = aux[t];
-            break;
+            done = true;
+        } else {
+            const int32_t a = adj[t];
+            if (a < 0) {
+                r = 0;  // `adjacent` initial value
+                done = true;
+            } else {
+                t = T[a];
+            }
         }
-        const int32_t a = adj[t];
-        if (a < 0) {
-            r = 0;  // `adjacent` initial value
-            break;
-        }
-        t = T[a];
     }
+    if (!done) atomicExch(ctr + CTR_ERR, 2);
     out[i] = r;
 }
 
@@ -624,7 +737,8 @@ extern "C" int obia_b200_enforce_connectivity(const int32_t *labels_in, int32_t 
     OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr, 0, CTR_WORDS * 4, st));
     {
         dim3 tiles((unsigned)ceil_div(W, kTile), (unsigned)ceil_div(H, kTile));
-        cc_local_kernel<<<tiles, 256, 0, st>>>(labels_in, w.parent, w.psize, w.visit, (int)H, (int)W, mask_label);
+        cc_local_kernel<<<tiles, 256, 0, st>>>(labels_in, w.parent, w.psize, w.visit, w.stamp, (int)H, (int)W,
+                                               mask_label);
         OBIA_LAUNCH_CHECK();
         const int64_t nborder = ((W - 1) / kTile) * H + ((H - 1) / kTile) * W;
         if (nborder > 0) {
@@ -647,15 +761,40 @@ extern "C" int obia_b200_enforce_connectivity(const int32_t *labels_in, int32_t 
     P.H = (int)H; P.W = (int)W; P.min_size = min_size; P.max_size = max_size;
     P.mask_label = mask_label; P.start_label = start_label;
     int32_t hctr[CTR_WORDS];
-    for (int round = 0; round < 100000; ++round) {
-        OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + CTR_CURSOR, 0, 2 * 4, st));  // cursor + changed
-        cc_small_adjacent_kernel<<<kNumSMs * 8, 128, 0, st>>>(labels_in, w.T, w.psize, w.adj, w.aux, w.queue,
-                                                              w.list, w.ctr, w.visit, P);
+    {
+        CcArrays A;
+        A.lab = labels_in; A.T = w.T; A.psize = w.psize; A.list = w.list;
+        A.adj = w.adj; A.aux = w.aux; A.queue = w.queue; A.ctr = w.ctr; A.stamp = w.stamp; A.visit = w.visit;
+        OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + CTR_CURSOR, 0, 4, st));
+        cc_small_adjacent_kernel<<<kNumSMs * 8, 128, 0, st>>>(A, P, w.dirty0);
         OBIA_LAUNCH_CHECK();
-        if (start_label == 0) break;  // no label-0 ambiguity: one round is exact
-        OBIA_CUDA_CHECK(cudaMemcpyAsync(hctr, w.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, st));
-        OBIA_CUDA_CHECK(cudaStreamSynchronize(st));
-        if (!hctr[CTR_CHANGED]) break;
+        if (start_label == 1) {   // start_label 0 has no label-0 ambiguity: round 1 is exact
+            int round_id = 1;
+            int cur = 0;   // dirty list written by the previous round
+            while (true) {
+                OBIA_CUDA_CHECK(cudaMemcpyAsync(hctr, w.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, st));
+                OBIA_CUDA_CHECK(cudaStreamSynchronize(st));
+                const int n_dirty = hctr[cur ? CTR_NDIRTY1 : CTR_NDIRTY0];
+                if (getenv("OBIA_B200_DEBUG"))
+                    fprintf(stderr, "[obia_b200] connectivity: round %d, %d small pieces, %d queued\n", round_id,
+                            hctr[CTR_NSMALL], n_dirty);
+                if (n_dirty == 0) break;
+                if (round_id > (1 << 28)) return set_err(OBIA_B200_ERR_CUDA, "enforce_connectivity: no fixed point");
+                // a batch of rounds without host round trips (an empty round costs a few microseconds)
+                const int batch = 16;
+                for (int b = 0; b < batch; ++b) {
+                    ++round_id;
+                    const int cur_ctr = cur ? CTR_NDIRTY1 : CTR_NDIRTY0, nxt_ctr = cur ? CTR_NDIRTY0 : CTR_NDIRTY1;
+                    OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + nxt_ctr, 0, 4, st));
+                    OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + CTR_CURSOR, 0, 4, st));   // queue space is recycled
+                    cc_small_round_kernel<<<kNumSMs * 4, 128, 0, st>>>(A, P, cur ? w.dirty1 : w.dirty0,
+                                                                       cur ? w.dirty0 : w.dirty1, cur_ctr, nxt_ctr,
+                                                                       round_id);
+                    OBIA_LAUNCH_CHECK();
+                    cur ^= 1;
+                }
+            }
+        }
     }
 
     cc_count_kernel<<<(unsigned)w.nblocks, 256, 0, st>>>(w.T, w.psize, w.blocksum, N, min_size);
@@ -665,11 +804,14 @@ extern "C" int obia_b200_enforce_connectivity(const int32_t *labels_in, int32_t 
     cc_number_kernel<<<(unsigned)w.nblocks, 256, 0, st>>>(w.T, w.psize, w.blocksum, w.aux, N, min_size,
                                                           start_label);
     OBIA_LAUNCH_CHECK();
-    cc_resolve_kernel<<<gridN, 256, 0, st>>>(labels_in, w.T, w.psize, w.adj, w.aux, labels_out, N, min_size,
-                                             mask_label);
+    cc_resolve_kernel<<<gridN, 256, 0, st>>>(labels_in, w.T, w.psize, w.adj, w.aux, labels_out, w.ctr, N,
+                                             min_size, mask_label);
     OBIA_LAUNCH_CHECK();
     OBIA_CUDA_CHECK(cudaMemcpyAsync(hctr, w.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, st));
     OBIA_CUDA_CHECK(cudaStreamSynchronize(st));
     if (n_labels_host) *n_labels_host = hctr[CTR_NKEPT];
+    if (hctr[CTR_ERR])
+        return set_err(OBIA_B200_ERR_CUDA, "enforce_connectivity: internal consistency check failed (%d)",
+                       hctr[CTR_ERR]);
     return OBIA_B200_OK;
 }

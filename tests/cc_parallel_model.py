@@ -7,8 +7,9 @@ phases; this file is the same decomposition written as slow, obviously
 order-free Python so the decomposition itself can be checked against the
 sequential oracle on the CPU (tests/test_cc_model.py), independent of CUDA.
 
-Phases (every per-piece step below only reads state of pieces with an earlier
-start pixel, so pieces can be processed in any order / in parallel):
+Phases (every decision taken at a scan position only reads what pieces had been
+given at EARLIER scan positions, so the per-piece steps can run in any order /
+in parallel and are iterated to the unique fixed point):
 
   1. 4-connected components of equal label; T[p] = smallest raster index of
      p's component (union-find with min-index roots on the GPU).

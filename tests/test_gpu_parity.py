@@ -239,6 +239,25 @@ def test_connectivity_exact_random():
                                       err_msg=f"{lab.shape} min={min_size} max={max_size} sl={start_label}")
 
 
+def test_connectivity_degenerate_everything_small():
+    """Noise labels with a large min_size: every piece is small, label-0 chains run across the whole
+    raster (start_label=1).  Must stay exact and must not take rounds proportional to host syncs."""
+    import time
+    import slic_oracle as so
+    from obia_b200 import pipeline
+    rng = np.random.RandomState(5)
+    for H, W, k, min_size in [(120, 150, 6, 40), (400, 400, 40, 500)]:
+        lab = rng.randint(1, k + 1, size=(H, W)).astype(np.int32)
+        want = so.enforce_connectivity(lab, min_size, 6 * min_size, 1)
+        t0 = time.perf_counter()
+        got, nlab = pipeline.enforce_connectivity(_cuda(lab), min_size, 6 * min_size, 1)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+        print(f"degenerate {H}x{W}: kept {nlab}, zero pixels {(want == 0).mean():.3f}, {dt * 1e3:.1f} ms")
+        assert dt < 20.0
+
+
 @pytest.mark.parametrize("compactness", [0.03, 0.3])
 def test_connectivity_exact_on_slic_output(compactness):
     import slic_oracle as so
