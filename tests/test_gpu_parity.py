@@ -188,6 +188,36 @@ def test_slic_full_agreement(H, W, C, n, compactness, kw):
         assert agree >= 0.995
 
 
+def test_slic_readme_quickstart_shape():
+    """BASELINE config c1 at reduced size: 3-band uint8-valued raster (SURVEY.md 8d generator),
+    slic n_segments scaled from 3000 @ 2048^2, compactness=10 -> Lab path + statistics."""
+    import slic_oracle as so
+    import stats_oracle
+    from obia_b200 import pipeline
+    S = 384
+    rng = np.random.RandomState(1)
+    yy, xx = np.mgrid[:S, :S].astype(np.float64)
+    raw = np.empty((S, S, 3), np.float32)
+    for c in range(3):
+        fr = [(0.004 * (c + 1), 0.003 * (c + 2)), (0.011, 0.007 * (c + 1)), (0.02 * (c + 1), 0.015)]
+        v = sum(np.sin(yy * a + c) + np.cos(xx * b - c) for a, b in fr)
+        v = (v - v.min()) / (v.max() - v.min()) * 255
+        raw[:, :, c] = np.clip(np.round(v + rng.uniform(-8, 8, v.shape)), 0, 255)
+    n = int(round(3000 * (S / 2048) ** 2))
+    want = so.create_segments_labels(raw.copy(), [0, 1, 2], n_segments=n, compactness=10)
+    res = pipeline.slic_labels(_cuda(raw), [0, 1, 2], n_segments=n, compactness=10)
+    got = res.labels.cpu().numpy()
+    agree = _agreement(got, want)
+    print(f"c1-shaped agreement {agree:.5f}, segments gpu={res.n_labels} oracle={want.max()}")
+    assert agree >= 0.995
+    ids = np.unique(got[got >= 0])
+    ref_stats, counts = stats_oracle.zonal_stats(got, raw, [0, 1, 2], ids, compute_dtype=np.float64)
+    st = pipeline.zonal_stats(res.labels, _cuda(raw), [0, 1, 2], resolution=1e-15).cpu().numpy()[ids]
+    np.testing.assert_array_equal(st[:, 0, 0], counts)
+    np.testing.assert_allclose(st[:, :, 1], ref_stats[:, :, 0], rtol=1e-5)
+    np.testing.assert_allclose(st[:, :, 2], ref_stats[:, :, 1], rtol=1e-5, atol=1e-9)
+
+
 def test_slic_masked_agreement():
     import slic_oracle as so
     from obia_b200 import pipeline
