@@ -291,6 +291,135 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
     }
 }
 
+// Many-band variant (Cz >= 24): lanes across BANDS.  One warp per label; the 32 labels of a row
+// segment are fetched with one coalesced load, then the warp visits only the matching pixels and
+// every lane reads and accumulates its own BPL bands of that pixel (a 64-band pixel is one 256-byte
+// coalesced request).  No shuffles: each lane owns its bands' sums from start to finish.
+template <int BPL>
+__global__ void __launch_bounds__(256)
+zonal_gather_bands_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw, ZonalWs w, int W,
+                          int C, ZBands zb, int Cz, int64_t max_label, double resolution,
+                          double *__restrict__ stats)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t L = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (L > max_label) return;
+    const int cnt_total = w.count[L];
+    const double NAND = __longlong_as_double(0x7ff8000000000000LL);
+    double *out = stats + L * Cz * 8;
+    if (cnt_total == 0) {
+        for (int i = lane; i < Cz * 8; i += 32) out[i] = ((i & 7) == 0 || (i & 7) == 7) ? 0.0 : NAND;
+        return;
+    }
+    const int x0 = w.xmin[L], x1 = w.xmax[L], y0 = w.ymin[L], y1 = w.ymax[L];
+    int bidx[BPL];
+    bool bok[BPL];
+#pragma unroll
+    for (int k = 0; k < BPL; ++k) {
+        const int b = lane + 32 * k;            // band slot b of the list <-> lane b % 32
+        bok[k] = b < Cz;
+        bidx[k] = zb.band[bok[k] ? b : 0];
+    }
+    float pivot[BPL], s1[BPL], s2[BPL], s3[BPL], s4[BPL], mn[BPL], mx[BPL];
+    double d1[BPL], d2[BPL], d3[BPL], d4[BPL];
+    const float INF = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int k = 0; k < BPL; ++k) {
+        s1[k] = s2[k] = s3[k] = s4[k] = 0.0f;
+        d1[k] = d2[k] = d3[k] = d4[k] = 0.0;
+        mn[k] = INF;
+        mx[k] = -INF;
+        pivot[k] = 0.0f;
+    }
+    bool have_pivot = false;
+    int pending = 0;
+    for (int y = y0; y <= y1; ++y) {
+        const int64_t row = (int64_t)y * W;
+        for (int xs = x0; xs <= x1; xs += 32) {
+            const int x = xs + lane;
+            const bool hit = (x <= x1) && (labels[row + x] == (int32_t)L);
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                // up to four matching pixels per trip: all their loads are issued before any is used
+                constexpr int U = 4;
+                int bpos[U];
+                int nu = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    bpos[u] = m ? (__ffs(m) - 1) : -1;
+                    if (m) {
+                        m &= m - 1;
+                        ++nu;
+                    }
+                }
+                float v[U][BPL];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (bpos[u] >= 0) {
+                        const float *p = raw + (row + xs + bpos[u]) * C;
+#pragma unroll
+                        for (int k = 0; k < BPL; ++k) v[u][k] = bok[k] ? p[bidx[k]] : 0.0f;
+                    }
+                }
+                if (!have_pivot) {
+                    have_pivot = true;
+#pragma unroll
+                    for (int k = 0; k < BPL; ++k) pivot[k] = v[0][k];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (bpos[u] < 0) continue;
+#pragma unroll
+                    for (int k = 0; k < BPL; ++k) {
+                        const float d = v[u][k] - pivot[k];
+                        const float dd = d * d;
+                        s1[k] += d;
+                        s2[k] += dd;
+                        s3[k] = fmaf(dd, d, s3[k]);
+                        s4[k] = fmaf(dd, dd, s4[k]);
+                        mn[k] = fminf(mn[k], v[u][k]);
+                        mx[k] = fmaxf(mx[k], v[u][k]);
+                    }
+                }
+                pending += nu;
+                if (pending >= 8) {
+                    pending = 0;
+#pragma unroll
+                    for (int k = 0; k < BPL; ++k) {
+                        d1[k] += (double)s1[k]; d2[k] += (double)s2[k];
+                        d3[k] += (double)s3[k]; d4[k] += (double)s4[k];
+                        s1[k] = s2[k] = s3[k] = s4[k] = 0.0f;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < BPL; ++k) {
+        if (!bok[k]) continue;
+        const double n = (double)cnt_total;
+        const double S1 = d1[k] + (double)s1[k], S2 = d2[k] + (double)s2[k];
+        const double S3 = d3[k] + (double)s3[k], S4 = d4[k] + (double)s4[k];
+        const double md = S1 / n, e2 = S2 / n, e3 = S3 / n, e4 = S4 / n;
+        const double mean = (double)pivot[k] + md;
+        double m2 = e2 - md * md;
+        if (m2 < 0.0) m2 = 0.0;
+        const double m3 = e3 - 3.0 * md * e2 + 2.0 * md * md * md;
+        const double m4 = e4 - 4.0 * md * e3 + 6.0 * md * md * e2 - 3.0 * md * md * md * md;
+        const double thr = resolution * mean;
+        const bool degenerate = m2 <= thr * thr;
+        double *o = out + (lane + 32 * k) * 8;
+        o[0] = n;
+        o[1] = mean;
+        o[2] = m2;
+        o[3] = (double)mn[k];
+        o[4] = (double)mx[k];
+        o[5] = degenerate ? NAND : m3 / (m2 * sqrt(m2));
+        o[6] = degenerate ? NAND : m4 / (m2 * m2) - 3.0;
+        o[7] = mean * n;
+    }
+}
+
 }  // namespace obia
 
 using namespace obia;
@@ -328,6 +457,16 @@ extern "C" int obia_b200_zonal_stats(const int32_t *labels, const float *raw, in
     OBIA_LAUNCH_CHECK();
     zonal_bbox_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(labels, w, N, (int)W, max_label);
     OBIA_LAUNCH_CHECK();
+    if (Cz >= 24) {
+        // many bands: lanes across bands, one pass over the raster for all of them
+        const unsigned g = (unsigned)ceil_div(n, 8);
+        if (Cz <= 32)
+            zonal_gather_bands_kernel<1><<<g, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label, resolution, stats);
+        else
+            zonal_gather_bands_kernel<2><<<g, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label, resolution, stats);
+        OBIA_LAUNCH_CHECK();
+        return OBIA_B200_OK;
+    }
     dim3 grid((unsigned)ceil_div(n, 8), (unsigned)ceil_div(Cz, kZB));
     // vector path: every 8-band pass reads 8 contiguous, 16-byte aligned floats of the pixel record
     bool vec = (C % 4 == 0) && (Cz % kZB == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0);

@@ -307,7 +307,9 @@ def test_connectivity_exact_on_slic_output(compactness):
 
 
 # ------------------------------------------------------------------ K4 ------
-@pytest.mark.parametrize("C,bands,quantize", [(3, None, True), (8, [7, 0, 3], False), (20, None, False)])
+@pytest.mark.parametrize("C,bands,quantize", [(3, None, True), (8, [7, 0, 3], False), (20, None, False),
+                                              (40, None, False), (64, list(range(63, 31, -1)), False),
+                                              (70, None, False)])
 def test_zonal_stats(C, bands, quantize):
     import slic_oracle as so
     import stats_oracle
