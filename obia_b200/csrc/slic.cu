@@ -470,7 +470,10 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
             atomicAdd(&a[2], (unsigned long long)((long long)sxl + (long long)cnt * tx0));
 #pragma unroll
             for (int c = 0; c < CP; ++c)
-                if (c < Cf) atomicAdd(&a[3 + c], (unsigned long long)__double2ll_rn((double)fs[c] * fix_scale));
+                // same 32-bit quantisation as the tile path, so the sum does not depend on which
+                // contributions took this route
+                if (c < Cf)
+                    atomicAdd(&a[3 + c], (unsigned long long)((long long)__float2int_rn(fs[c] * fix_scale32) * fix_ratio));
         }
     };
     auto px_val = [&](int j, int c) -> float {

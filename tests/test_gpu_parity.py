@@ -218,6 +218,24 @@ def test_slic_readme_quickstart_shape():
     np.testing.assert_allclose(st[:, :, 2], ref_stats[:, :, 1], rtol=1e-5, atol=1e-9)
 
 
+@pytest.mark.parametrize("C", [3, 8, 20, 40])
+def test_slic_is_deterministic(C):
+    """Centre sums are integer (fixed point), so labels and centres are bit-identical run to run,
+    whichever route (tile accumulator or direct HBM) a contribution takes."""
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    raw = _cuda(synth_raster(300, 420, C, seed=C))
+    ref = None
+    for rep in range(3):
+        res = pipeline.slic_labels(raw, None, n_segments=400, compactness=0.2, keep_intermediates=True)
+        cur = (res.pre_connectivity.cpu().numpy(), res.labels.cpu().numpy(), res.centres.cpu().numpy())
+        if ref is None:
+            ref = cur
+        else:
+            for a, b in zip(ref, cur):
+                np.testing.assert_array_equal(a, b)
+
+
 def test_slic_masked_agreement():
     import slic_oracle as so
     from obia_b200 import pipeline
