@@ -19,6 +19,10 @@
 // Features are band-planar so each lane streams 128-bit loads (4 pixels).
 #include "common.cuh"
 
+#ifndef OBIA_NS
+#define OBIA_NS 2   // strip phases per CTA tile (32 x (32*NS) pixels for 4 px / lane)
+#endif
+
 namespace obia {
 
 constexpr int kWarps = 8;
@@ -203,8 +207,10 @@ template <int CP> struct Traits {
     static constexpr int kRec = (CP <= 4) ? 768 : (CP == 8) ? 640 : (CP == 16) ? 288 : (CP == 32) ? 128 : 64;
 };
 
-// Warp strip: 16 pixels wide x (32 / (16/PX)) rows; a CTA tile is 2 x 4 strips (32 px wide).
-template <int CP, int PX>
+// Warp strip: 16 pixels wide x (32 / (16/PX)) rows; a CTA tile is 2 x 4 strips (32 px wide) times
+// NS vertical phases: the candidate list, its sort, the centre records and the tile accumulators
+// are set up once and reused by NS strips per warp, which amortises the latency-bound set-up.
+template <int CP, int PX, int NS>
 __global__ void __launch_bounds__(kWarps * 32, (CP <= 16) ? 3 : 1)
 slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restrict__ mask,
                           const float *__restrict__ centres, const int32_t *__restrict__ head,
@@ -232,8 +238,8 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     __shared__ __align__(16) int s_rec[kRec][NF + 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * TH;
-    const int tx1 = min(tx0 + 32, W) - 1, ty1 = min(ty0 + TH, H) - 1;  // inclusive
+    const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * (TH * NS);
+    const int tx1 = min(tx0 + 32, W) - 1, ty1 = min(ty0 + TH * NS, H) - 1;  // inclusive
 
     // ---- collect candidate centre ids -----------------------------------
     if (tid == 0) {
@@ -275,8 +281,10 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
         s_sorted[r] = k;
     }
 
+    const bool single_chunk = nids <= kChk;
+    for (int sp = 0; sp < NS; ++sp) {
     // ---- this lane's pixels ----------------------------------------------
-    const int sx0 = tx0 + (warp & 1) * 16, sy0 = ty0 + (warp >> 1) * RW;   // strip origin
+    const int sx0 = tx0 + (warp & 1) * 16, sy0 = ty0 + sp * TH + (warp >> 1) * RW;   // strip origin
     const int y = sy0 + lane / LPR;
     const int xb = sx0 + (lane % LPR) * PX;
     const bool row_ok = y < H;
@@ -329,13 +337,12 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     float wbound = INF;  // upper bound of every strip pixel's final distance (pruning bound)
 
     // ---- evaluate candidates chunk by chunk ------------------------------------
-#ifdef OBIA_EXP_SKIP_EVAL
-    nids = 0;
-#endif
     for (int c0 = 0; c0 < nids; c0 += kChk) {
         const int nc = min(kChk, nids - c0);
-        __syncthreads();  // previous chunk fully consumed; s_sorted complete
-        for (int i = tid; i < nc * (2 + CP); i += NT) {
+        // the centre records are loaded once when they all fit (the usual case)
+        const bool load_chunk = !(single_chunk && sp > 0);
+        if (load_chunk) __syncthreads();  // previous chunk fully consumed; s_sorted complete
+        for (int i = tid; load_chunk && i < nc * (2 + CP); i += NT) {
             const int s = i / (2 + CP), f = i % (2 + CP);
             const int k = s_sorted[c0 + s];
             const float *rec = centres + (int64_t)k * (2 + Cf);
@@ -358,7 +365,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
                 s_nf[s][c] = (c < Cf) ? -rec[2 + c] : 0.0f;
             }
         }
-        __syncthreads();
+        if (load_chunk) __syncthreads();
 
         // Each lane owns kChk/32 candidates: does the window touch the strip, and what is a
         // lower bound of the spatial term over the strip (deflated so rounding can never lift
@@ -489,10 +496,6 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
 #pragma unroll
     for (int j = PX - 1; j >= 0; --j)
         if (((vmask >> j) & 1u) && bests[j] >= 0) lead = bests[j];
-#ifdef OBIA_EXP_SKIP_UPDATE
-    lead = -1;
-    vmask = 0;
-#endif
     if (lead >= 0) {
         int cnt = 0, sxl = 0;
         float fs[CP];
@@ -521,7 +524,6 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
         emit(bests[j], kcur, 1, xb + j - tx0, fs);
     }
     __syncthreads();
-#ifndef OBIA_EXP_SKIP_REDUCE
     {
         const int nrec = min(s_nrec, kRec);
         for (int e = tid; e < nrec * NF; e += NT) {
@@ -530,11 +532,10 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
             if (v != 0) atomicAdd(&s_acc[s_rec[r][0]][f], v);
         }
     }
-#endif
     __syncthreads();
-#ifdef OBIA_EXP_SKIP_FLUSH
-    return;
-#endif
+    if (tid == 0) s_nrec = 0;
+    __syncthreads();
+    }   // strip phases
     const int nslots = min(nids, kAcc);
     for (int i = tid; i < nslots * (3 + Cf); i += NT) {
         const int slot = i / (3 + Cf), f = i % (3 + Cf);
@@ -550,7 +551,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     }
 }
 
-template <int CP, int PX>
+template <int CP, int PX, int NS>
 static int launch_assign(const float *feat, const uint8_t *mask, const float *centres, const SlicWs &w,
                          int32_t *labels, int64_t H, int64_t W, int64_t pitch, int Cf, float sw,
                          int step_y, int step_x, int start_label, int ignore_color, double fix_scale,
@@ -559,15 +560,17 @@ static int launch_assign(const float *feat, const uint8_t *mask, const float *ce
     // 32-bit fixed point for the per-tile shared-memory sums.  fix_scale obeys
     //   max|feature| * fix_scale * reach <= 2^62,  reach = min(H*W, (4*step_y+1)*(4*step_x+1)),
     // so with bits_px = ceil(log2(reach+1)):  max|feature| * (fix_scale * 2^(bits_px-42)) <= 2^20,
-    // and a tile of <= 1024 pixels stays below 2^30.
+    // and a tile of <= 1024 * NS pixels stays below 2^30 once scaled down by NS.
     const int64_t reach = std::min<int64_t>(H * W, (int64_t)(4 * step_y + 1) * (4 * step_x + 1));
     int bits_px = 1;
     while ((1LL << bits_px) < reach + 1) ++bits_px;
-    const float fix_scale32 = (float)ldexp(fix_scale, bits_px - 42);
-    const long long fix_ratio = 1LL << (42 - bits_px);
-    dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 4 * (32 / (16 / PX))));
+    int lg_ns = 0;
+    while ((1 << lg_ns) < NS) ++lg_ns;
+    const float fix_scale32 = (float)ldexp(fix_scale, bits_px - 42 - lg_ns);
+    const long long fix_ratio = 1LL << (42 - bits_px + lg_ns);
+    dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, NS * 4 * (32 / (16 / PX))));
     prof_begin(st);
-    slic_assign_update_kernel<CP, PX><<<grid, kWarps * 32, 0, st>>>(
+    slic_assign_update_kernel<CP, PX, NS><<<grid, kWarps * 32, 0, st>>>(
         feat, mask, centres, w.head, w.next, labels, w.acc, (int)H, (int)W, pitch, Cf, sw, step_y, step_x,
         (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, fix_scale32, fix_ratio, status);
     prof_end(st);
@@ -628,19 +631,19 @@ extern "C" int obia_b200_slic_iterate(const float *features, const uint8_t *mask
         OBIA_LAUNCH_CHECK();
         int rc;
         if (Cf <= 4)
-            rc = launch_assign<4, 4>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+            rc = launch_assign<4, 4, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                      start_label, ignore_color, fix_scale, status, st);
         else if (Cf <= 8)
-            rc = launch_assign<8, 4>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+            rc = launch_assign<8, 4, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                      start_label, ignore_color, fix_scale, status, st);
         else if (Cf <= 16)
-            rc = launch_assign<16, 2>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+            rc = launch_assign<16, 2, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                       start_label, ignore_color, fix_scale, status, st);
         else if (Cf <= 32)
-            rc = launch_assign<32, 1>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+            rc = launch_assign<32, 1, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                       start_label, ignore_color, fix_scale, status, st);
         else
-            rc = launch_assign<64, 1>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+            rc = launch_assign<64, 1, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                       start_label, ignore_color, fix_scale, status, st);
         if (rc) return rc;
     }

@@ -11,7 +11,7 @@ for comp in (0.1, 10.0):
     res = pipeline.slic_labels(raw, None, n_segments=200000, compactness=comp, max_num_iter=2, enforce_connectivity=False)
     torch.cuda.synchronize()
     lib.obia_b200_profile_enable(1)
-    for _ in range(5):
+    for _ in range(3):
         res = pipeline.slic_labels(raw, None, n_segments=200000, compactness=comp, max_num_iter=1, enforce_connectivity=False)
     torch.cuda.synchronize()
     lib.obia_b200_profile_enable(0)
