@@ -351,6 +351,7 @@ struct CcParams {
     int H, W;
     int64_t min_size, max_size;
     int32_t mask_label, start_label;
+    int32_t optimistic;   // round 1: every piece counts as labelled from its own start pixel
 };
 
 // Scan position at which pixel q (not in piece t) receives a label > mask label, kTInf if never:
@@ -359,6 +360,12 @@ struct CcParams {
 __device__ __forceinline__ int32_t label_time(const int32_t *lab, const int32_t *T, const int32_t *psize,
                                               const int32_t *aux, const CcParams &P, int32_t q, int32_t t)
 {
+    if (P.optimistic) {
+        // one load per neighbour: T is -1 on masked pixels, and in round 1 both kept and merged
+        // pieces are taken as labelled from their start (merged ones are re-checked in round 2)
+        const int32_t tq = T[q];
+        return (tq < 0 || tq == t) ? kTInf : tq;
+    }
     if (lab[q] == P.mask_label) return kTInf;
     const int32_t tq = T[q];
     if (tq == t) return kTInf;
@@ -390,7 +397,7 @@ __device__ int bfs_piece(const int32_t *lab, const int32_t *T, const int32_t *ps
         for (int d = 0; d < 4; ++d) {
             int32_t q;
             if (!nbr(d, py, px, P.H, P.W, q)) continue;
-            const bool same = (lab[q] == L) && (T[q] == t);
+            const bool same = T[q] == t;   // a piece is a set of equal-label pixels: T alone identifies it
             if (same) {
                 if (!visit[q]) {
                     visit[q] = 1;
@@ -759,15 +766,17 @@ extern "C" int obia_b200_enforce_connectivity(const int32_t *labels_in, int32_t 
 
     CcParams P;
     P.H = (int)H; P.W = (int)W; P.min_size = min_size; P.max_size = max_size;
-    P.mask_label = mask_label; P.start_label = start_label;
+    P.mask_label = mask_label; P.start_label = start_label; P.optimistic = 0;
     int32_t hctr[CTR_WORDS];
     {
         CcArrays A;
         A.lab = labels_in; A.T = w.T; A.psize = w.psize; A.list = w.list;
         A.adj = w.adj; A.aux = w.aux; A.queue = w.queue; A.ctr = w.ctr; A.stamp = w.stamp; A.visit = w.visit;
         OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + CTR_CURSOR, 0, 4, st));
+        P.optimistic = 1;
         cc_small_adjacent_kernel<<<kNumSMs * 8, 128, 0, st>>>(A, P, w.dirty0);
         OBIA_LAUNCH_CHECK();
+        P.optimistic = 0;
         if (start_label == 1) {   // start_label 0 has no label-0 ambiguity: round 1 is exact
             int round_id = 1;
             int cur = 0;   // dirty list written by the previous round
