@@ -438,3 +438,59 @@ def test_create_segments_errors():
         create_objects(segs, img, calculate_spectral=False, calculate_textural=False)
     with pytest.raises(NotImplementedError):
         create_objects(segs, img, calculate_structural=True)
+
+
+# ------------------------------------------------------------------ fuzz ------
+def _fuzz_cases():
+    rng = np.random.RandomState(2024)
+    cases = []
+    for i in range(28):
+        H, W = int(rng.randint(9, 190)), int(rng.randint(9, 190))
+        C = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 9, 13, 16, 17, 33]))
+        n = int(rng.choice([2, 5, 17, 60, 150, 400, 2000]))
+        kw = dict(n_segments=n, compactness=float(rng.choice([0.02, 0.1, 0.5, 3.0, 20.0])),
+                  max_num_iter=int(rng.choice([1, 3, 10])), start_label=int(rng.randint(0, 2)))
+        if rng.rand() < 0.3:
+            kw["sigma"] = float(rng.choice([0.6, 1.5]))
+        if rng.rand() < 0.3:
+            kw["min_size_factor"] = float(rng.choice([0.1, 0.9]))
+            kw["max_size_factor"] = float(rng.choice([1.5, 5]))
+        if rng.rand() < 0.2:
+            kw["enforce_connectivity"] = False
+        masked = rng.rand() < 0.3
+        cases.append((i, H, W, C, kw, masked))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(), ids=lambda c: f"fuzz{c[0]}")
+def test_slic_fuzz_against_oracle(case):
+    """Random shapes (ragged tile edges, W % 4 != 0), band counts (every kernel instantiation),
+    n_segments from 2 to more than one per 10 pixels, both start labels, masks, sigma."""
+    import slic_oracle as so
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    i, H, W, C, kw, masked = case
+    raw = synth_raster(H, W, C, seed=100 + i, quantize=(C == 3))
+    mask = None
+    if masked:
+        yy, xx = np.mgrid[:H, :W]
+        mask = (np.sin(yy / 11.0) + np.cos(xx / 7.0)) > -0.8
+        if mask.sum() < 20:
+            mask[:] = True
+    so.USE_FMA = True
+    try:
+        try:
+            want = so.create_segments_labels(raw.copy(), None, mask=mask, **kw)
+            err = None
+        except Exception as e:          # whatever the reference path raises, the product must raise too
+            want, err = None, e
+    finally:
+        so.USE_FMA = False
+    if err is not None:
+        with pytest.raises(Exception):
+            pipeline.slic_labels(_cuda(raw), None, mask=mask, **kw)
+        return
+    res = pipeline.slic_labels(_cuda(raw), None, mask=mask, **kw)
+    got = res.labels.cpu().numpy()
+    agree = _agreement(got, want)
+    assert agree >= 0.995, f"{case}: agreement {agree:.4f}"
