@@ -135,22 +135,28 @@ cc_local_kernel(const int32_t *__restrict__ lab, int32_t *__restrict__ parent, i
     __shared__ int32_t s_lab[kTile * kTile];
     __shared__ int s_par[kTile * kTile];
     const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
-    for (int i = threadIdx.x; i < kTile * kTile; i += 256) {
-        const int ly = i / kTile, lx = i % kTile;
-        const int y = y0 + ly, x = x0 + lx;
-        s_lab[i] = (y < H && x < W) ? lab[(int64_t)y * W + x] : mask_label;
-        s_par[i] = i;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // a warp = one tile row: every pixel is linked to the first pixel of its horizontal run
+    // with a ballot (no atomics)
+    for (int ly = warp; ly < kTile; ly += 8) {
+        const int y = y0 + ly, x = x0 + lane;
+        const int32_t l = (y < H && x < W) ? lab[(int64_t)y * W + x] : mask_label;
+        const int32_t lp = __shfl_up_sync(0xffffffffu, l, 1);
+        const bool head = (lane == 0) || (l != lp) || (l == mask_label);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+        s_lab[ly * kTile + lane] = l;
+        s_par[ly * kTile + lane] = ly * kTile + start;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kTile * kTile; i += 256) {
+    // vertical joins, once per pair of overlapping runs (at the first column of the overlap)
+    for (int i = threadIdx.x + kTile; i < kTile * kTile; i += 256) {
         const int32_t l = s_lab[i];
-        if (l == mask_label) continue;
-        const int ly = i / kTile, lx = i % kTile;
-        const bool up = ly > 0 && s_lab[i - kTile] == l;
-        const bool left = lx > 0 && s_lab[i - 1] == l;
-        if (up) uf_union_s(s_par, i, i - kTile);
-        // the row above already joins the two pixels when both upper neighbours match
-        if (left && !(up && s_lab[i - kTile - 1] == l)) uf_union_s(s_par, i, i - 1);
+        if (l == mask_label || s_lab[i - kTile] != l) continue;
+        const bool cur_head = (i % kTile) == 0 || s_lab[i - 1] != l;   // from labels: s_par is being rewritten
+        const int up = i - kTile;
+        const bool up_head = (up % kTile) == 0 || s_lab[up - 1] != l;
+        if (cur_head || up_head) uf_union_s(s_par, i, up);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kTile * kTile; i += 256) {

@@ -383,9 +383,11 @@ extern "C" int obia_b200_slic_features(const float *raw, int64_t H, int64_t W, i
         OBIA_CUDA_CHECK(cudaFuncSetAttribute(features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_pixels = H * W;
     const float idiff = imax - imin;
+    // x / 1.0f is x: skip the IEEE division in the usual case (obia's per-band normalisation
+    // already maps every band to [0, 1], so skimage's global rescale is the identity)
+    const int rescale = (imax != imin && idiff != 1.0f) ? 1 : 0;
     features_kernel<<<(int)ceil_div(n_pixels, kFeatPix), kFeatPix, smem, (cudaStream_t)stream>>>(
-        raw, n_pixels, W, C, Cs, tab, imin, idiff, imax != imin ? 1 : 0, to_lab, ratio, features, pitch,
-        H * pitch);
+        raw, n_pixels, W, C, Cs, tab, imin, idiff, rescale, to_lab, ratio, features, pitch, H * pitch);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
 }

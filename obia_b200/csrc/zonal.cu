@@ -73,8 +73,10 @@ zonal_bbox_kernel(const int32_t *__restrict__ labels, ZonalWs w, int64_t N, int 
         const int len = end - lane;
         atomicMin(w.xmin + l, x);
         atomicMax(w.xmax + l, x + len - 1);
-        atomicMin(w.ymin + l, y);
-        atomicMax(w.ymax + l, y);
+        // a row can only be the label's first / last one if the pixel above / below the run head
+        // carries another label (otherwise a smaller / larger y is reported by that row)
+        if (y == 0 || labels[i - W] != l) atomicMin(w.ymin + l, y);
+        if (i + W >= N || labels[i + W] != l) atomicMax(w.ymax + l, y);
         atomicAdd(w.count + l, len);
     }
 }
