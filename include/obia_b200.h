@@ -99,6 +99,18 @@ int obia_b200_gaussian_planar(const float *in, float *tmp, float *out,
                               const double *weights_x_host, int32_t radius_x,
                               float ratio, void *stream);
 
+/* maskSLIC initialisation, the k-means part: replaces
+ * `scipy.cluster.vq.kmeans2(coord[idx_dense], coord[idx], iter=5)` inside skimage's
+ * `_get_mask_centroids` (reached from segment_boundaries.py:51 when `mask=` is passed, i.e. for
+ * every tile of obia/utils/tiling.py:137-143 and :275-281).  Bit-identical to scipy for pixel
+ * coordinates (float64 distances in feature order, lowest index wins ties, exact integer sums).
+ *   points_yx    [m][2] int32 (y, x) of the dense sample, device
+ *   centroids_yx [n][2] float64 in/out, device
+ */
+int64_t obia_b200_mask_kmeans_workspace_bytes(int64_t n);
+int obia_b200_mask_kmeans(const int32_t *points_yx, int64_t m, double *centroids_yx,
+                          int64_t n, int32_t iters, void *workspace, void *stream);
+
 /* ---------------------------------------------------------------- K2 ----
  * SLIC iterations: replaces Cython `_slic_cython`
  * (skimage/segmentation/_slic.pyx) reached from segment_boundaries.py:51.

@@ -74,6 +74,33 @@ def normalize_inplace(raw, minmax_dev):
                "normalize_inplace")
 
 
+def mask_centroids_device(mask_dev, n_segments):
+    """maskSLIC initial centres (skimage `_get_mask_centroids`) with the k-means sweeps on the GPU.
+
+    Host part: the two RandomState(123) draws (cached per mask size) and the nearest-centroid
+    steps; device part: `obia_b200_mask_kmeans` (bit-identical to scipy's kmeans2 on pixel
+    coordinates).  Returns (yx float64 (n, 2) numpy, steps (3,)).
+    """
+    lib = _lib.load()
+    coord = torch.nonzero(mask_dev)                 # row-major, like np.nonzero
+    n_coord = int(coord.shape[0])
+    if n_coord == 0:
+        # scikit-image fails on `image[mask].min()` of an empty selection
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    if n_segments <= 0:
+        raise ValueError("n_segments must be positive")
+    idx, idx_dense = slic_host.mask_sample_indices(n_coord, n_segments)
+    dev = mask_dev.device
+    pts = coord.index_select(0, torch.from_numpy(idx_dense).to(dev)).to(torch.int32).contiguous()
+    cent = coord.index_select(0, torch.from_numpy(idx).to(dev)).to(torch.float64).contiguous()
+    n = int(cent.shape[0])
+    ws = torch.empty((lib.obia_b200_mask_kmeans_workspace_bytes(n),), dtype=torch.uint8, device=dev)
+    _lib.check(lib.obia_b200_mask_kmeans(_p(pts), int(pts.shape[0]), _p(cent), n, 5, _p(ws), _stream_ptr()),
+               "mask_kmeans")
+    yx = cent.cpu().numpy()
+    return yx, slic_host.steps_from_centroids(yx)
+
+
 @dataclass
 class SlicResult:
     labels: torch.Tensor            # (H, W) int32; masked pixels = -1 when a mask was given
@@ -167,7 +194,7 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
     if init_centroids is not None:
         yx, steps = init_centroids
     elif mask_dev is not None:
-        yx, steps = slic_host.mask_centroids(mask_dev.cpu().numpy(), int(n_segments))
+        yx, steps = mask_centroids_device(mask_dev, int(n_segments))
     else:
         yx, steps = slic_host.grid_centroids(H, W, n_segments)
     n = int(yx.shape[0])

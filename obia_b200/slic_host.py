@@ -100,6 +100,46 @@ def mask_centroids(mask_hw, n_segments):
     return centroids[:, 1:3].copy(), steps
 
 
+_CHOICE_CACHE = {}
+
+
+def mask_sample_indices(n_coord, n_segments):
+    """(idx, idx_dense) of `_get_mask_centroids`: two draws from RandomState(123).
+
+    They depend only on the number of mask pixels and n_segments, so tiles with equal counts
+    share them (cached; the legacy permutation is O(n_coord) on the host).
+    """
+    key = (int(n_coord), int(n_segments))
+    hit = _CHOICE_CACHE.get(key)
+    if hit is None:
+        rng = np.random.RandomState(123)
+        idx_full = np.arange(n_coord, dtype=int)
+        idx = np.sort(rng.choice(idx_full, min(n_segments, n_coord), replace=False))
+        n_dense = int((10 ** 2) * n_segments)
+        idx_dense = np.sort(rng.choice(idx_full, min(n_dense, n_coord), replace=False))
+        if len(_CHOICE_CACHE) > 256:
+            _CHOICE_CACHE.clear()
+        hit = _CHOICE_CACHE[key] = (idx, idx_dense)
+    return hit
+
+
+def steps_from_centroids(centroids_yx):
+    """`steps` of `_get_mask_centroids`: mean |centroid - nearest other centroid| per axis (z, y, x)."""
+    c = np.concatenate([np.zeros((len(centroids_yx), 1)), np.asarray(centroids_yx, dtype=np.float64)], axis=1)
+    if len(c) > 1:
+        if len(c) <= 2048:
+            from scipy.spatial.distance import pdist, squareform
+            dist = squareform(pdist(c))
+            np.fill_diagonal(dist, np.inf)
+            closest = dist.argmin(-1)
+        else:
+            from scipy.spatial import cKDTree
+            _, nn = cKDTree(c).query(c, k=2)
+            closest = nn[:, 1]
+        return np.abs(c - c[closest, :]).mean(0)
+    return np.abs(c - c[[0], :]).mean(0)
+
+
 def gaussian_taps(sigma):
     """scipy.ndimage `_gaussian_kernel1d(sigma, 0, int(4*sigma+0.5))` (symmetric, float64)."""
     sd = float(sigma)

@@ -236,6 +236,19 @@ def test_slic_is_deterministic(C):
                 np.testing.assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize("n", [3, 25, 140])
+def test_mask_centroids_bitexact_vs_scipy(n):
+    """GPU k-means of the maskSLIC initialisation == scipy.cluster.vq.kmeans2 (as skimage calls it)."""
+    import slic_oracle as so
+    from obia_b200 import pipeline
+    yy, xx = np.mgrid[:170, :230]
+    mask = (((yy - 80) ** 2 / 70.0 ** 2 + (xx - 120) ** 2 / 100.0 ** 2) < 1.0) & ((yy + xx) % 7 != 0)
+    want_c, want_steps = so._get_mask_centroids(mask[np.newaxis].astype(np.uint8), n, True)
+    yx, steps = pipeline.mask_centroids_device(_cuda(mask.astype(np.uint8)), n)
+    np.testing.assert_array_equal(yx, want_c[:, 1:])
+    np.testing.assert_array_equal(steps, want_steps)
+
+
 def test_slic_masked_agreement():
     import slic_oracle as so
     from obia_b200 import pipeline
