@@ -123,7 +123,7 @@ def create_objects(
     out.insert(0, "segment_id", np.asarray(segments["segment_id"]))
     out["geometry"] = segments["geometry"].to_numpy() if len(segments) else None
     from .segment_boundaries import SegmentsFrame
-    out = SegmentsFrame(out)
+    out = SegmentsFrame(out, copy=False)
     out.label_raster = raster
     out.segment_labels = row_labels
     out.crs = getattr(segments, "crs", None)

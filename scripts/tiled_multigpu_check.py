@@ -35,6 +35,15 @@ def main():
     yy, xx = np.mgrid[:H, :W]
     mask = (np.sin(yy / 90.0) + np.cos(xx / 70.0)) > -1.2
     kw = dict(tile_size=args.tile, buffer=args.buffer, crown_radius=8, compactness=0.2)
+    # warm up NCCL (communicator set-up, first point-to-point) outside the timed call
+    w = torch.zeros(1, device=dev)
+    dist.all_reduce(w)
+    if world > 1:
+        if rank % 2 == 0 and rank + 1 < world:
+            dist.send(w, rank + 1)
+        elif rank % 2 == 1:
+            dist.recv(w, rank - 1)
+    dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     labels, n, (x0, x1) = create_tiled_segments(raw, None, mask, distributed=True, **kw)
@@ -53,7 +62,8 @@ def main():
         same = bool((single == full).all().item())
         ok = same and n == n1
         print(f"tiled multi-GPU check: world={world} size={H} tiles={args.tile} segments multi={n} single={n1} "
-              f"identical={same}  t_multi={t_multi:.2f}s t_single={t_single:.2f}s", flush=True)
+              f"identical={same}  t_multi={t_multi:.2f}s ({H * W / 1e6 / t_multi:.1f} MP/s) "
+              f"t_single={t_single:.2f}s ({H * W / 1e6 / t_single:.1f} MP/s)", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if not ok:
