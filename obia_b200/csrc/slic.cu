@@ -640,10 +640,10 @@ extern "C" int obia_b200_slic_iterate(const float *features, const uint8_t *mask
             rc = launch_assign<16, 2, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                       start_label, ignore_color, fix_scale, status, st);
         else if (Cf <= 32)
-            rc = launch_assign<32, 1, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+            rc = launch_assign<32, 2, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                       start_label, ignore_color, fix_scale, status, st);
         else
-            rc = launch_assign<64, 1, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+            rc = launch_assign<64, 2, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                       start_label, ignore_color, fix_scale, status, st);
         if (rc) return rc;
     }
