@@ -144,6 +144,27 @@ int obia_b200_slic_iterate(const float *features, const uint8_t *mask,
                            int32_t start_label, int32_t ignore_color,
                            double fix_scale, int32_t *status, void *stream);
 
+/* The same iteration, one sweep at a time, for a raster sharded by ROW STRIPS across GPUs (global
+ * multi-GPU SLIC): `features`/`mask`/`labels` hold the strip [y_offset, y_offset + H) of a raster with
+ * H_total rows; `centres` is the full (replicated) centre table.  A sweep leaves this strip's
+ * contribution to the centre sums in the accumulator table at the START of `workspace`
+ * ([n][3+Cf] int64: count, sum y, sum x, fixed-point colour sums).  The caller sums that table over
+ * the ranks (ncclAllReduce on int64: exact, order-independent) and calls `finish_sweep`, so every rank
+ * derives identical centres and the result is bit-identical to the single-GPU run.
+ * `slic_iterate` == begin; { sweep(y_offset=0, H_total=H); finish_sweep } x max_num_iter.
+ * workspace: obia_b200_slic_workspace_bytes(H_total, W, Cf, n, step_y, step_x). */
+int obia_b200_slic_begin(int32_t *labels, void *workspace, int64_t H, int64_t W,
+                         int64_t H_total, int32_t Cf, int64_t n, int32_t step_y,
+                         int32_t step_x, int32_t start_label, int32_t *status, void *stream);
+int obia_b200_slic_sweep(const float *features, const uint8_t *mask, const float *centres,
+                         int32_t *labels, void *workspace, int64_t H, int64_t W, int64_t pitch,
+                         int32_t Cf, int64_t n, float step, int32_t step_y, int32_t step_x,
+                         int32_t start_label, int32_t ignore_color, double fix_scale,
+                         int64_t y_offset, int64_t H_total, int32_t *status, void *stream);
+int obia_b200_slic_finish_sweep(float *centres, void *workspace, int64_t H_total, int64_t W,
+                                int32_t Cf, int64_t n, int32_t step_y, int32_t step_x,
+                                double fix_scale, void *stream);
+
 /* ---------------------------------------------------------------- K3 ----
  * Enforce connectivity: replaces Cython `_enforce_label_connectivity_cython`
  * (sequential raster-scan BFS) reached from segment_boundaries.py:51.

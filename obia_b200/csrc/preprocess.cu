@@ -319,6 +319,8 @@ extern "C" int obia_b200_band_minmax(const float *raw, int64_t n_pixels, int32_t
 {
     if (!raw || !out || !nonfinite || n_pixels <= 0 || C <= 0 || C > 4096)
         return set_err(OBIA_B200_ERR_ARG, "band_minmax: bad argument");
+    if (reinterpret_cast<uintptr_t>(raw) & 15)
+        return set_err(OBIA_B200_ERR_ARG, "band_minmax: raw must be 16-byte aligned (128-bit loads)");
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t *keys = reinterpret_cast<uint32_t *>(out);
     minmax_init_kernel<<<(int)ceil_div(C, 128), 128, 0, st>>>(keys, nonfinite, C);
@@ -345,6 +347,8 @@ extern "C" int obia_b200_normalize_inplace(float *raw, int64_t n_pixels, int32_t
 {
     if (!raw || !minmax || n_pixels <= 0 || C <= 0)
         return set_err(OBIA_B200_ERR_ARG, "normalize_inplace: bad argument");
+    if (reinterpret_cast<uintptr_t>(raw) & 15)
+        return set_err(OBIA_B200_ERR_ARG, "normalize_inplace: raw must be 16-byte aligned (128-bit loads)");
     const int64_t n_elems = n_pixels * C;
     const int unit = C / gcd_i(C, 1024);
     int64_t grid = std::min<int64_t>(ceil_div(n_elems / 4 + 1, 256 * 4), (int64_t)kNumSMs * 16);
@@ -367,6 +371,8 @@ extern "C" int obia_b200_slic_features(const float *raw, int64_t H, int64_t W, i
         return set_err(OBIA_B200_ERR_UNSUPPORTED, "slic_features: at most %d segmentation bands",
                        OBIA_B200_MAX_BANDS);
     if (to_lab && Cs != 3) return set_err(OBIA_B200_ERR_ARG, "slic_features: Lab needs 3 bands");
+    if ((reinterpret_cast<uintptr_t>(raw) & 15) || (reinterpret_cast<uintptr_t>(features) & 15))
+        return set_err(OBIA_B200_ERR_ARG, "slic_features: raw and features must be 16-byte aligned");
     if (pitch < W || (pitch & 3)) return set_err(OBIA_B200_ERR_ARG, "slic_features: bad pitch");
     BandTable tab;
     memset(&tab, 0, sizeof(tab));

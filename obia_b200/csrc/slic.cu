@@ -218,8 +218,11 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
                           unsigned long long *__restrict__ acc, int H, int W, int64_t pitch, int Cf,
                           float spatial_weight, int step_y, int step_x, int ncy, int ncx,
                           int start_label, int ignore_color, double fix_scale, float fix_scale32,
-                          long long fix_ratio, int32_t *status)
+                          long long fix_ratio, int32_t *status, int y_off, int Hg)
 {
+    // (H, W) is the strip resident on this GPU; it is rows [y_off, y_off + H) of a raster with Hg
+    // rows.  Memory is addressed with strip-local rows, the arithmetic (centre windows, spatial
+    // term, centre sums) uses global rows, so a sharded run is bit-identical to a single-GPU one.
     constexpr int LPR = 16 / PX;   // lanes per strip row
     constexpr int RW = 32 / LPR;   // rows per warp strip
     constexpr int TH = 4 * RW;     // tile rows (tile is 32 wide)
@@ -252,8 +255,8 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
         // a centre at cy reaches rows y with  y - 2s <= cy < y + 1 + 2s; two pixels
         // of slack absorb the float rounding of the cell index.  Centres always lie
         // inside the raster, so cells need no clamping beyond the grid itself.
-        const int gy_lo = max(0, floordiv_i(ty0 - 2 * step_y - 2, step_y));
-        const int gy_hi = min(ncy - 1, floordiv_i(ty1 + 2 * step_y + 2, step_y));
+        const int gy_lo = max(0, floordiv_i(ty0 + y_off - 2 * step_y - 2, step_y));
+        const int gy_hi = min(ncy - 1, floordiv_i(ty1 + y_off + 2 * step_y + 2, step_y));
         const int gx_lo = max(0, floordiv_i(tx0 - 2 * step_x - 2, step_x));
         const int gx_hi = min(ncx - 1, floordiv_i(tx1 + 2 * step_x + 2, step_x));
         const int ny = gy_hi - gy_lo + 1, nx = gx_hi - gx_lo + 1;
@@ -332,8 +335,9 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     }
     // warp strip (inclusive), clipped to the image
     const int wx0 = sx0, wx1 = min(sx0 + 16, W) - 1;
-    const int wy0 = sy0, wy1 = min(sy0 + RW, H) - 1;
-    const float fy = (float)y;
+    const int wy0 = sy0 + y_off, wy1 = min(sy0 + RW, H) - 1 + y_off;
+    const int yg = y + y_off;   // global row
+    const float fy = (float)yg;
     float wbound = INF;  // upper bound of every strip pixel's final distance (pruning bound)
 
     // ---- evaluate candidates chunk by chunk ------------------------------------
@@ -356,7 +360,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
                 const float xhi = __fadd_rn(__fadd_rn(cx, (float)(2 * step_x)), 1.0f);
                 int4 w;
                 w.x = trunc_i((0.0f > ylo) ? 0.0f : ylo);
-                w.y = trunc_i(((float)H < yhi) ? (float)H : yhi);
+                w.y = trunc_i(((float)Hg < yhi) ? (float)Hg : yhi);
                 w.z = trunc_i((0.0f > xlo) ? 0.0f : xlo);
                 w.w = trunc_i(((float)W < xhi) ? (float)W : xhi);
                 s_win[s] = w;
@@ -405,7 +409,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
             }
             const float2 c = s_cyx[s];
             eval_candidate<CP, PX, true>(px2, px1, nx2, nx1, fy, c.x, c.y, s_win[s], s_nf[s], spatial_weight,
-                                         ignore_color, y, xb, 0, tb, ts);
+                                         ignore_color, yg, xb, 0, tb, ts);
             float m = tb[0];
 #pragma unroll
             for (int j = 1; j < PX; ++j) m = fmaxf(m, tb[j]);
@@ -425,10 +429,10 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
                 const bool full = w.x <= wy0 && w.y > wy1 && w.z <= wx0 && w.w > wx1;
                 if (full)
                     eval_candidate<CP, PX, false>(px2, px1, nx2, nx1, fy, c.x, c.y, w, s_nf[s], spatial_weight,
-                                                  ignore_color, y, xb, c0 + s, best, bests);
+                                                  ignore_color, yg, xb, c0 + s, best, bests);
                 else
                     eval_candidate<CP, PX, true>(px2, px1, nx2, nx1, fy, c.x, c.y, w, s_nf[s], spatial_weight,
-                                                 ignore_color, y, xb, c0 + s, best, bests);
+                                                 ignore_color, yg, xb, c0 + s, best, bests);
             }
         }
     }
@@ -473,7 +477,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
             // no tile accumulator for this centre (or record pool full): add to HBM directly
             unsigned long long *a = acc + (int64_t)kcur * (3 + Cf);
             atomicAdd(&a[0], (unsigned long long)cnt);
-            atomicAdd(&a[1], (unsigned long long)((long long)cnt * y));
+            atomicAdd(&a[1], (unsigned long long)((long long)cnt * yg));
             atomicAdd(&a[2], (unsigned long long)((long long)sxl + (long long)cnt * tx0));
 #pragma unroll
             for (int c = 0; c < CP; ++c)
@@ -544,7 +548,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
         const long long v = s_acc[slot][f];
         long long g;
         if (f == 0) g = v;
-        else if (f == 1) g = v + (long long)cnt * ty0;
+        else if (f == 1) g = v + (long long)cnt * (ty0 + y_off);
         else if (f == 2) g = v + (long long)cnt * tx0;
         else g = v * fix_ratio;
         if (g != 0) atomicAdd(&acc[(int64_t)s_sorted[slot] * (3 + Cf) + f], (unsigned long long)g);
@@ -555,13 +559,13 @@ template <int CP, int PX, int NS>
 static int launch_assign(const float *feat, const uint8_t *mask, const float *centres, const SlicWs &w,
                          int32_t *labels, int64_t H, int64_t W, int64_t pitch, int Cf, float sw,
                          int step_y, int step_x, int start_label, int ignore_color, double fix_scale,
-                         int32_t *status, cudaStream_t st)
+                         int32_t *status, int y_off, int64_t Hg, cudaStream_t st)
 {
     // 32-bit fixed point for the per-tile shared-memory sums.  fix_scale obeys
     //   max|feature| * fix_scale * reach <= 2^62,  reach = min(H*W, (4*step_y+1)*(4*step_x+1)),
     // so with bits_px = ceil(log2(reach+1)):  max|feature| * (fix_scale * 2^(bits_px-42)) <= 2^20,
     // and a tile of <= 1024 * NS pixels stays below 2^30 once scaled down by NS.
-    const int64_t reach = std::min<int64_t>(H * W, (int64_t)(4 * step_y + 1) * (4 * step_x + 1));
+    const int64_t reach = std::min<int64_t>(Hg * W, (int64_t)(4 * step_y + 1) * (4 * step_x + 1));
     int bits_px = 1;
     while ((1LL << bits_px) < reach + 1) ++bits_px;
     int lg_ns = 0;
@@ -572,7 +576,7 @@ static int launch_assign(const float *feat, const uint8_t *mask, const float *ce
     prof_begin(st);
     slic_assign_update_kernel<CP, PX, NS><<<grid, kWarps * 32, 0, st>>>(
         feat, mask, centres, w.head, w.next, labels, w.acc, (int)H, (int)W, pitch, Cf, sw, step_y, step_x,
-        (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, fix_scale32, fix_ratio, status);
+        (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, fix_scale32, fix_ratio, status, y_off, (int)Hg);
     prof_end(st);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
@@ -596,6 +600,93 @@ extern "C" int64_t obia_b200_slic_workspace_bytes(int64_t H, int64_t W, int32_t 
     return slic_ws_layout(nullptr, H, W, Cf, n, step_y, step_x).bytes;
 }
 
+static int slic_check_args(const void *features, const void *centres, const void *labels, const void *workspace,
+                           const void *status, int64_t H, int64_t W, int64_t pitch, int32_t Cf, int64_t n,
+                           float step, int32_t step_y, int32_t step_x, int32_t start_label, double fix_scale)
+{
+    if (!features || !centres || !labels || !workspace || !status || H <= 0 || W <= 0 || Cf <= 0 || n <= 0 ||
+        step_y <= 0 || step_x <= 0 || !(step > 0.0f) || !(fix_scale > 0.0))
+        return set_err(OBIA_B200_ERR_ARG, "slic: bad argument");
+    if (H > 2000000000 || W > 2000000000 || n > 2000000000)
+        return set_err(OBIA_B200_ERR_UNSUPPORTED, "slic: dimension exceeds int32");
+    if (pitch < W || (pitch & 3)) return set_err(OBIA_B200_ERR_ARG, "slic: pitch must be a multiple of 4 and >= W");
+    if ((reinterpret_cast<uintptr_t>(features) & 15) || (reinterpret_cast<uintptr_t>(labels) & 15) ||
+        (reinterpret_cast<uintptr_t>(workspace) & 15))
+        return set_err(OBIA_B200_ERR_ARG, "slic: features, labels and workspace must be 16-byte aligned");
+    if (Cf > 64) return set_err(OBIA_B200_ERR_UNSUPPORTED, "slic: more than 64 feature channels");
+    if (start_label != 0 && start_label != 1) return set_err(OBIA_B200_ERR_ARG, "start_label should be 0 or 1.");
+    return OBIA_B200_OK;
+}
+
+extern "C" int obia_b200_slic_begin(int32_t *labels, void *workspace, int64_t H, int64_t W, int64_t H_total,
+                                    int32_t Cf, int64_t n, int32_t step_y, int32_t step_x, int32_t start_label,
+                                    int32_t *status, void *stream)
+{
+    if (!labels || !workspace || !status || H <= 0 || W <= 0 || H_total < H || Cf <= 0 || n <= 0)
+        return set_err(OBIA_B200_ERR_ARG, "slic_begin: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    SlicWs w = slic_ws_layout(workspace, H_total, W, Cf, n, step_y, step_x);
+    OBIA_CUDA_CHECK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st));
+    OBIA_CUDA_CHECK(cudaMemsetAsync(w.acc, 0, (size_t)n * (3 + Cf) * 8, st));
+    fill_i32_kernel<<<kNumSMs * 4, 256, 0, st>>>(labels, H * W, start_label - 1);
+    OBIA_LAUNCH_CHECK();
+    return OBIA_B200_OK;
+}
+
+extern "C" int obia_b200_slic_sweep(const float *features, const uint8_t *mask, const float *centres,
+                                    int32_t *labels, void *workspace, int64_t H, int64_t W, int64_t pitch,
+                                    int32_t Cf, int64_t n, float step, int32_t step_y, int32_t step_x,
+                                    int32_t start_label, int32_t ignore_color, double fix_scale,
+                                    int64_t y_offset, int64_t H_total, int32_t *status, void *stream)
+{
+    int rc = slic_check_args(features, centres, labels, workspace, status, H, W, pitch, Cf, n, step, step_y, step_x,
+                             start_label, fix_scale);
+    if (rc) return rc;
+    if (y_offset < 0 || y_offset + H > H_total) return set_err(OBIA_B200_ERR_ARG, "slic_sweep: strip outside the raster");
+    cudaStream_t st = (cudaStream_t)stream;
+    SlicWs w = slic_ws_layout(workspace, H_total, W, Cf, n, step_y, step_x);
+    // `1.0 / (step * step)`: float product, double division, float store
+    const float step_sq = step * step;
+    const float sw = (float)(1.0 / (double)step_sq);
+    OBIA_CUDA_CHECK(cudaMemsetAsync(w.head, 0xff, (size_t)(w.ncy * w.ncx) * 4, st));
+    slic_centres_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
+        const_cast<float *>(centres), w.acc, w.head, w.next, n, Cf, 0, 1.0 / fix_scale, step_y, step_x, w.ncy, w.ncx);
+    OBIA_LAUNCH_CHECK();
+    const int yo = (int)y_offset;
+    if (Cf <= 4)
+        rc = launch_assign<4, 4, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+                                          start_label, ignore_color, fix_scale, status, yo, H_total, st);
+    else if (Cf <= 8)
+        rc = launch_assign<8, 4, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+                                          start_label, ignore_color, fix_scale, status, yo, H_total, st);
+    else if (Cf <= 16)
+        rc = launch_assign<16, 2, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+                                           start_label, ignore_color, fix_scale, status, yo, H_total, st);
+    else if (Cf <= 32)
+        rc = launch_assign<32, 2, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+                                           start_label, ignore_color, fix_scale, status, yo, H_total, st);
+    else
+        rc = launch_assign<64, 2, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+                                           start_label, ignore_color, fix_scale, status, yo, H_total, st);
+    return rc;
+}
+
+extern "C" int obia_b200_slic_finish_sweep(float *centres, void *workspace, int64_t H_total, int64_t W, int32_t Cf,
+                                           int64_t n, int32_t step_y, int32_t step_x, double fix_scale,
+                                           void *stream)
+{
+    if (!centres || !workspace || H_total <= 0 || W <= 0 || Cf <= 0 || n <= 0 || !(fix_scale > 0.0))
+        return set_err(OBIA_B200_ERR_ARG, "slic_finish_sweep: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    SlicWs w = slic_ws_layout(workspace, H_total, W, Cf, n, step_y, step_x);
+    // means of the sweep's assignment; also zeroes the sums for the next sweep
+    OBIA_CUDA_CHECK(cudaMemsetAsync(w.head, 0xff, (size_t)(w.ncy * w.ncx) * 4, st));
+    slic_centres_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(centres, w.acc, w.head, w.next, n, Cf, 1,
+                                                                   1.0 / fix_scale, step_y, step_x, w.ncy, w.ncx);
+    OBIA_LAUNCH_CHECK();
+    return OBIA_B200_OK;
+}
+
 extern "C" int obia_b200_slic_iterate(const float *features, const uint8_t *mask, float *centres,
                                       int32_t *labels, void *workspace, int64_t H, int64_t W,
                                       int64_t pitch, int32_t Cf, int64_t n, float step, int32_t step_y,
@@ -603,56 +694,16 @@ extern "C" int obia_b200_slic_iterate(const float *features, const uint8_t *mask
                                       int32_t ignore_color, double fix_scale, int32_t *status,
                                       void *stream)
 {
-    if (!features || !centres || !labels || !workspace || !status || H <= 0 || W <= 0 || Cf <= 0 ||
-        n <= 0 || step_y <= 0 || step_x <= 0 || max_num_iter < 0 || !(step > 0.0f) || !(fix_scale > 0.0))
-        return set_err(OBIA_B200_ERR_ARG, "slic_iterate: bad argument");
-    if (H > 2000000000 / 1 || W > 2000000000 || n > 2000000000)
-        return set_err(OBIA_B200_ERR_UNSUPPORTED, "slic_iterate: dimension exceeds int32");
-    if (pitch < W || (pitch & 3)) return set_err(OBIA_B200_ERR_ARG, "slic_iterate: pitch must be a multiple of 4 and >= W");
-    if (Cf > 64) return set_err(OBIA_B200_ERR_UNSUPPORTED, "slic_iterate: more than 64 feature channels");
-    if (start_label != 0 && start_label != 1) return set_err(OBIA_B200_ERR_ARG, "start_label should be 0 or 1.");
-    cudaStream_t st = (cudaStream_t)stream;
-    SlicWs w = slic_ws_layout(workspace, H, W, Cf, n, step_y, step_x);
-
-    // `1.0 / (step * step)`: float product, double division, float store
-    const float step_sq = step * step;
-    const float sw = (float)(1.0 / (double)step_sq);
-
-    OBIA_CUDA_CHECK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st));
-    OBIA_CUDA_CHECK(cudaMemsetAsync(w.acc, 0, (size_t)n * (3 + Cf) * 8, st));
-    fill_i32_kernel<<<kNumSMs * 4, 256, 0, st>>>(labels, H * W, start_label - 1);
-    OBIA_LAUNCH_CHECK();
-
-    for (int it = 0; it < max_num_iter; ++it) {
-        OBIA_CUDA_CHECK(cudaMemsetAsync(w.head, 0xff, (size_t)(w.ncy * w.ncx) * 4, st));
-        slic_centres_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
-            centres, w.acc, w.head, w.next, n, Cf, it > 0 ? 1 : 0, 1.0 / fix_scale, step_y, step_x, w.ncy,
-            w.ncx);
-        OBIA_LAUNCH_CHECK();
-        int rc;
-        if (Cf <= 4)
-            rc = launch_assign<4, 4, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
-                                     start_label, ignore_color, fix_scale, status, st);
-        else if (Cf <= 8)
-            rc = launch_assign<8, 4, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
-                                     start_label, ignore_color, fix_scale, status, st);
-        else if (Cf <= 16)
-            rc = launch_assign<16, 2, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
-                                      start_label, ignore_color, fix_scale, status, st);
-        else if (Cf <= 32)
-            rc = launch_assign<32, 2, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
-                                      start_label, ignore_color, fix_scale, status, st);
-        else
-            rc = launch_assign<64, 2, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
-                                      start_label, ignore_color, fix_scale, status, st);
-        if (rc) return rc;
+    int rc = slic_check_args(features, centres, labels, workspace, status, H, W, pitch, Cf, n, step, step_y, step_x,
+                             start_label, fix_scale);
+    if (rc) return rc;
+    if (max_num_iter < 0) return set_err(OBIA_B200_ERR_ARG, "slic_iterate: bad argument");
+    rc = obia_b200_slic_begin(labels, workspace, H, W, H, Cf, n, step_y, step_x, start_label, status, stream);
+    for (int it = 0; it < max_num_iter && !rc; ++it) {
+        rc = obia_b200_slic_sweep(features, mask, centres, labels, workspace, H, W, pitch, Cf, n, step, step_y,
+                                  step_x, start_label, ignore_color, fix_scale, 0, H, status, stream);
+        // the reference updates the centres after every sweep, the last one included
+        if (!rc) rc = obia_b200_slic_finish_sweep(centres, workspace, H, W, Cf, n, step_y, step_x, fix_scale, stream);
     }
-    if (max_num_iter > 0) {
-        // means of the last assignment (the reference updates after every sweep)
-        OBIA_CUDA_CHECK(cudaMemsetAsync(w.head, 0xff, (size_t)(w.ncy * w.ncx) * 4, st));
-        slic_centres_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(
-            centres, w.acc, w.head, w.next, n, Cf, 1, 1.0 / fix_scale, step_y, step_x, w.ncy, w.ncx);
-        OBIA_LAUNCH_CHECK();
-    }
-    return OBIA_B200_OK;
+    return rc;
 }

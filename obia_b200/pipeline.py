@@ -41,6 +41,12 @@ def _require_cuda(t, name, dtype=None):
     return t
 
 
+def _aligned(t):
+    """The kernels use 128-bit loads: a view that starts off a 16-byte boundary (e.g. a row slice of
+    a raster whose row size is not a multiple of 16 bytes) is copied to a fresh allocation."""
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
 def _i32_array(values):
     arr = (ctypes.c_int32 * len(values))(*[int(v) for v in values])
     return arr
@@ -54,7 +60,7 @@ def band_minmax(raw, mask=None):
     because the host needs it to validate the input the way numpy/skimage do.
     """
     lib = _lib.load()
-    _require_cuda(raw, "raw", torch.float32)
+    raw = _aligned(_require_cuda(raw, "raw", torch.float32))
     H, W, C = raw.shape
     out = torch.empty((C, 4), dtype=torch.float32, device=raw.device)
     flags = torch.empty((C,), dtype=torch.int32, device=raw.device)
@@ -70,8 +76,11 @@ def normalize_inplace(raw, minmax_dev):
     lib = _lib.load()
     _require_cuda(raw, "raw", torch.float32)
     H, W, C = raw.shape
-    _lib.check(lib.obia_b200_normalize_inplace(_p(raw), H * W, C, _p(minmax_dev), _stream_ptr()),
+    work = _aligned(raw)
+    _lib.check(lib.obia_b200_normalize_inplace(_p(work), H * W, C, _p(minmax_dev), _stream_ptr()),
                "normalize_inplace")
+    if work is not raw:
+        raw.copy_(work)
 
 
 def mask_centroids_device(mask_dev, n_segments):
@@ -133,6 +142,7 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
     _require_cuda(raw, "raw", torch.float32)
     if raw.dim() != 3:
         raise ValueError("raw must be (H, W, C)")
+    raw = _aligned(raw)
     if channel_axis not in (-1, 2):
         raise NotImplementedError("only channel_axis=-1 (obia always passes H, W, C)")
     if slic_zero:
@@ -287,7 +297,7 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
 def enforce_connectivity(labels, min_size, max_size, start_label=1):
     """K3 on its own: (labels_out int32 (H, W), number of kept segments)."""
     lib = _lib.load()
-    _require_cuda(labels, "labels", torch.int32)
+    labels = _aligned(_require_cuda(labels, "labels", torch.int32))
     H, W = (int(s) for s in labels.shape)
     ws = torch.empty((lib.obia_b200_connectivity_workspace_bytes(H, W),), dtype=torch.uint8,
                      device=labels.device)
@@ -306,8 +316,8 @@ def zonal_stats(labels, raw, bands=None, max_label=None, resolution=1e-6):
     Fields: STAT_FIELDS.  Labels < 0 (obia's -1 = masked) are ignored.
     """
     lib = _lib.load()
-    _require_cuda(labels, "labels", torch.int32)
-    _require_cuda(raw, "raw", torch.float32)
+    labels = _aligned(_require_cuda(labels, "labels", torch.int32))
+    raw = _aligned(_require_cuda(raw, "raw", torch.float32))
     H, W, C = (int(s) for s in raw.shape)
     if tuple(labels.shape) != (H, W):
         raise ValueError("labels and raster shapes differ")

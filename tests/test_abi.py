@@ -44,6 +44,10 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b"bad argument" in lib.obia_b200_last_error()
     rc = lib.obia_b200_band_minmax(None, 0, 3, None, None, None, None)
     assert rc == -1
+    # pointers that would make the 128-bit loads fault are rejected, not dereferenced
+    rc = lib.obia_b200_band_minmax(ctypes.c_void_p(0x1008), 10, 3, None, ctypes.c_void_p(0x2000),
+                                   ctypes.c_void_p(0x3000), None)
+    assert rc == -1 and b"aligned" in lib.obia_b200_last_error()
 
 
 def test_missing_library_fails_loudly(monkeypatch):

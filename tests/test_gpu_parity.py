@@ -507,3 +507,67 @@ def test_slic_fuzz_against_oracle(case):
     got = res.labels.cpu().numpy()
     agree = _agreement(got, want)
     assert agree >= 0.995, f"{case}: agreement {agree:.4f}"
+
+
+def test_misaligned_views_are_handled():
+    """Row slices of a raster whose row size is not a multiple of 16 bytes start off a 16-byte
+    boundary: the host layer must realign them (the kernels use 128-bit loads)."""
+    import slic_oracle as so
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    base = synth_raster(131, 111, 3, seed=5, quantize=True)           # 111 * 3 * 4 = 1332 bytes per row
+    t = _cuda(base)
+    view = t[7:]                                                        # contiguous, misaligned start
+    assert view.is_contiguous() and view.data_ptr() % 16 != 0
+    res = pipeline.slic_labels(view, None, n_segments=40, compactness=10.0)
+    want = so.create_segments_labels(base[7:].copy(), None, n_segments=40, compactness=10.0)
+    assert _agreement(res.labels.cpu().numpy(), want) >= 0.995
+    lab_view = torch.cat([torch.zeros((1, 111), dtype=torch.int32, device="cuda"), res.labels])[1:]
+    st = pipeline.zonal_stats(lab_view, view, None)
+    assert int(st[:, 0, 0].sum().item()) == int((res.labels >= 0).sum().item())
+    out, _ = pipeline.enforce_connectivity(lab_view, 3, 400, 1)
+    assert out.shape == lab_view.shape
+
+
+# ------------------------------------------------ sharded (multi-GPU) path, emulated on one GPU ---
+@pytest.mark.parametrize("world,C,n,compactness", [(2, 4, 300, 0.2), (3, 3, 150, 10.0), (4, 8, 500, 0.1)])
+def test_sharded_global_slic_is_bit_identical(world, C, n, compactness):
+    """Row strips + summed int64 centre sums give exactly the single-GPU labels; merged strip
+    statistics equal the one-pass statistics (the NCCL all-reduce is replaced by a tensor sum)."""
+    from obia_b200 import pipeline
+    from obia_b200.sharded import ShardedSlic, combine_stats, split_rows
+    from gpu_helpers import synth_raster
+    H, W = 270, 333
+    raw = _cuda(synth_raster(H, W, C, seed=world, quantize=(C == 3)))
+    kw = dict(n_segments=n, compactness=compactness, max_num_iter=6)
+    ref = pipeline.slic_labels(raw, None, **kw)
+    ref_stats = pipeline.zonal_stats(ref.labels, raw, None, max_label=ref.n_labels + 1)
+    strips = [ShardedSlic(raw[r0:r0 + h].contiguous(), r0, H, None, **kw) for r0, h in split_rows(H, world)]
+    mms = [s.local_minmax() for s in strips]
+    lo = torch.stack([m[0][:, 0] for m in mms]).amin(0)
+    hi = torch.stack([m[0][:, 1] for m in mms]).amax(0)
+    fl = torch.stack([m[1] for m in mms]).amax(0)
+    mm = torch.stack([lo, hi, lo, hi], dim=1)
+    for s in strips:
+        s.prepare(mm, fl)
+    for _ in range(kw["max_num_iter"]):
+        for s in strips:
+            s.sweep()
+        total = torch.stack([s.acc() for s in strips]).sum(0)          # == all_reduce(SUM)
+        for s in strips:
+            s.acc().copy_(total)
+            s.finish_sweep()
+    full = torch.cat([s.labels for s in strips], dim=0).contiguous()    # == all_gather
+    for s in strips:
+        s.check_status()
+        s.connect(full)
+    got = torch.cat([s.final for s in strips], dim=0)
+    assert torch.equal(got, ref.labels)
+    assert all(s.n_labels == ref.n_labels for s in strips)
+    merged = combine_stats([s.strip_stats() for s in strips])
+    a, b = merged.cpu().numpy(), ref_stats.cpu().numpy()
+    np.testing.assert_array_equal(a[:, :, 0], b[:, :, 0])
+    np.testing.assert_array_equal(a[:, :, 3:5], b[:, :, 3:5])
+    np.testing.assert_allclose(a[:, :, 1:3], b[:, :, 1:3], rtol=1e-6, atol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(a[:, :, 5], b[:, :, 5], rtol=1e-5, atol=1e-5, equal_nan=True)
+    np.testing.assert_allclose(a[:, :, 6] + 3, b[:, :, 6] + 3, rtol=1e-5, equal_nan=True)

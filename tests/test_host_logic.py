@@ -77,3 +77,28 @@ def test_stats_oracle_is_numpy_scipy():
         np.testing.assert_allclose(out[i, 1, 1], np.var(px[:, 2]), rtol=1e-5)
         np.testing.assert_allclose(out[i, 0, 4], skew(px[:, 0].astype(np.float64)), rtol=1e-3, atol=1e-4)
         np.testing.assert_allclose(out[i, 0, 5], kurtosis(px[:, 0].astype(np.float64)), rtol=1e-3, atol=1e-3)
+
+
+def test_combine_stats_matches_numpy_scipy():
+    """Merging per-strip statistics (sharded multi-GPU path) == statistics of the concatenation."""
+    import torch
+    from scipy.stats import kurtosis, skew
+    from obia_b200.sharded import combine_stats, split_rows
+    rng = np.random.RandomState(0)
+
+    def table(x):
+        if len(x) == 0:
+            return [0] + [np.nan] * 6 + [0]
+        return [len(x), x.mean(), x.var(), x.min(), x.max(), skew(x), kurtosis(x), x.sum()]
+
+    for parts in ([rng.rand(50) * 3 + 1, rng.rand(7) + 5, np.array([]), rng.rand(1) * 2],
+                  [np.array([]), np.array([])], [np.full(5, 2.5), np.full(3, 2.5)],
+                  [rng.normal(100, 1, 1000), rng.normal(100, 1, 3), rng.normal(100, 1, 40)]):
+        T = [torch.tensor(table(p), dtype=torch.float64).view(1, 1, 8) for p in parts]
+        out = combine_stats(T, resolution=1e-15)[0, 0].numpy()
+        allx = np.concatenate(parts)
+        ref = np.array(table(allx))
+        if len(allx) and allx.var() == 0:
+            ref[5] = ref[6] = np.nan          # scipy: (nearly) constant data -> NaN
+        np.testing.assert_allclose(out, ref, rtol=1e-8, atol=1e-12, equal_nan=True)
+    assert split_rows(10, 3) == [(0, 4), (4, 3), (7, 3)] and split_rows(4, 4) == [(0, 1)] * 0 + [(0, 1), (1, 1), (2, 1), (3, 1)]
