@@ -207,6 +207,30 @@ int obia_b200_zonal_stats(const int32_t *labels, const float *raw, int64_t H,
                           int32_t Cz, int64_t max_label, double resolution,
                           double *stats, void *workspace, void *stream);
 
+/* ---------------------------------------------------------------- K5 ----
+ * Per-segment GLCM texture features: replaces calculate_textural_stats
+ * (obia/segmentation/segment_statistics.py:179-298) as create_objects calls it
+ * for every segment (:496-508).  Per (segment, band): the bounding-box crop
+ * with pixels outside the segment (and NaN samples) set to 0 (:214-247),
+ * min/max-scaled to uint8 over the whole crop (:251-258), skimage
+ * graycomatrix(distances=[2], angles=[0,pi/4,pi/2,3pi/4], levels=256,
+ * symmetric=True, normed=True) (:261-268), then the mean over the angles of
+ * graycoprops contrast, dissimilarity, homogeneity, ASM, energy, correlation
+ * (:285-296).  The band axis slip at :214 is fixed (band-first crop indexed by
+ * band), see DESIGN.md.
+ *   labels, raw, bands_host, max_label   as for obia_b200_zonal_stats
+ *   quantise_f64  0: scale in float32 (float32 rasters); 1: in float64 (the
+ *                 reference's masked crop of an integer raster is float64)
+ *   features      [max_label+1][n_bands][6] float64 out, order as above;
+ *                 labels without pixels / bands without a valid sample -> NaN
+ */
+int64_t obia_b200_texture_workspace_bytes(int64_t max_label);
+int obia_b200_texture_stats(const int32_t *labels, const float *raw, int64_t H,
+                            int64_t W, int32_t C, const int32_t *bands_host,
+                            int32_t n_bands, int64_t max_label,
+                            int32_t quantise_f64, double *features,
+                            void *workspace, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,70 @@
+// Per-label bounding boxes and pixel counts of a label raster: one pass (4 B/pixel), one set of
+// atomics per run of equal labels inside a warp.  Shared by K4 (zonal.cu) and the texture
+// kernel (texture.cu); `static` so every translation unit gets its own copy.
+#pragma once
+#include "common.cuh"
+
+namespace obia {
+
+struct ZonalWs {
+    int32_t *xmin, *xmax, *ymin, *ymax, *count;
+    int64_t bytes;
+};
+
+static inline ZonalWs zonal_ws_layout(void *base, int64_t max_label)
+{
+    ZonalWs w;
+    const int64_t n = max_label + 1;
+    char *p = (char *)base;
+    const int64_t stride = round_up(n * 4, 256);
+    w.xmin = (int32_t *)(p);
+    w.xmax = (int32_t *)(p + stride);
+    w.ymin = (int32_t *)(p + 2 * stride);
+    w.ymax = (int32_t *)(p + 3 * stride);
+    w.count = (int32_t *)(p + 4 * stride);
+    w.bytes = 5 * stride;
+    return w;
+}
+
+static __global__ void zonal_init_kernel(ZonalWs w, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    w.xmin[i] = 0x7fffffff;
+    w.ymin[i] = 0x7fffffff;
+    w.xmax[i] = -1;
+    w.ymax[i] = -1;
+    w.count[i] = 0;
+}
+
+static __global__ void __launch_bounds__(256)
+zonal_bbox_kernel(const int32_t *__restrict__ labels, ZonalWs w, int64_t N, int W, int64_t max_label)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int32_t l = -1;
+    int x = 0, y = 0;
+    if (i < N) {
+        l = labels[i];
+        if (l < 0 || (int64_t)l > max_label) l = -1;
+        y = (int)(i / W);
+        x = (int)(i - (int64_t)y * W);
+    }
+    const int32_t prev = __shfl_up_sync(0xffffffffu, l, 1);
+    const bool is_head = (lane == 0) || (prev != l) || (x == 0);
+    const unsigned heads = __ballot_sync(0xffffffffu, is_head);
+    if (is_head && l >= 0) {
+        const unsigned later = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
+        const int end = later ? (__ffs(later) - 1) : 32;
+        const int len = end - lane;
+        atomicMin(w.xmin + l, x);
+        atomicMax(w.xmax + l, x + len - 1);
+        // a row can only be the label's first / last one if the pixel above / below the run head
+        // carries another label (otherwise a smaller / larger y is reported by that row)
+        if (y == 0 || labels[i - W] != l) atomicMin(w.ymin + l, y);
+        if (i + W >= N || labels[i + W] != l) atomicMax(w.ymax + l, y);
+        atomicAdd(w.count + l, len);
+    }
+}
+
+}  // namespace obia

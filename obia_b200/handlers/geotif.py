@@ -26,6 +26,25 @@ class Image:
         self.rasterio_obj = rasterio_obj
 
     # -- B200 additions (not part of the reference contract) ------------------
+    def stats_in_float64(self):
+        """True when the reference would compute the per-segment features in float64.
+
+        `create_objects` re-reads the FILE in its native dtype (obia/utils/utils.py:45-48) and
+        `np.where(mask, crop, nan)` (:64) promotes integer rasters to float64, float32 rasters
+        stay float32.  An in-memory `img_data` of integer dtype counts as an integer raster.
+        """
+        obj = self.rasterio_obj
+        dtypes = getattr(obj, "dtypes", None)
+        if dtypes:
+            return np.dtype(dtypes[0]) != np.float32
+        dt = getattr(self.img_data, "dtype", None)
+        if dt is None:
+            return False
+        if not isinstance(dt, np.dtype):   # torch dtype
+            import torch
+            return dt not in (torch.float32, torch.float16, torch.bfloat16)
+        return dt != np.float32
+
     def device_raw(self, device=None, refresh=False):
         """Raw (un-normalised) raster as a CUDA float32 (H, W, C) tensor, uploaded once.
 

@@ -21,6 +21,7 @@ import torch
 from . import _lib, slic_host
 
 STAT_FIELDS = ("count", "mean", "variance", "min", "max", "skewness", "kurtosis", "sum")
+TEXTURE_FIELDS = ("contrast", "dissimilarity", "homogeneity", "ASM", "energy", "correlation")
 
 
 def _stream_ptr():
@@ -343,3 +344,37 @@ def zonal_stats(labels, raw, bands=None, max_label=None, resolution=1e-6):
         if Cz > 64:
             stats[:, c0:c0 + len(sub)] = view
     return stats
+
+
+def texture_stats(labels, raw, bands=None, max_label=None, quantise_f64=False):
+    """Per-label, per-band GLCM texture features, float64 (max_label+1, n_bands, 6) on the device.
+
+    Fields: TEXTURE_FIELDS (mean over the four angles at distance 2, segment_statistics.py:261-296).
+    `quantise_f64`: the reference scales the crop to uint8 in the dtype of its masked crop --
+    float32 for float32 rasters (False), float64 for integer rasters (True).
+    """
+    lib = _lib.load()
+    labels = _aligned(_require_cuda(labels, "labels", torch.int32))
+    raw = _aligned(_require_cuda(raw, "raw", torch.float32))
+    H, W, C = (int(s) for s in raw.shape)
+    if tuple(labels.shape) != (H, W):
+        raise ValueError("labels and raster shapes differ")
+    if bands is None:
+        bands = list(range(C))
+    bands = [int(b) for b in bands]
+    if max_label is None:
+        max_label = int(labels.max().item())
+    max_label = max(int(max_label), 0)
+    nb = len(bands)
+    feats = torch.empty((max_label + 1, nb, 6), dtype=torch.float64, device=raw.device)
+    ws = torch.empty((lib.obia_b200_texture_workspace_bytes(max_label),), dtype=torch.uint8, device=raw.device)
+    for c0 in range(0, nb, 64):   # kernel-parameter table holds 64 bands per call
+        sub = bands[c0:c0 + 64]
+        view = feats if nb <= 64 else torch.empty((max_label + 1, len(sub), 6), dtype=torch.float64,
+                                                  device=raw.device)
+        _lib.check(lib.obia_b200_texture_stats(_p(labels), _p(raw), H, W, C, _i32_array(sub), len(sub),
+                                               max_label, int(bool(quantise_f64)), _p(view), _p(ws),
+                                               _stream_ptr()), "texture_stats")
+        if nb > 64:
+            feats[:, c0:c0 + len(sub)] = view
+    return feats

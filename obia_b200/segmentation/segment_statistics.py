@@ -12,9 +12,12 @@ is replaced by ONE fused pass of the CUDA zonal-statistics kernel over the label
 raster.  Statistics are taken over the RAW raster values, like the reference
 (which re-reads the file, obia/utils/utils.py:45-48).
 
-Not on the GPU path yet: GLCM texture columns are emitted as NaN
-(`calculate_textural` keeps the reference's default so the column set is the one
-`classify` expects); the point-cloud columns are NaN in the reference too.
+The GLCM texture columns (`calculate_textural_stats`, :179-298) come from the CUDA
+texture kernel (one CTA per segment, see csrc/texture.cu).  ONE documented
+deviation: the reference indexes its band-first crop with `[:, :, band]` (:214) --
+an axis slip that takes column `band` of every band and raises IndexError for
+crops narrower than the band index; here the band is indexed.
+The point-cloud columns are NaN in the reference too.
 """
 from __future__ import annotations
 
@@ -93,32 +96,53 @@ def create_objects(
     raster, row_labels = _labels_of(segments)
     n_rows = len(row_labels)
     float_cols = columns[1:-1]
-    # one (n_columns, n_rows) float64 block, column-major for pandas (zero-copy): the statistics
-    # are the leading columns in the reference's order; texture / point-cloud columns stay NaN
+    # one (n_columns, n_rows) float64 block, column-major for pandas (zero-copy): the spectral
+    # statistics, then the texture features, in the reference's order; point-cloud columns stay NaN
     import torch
     block = np.empty((len(float_cols), n_rows), dtype=np.float64)
-    n_stat = 0
-    if len(spectral_bands) > 0 and n_rows > 0:
-        for b in spectral_bands:
-            if b < 0 or b >= n_bands:
-                # the reference indexes the (C, h, w) crop with the band number (:144)
-                raise IndexError(f"index {b} is out of bounds for axis 0 with size {n_bands}")
+    # the reference computes in the dtype of its masked crop: float32 for float32 rasters,
+    # float64 for integer rasters (np.where(mask, crop, nan), utils.py:64)
+    in_f64 = bool(getattr(image, "stats_in_float64", lambda: False)())
+    want = [("mean", calc_mean), ("variance", calc_variance), ("min", calc_min), ("max", calc_max),
+            ("skewness", calc_skewness), ("kurtosis", calc_kurtosis)]
+    tex_want = [("contrast", calc_contrast), ("dissimilarity", calc_dissimilarity),
+                ("homogeneity", calc_homogeneity), ("ASM", calc_ASM), ("energy", calc_energy),
+                ("correlation", calc_correlation)]
+    fields = [pipeline.STAT_FIELDS.index(name) for name, on in want if on]
+    tex_fields = [pipeline.TEXTURE_FIELDS.index(name) for name, on in tex_want if on]
+    n_spec = len(spectral_bands) * len(fields)          # spectral columns come first (:64-89) ...
+    n_tex = len(textural_bands) * len(tex_fields)       # ... then the texture columns (:90-101)
+    for b in list(spectral_bands) + (list(textural_bands) if calculate_textural else []):
+        if b < 0 or b >= n_bands:
+            # the reference indexes the (C, h, w) crop with the band number (:144)
+            raise IndexError(f"index {b} is out of bounds for axis 0 with size {n_bands}")
+    filled = np.zeros(len(float_cols), dtype=bool)
+    if n_rows > 0:
         max_label = int(row_labels.max())
-        # the reference computes in float32 for float32 rasters (np.where keeps float32):
-        # scipy's "nearly constant" NaN rule uses that dtype's resolution
-        stats = pipeline.zonal_stats(raster, raw, spectral_bands, max_label=max_label, resolution=1e-6)
-        names = pipeline.STAT_FIELDS
-        want = [("mean", calc_mean), ("variance", calc_variance), ("min", calc_min), ("max", calc_max),
-                ("skewness", calc_skewness), ("kurtosis", calc_kurtosis)]
-        fields = [names.index(name) for name, on in want if on]
-        if fields:
+        rows = None
+        # the reference computes the spectral statistics whatever `calculate_spectral` says (:485-491)
+        if n_spec > 0:
+            # scipy's "nearly constant" NaN rule uses the compute dtype's resolution
+            stats = pipeline.zonal_stats(raster, raw, spectral_bands, max_label=max_label,
+                                         resolution=1e-15 if in_f64 else 1e-6)
             rows = torch.from_numpy(row_labels).to(stats.device)
             sel = stats.index_select(0, rows)[:, :, fields]                  # (rows, Cz, nstat)
-            sel = sel.permute(1, 2, 0).reshape(len(spectral_bands) * len(fields), n_rows).contiguous()
-            n_stat = sel.shape[0]
-            assert float_cols[:n_stat] == [f"b{b}_{name}" for b in spectral_bands for name, on in want if on]
-            torch.from_numpy(block[:n_stat]).copy_(sel)
-    block[n_stat:] = np.nan
+            sel = sel.permute(1, 2, 0).reshape(n_spec, n_rows).contiguous()
+            assert float_cols[:n_spec] == [f"b{b}_{name}" for b in spectral_bands for name, on in want if on]
+            torch.from_numpy(block[:n_spec]).copy_(sel)
+            filled[:n_spec] = True
+        if calculate_textural and n_tex > 0:                                 # (:494-506)
+            feats = pipeline.texture_stats(raster, raw, textural_bands, max_label=max_label,
+                                           quantise_f64=in_f64)
+            if rows is None:
+                rows = torch.from_numpy(row_labels).to(feats.device)
+            sel = feats.index_select(0, rows)[:, :, tex_fields]
+            sel = sel.permute(1, 2, 0).reshape(n_tex, n_rows).contiguous()
+            assert float_cols[n_spec:n_spec + n_tex] == [f"b{b}_{name}" for b in textural_bands
+                                                         for name, on in tex_want if on]
+            torch.from_numpy(block[n_spec:n_spec + n_tex]).copy_(sel)
+            filled[n_spec:n_spec + n_tex] = True
+    block[~filled] = np.nan
     out = pd.DataFrame(block.T, columns=float_cols, copy=False)
     out.insert(0, "segment_id", np.asarray(segments["segment_id"]))
     out["geometry"] = segments["geometry"].to_numpy() if len(segments) else None

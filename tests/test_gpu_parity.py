@@ -392,6 +392,64 @@ def test_zonal_stats_edge_cases():
     assert np.isnan(want[[0, 2], :, 4]).all()
 
 
+# ------------------------------------------------------------------ K5 ------
+@pytest.mark.parametrize("C,bands,f64,quantize", [(3, None, True, True), (8, [7, 0, 3], False, False),
+                                                  (4, [2], False, False)])
+def test_texture_stats(C, bands, f64, quantize):
+    """GLCM texture features per segment vs the oracle (integer pair sums -> 1e-9 relative)."""
+    import slic_oracle as so
+    import texture_oracle
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    H, W, n = 96, 130, 40
+    raw = synth_raster(H, W, C, seed=C + 11, quantize=quantize)
+    if not quantize:
+        raw = raw * 1000 - 300
+    labels = so.create_segments_labels(raw.copy(), None, n_segments=n, compactness=0.5 if C != 3 else 10)
+    labels = labels.astype(np.int32)
+    labels[:5, :7] = -1
+    bands = list(range(C)) if bands is None else bands
+    ids = np.unique(labels[labels >= 0])
+    want = texture_oracle.textural_stats(labels, raw, bands, ids,
+                                         compute_dtype=np.float64 if f64 else np.float32)
+    got = pipeline.texture_stats(_cuda(labels), _cuda(raw), bands, quantise_f64=f64).cpu().numpy()[ids]
+    assert not np.isnan(want).any()
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12)
+
+
+def test_texture_stats_edge_cases():
+    """single pixel, constant segment, missing labels, masked pixels, a band without valid samples,
+    crops beyond the shared-memory tile (> 4096 px) and beyond the 16-bit counters (>= 65536 px)."""
+    import texture_oracle
+    from obia_b200 import pipeline
+    rs = np.random.RandomState(3)
+    H, W = 300, 310
+    labels = np.full((H, W), 2, np.int32)              # label 2: crop = whole raster (93 000 px, wide path)
+    labels[0, 0] = 0                                   # single pixel
+    labels[5:9, 5:9] = 5                               # constant-valued block
+    labels[100:180, 100:190] = 6                       # 7200 px crop: not staged
+    labels[120:130, 120:140] = 7                       # hole inside label 6
+    labels[200:, 250:] = -1                            # masked
+    labels[299, 309] = 9                               # label 9 (1, 3, 4, 8 missing)
+    labels[40:60, 40:41] = 10                          # one column wide: no pairs for three angles
+    raw = (rs.rand(H, W, 2) * 10).astype(np.float32)
+    raw[5:9, 5:9] = 3.25
+    raw[labels == 7, 1] = np.nan                       # label 7 has no valid sample in band 1
+    raw[150, 150, 0] = np.nan                          # a NaN sample inside label 6 counts as outside
+    ids = np.array([0, 2, 5, 6, 7, 9, 10])
+    want = texture_oracle.textural_stats(labels, raw, [0, 1], ids)
+    got = pipeline.texture_stats(_cuda(labels), _cuda(raw), [0, 1]).cpu().numpy()
+    assert got.shape == (11, 2, 6)
+    assert np.isnan(got[[1, 3, 4, 8]]).all()
+    assert np.isnan(got[7, 1]).all() and np.isnan(want[4, 1]).all()
+    np.testing.assert_allclose(got[ids], want, rtol=1e-9, atol=1e-12, equal_nan=True)
+    # single pixel / constant crop: empty or single-bin matrices -> correlation 1
+    assert got[0, 0, 5] == 1.0 and got[5, 0, 5] == 1.0 and got[5, 0, 3] == 1.0
+    # run to run identical (integer sums; the homogeneity sum has a fixed reduction order)
+    again = pipeline.texture_stats(_cuda(labels), _cuda(raw), [0, 1]).cpu().numpy()
+    np.testing.assert_array_equal(got, again)
+
+
 # ------------------------------------------------------------- end to end ---
 def test_segment_end_to_end_columns_and_values():
     import slic_oracle as so
@@ -427,6 +485,13 @@ def test_segment_end_to_end_columns_and_values():
         np.testing.assert_allclose(seg.segments[f"b{j}_mean"].to_numpy(), want[:, j, 0], rtol=1e-5)
         np.testing.assert_allclose(seg.segments[f"b{j}_variance"].to_numpy(), want[:, j, 1], rtol=2e-5, atol=1e-9)
         np.testing.assert_array_equal(seg.segments[f"b{j}_max"].to_numpy(), want[:, j, 3])
+    # texture columns: GLCM features of the raw values (float32 arithmetic: img_data is float32)
+    import texture_oracle
+    wt = texture_oracle.textural_stats(labels, raw, [0, 1, 2], rows)
+    for j in range(3):
+        for f, name in enumerate(texture_oracle.TEXTURE_NAMES):
+            np.testing.assert_allclose(seg.segments[f"b{j}_{name}"].to_numpy(), wt[:, j, f], rtol=1e-9, atol=1e-12)
+    assert seg.segments[["pai", "fhd", "ch", "mean_intensity", "variance_intensity"]].isna().all().all()
 
 
 def test_create_segments_errors():
