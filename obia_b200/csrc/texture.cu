@@ -24,15 +24,18 @@
 // sum u^2 = sum over increments of (2c + 1).  The histogram is cleared by replaying the pairs, so a
 // persistent CTA zeroes its 64 KB once.
 //
-// One CTA per segment; 16-bit counters (3 CTAs / SM) for bounding boxes below 65 536 pixels, a
-// second launch with 32-bit counters (1 CTA / SM) for the rare larger ones.
+// One CTA per segment, all bands of a chunk of 8 share two passes over the crop (min/max, then
+// quantised levels staged in shared memory); 16-bit counters (2 CTAs / SM) for bounding boxes
+// below 65 536 pixels, a second launch with 32-bit counters (1 CTA / SM) for the rare larger ones.
+#include <type_traits>
+
 #include "common.cuh"
 #include "bbox.cuh"
 
 namespace obia {
 
 constexpr int kBins = 256 * 257 / 2;   // unordered level pairs
-constexpr int kTile = 4096;            // crop pixels staged in shared memory as uint8
+constexpr int kTile = 2048;            // crop pixels staged in shared memory as uint8, per band
 constexpr int kTexFields = 6;
 
 struct TexBands {
@@ -46,6 +49,105 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
+constexpr int kBC = 8;                 // bands processed per pass over the crop
+
+struct TexSmem {                       // fixed-size part of the dynamic shared memory, after the histogram
+    double lut[256];                   // 1 / (1 + d^2)
+    unsigned long long red[32][8];     // per-warp partial sums of one angle
+    unsigned long long sums[kBC][4][8];   // per (band, angle): s1 s2 sa sb sc sdiag soff | homogeneity (double bits)
+    double props[kBC][4][kTexFields];
+    float wmn[32][kBC], wmx[32][kBC];
+    unsigned wany[32];
+    float mn[kBC], mx[kBC];
+    unsigned any;
+};
+
+// The four angle passes of one band: accumulate the pair sums (and the multiplicity histogram),
+// publish them, clear the histogram by replaying the pairs.  STAGED crops (<= kTile pixels, levels
+// in shared memory) keep every per-thread and per-warp sum in 32 bits.
+template <bool WIDE, bool STAGED, int NW, typename LevelFn>
+__device__ __forceinline__ void band_passes(unsigned *hist, TexSmem &S, int b, int h, int w, int warp, int lane,
+                                            int tid, LevelFn level)
+{
+    using acc_t = typename std::conditional<STAGED, unsigned, unsigned long long>::type;
+#pragma unroll 1
+    for (int a = 0; a < 4; ++a) {
+        const int dr = (a == 0) ? 0 : (a == 2) ? 2 : 1;
+        const int dc = (a == 0) ? 2 : (a == 1) ? 1 : (a == 2) ? 0 : -1;
+        const int nr = h - dr, ncw = w - (dc < 0 ? -dc : dc), c_lo = dc < 0 ? -dc : 0;
+        acc_t s1 = 0, s2 = 0, sa = 0, sb = 0, sc = 0, sdiag = 0, soff = 0;
+        double sh = 0.0;
+        for (int r = warp; r < nr; r += NW)
+            for (int c = c_lo + lane; c < c_lo + ncw; c += 32) {
+                const int i = level(r, c), j = level(r + dr, c + dc);
+                const int d = i > j ? i - j : j - i;
+                s1 += (unsigned)d;
+                s2 += (unsigned)(d * d);
+                sh += S.lut[d];
+                sa += (unsigned)(i + j);
+                sb += (unsigned)(i * i + j * j);
+                sc += (unsigned)(i * j);
+                const int lo = min(i, j), hi = max(i, j);
+                const int bin = hi * (hi + 1) / 2 + lo;
+                unsigned old;
+                if (WIDE) {
+                    old = atomicAdd(&hist[bin], 1u);
+                } else {
+                    const int sft = (bin & 1) * 16;
+                    old = (atomicAdd(&hist[bin >> 1], 1u << sft) >> sft) & 0xffffu;
+                }
+                if (d == 0)
+                    sdiag += (acc_t)2 * old + 1;
+                else
+                    soff += (acc_t)2 * old + 1;
+            }
+        unsigned long long t1, t2, ta, tb_, tc, td, to;
+        if (STAGED) {   // one REDUX each
+            t1 = __reduce_add_sync(0xffffffffu, (unsigned)s1);
+            t2 = __reduce_add_sync(0xffffffffu, (unsigned)s2);
+            ta = __reduce_add_sync(0xffffffffu, (unsigned)sa);
+            tb_ = __reduce_add_sync(0xffffffffu, (unsigned)sb);
+            tc = __reduce_add_sync(0xffffffffu, (unsigned)sc);
+            td = __reduce_add_sync(0xffffffffu, (unsigned)sdiag);
+            to = __reduce_add_sync(0xffffffffu, (unsigned)soff);
+        } else {
+            t1 = warp_sum_u64(s1);
+            t2 = warp_sum_u64(s2);
+            ta = warp_sum_u64(sa);
+            tb_ = warp_sum_u64(sb);
+            tc = warp_sum_u64(sc);
+            td = warp_sum_u64(sdiag);
+            to = warp_sum_u64(soff);
+        }
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) sh += __shfl_xor_sync(0xffffffffu, sh, s);
+        if (lane == 0) {
+            unsigned long long *rw = S.red[warp];
+            rw[0] = t1; rw[1] = t2; rw[2] = ta; rw[3] = tb_; rw[4] = tc; rw[5] = td; rw[6] = to;
+            rw[7] = (unsigned long long)__double_as_longlong(sh);
+        }
+        __syncthreads();   // partial sums published; every increment of this angle has landed
+        if (tid < 7) {
+            unsigned long long t = 0;
+            for (int i = 0; i < NW; ++i) t += S.red[i][tid];
+            S.sums[b][a][tid] = t;
+        } else if (tid == 7) {
+            double t = 0.0;
+            for (int i = 0; i < NW; ++i) t += __longlong_as_double((long long)S.red[i][7]);
+            S.sums[b][a][7] = (unsigned long long)__double_as_longlong(t);
+        }
+        // clear the histogram by replaying the pairs (all non-zero words were touched)
+        for (int r = warp; r < nr; r += NW)
+            for (int c = c_lo + lane; c < c_lo + ncw; c += 32) {
+                const int i = level(r, c), j = level(r + dr, c + dc);
+                const int lo = min(i, j), hi = max(i, j);
+                const int bin = hi * (hi + 1) / 2 + lo;
+                hist[WIDE ? bin : (bin >> 1)] = 0u;
+            }
+        __syncthreads();   // histogram clean, S.red free
+    }
+}
+
 template <bool WIDE, int NT>
 __global__ void __launch_bounds__(NT)
 texture_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw, ZonalWs bb, int W, int C,
@@ -55,15 +157,12 @@ texture_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw
     constexpr int kHistWords = WIDE ? kBins : (kBins + 1) / 2;
     constexpr int NW = NT / 32;
     unsigned *hist = reinterpret_cast<unsigned *>(smem);
-    double *lut = reinterpret_cast<double *>(smem + (size_t)kHistWords * 4);
-    unsigned long long *red = reinterpret_cast<unsigned long long *>(lut + 256);   // [NW][8]
-    double *redd = reinterpret_cast<double *>(red + NW * 8);                         // [NW]
-    float *redf = reinterpret_cast<float *>(redd + NW);                              // [NW][2] + flags
-    unsigned char *tile = reinterpret_cast<unsigned char *>(redf + NW * 4);
+    TexSmem &S = *reinterpret_cast<TexSmem *>(smem + (size_t)kHistWords * 4);
+    unsigned char *tiles = smem + (size_t)kHistWords * 4 + sizeof(TexSmem);   // [kBC][kTile], 16-bit launch only
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < kHistWords; i += NT) hist[i] = 0u;
-    for (int i = tid; i < 256; i += NT) lut[i] = 1.0 / (1.0 + (double)i * (double)i);
+    for (int i = tid; i < 256; i += NT) S.lut[i] = 1.0 / (1.0 + (double)i * (double)i);
     __syncthreads();
 
     const double NAN_D = __longlong_as_double(0x7ff8000000000000LL);
@@ -82,168 +181,150 @@ texture_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw
         const bool staged = !WIDE && area <= kTile;
         const int lab = (int)L;
 
-        for (int k = 0; k < nb; ++k) {
-            const int band = tb.band[k];
-            // sample of the crop at (r, c): the raster value inside the segment, 0 outside / NaN
-            auto sample = [&](int r, int c, bool &valid) -> float {
-                const int64_t p = (int64_t)(y0 + r) * W + (x0 + c);
-                float v = 0.0f;
-                valid = false;
-                if (labels[p] == lab) {
-                    v = raw[p * C + band];
-                    valid = (v == v);
-                    if (!valid) v = 0.0f;
-                }
-                return v;
-            };
-            // ---- min / max of the crop --------------------------------------------------------
-            float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
-            int any = 0;
-            for (int64_t p = tid; p < area; p += NT) {
-                bool valid;
-                const float v = sample((int)(p / w), (int)(p % w), valid);
-                mn = fminf(mn, v);
-                mx = fmaxf(mx, v);
-                any |= valid ? 1 : 0;
-            }
+        for (int k0 = 0; k0 < nb; k0 += kBC) {
+            const int nbc = min(kBC, nb - k0);
+            // ---- pass 1 over the crop: min / max of every band of this chunk ----------------------
+            // sample = raster value inside the segment, 0 outside the segment and for NaN samples
+            float mn[kBC], mx[kBC];
+            unsigned anym = 0;
 #pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) {
-                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, s));
-                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-                any |= __shfl_xor_sync(0xffffffffu, any, s);
+            for (int b = 0; b < kBC; ++b) {
+                mn[b] = __int_as_float(0x7f800000);
+                mx[b] = __int_as_float(0xff800000);
             }
-            if (lane == 0) {
-                redf[warp * 4] = mn;
-                redf[warp * 4 + 1] = mx;
-                redf[warp * 4 + 2] = __int_as_float(any);
-            }
-            __syncthreads();
-            any = 0;
-            for (int i = 0; i < NW; ++i) {
-                mn = fminf(mn, redf[i * 4]);
-                mx = fmaxf(mx, redf[i * 4 + 1]);
-                any |= __float_as_int(redf[i * 4 + 2]);
-            }
-            __syncthreads();   // redf is reused by the next band
-            if (!any) {        // no valid sample: every feature is NaN (:217-231)
-                for (int i = tid; i < kTexFields; i += NT) o[k * kTexFields + i] = NAN_D;
-                continue;
-            }
-            const bool flat = (mx == mn);
-            const float span32 = __fsub_rn(mx, mn);
-            const double span64 = (double)mx - (double)mn;
-            // the reference's arithmetic in the dtype of its masked crop (float32 rasters stay
-            // float32, integer rasters become float64), truncated by astype(uint8)
-            auto quantise = [&](float v) -> int {
-                if (flat) return 0;
-                if (f64) return (int)(((double)v - (double)mn) / span64 * 255.0);
-                return (int)__fmul_rn(__fdiv_rn(__fsub_rn(v, mn), span32), 255.0f);
-            };
-            if (staged) {
-                for (int p = tid; p < (int)area; p += NT) {
-                    bool valid;
-                    tile[p] = (unsigned char)quantise(sample(p / w, p % w, valid));
-                }
-                __syncthreads();
-            }
-            auto level = [&](int r, int c) -> int {
-                if (staged) return tile[r * w + c];
-                bool valid;
-                return quantise(sample(r, c, valid));
-            };
-
-            double feat[kTexFields] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // sums over the angles (thread 0)
-#pragma unroll 1
-            for (int a = 0; a < 4; ++a) {
-                const int dr = (a == 0) ? 0 : (a == 2) ? 2 : 1;
-                const int dc = (a == 0) ? 2 : (a == 1) ? 1 : (a == 2) ? 0 : -1;
-                const int nr = h - dr, ncw = w - (dc < 0 ? -dc : dc), c_lo = dc < 0 ? -dc : 0;
-                const int64_t npairs = (nr > 0 && ncw > 0) ? (int64_t)nr * ncw : 0;
-                unsigned long long s1 = 0, s2 = 0, sa = 0, sb = 0, sc = 0, sdiag = 0, soff = 0;
-                double sh = 0.0;
-                for (int64_t t = tid; t < npairs; t += NT) {
-                    const int r = (int)(t / ncw), c = c_lo + (int)(t % ncw);
-                    const int i = level(r, c), j = level(r + dr, c + dc);
-                    const int d = i > j ? i - j : j - i;
-                    s1 += (unsigned)d;
-                    s2 += (unsigned)(d * d);
-                    sh += lut[d];
-                    sa += (unsigned)(i + j);
-                    sb += (unsigned)(i * i + j * j);
-                    sc += (unsigned)(i * j);
-                    const int lo = min(i, j), hi = max(i, j);
-                    const int bin = hi * (hi + 1) / 2 + lo;
-                    unsigned old;
-                    if (WIDE) {
-                        old = atomicAdd(&hist[bin], 1u);
-                    } else {
-                        const int sft = (bin & 1) * 16;
-                        old = (atomicAdd(&hist[bin >> 1], 1u << sft) >> sft) & 0xffffu;
-                    }
-                    if (d == 0)
-                        sdiag += 2ull * old + 1ull;
-                    else
-                        soff += 2ull * old + 1ull;
-                }
-                s1 = warp_sum_u64(s1);
-                s2 = warp_sum_u64(s2);
-                sa = warp_sum_u64(sa);
-                sb = warp_sum_u64(sb);
-                sc = warp_sum_u64(sc);
-                sdiag = warp_sum_u64(sdiag);
-                soff = warp_sum_u64(soff);
+            for (int r = warp; r < h; r += NW)
+                for (int c = lane; c < w; c += 32) {
+                    const int64_t p = (int64_t)(y0 + r) * W + (x0 + c);
+                    const bool inside = labels[p] == lab;
 #pragma unroll
-                for (int s = 16; s >= 1; s >>= 1) sh += __shfl_xor_sync(0xffffffffu, sh, s);
-                if (lane == 0) {
-                    unsigned long long *rw = red + warp * 8;
-                    rw[0] = s1; rw[1] = s2; rw[2] = sa; rw[3] = sb; rw[4] = sc; rw[5] = sdiag; rw[6] = soff;
-                    redd[warp] = sh;
-                }
-                __syncthreads();   // sums published; every increment of this angle has landed
-                // clear the histogram by replaying the pairs (all non-zero words were touched)
-                for (int64_t t = tid; t < npairs; t += NT) {
-                    const int r = (int)(t / ncw), c = c_lo + (int)(t % ncw);
-                    const int i = level(r, c), j = level(r + dr, c + dc);
-                    const int lo = min(i, j), hi = max(i, j);
-                    const int bin = hi * (hi + 1) / 2 + lo;
-                    hist[WIDE ? bin : (bin >> 1)] = 0u;
-                }
-                if (tid == 0) {
-                    unsigned long long S1 = 0, S2 = 0, SA = 0, SB = 0, SC = 0, SD = 0, SO = 0;
-                    double SH = 0.0;
-                    for (int i = 0; i < NW; ++i) {
-                        const unsigned long long *rw = red + i * 8;
-                        S1 += rw[0]; S2 += rw[1]; SA += rw[2]; SB += rw[3]; SC += rw[4]; SD += rw[5]; SO += rw[6];
-                        SH += redd[i];
-                    }
-                    if (npairs == 0) {
-                        feat[5] += 1.0;   // empty matrix: all sums 0, correlation 1 (std < 1e-15)
-                    } else {
-                        const double N = (double)npairs;
-                        const double asm_ = ((double)SO + 2.0 * (double)SD) / (2.0 * N * N);
-                        feat[0] += (double)S2 / N;
-                        feat[1] += (double)S1 / N;
-                        feat[2] += SH / N;
-                        feat[3] += asm_;
-                        feat[4] += sqrt(asm_);
-                        // var = (2N SB - SA^2) / 4N^2, cov = (4N SC - SA^2) / 4N^2, exact in 128 bits
-                        const unsigned __int128 sa2 = (unsigned __int128)SA * SA;
-                        const unsigned __int128 vnum = (unsigned __int128)(2ull * (unsigned long long)npairs) * SB - sa2;
-                        if (vnum == 0) {
-                            feat[5] += 1.0;
-                        } else {
-                            const unsigned __int128 c4 = (unsigned __int128)(4ull * (unsigned long long)npairs) * SC;
-                            const double cnum = (c4 >= sa2) ? (double)(c4 - sa2) : -(double)(sa2 - c4);
-                            feat[5] += cnum / (double)vnum;
+                    for (int b = 0; b < kBC; ++b) {
+                        if (b < nbc) {
+                            float v = inside ? raw[p * C + tb.band[k0 + b]] : 0.0f;
+                            const bool valid = inside && (v == v);
+                            if (!valid) v = 0.0f;
+                            mn[b] = fminf(mn[b], v);
+                            mx[b] = fmaxf(mx[b], v);
+                            anym |= (valid ? 1u : 0u) << b;
                         }
                     }
                 }
-                __syncthreads();   // histogram clean, reduction scratch free
-            }
-            if (tid == 0) {
 #pragma unroll
-                for (int i = 0; i < kTexFields; ++i) o[k * kTexFields + i] = feat[i] / 4.0;
+            for (int b = 0; b < kBC; ++b) {
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) {
+                    mn[b] = fminf(mn[b], __shfl_xor_sync(0xffffffffu, mn[b], s));
+                    mx[b] = fmaxf(mx[b], __shfl_xor_sync(0xffffffffu, mx[b], s));
+                }
+                if (lane == 0) {
+                    S.wmn[warp][b] = mn[b];
+                    S.wmx[warp][b] = mx[b];
+                }
             }
+            anym = __reduce_or_sync(0xffffffffu, anym);
+            if (lane == 0) S.wany[warp] = anym;
+            __syncthreads();
+            if (tid < kBC) {
+                float a = S.wmn[0][tid], z = S.wmx[0][tid];
+                for (int i = 1; i < NW; ++i) {
+                    a = fminf(a, S.wmn[i][tid]);
+                    z = fmaxf(z, S.wmx[i][tid]);
+                }
+                S.mn[tid] = a;
+                S.mx[tid] = z;
+            }
+            if (tid == 32) {
+                unsigned m = 0;
+                for (int i = 0; i < NW; ++i) m |= S.wany[i];
+                S.any = m;
+            }
+            __syncthreads();
+            // the reference's arithmetic in the dtype of its masked crop (float32 rasters stay
+            // float32, integer rasters become float64), truncated by astype(uint8)
+            auto quantise = [&](float v, float lo, float hi) -> int {
+                if (hi == lo) return 0;
+                if (f64) return (int)(((double)v - (double)lo) / ((double)hi - (double)lo) * 255.0);
+                return (int)__fmul_rn(__fdiv_rn(__fsub_rn(v, lo), __fsub_rn(hi, lo)), 255.0f);
+            };
+            // ---- pass 2 over the crop: quantised levels of every band into shared memory ----------
+            if (staged) {
+                for (int r = warp; r < h; r += NW)
+                    for (int c = lane; c < w; c += 32) {
+                        const int64_t p = (int64_t)(y0 + r) * W + (x0 + c);
+                        const bool inside = labels[p] == lab;
+#pragma unroll
+                        for (int b = 0; b < kBC; ++b) {
+                            if (b < nbc) {
+                                float v = inside ? raw[p * C + tb.band[k0 + b]] : 0.0f;
+                                if (!(v == v)) v = 0.0f;
+                                tiles[b * kTile + r * w + c] = (unsigned char)quantise(v, S.mn[b], S.mx[b]);
+                            }
+                        }
+                    }
+                __syncthreads();
+            }
+            const unsigned any_bands = S.any;
+
+            for (int b = 0; b < nbc; ++b) {
+                if (!((any_bands >> b) & 1u)) continue;   // no valid sample: NaN features (:217-231)
+                if (staged) {
+                    const unsigned char *tile = tiles + b * kTile;
+                    band_passes<WIDE, true, NW>(hist, S, b, h, w, warp, lane, tid,
+                                                [&](int r, int c) -> int { return tile[r * w + c]; });
+                } else {
+                    const int band = tb.band[k0 + b];
+                    const float lo_v = S.mn[b], hi_v = S.mx[b];
+                    band_passes<WIDE, false, NW>(hist, S, b, h, w, warp, lane, tid, [&](int r, int c) -> int {
+                        const int64_t p = (int64_t)(y0 + r) * W + (x0 + c);
+                        float v = (labels[p] == lab) ? raw[p * C + band] : 0.0f;
+                        if (!(v == v)) v = 0.0f;
+                        return quantise(v, lo_v, hi_v);
+                    });
+                }
+            }
+            // ---- features of the chunk: one thread per (band, angle), then the mean over the angles ----
+            if (tid < nbc * 4) {
+                const int b = tid >> 2, a = tid & 3;
+                const int dr = (a == 0) ? 0 : (a == 2) ? 2 : 1;
+                const int dc = (a == 0) ? 2 : (a == 1) ? 1 : (a == 2) ? 0 : -1;
+                const int nr = h - dr, ncw = w - (dc < 0 ? -dc : dc);
+                const unsigned long long npairs = (nr > 0 && ncw > 0) ? (unsigned long long)nr * ncw : 0ull;
+                double *pr = S.props[b][a];
+                if (npairs == 0) {
+                    // empty matrix: every weighted sum is 0 and correlation is 1 (std < 1e-15)
+                    pr[0] = pr[1] = pr[2] = pr[3] = pr[4] = 0.0;
+                    pr[5] = 1.0;
+                } else {
+                    const unsigned long long *q = S.sums[b][a];
+                    const unsigned long long S1 = q[0], S2 = q[1], SA = q[2], SB = q[3], SC = q[4], SD = q[5], SO = q[6];
+                    const double SH = __longlong_as_double((long long)q[7]);
+                    const double N = (double)npairs;
+                    const double asm_ = ((double)SO + 2.0 * (double)SD) / (2.0 * N * N);
+                    pr[0] = (double)S2 / N;
+                    pr[1] = (double)S1 / N;
+                    pr[2] = SH / N;
+                    pr[3] = asm_;
+                    pr[4] = sqrt(asm_);
+                    // var = (2N SB - SA^2) / 4N^2, cov = (4N SC - SA^2) / 4N^2: exact in 128 bits
+                    const unsigned __int128 sa2 = (unsigned __int128)SA * SA;
+                    const unsigned __int128 vnum = (unsigned __int128)(2ull * npairs) * SB - sa2;
+                    if (vnum == 0) {
+                        pr[5] = 1.0;
+                    } else {
+                        const unsigned __int128 c4 = (unsigned __int128)(4ull * npairs) * SC;
+                        const double cnum = (c4 >= sa2) ? (double)(c4 - sa2) : -(double)(sa2 - c4);
+                        pr[5] = cnum / (double)vnum;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < nbc * kTexFields) {
+                const int b = tid / kTexFields, f = tid % kTexFields;
+                double v = NAN_D;
+                if ((any_bands >> b) & 1u)
+                    v = (((S.props[b][0][f] + S.props[b][1][f]) + S.props[b][2][f]) + S.props[b][3][f]) / 4.0;
+                o[(k0 + b) * kTexFields + f] = v;
+            }
+            __syncthreads();   // S.* and the tiles are reused by the next chunk / segment
         }
     }
 }
@@ -251,8 +332,7 @@ texture_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw
 template <bool WIDE, int NT> static size_t texture_smem_bytes()
 {
     const size_t hist_words = WIDE ? kBins : (kBins + 1) / 2;
-    const size_t nw = NT / 32;
-    return hist_words * 4 + 256 * 8 + nw * 8 * 8 + nw * 8 + nw * 4 * 4 + (WIDE ? 16 : kTile);
+    return hist_words * 4 + sizeof(TexSmem) + (WIDE ? 16 : (size_t)kBC * kTile);
 }
 
 }  // namespace obia
@@ -298,9 +378,13 @@ extern "C" int obia_b200_texture_stats(const int32_t *labels, const float *raw, 
     const size_t sm_s = texture_smem_bytes<false, NT_S>(), sm_w = texture_smem_bytes<true, NT_W>();
     OBIA_CUDA_CHECK(cudaFuncSetAttribute(texture_kernel<false, NT_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_s));
     OBIA_CUDA_CHECK(cudaFuncSetAttribute(texture_kernel<true, NT_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_w));
-    // persistent CTAs: 3 per SM with 16-bit counters, 1 per SM with 32-bit counters
-    const unsigned g_s = (unsigned)(n < (int64_t)sms * 3 ? n : (int64_t)sms * 3);
-    const unsigned g_w = (unsigned)(n < (int64_t)sms ? n : (int64_t)sms);
+    // persistent CTAs: as many as fit per SM (shared-memory bound: 2 with 16-bit counters, 1 with 32-bit)
+    int occ_s = 1, occ_w = 1;
+    OBIA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, texture_kernel<false, NT_S>, NT_S, sm_s));
+    OBIA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, texture_kernel<true, NT_W>, NT_W, sm_w));
+    const int64_t cap_s = (int64_t)sms * (occ_s > 0 ? occ_s : 1), cap_w = (int64_t)sms * (occ_w > 0 ? occ_w : 1);
+    const unsigned g_s = (unsigned)(n < cap_s ? n : cap_s);
+    const unsigned g_w = (unsigned)(n < cap_w ? n : cap_w);
     texture_kernel<false, NT_S><<<g_s, NT_S, sm_s, st>>>(labels, raw, w, (int)W, C, tb, n_bands, max_label,
                                                          quantise_f64, features);
     OBIA_LAUNCH_CHECK();
