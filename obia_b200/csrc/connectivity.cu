@@ -159,12 +159,30 @@ cc_local_kernel(const int32_t *__restrict__ lab, int32_t *__restrict__ parent, i
         if (cur_head || up_head) uf_union_s(s_par, i, up);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kTile * kTile; i += 256) {
+    // Only run heads can be roots (every other pixel points at its run head and is never
+    // re-parented), so the chains are walked once per run, not once per pixel: heads are
+    // compressed to their root first, then every pixel is two loads away from it.
+    int head_root[kTile * kTile / 256];
+#pragma unroll
+    for (int k = 0; k < kTile * kTile / 256; ++k) {
+        const int i = threadIdx.x + k * 256;
+        const int32_t l = s_lab[i];
+        const bool is_head = (i % kTile) == 0 || s_lab[i - 1] != l || l == mask_label;
+        head_root[k] = is_head ? uf_find_s(s_par, i) : -1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kTile * kTile / 256; ++k)
+        if (head_root[k] >= 0) s_par[threadIdx.x + k * 256] = head_root[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kTile * kTile / 256; ++k) {
+        const int i = threadIdx.x + k * 256;
         const int ly = i / kTile, lx = i % kTile;
         const int y = y0 + ly, x = x0 + lx;
         if (y >= H || x >= W) continue;
         const int64_t g = (int64_t)y * W + x;
-        const int r = uf_find_s(s_par, i);
+        const int r = s_par[s_par[i]];
         parent[g] = (int32_t)((int64_t)(y0 + r / kTile) * W + x0 + r % kTile);
         psize[g] = 0;
         visit[g] = 0;

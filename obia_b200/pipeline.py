@@ -202,20 +202,30 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
     Cf = 3 if to_lab else Cs
 
     # ---- centres --------------------------------------------------------------
-    if init_centroids is not None:
-        yx, steps = init_centroids
-    elif mask_dev is not None:
-        yx, steps = mask_centroids_device(mask_dev, int(n_segments))
+    if init_centroids is not None or mask_dev is not None:
+        if init_centroids is not None:
+            yx, steps = init_centroids
+        else:
+            yx, steps = mask_centroids_device(mask_dev, int(n_segments))
+        n = int(yx.shape[0])
+        centres_np = np.zeros((n, 2 + Cf), dtype=np.float32)
+        centres_np[:, :2] = yx.astype(np.float32)
+        centres = torch.from_numpy(centres_np).to(dev)
     else:
-        yx, steps = slic_host.grid_centroids(H, W, n_segments)
-    n = int(yx.shape[0])
+        # regular grid (skimage regular_grid, y-major): laid out on the device, the host only
+        # derives the per-axis start / step (integers < 2^24: exact in float32)
+        starts, isteps = slic_host.regular_grid_steps((1, H, W), n_segments)
+        ys = torch.arange(starts[1], H, isteps[1] or 1, device=dev, dtype=torch.float32)
+        xs = torch.arange(starts[2], W, isteps[2] or 1, device=dev, dtype=torch.float32)
+        n = int(ys.numel() * xs.numel())
+        centres = torch.zeros((n, 2 + Cf), dtype=torch.float32, device=dev)
+        centres[:, 0] = ys.repeat_interleave(xs.numel())
+        centres[:, 1] = xs.repeat(ys.numel())
+        steps = [1.0 if s is None else float(s) for s in isteps]
     step = float(max(steps))
     step_y, step_x = slic_host.window_steps(H, W, n)
     if not step > 0:
         raise ValueError("degenerate SLIC initialisation (step == 0)")
-    centres_np = np.zeros((n, 2 + Cf), dtype=np.float32)
-    centres_np[:, :2] = yx.astype(np.float32)
-    centres = torch.from_numpy(centres_np).to(dev)
 
     # ---- K1b: features ----------------------------------------------------------
     ratio = f32(1.0 / compactness)
