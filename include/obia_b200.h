@@ -69,6 +69,18 @@ int obia_b200_band_minmax(const float *raw, int64_t n_pixels, int32_t C,
 int obia_b200_normalize_inplace(float *raw, int64_t n_pixels, int32_t C,
                                 const float *minmax, void *stream);
 
+/* Same arithmetic, written to another buffer (the raw raster stays intact for
+ * the statistics).  `out` may be page-locked HOST memory that the device can
+ * address (cudaHostAlloc / cudaHostRegister under UVA): the kernel then streams
+ * the normalised raster straight into the caller's `img_data` over PCIe, with
+ * no staging copy and without occupying the copy engine the small read-backs
+ * of the SLIC path use.  max_ctas > 0 caps the grid (a handful of CTAs
+ * saturates PCIe and leaves the SMs to the SLIC kernels running concurrently).
+ */
+int obia_b200_normalize_to(const float *raw, float *out, int64_t n_pixels,
+                           int32_t C, const float *minmax, int32_t max_ctas,
+                           void *stream);
+
 /* Fused band select + obia min-max normalise + skimage global rescale +
  * optional RGB->CIELAB + multiply by 1/compactness, written band-planar.
  * Replaces segment_boundaries.py:35-43 and, inside skimage.segmentation.slic

@@ -25,6 +25,7 @@ SIGNATURES = {
     "obia_b200_profile_read": (ctypes.c_int, [_vp, _vp]),
     "obia_b200_band_minmax": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "obia_b200_normalize_inplace": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "obia_b200_normalize_to": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _vp]),
     "obia_b200_slic_features": (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _i32, _vp, _vp, _f32, _f32,
                                                _i32, _f32, _vp, _i64, _vp]),
     "obia_b200_gaussian_planar": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _i32, _vp,

@@ -140,9 +140,11 @@ __global__ void minmax_finish_kernel(uint32_t *keys, int C, int has_mask)
 
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
-// ------------------------------------------------------ in-place normalise --
+// ----------------------------------------------------------- normalise --
+// src == dst: in place.  dst may be device-accessible (pinned, mapped) HOST memory: the stores are
+// full 16-byte vectors, coalesced per warp, so they stream over PCIe without the copy engine.
 __global__ void __launch_bounds__(256)
-normalize_inplace_kernel(float *raw, int64_t n_elems, int C, const float *__restrict__ minmax)
+normalize_kernel(const float *src, float *dst, int64_t n_elems, int C, const float *__restrict__ minmax)
 {
     const int64_t NT = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,20 +156,21 @@ normalize_inplace_kernel(float *raw, int64_t n_elems, int C, const float *__rest
         mn[j] = minmax[band * 4 + 0];
         d[j] = __fsub_rn(minmax[band * 4 + 1], mn[j]);
     }
-    float4 *raw4 = reinterpret_cast<float4 *>(raw);
+    const float4 *src4 = reinterpret_cast<const float4 *>(src);
+    float4 *dst4 = reinterpret_cast<float4 *>(dst);
     for (int64_t v = tid; v < nvec; v += NT) {
-        float4 x = raw4[v];
+        float4 x = src4[v];
         x.x = __fdiv_rn(__fsub_rn(x.x, mn[0]), d[0]);
         x.y = __fdiv_rn(__fsub_rn(x.y, mn[1]), d[1]);
         x.z = __fdiv_rn(__fsub_rn(x.z, mn[2]), d[2]);
         x.w = __fdiv_rn(__fsub_rn(x.w, mn[3]), d[3]);
-        raw4[v] = x;
+        dst4[v] = x;
     }
     if (tid < (n_elems & 3)) {
         int64_t e = nvec * 4 + tid;
         int band = (int)(e % C);
         float m = minmax[band * 4 + 0];
-        raw[e] = __fdiv_rn(__fsub_rn(raw[e], m), __fsub_rn(minmax[band * 4 + 1], m));
+        dst[e] = __fdiv_rn(__fsub_rn(src[e], m), __fsub_rn(minmax[band * 4 + 1], m));
     }
 }
 
@@ -353,7 +356,24 @@ extern "C" int obia_b200_normalize_inplace(float *raw, int64_t n_pixels, int32_t
     const int unit = C / gcd_i(C, 1024);
     int64_t grid = std::min<int64_t>(ceil_div(n_elems / 4 + 1, 256 * 4), (int64_t)kNumSMs * 16);
     grid = round_up(std::max<int64_t>(grid, 1), unit);
-    normalize_inplace_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(raw, n_elems, C, minmax);
+    normalize_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(raw, raw, n_elems, C, minmax);
+    OBIA_LAUNCH_CHECK();
+    return OBIA_B200_OK;
+}
+
+extern "C" int obia_b200_normalize_to(const float *raw, float *out, int64_t n_pixels, int32_t C,
+                                      const float *minmax, int32_t max_ctas, void *stream)
+{
+    if (!raw || !out || !minmax || n_pixels <= 0 || C <= 0)
+        return set_err(OBIA_B200_ERR_ARG, "normalize_to: bad argument");
+    if ((reinterpret_cast<uintptr_t>(raw) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+        return set_err(OBIA_B200_ERR_ARG, "normalize_to: raw and out must be 16-byte aligned (128-bit accesses)");
+    const int64_t n_elems = n_pixels * C;
+    const int unit = C / gcd_i(C, 1024);
+    int64_t grid = std::min<int64_t>(ceil_div(n_elems / 4 + 1, 256 * 4), (int64_t)kNumSMs * 16);
+    if (max_ctas > 0) grid = std::min<int64_t>(grid, max_ctas);
+    grid = round_up(std::max<int64_t>(grid, 1), unit);
+    normalize_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(raw, out, n_elems, C, minmax);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
 }

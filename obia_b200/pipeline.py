@@ -72,6 +72,22 @@ def band_minmax(raw, mask=None):
     return out, flags
 
 
+def normalize_to_host(raw, host, minmax_dev, max_ctas=16):
+    """Normalised copy of `raw` written by the kernel straight into the page-locked host tensor
+    `host` (same shape, float32, contiguous); see obia_b200_normalize_to.  Asynchronous.
+    16 CTAs keep PCIe busy and cost the concurrently running SLIC kernels the least (measured on
+    c2: 8 / 16 / 64 / 148 CTAs -> 152 / 149 / 160 / 190 ms end to end)."""
+    lib = _lib.load()
+    _require_cuda(raw, "raw", torch.float32)
+    H, W, C = raw.shape
+    if not (host.is_pinned() and host.is_contiguous() and host.dtype == torch.float32
+            and tuple(host.shape) == tuple(raw.shape)):
+        raise ValueError("normalize_to_host needs a pinned, contiguous float32 host tensor of raw's shape")
+    work = _aligned(raw)
+    _lib.check(lib.obia_b200_normalize_to(_p(work), ctypes.c_void_p(host.data_ptr()), H * W, C, _p(minmax_dev),
+                                          int(max_ctas), _stream_ptr()), "normalize_to")
+
+
 def normalize_inplace(raw, minmax_dev):
     """`img_data[:, :, i] = normalize_band(...)` for every band (segment_boundaries.py:31-33)."""
     lib = _lib.load()

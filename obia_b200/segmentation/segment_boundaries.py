@@ -71,17 +71,27 @@ def _apply_image_mutation(image, raw, minmax_dev, stream=None, after=None):
     with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
         if stream is not None and after is not None:
             stream.wait_stream(after)
-        tmp = raw.clone()
-        pipeline.normalize_inplace(tmp, minmax_dev)
+        host = None
         if isinstance(data, torch.Tensor):
-            data.copy_(tmp.to(data.device, dtype=data.dtype))
+            host = data
         else:
             arr = np.asarray(data)
             if arr.dtype == np.float32 and arr.flags.c_contiguous and arr.flags.writeable:
                 host = torch.from_numpy(arr)
-                host.copy_(tmp, non_blocking=stream is not None and host.is_pinned())
-            else:
-                arr[...] = tmp.cpu().numpy()
+        if (host is not None and not host.is_cuda and host.dtype == torch.float32 and host.is_contiguous()
+                and host.is_pinned() and host.data_ptr() % 16 == 0):
+            # page-locked img_data: the kernel streams the normalised raster straight into it over
+            # PCIe (no staging copy; the copy engine stays free for the SLIC path's small read-backs)
+            pipeline.normalize_to_host(raw, host, minmax_dev)
+            return
+        tmp = raw.clone()
+        pipeline.normalize_inplace(tmp, minmax_dev)
+        if isinstance(data, torch.Tensor):
+            data.copy_(tmp.to(data.device, dtype=data.dtype))
+        elif host is not None:
+            host.copy_(tmp)
+        else:
+            arr[...] = tmp.cpu().numpy()
 
 
 def frame_from_labels(labels, start_label, n_labels, connected, image=None, polygonize=False):
@@ -142,7 +152,7 @@ def frame_from_labels(labels, start_label, n_labels, connected, image=None, poly
 
 
 def create_segments(image, segmentation_bands=None, method="slic", *, mutate_image=True,
-                    polygonize=False, **kwargs):
+                    polygonize=False, _defer_mutation_sync=False, **kwargs):
     """
     :param image: Image (obia_b200.handlers.geotif.Image) -- `img_data` (H, W, C) float32.
     :param segmentation_bands: band indices used for segmentation (None = all).
@@ -194,8 +204,12 @@ def create_segments(image, segmentation_bands=None, method="slic", *, mutate_ima
         if side is not None:
             side.synchronize()
         raise
+    pending = None
     if side is not None:
-        side.synchronize()
+        if _defer_mutation_sync:
+            pending = side      # segment() waits for the write-back after the statistics are queued
+        else:
+            side.synchronize()
     elif mutate_image:
         _apply_image_mutation(image, raw, res.minmax)
 
@@ -203,4 +217,5 @@ def create_segments(image, segmentation_bands=None, method="slic", *, mutate_ima
     gdf = frame_from_labels(res.labels, res.start_label, res.n_labels, connected, image=image,
                             polygonize=polygonize)
     gdf.slic_result = res
+    gdf._pending_mutation = pending
     return gdf

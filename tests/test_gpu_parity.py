@@ -494,6 +494,29 @@ def test_segment_end_to_end_columns_and_values():
     assert seg.segments[["pai", "fhd", "ch", "mean_intensity", "variance_intensity"]].isna().all().all()
 
 
+def test_image_mutation_into_pinned_host_memory():
+    """Page-locked img_data is normalised by a kernel writing straight into host memory
+    (obia_b200_normalize_to); the result is bit-identical to numpy's normalize_band."""
+    import slic_oracle as so
+    from obia_b200.handlers.geotif import Image
+    from obia_b200.segmentation.segment_boundaries import create_segments
+    from gpu_helpers import synth_raster
+    for (H, W, C) in ((64, 80, 4), (33, 47, 3), (50, 50, 5)):
+        raw = synth_raster(H, W, C, seed=H) * 50 - 7
+        pinned = torch.empty((H, W, C), dtype=torch.float32, pin_memory=True)
+        pinned.copy_(torch.from_numpy(raw))
+        img = Image(pinned.numpy(), None, None, None, None)
+        create_segments(img, n_segments=20, compactness=0.5)
+        want = raw.copy()
+        for b in range(C):
+            want[:, :, b] = so.normalize_band(want[:, :, b])
+        np.testing.assert_array_equal(pinned.numpy(), want)
+        # same through a pinned torch tensor as img_data
+        pinned.copy_(torch.from_numpy(raw))
+        create_segments(Image(pinned, None, None, None, None), n_segments=20, compactness=0.5)
+        np.testing.assert_array_equal(pinned.numpy(), want)
+
+
 def test_create_segments_errors():
     from obia_b200.handlers.geotif import Image
     from obia_b200.segmentation.segment_boundaries import create_segments
