@@ -118,10 +118,28 @@ int obia_b200_gaussian_planar(const float *in, float *tmp, float *out,
  * coordinates (float64 distances in feature order, lowest index wins ties, exact integer sums).
  *   points_yx    [m][2] int32 (y, x) of the dense sample, device
  *   centroids_yx [n][2] float64 in/out, device
+ *   extent_y/x   all coordinates lie in [0, extent): the raster (tile) shape
+ * More than 1024 centroids: the nearest centroid is found through a uniform
+ * grid over the centroids, visited ring by ring with an exact stopping bound,
+ * so the assignment (ties included) is the brute-force one at O(1) distance
+ * evaluations per point instead of n.
  */
-int64_t obia_b200_mask_kmeans_workspace_bytes(int64_t n);
+int64_t obia_b200_mask_kmeans_workspace_bytes(int64_t n, int64_t extent_y,
+                                              int64_t extent_x);
 int obia_b200_mask_kmeans(const int32_t *points_yx, int64_t m, double *centroids_yx,
-                          int64_t n, int32_t iters, void *workspace, void *stream);
+                          int64_t n, int32_t iters, int64_t extent_y,
+                          int64_t extent_x, void *workspace, void *stream);
+
+/* Nearest OTHER centroid of every centroid: skimage's
+ * `dist = squareform(pdist(centroids)); np.fill_diagonal(dist, np.inf);
+ * closest = dist.argmin(-1)` in `_get_mask_centroids` (Euclidean float64
+ * distances, lowest index among equal minima), without the n x n matrix.
+ *   closest   [n] int32 out, device
+ *   workspace obia_b200_mask_kmeans_workspace_bytes(n, extent_y, extent_x)
+ */
+int obia_b200_nearest_centroid(const double *centroids_yx, int64_t n,
+                               int64_t extent_y, int64_t extent_x,
+                               int32_t *closest, void *workspace, void *stream);
 
 /* ---------------------------------------------------------------- K2 ----
  * SLIC iterations: replaces Cython `_slic_cython`

@@ -103,9 +103,9 @@ def normalize_inplace(raw, minmax_dev):
 def mask_centroids_device(mask_dev, n_segments):
     """maskSLIC initial centres (skimage `_get_mask_centroids`) with the k-means sweeps on the GPU.
 
-    Host part: the two RandomState(123) draws (cached per mask size) and the nearest-centroid
-    steps; device part: `obia_b200_mask_kmeans` (bit-identical to scipy's kmeans2 on pixel
-    coordinates).  Returns (yx float64 (n, 2) numpy, steps (3,)).
+    Host part: the two RandomState(123) draws (cached per mask size) and the mean of the
+    nearest-centroid offsets; device part: `obia_b200_mask_kmeans` (bit-identical to scipy's
+    kmeans2 on pixel coordinates) and, beyond 2048 centroids, `obia_b200_nearest_centroid`.  Returns (yx float64 (n, 2) numpy, steps (3,)).
     """
     lib = _lib.load()
     coord = torch.nonzero(mask_dev)                 # row-major, like np.nonzero
@@ -120,11 +120,20 @@ def mask_centroids_device(mask_dev, n_segments):
     pts = coord.index_select(0, torch.from_numpy(idx_dense).to(dev)).to(torch.int32).contiguous()
     cent = coord.index_select(0, torch.from_numpy(idx).to(dev)).to(torch.float64).contiguous()
     n = int(cent.shape[0])
-    ws = torch.empty((lib.obia_b200_mask_kmeans_workspace_bytes(n),), dtype=torch.uint8, device=dev)
-    _lib.check(lib.obia_b200_mask_kmeans(_p(pts), int(pts.shape[0]), _p(cent), n, 5, _p(ws), _stream_ptr()),
+    H, W = (int(v) for v in mask_dev.shape)
+    ws = torch.empty((lib.obia_b200_mask_kmeans_workspace_bytes(n, H, W),), dtype=torch.uint8, device=dev)
+    _lib.check(lib.obia_b200_mask_kmeans(_p(pts), int(pts.shape[0]), _p(cent), n, 5, H, W, _p(ws), _stream_ptr()),
                "mask_kmeans")
+    if n <= 2048:
+        yx = cent.cpu().numpy()
+        return yx, slic_host.steps_from_centroids(yx)
+    # many centroids: the nearest-other-centroid search runs on the device as well (the host
+    # version needs scipy's n x n pdist matrix, or a k-d tree that breaks ties differently)
+    closest = torch.empty((n,), dtype=torch.int32, device=dev)
+    _lib.check(lib.obia_b200_nearest_centroid(_p(cent), n, H, W, _p(closest), _p(ws), _stream_ptr()),
+               "nearest_centroid")
     yx = cent.cpu().numpy()
-    return yx, slic_host.steps_from_centroids(yx)
+    return yx, slic_host.steps_from_centroids(yx, closest=closest.cpu().numpy())
 
 
 @dataclass

@@ -123,9 +123,14 @@ def mask_sample_indices(n_coord, n_segments):
     return hit
 
 
-def steps_from_centroids(centroids_yx):
-    """`steps` of `_get_mask_centroids`: mean |centroid - nearest other centroid| per axis (z, y, x)."""
+def steps_from_centroids(centroids_yx, closest=None):
+    """`steps` of `_get_mask_centroids`: mean |centroid - nearest other centroid| per axis (z, y, x).
+
+    `closest`: index of the nearest other centroid when the caller already has it (device search).
+    """
     c = np.concatenate([np.zeros((len(centroids_yx), 1)), np.asarray(centroids_yx, dtype=np.float64)], axis=1)
+    if closest is not None and len(c) > 1:
+        return np.abs(c - c[np.asarray(closest, dtype=np.int64), :]).mean(0)
     if len(c) > 1:
         if len(c) <= 2048:
             from scipy.spatial.distance import pdist, squareform

@@ -249,6 +249,21 @@ def test_mask_centroids_bitexact_vs_scipy(n):
     np.testing.assert_array_equal(steps, want_steps)
 
 
+@pytest.mark.parametrize("n", [1500, 2600])
+def test_mask_centroids_grid_search_bitexact_vs_scipy(n):
+    """More than 1024 centroids: the grid-accelerated nearest-centroid search (k-means sweeps, and
+    beyond 2048 centroids the nearest-other-centroid steps) equals scipy's brute force bit for bit."""
+    import slic_oracle as so
+    from obia_b200 import pipeline
+    yy, xx = np.mgrid[:420, :510]
+    mask = (((yy - 200) ** 2 / 190.0 ** 2 + (xx - 260) ** 2 / 240.0 ** 2) < 1.0) & ((yy * 3 + xx) % 11 != 0)
+    mask[100:140, 200:330] = False                       # a hole: empty grid cells inside the support
+    want_c, want_steps = so._get_mask_centroids(mask[np.newaxis].astype(np.uint8), n, True)
+    yx, steps = pipeline.mask_centroids_device(_cuda(mask.astype(np.uint8)), n)
+    np.testing.assert_array_equal(yx, want_c[:, 1:])
+    np.testing.assert_array_equal(steps, want_steps)
+
+
 def test_slic_masked_agreement():
     import slic_oracle as so
     from obia_b200 import pipeline
