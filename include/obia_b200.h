@@ -172,7 +172,8 @@ int obia_b200_slic_iterate(const float *features, const uint8_t *mask,
                            int64_t n, float step, int32_t step_y,
                            int32_t step_x, int32_t max_num_iter,
                            int32_t start_label, int32_t ignore_color,
-                           double fix_scale, int32_t *status, void *stream);
+                           int32_t slic_zero, double fix_scale, int32_t *status,
+                           void *stream);
 
 /* The same iteration, one sweep at a time, for a raster sharded by ROW STRIPS across GPUs (global
  * multi-GPU SLIC): `features`/`mask`/`labels` hold the strip [y_offset, y_offset + H) of a raster with
@@ -189,11 +190,21 @@ int obia_b200_slic_begin(int32_t *labels, void *workspace, int64_t H, int64_t W,
 int obia_b200_slic_sweep(const float *features, const uint8_t *mask, const float *centres,
                          int32_t *labels, void *workspace, int64_t H, int64_t W, int64_t pitch,
                          int32_t Cf, int64_t n, float step, int32_t step_y, int32_t step_x,
-                         int32_t start_label, int32_t ignore_color, double fix_scale,
-                         int64_t y_offset, int64_t H_total, int32_t *status, void *stream);
+                         int32_t start_label, int32_t ignore_color, int32_t slic_zero,
+                         double fix_scale, int64_t y_offset, int64_t H_total, int32_t *status,
+                         void *stream);
 int obia_b200_slic_finish_sweep(float *centres, void *workspace, int64_t H_total, int64_t W,
                                 int32_t Cf, int64_t n, int32_t step_y, int32_t step_x,
                                 double fix_scale, void *stream);
+/* slic_zero (SLICO, `_slic.pyx` "update the color distance maxima"): with slic_zero != 0 a sweep
+ * divides every colour distance by the centre's running maximum (initialised to 1 by slic_begin);
+ * after finish_sweep this call raises each centre's maximum to the largest colour distance of the
+ * pixels currently assigned to it.  Sharded runs take the element-wise maximum of the float table
+ * (the last n floats of the workspace) over the strips. */
+int obia_b200_slic_update_max_color(const float *features, const uint8_t *mask, const float *centres,
+                                    const int32_t *labels, void *workspace, int64_t H, int64_t W,
+                                    int64_t H_total, int64_t pitch, int32_t Cf, int64_t n,
+                                    int32_t step_y, int32_t step_x, int32_t start_label, void *stream);
 
 /* ---------------------------------------------------------------- K3 ----
  * Enforce connectivity: replaces Cython `_enforce_label_connectivity_cython`

@@ -32,6 +32,7 @@ struct SlicWs {
     unsigned long long *acc;  // [n][3+Cf] count, sum y, sum x, fixed-point colour sums
     int32_t *head;            // [ncy*ncx] cell -> first centre
     int32_t *next;            // [n]
+    float *maxdc;             // [n] SLICO: largest colour distance seen per centre (slic_zero)
     int64_t ncy, ncx;
     int64_t bytes;
 };
@@ -48,6 +49,8 @@ static SlicWs slic_ws_layout(void *base, int64_t H, int64_t W, int Cf, int64_t n
     w.head = (int32_t *)(p + off);
     off += round_up(w.ncy * w.ncx * 4, 256);
     w.next = (int32_t *)(p + off);
+    off += round_up(n * 4, 256);
+    w.maxdc = (float *)(p + off);
     off += round_up(n * 4, 256);
     w.bytes = off;
     return w;
@@ -132,11 +135,11 @@ __device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
 // contracted).  CHECK = per-pixel window test (skipped when the whole warp strip is inside).
 // Candidate slots are sorted by centre index and visited in ascending order, so a strict
 // "less than" update is exactly the reference's rule (lowest k wins exact ties).
-template <int CP, int PX, bool CHECK>
+template <int CP, int PX, bool CHECK, bool SZ>
 __device__ __forceinline__ void eval_candidate(const u64 (&px2)[(PX + 1) / 2][CP], const float (&px1)[CP],
                                                const u64 (&nx2)[(PX + 1) / 2], float nx1, float fy,
                                                float cy, float cx, const int4 w,
-                                               const float *__restrict__ nf, float spatial_weight,
+                                               const float *__restrict__ nf, float mdc, float spatial_weight,
                                                int ignore_color, int y, int xb, int slot,
                                                float (&best)[PX], int (&bests)[PX])
 {
@@ -165,6 +168,11 @@ __device__ __forceinline__ void eval_candidate(const u64 (&px2)[(PX + 1) / 2][CP
                     const u64 t2 = add2(px2[p][c], pack2(m, m));
                     acc = fma2(t2, t2, acc);
                 }
+                if (SZ) {   // SLICO: colour distance relative to the centre's running maximum
+                    float a0, a1;
+                    unpack2(acc, a0, a1);
+                    acc = pack2(__fdiv_rn(a0, mdc), __fdiv_rn(a1, mdc));
+                }
                 d2 = add2(d2, acc);
             }
             float d[2];
@@ -189,6 +197,7 @@ __device__ __forceinline__ void eval_candidate(const u64 (&px2)[(PX + 1) / 2][CP
                 const float t = __fadd_rn(px1[c], nf[c]);
                 acc = __fmaf_rn(t, t, acc);
             }
+            if (SZ) acc = __fdiv_rn(acc, mdc);
             d = __fadd_rn(d, acc);
         }
         const bool v = !CHECK || (unsigned)(0 - lo) < (unsigned)span;
@@ -210,10 +219,11 @@ template <int CP> struct Traits {
 // Warp strip: 16 pixels wide x (32 / (16/PX)) rows; a CTA tile is 2 x 4 strips (32 px wide) times
 // NS vertical phases: the candidate list, its sort, the centre records and the tile accumulators
 // are set up once and reused by NS strips per warp, which amortises the latency-bound set-up.
-template <int CP, int PX, int NS>
+template <int CP, int PX, int NS, bool SZ>
 __global__ void __launch_bounds__(kWarps * 32, (CP <= 16) ? 3 : 1)
 slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restrict__ mask,
-                          const float *__restrict__ centres, const int32_t *__restrict__ head,
+                          const float *__restrict__ centres, const float *__restrict__ maxdc,
+                          const int32_t *__restrict__ head,
                           const int32_t *__restrict__ next, int32_t *__restrict__ labels,
                           unsigned long long *__restrict__ acc, int H, int W, int64_t pitch, int Cf,
                           float spatial_weight, int step_y, int step_x, int ncy, int ncx,
@@ -237,6 +247,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     __shared__ int4 s_win[kChk];
     __shared__ float2 s_cyx[kChk];
     __shared__ __align__(16) float s_nf[kChk][CP];  // negated centre colours
+    __shared__ float s_mdc[SZ ? kChk : 1];          // SLICO colour-distance maxima
     __shared__ int s_acc[kAcc][NF];
     __shared__ __align__(16) int s_rec[kRec][NF + 1];
 
@@ -364,6 +375,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
                 w.z = trunc_i((0.0f > xlo) ? 0.0f : xlo);
                 w.w = trunc_i(((float)W < xhi) ? (float)W : xhi);
                 s_win[s] = w;
+                if (SZ) s_mdc[s] = maxdc[k];
             } else if (f >= 2) {
                 const int c = f - 2;
                 s_nf[s][c] = (c < Cf) ? -rec[2 + c] : 0.0f;
@@ -408,8 +420,8 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
                 ts[j] = -1;
             }
             const float2 c = s_cyx[s];
-            eval_candidate<CP, PX, true>(px2, px1, nx2, nx1, fy, c.x, c.y, s_win[s], s_nf[s], spatial_weight,
-                                         ignore_color, yg, xb, 0, tb, ts);
+            eval_candidate<CP, PX, true, SZ>(px2, px1, nx2, nx1, fy, c.x, c.y, s_win[s], s_nf[s],
+                                             SZ ? s_mdc[s] : 1.0f, spatial_weight, ignore_color, yg, xb, 0, tb, ts);
             float m = tb[0];
 #pragma unroll
             for (int j = 1; j < PX; ++j) m = fmaxf(m, tb[j]);
@@ -427,12 +439,13 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
                 const float2 c = s_cyx[s];
                 const int4 w = s_win[s];
                 const bool full = w.x <= wy0 && w.y > wy1 && w.z <= wx0 && w.w > wx1;
+                const float mdc = SZ ? s_mdc[s] : 1.0f;
                 if (full)
-                    eval_candidate<CP, PX, false>(px2, px1, nx2, nx1, fy, c.x, c.y, w, s_nf[s], spatial_weight,
-                                                  ignore_color, yg, xb, c0 + s, best, bests);
+                    eval_candidate<CP, PX, false, SZ>(px2, px1, nx2, nx1, fy, c.x, c.y, w, s_nf[s], mdc,
+                                                      spatial_weight, ignore_color, yg, xb, c0 + s, best, bests);
                 else
-                    eval_candidate<CP, PX, true>(px2, px1, nx2, nx1, fy, c.x, c.y, w, s_nf[s], spatial_weight,
-                                                 ignore_color, yg, xb, c0 + s, best, bests);
+                    eval_candidate<CP, PX, true, SZ>(px2, px1, nx2, nx1, fy, c.x, c.y, w, s_nf[s], mdc,
+                                                     spatial_weight, ignore_color, yg, xb, c0 + s, best, bests);
             }
         }
     }
@@ -556,7 +569,8 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
 }
 
 template <int CP, int PX, int NS>
-static int launch_assign(const float *feat, const uint8_t *mask, const float *centres, const SlicWs &w,
+static int launch_assign(const float *feat, const uint8_t *mask, const float *centres, int slic_zero,
+                         const SlicWs &w,
                          int32_t *labels, int64_t H, int64_t W, int64_t pitch, int Cf, float sw,
                          int step_y, int step_x, int start_label, int ignore_color, double fix_scale,
                          int32_t *status, int y_off, int64_t Hg, cudaStream_t st)
@@ -574,9 +588,14 @@ static int launch_assign(const float *feat, const uint8_t *mask, const float *ce
     const long long fix_ratio = 1LL << (42 - bits_px + lg_ns);
     dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, NS * 4 * (32 / (16 / PX))));
     prof_begin(st);
-    slic_assign_update_kernel<CP, PX, NS><<<grid, kWarps * 32, 0, st>>>(
-        feat, mask, centres, w.head, w.next, labels, w.acc, (int)H, (int)W, pitch, Cf, sw, step_y, step_x,
-        (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, fix_scale32, fix_ratio, status, y_off, (int)Hg);
+    if (slic_zero)
+        slic_assign_update_kernel<CP, PX, NS, true><<<grid, kWarps * 32, 0, st>>>(
+            feat, mask, centres, w.maxdc, w.head, w.next, labels, w.acc, (int)H, (int)W, pitch, Cf, sw, step_y, step_x,
+            (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, fix_scale32, fix_ratio, status, y_off, (int)Hg);
+    else
+        slic_assign_update_kernel<CP, PX, NS, false><<<grid, kWarps * 32, 0, st>>>(
+            feat, mask, centres, w.maxdc, w.head, w.next, labels, w.acc, (int)H, (int)W, pitch, Cf, sw, step_y, step_x,
+            (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, fix_scale32, fix_ratio, status, y_off, (int)Hg);
     prof_end(st);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
@@ -587,6 +606,37 @@ __global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) p[i] = v;
+}
+
+// SLICO (slic_zero): after the centres of a sweep are known, every pixel's colour distance to its
+// own (new) centre raises that centre's running maximum (_slic.pyx "update the color distance
+// maxima").  Distances are non-negative floats, so an unsigned atomicMax on the bit pattern is the
+// float maximum; max is order-free, hence deterministic.
+__global__ void __launch_bounds__(256)
+slic_max_color_kernel(const float *__restrict__ feat, const uint8_t *__restrict__ mask,
+                      const float *__restrict__ centres, const int32_t *__restrict__ labels,
+                      float *maxdc, int H, int W, int64_t pitch, int Cf, int64_t n, int start_label)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)H * W) return;
+    if (mask && !mask[i]) return;
+    const int k = labels[i] - start_label;
+    if (k < 0 || k >= n) return;
+    const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+    const float *c = centres + (int64_t)k * (2 + Cf) + 2;
+    const float *f = feat + (int64_t)y * pitch + x;
+    float acc = 0.0f;
+    for (int ch = 0; ch < Cf; ++ch) {
+        const float t = __fsub_rn(f[(int64_t)ch * H * pitch], c[ch]);
+        acc = __fmaf_rn(t, t, acc);   // same contraction as the assignment kernel
+    }
+    if (acc == acc && acc > maxdc[k]) atomicMax(reinterpret_cast<unsigned *>(maxdc + k), __float_as_uint(acc));
+}
+
+__global__ void fill_f32_kernel(float *p, int64_t n, float v)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 }  // namespace obia
@@ -630,14 +680,17 @@ extern "C" int obia_b200_slic_begin(int32_t *labels, void *workspace, int64_t H,
     OBIA_CUDA_CHECK(cudaMemsetAsync(w.acc, 0, (size_t)n * (3 + Cf) * 8, st));
     fill_i32_kernel<<<kNumSMs * 4, 256, 0, st>>>(labels, H * W, start_label - 1);
     OBIA_LAUNCH_CHECK();
+    fill_f32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(w.maxdc, n, 1.0f);   // np.ones(n_segments)
+    OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
 }
 
 extern "C" int obia_b200_slic_sweep(const float *features, const uint8_t *mask, const float *centres,
                                     int32_t *labels, void *workspace, int64_t H, int64_t W, int64_t pitch,
                                     int32_t Cf, int64_t n, float step, int32_t step_y, int32_t step_x,
-                                    int32_t start_label, int32_t ignore_color, double fix_scale,
-                                    int64_t y_offset, int64_t H_total, int32_t *status, void *stream)
+                                    int32_t start_label, int32_t ignore_color, int32_t slic_zero,
+                                    double fix_scale, int64_t y_offset, int64_t H_total, int32_t *status,
+                                    void *stream)
 {
     int rc = slic_check_args(features, centres, labels, workspace, status, H, W, pitch, Cf, n, step, step_y, step_x,
                              start_label, fix_scale);
@@ -654,19 +707,19 @@ extern "C" int obia_b200_slic_sweep(const float *features, const uint8_t *mask, 
     OBIA_LAUNCH_CHECK();
     const int yo = (int)y_offset;
     if (Cf <= 4)
-        rc = launch_assign<4, 4, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+        rc = launch_assign<4, 4, OBIA_NS>(features, mask, centres, slic_zero, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                           start_label, ignore_color, fix_scale, status, yo, H_total, st);
     else if (Cf <= 8)
-        rc = launch_assign<8, 4, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+        rc = launch_assign<8, 4, OBIA_NS>(features, mask, centres, slic_zero, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                           start_label, ignore_color, fix_scale, status, yo, H_total, st);
     else if (Cf <= 16)
-        rc = launch_assign<16, 2, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+        rc = launch_assign<16, 2, OBIA_NS>(features, mask, centres, slic_zero, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                            start_label, ignore_color, fix_scale, status, yo, H_total, st);
     else if (Cf <= 32)
-        rc = launch_assign<32, 2, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+        rc = launch_assign<32, 2, OBIA_NS>(features, mask, centres, slic_zero, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                            start_label, ignore_color, fix_scale, status, yo, H_total, st);
     else
-        rc = launch_assign<64, 2, OBIA_NS>(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
+        rc = launch_assign<64, 2, OBIA_NS>(features, mask, centres, slic_zero, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                            start_label, ignore_color, fix_scale, status, yo, H_total, st);
     return rc;
 }
@@ -687,12 +740,28 @@ extern "C" int obia_b200_slic_finish_sweep(float *centres, void *workspace, int6
     return OBIA_B200_OK;
 }
 
+extern "C" int obia_b200_slic_update_max_color(const float *features, const uint8_t *mask, const float *centres,
+                                               const int32_t *labels, void *workspace, int64_t H, int64_t W,
+                                               int64_t H_total, int64_t pitch, int32_t Cf, int64_t n,
+                                               int32_t step_y, int32_t step_x, int32_t start_label, void *stream)
+{
+    if (!features || !centres || !labels || !workspace || H <= 0 || W <= 0 || H_total < H || Cf <= 0 || n <= 0 ||
+        pitch < W)
+        return set_err(OBIA_B200_ERR_ARG, "slic_update_max_color: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    SlicWs w = slic_ws_layout(workspace, H_total, W, Cf, n, step_y, step_x);
+    slic_max_color_kernel<<<(unsigned)ceil_div(H * W, 256), 256, 0, st>>>(features, mask, centres, labels, w.maxdc,
+                                                                         (int)H, (int)W, pitch, Cf, n, start_label);
+    OBIA_LAUNCH_CHECK();
+    return OBIA_B200_OK;
+}
+
 extern "C" int obia_b200_slic_iterate(const float *features, const uint8_t *mask, float *centres,
                                       int32_t *labels, void *workspace, int64_t H, int64_t W,
                                       int64_t pitch, int32_t Cf, int64_t n, float step, int32_t step_y,
                                       int32_t step_x, int32_t max_num_iter, int32_t start_label,
-                                      int32_t ignore_color, double fix_scale, int32_t *status,
-                                      void *stream)
+                                      int32_t ignore_color, int32_t slic_zero, double fix_scale,
+                                      int32_t *status, void *stream)
 {
     int rc = slic_check_args(features, centres, labels, workspace, status, H, W, pitch, Cf, n, step, step_y, step_x,
                              start_label, fix_scale);
@@ -701,9 +770,12 @@ extern "C" int obia_b200_slic_iterate(const float *features, const uint8_t *mask
     rc = obia_b200_slic_begin(labels, workspace, H, W, H, Cf, n, step_y, step_x, start_label, status, stream);
     for (int it = 0; it < max_num_iter && !rc; ++it) {
         rc = obia_b200_slic_sweep(features, mask, centres, labels, workspace, H, W, pitch, Cf, n, step, step_y,
-                                  step_x, start_label, ignore_color, fix_scale, 0, H, status, stream);
+                                  step_x, start_label, ignore_color, slic_zero, fix_scale, 0, H, status, stream);
         // the reference updates the centres after every sweep, the last one included
         if (!rc) rc = obia_b200_slic_finish_sweep(centres, workspace, H, W, Cf, n, step_y, step_x, fix_scale, stream);
+        if (!rc && slic_zero)
+            rc = obia_b200_slic_update_max_color(features, mask, centres, labels, workspace, H, W, H, pitch, Cf, n,
+                                                 step_y, step_x, start_label, stream);
     }
     return rc;
 }

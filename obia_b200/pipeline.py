@@ -171,8 +171,6 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
     raw = _aligned(raw)
     if channel_axis not in (-1, 2):
         raise NotImplementedError("only channel_axis=-1 (obia always passes H, W, C)")
-    if slic_zero:
-        raise NotImplementedError("slic_zero=True (SLICO) is not implemented on the B200 path yet")
     if spacing is not None and tuple(float(s) for s in np.ravel(spacing)) not in ((1.0, 1.0), (1.0, 1.0, 1.0)):
         raise NotImplementedError("anisotropic `spacing` is not implemented on the B200 path")
     if start_label not in (0, 1):
@@ -289,8 +287,8 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
     def run(ignore_color):
         _lib.check(lib.obia_b200_slic_iterate(
             _p(feats), _p(mask_dev), _p(centres), _p(labels), _p(ws), H, W, pitch, Cf, n, step,
-            step_y, step_x, int(max_num_iter), int(start_label), int(ignore_color), fix_scale,
-            _p(status), _stream_ptr()), "slic_iterate")
+            step_y, step_x, int(max_num_iter), int(start_label), int(ignore_color), int(bool(slic_zero)),
+            fix_scale, _p(status), _stream_ptr()), "slic_iterate")
         if int(status[0].item()) != 0:
             raise _lib.ObiaB200Error("slic_iterate: a tile collected more than 1024 candidate centres "
                                      "(degenerate centre distribution)")

@@ -100,7 +100,7 @@ class ShardedSlic:
     def sweep(self):
         _lib.check(self.lib.obia_b200_slic_sweep(
             _p(self.feats), None, _p(self.centres), _p(self.labels), _p(self.ws), self.h, self.W, self.pitch, self.Cf,
-            self.n, self.step, self.step_y, self.step_x, self.start_label, 0, self.fix_scale, self.row0, self.H,
+            self.n, self.step, self.step_y, self.step_x, self.start_label, 0, 0, self.fix_scale, self.row0, self.H,
             _p(self.status), _stream_ptr()), "slic_sweep")
 
     def acc(self):

@@ -34,7 +34,7 @@ def to_planar(features_hwc):
     return t, pitch
 
 
-def run_slic_iterate(features_hwc, mask, centres_yxc, step, iters, start_label=1, ignore_color=False,
+def run_slic_iterate(features_hwc, mask, centres_yxc, step, iters, start_label=1, ignore_color=False, slic_zero=False,
                      fix_scale=None):
     """Run obia_b200_slic_iterate on oracle-prepared features/centres.
 
@@ -55,7 +55,7 @@ def run_slic_iterate(features_hwc, mask, centres_yxc, step, iters, start_label=1
     p = pipeline._p
     _lib.check(lib.obia_b200_slic_iterate(p(feats), p(mask_t), p(centres), p(labels), p(ws), H, W, pitch, C, n,
                                           float(step), step_y, step_x, int(iters), int(start_label),
-                                          int(ignore_color), float(fix_scale), p(status),
+                                          int(ignore_color), int(slic_zero), float(fix_scale), p(status),
                                           pipeline._stream_ptr()), "slic_iterate")
     torch.cuda.synchronize()
     assert int(status[0].item()) == 0

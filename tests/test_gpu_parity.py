@@ -168,6 +168,8 @@ def _agreement(a, b):
     (180, 220, 8, 120, 0.05, dict(max_num_iter=5)),
     (150, 150, 6, 80, 0.2, dict(start_label=0, min_size_factor=0.3)),
     (120, 160, 3, 60, 5.0, dict(sigma=1.0)),
+    (200, 260, 5, 130, 0.5, dict(slic_zero=True)),                      # SLICO
+    (160, 160, 3, 70, 10.0, dict(slic_zero=True, max_num_iter=6)),      # SLICO on the Lab path
 ])
 def test_slic_full_agreement(H, W, C, n, compactness, kw):
     """Whole create_segments path vs the oracle: >= 99.5 % identical labels."""
@@ -186,6 +188,34 @@ def test_slic_full_agreement(H, W, C, n, compactness, kw):
         agree = _agreement(got, want)
         print(f"fma={fma} agreement {agree:.5f} labels gpu={res.n_labels} oracle={want.max()}")
         assert agree >= 0.995
+
+
+def test_slic_zero_pre_connectivity_and_masked():
+    """SLICO (slic_zero=True): the assignment before connectivity agrees with the oracle pixel for
+    pixel (>= 99.5 %), also with a mask (maskSLIC runs its spatial-only pass first)."""
+    import slic_oracle as so
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    H, W, C, n = 150, 190, 4, 90
+    raw = synth_raster(H, W, C, seed=17)
+    yy, xx = np.mgrid[:H, :W]
+    mask = ((yy - 70) ** 2 / 65.0 ** 2 + (xx - 95) ** 2 / 90.0 ** 2) < 1.0
+    for m in (None, mask):
+        res = pipeline.slic_labels(_cuda(raw), None, n_segments=n, compactness=0.3, slic_zero=True,
+                                   enforce_connectivity=False, mask=None if m is None else _cuda(m))
+        so.USE_FMA = True
+        try:
+            want = so.create_segments_labels(raw.copy(), None, n_segments=n, compactness=0.3, slic_zero=True,
+                                             enforce_connectivity=False, mask=m)
+        finally:
+            so.USE_FMA = False
+        got = res.labels.cpu().numpy()
+        agree = float((got == want).mean())
+        assert agree >= 0.995, agree
+        # and it is a different segmentation from plain SLIC (the mode is really on)
+        plain = pipeline.slic_labels(_cuda(raw), None, n_segments=n, compactness=0.3, enforce_connectivity=False,
+                                     mask=None if m is None else _cuda(m)).labels.cpu().numpy()
+        assert float((plain == got).mean()) < 0.999
 
 
 def test_slic_readme_quickstart_shape():
