@@ -66,9 +66,10 @@ struct TexSmem {                       // fixed-size part of the dynamic shared 
 // publish them, clear the histogram by replaying the pairs.  STAGED crops (<= kTile pixels, levels
 // in shared memory) keep every per-thread and per-warp sum in 32 bits.
 template <bool WIDE, bool STAGED, int NW, typename LevelFn>
-__device__ __forceinline__ void band_passes(unsigned *hist, TexSmem &S, int b, int h, int w, int warp, int lane,
-                                            int tid, LevelFn level)
+__device__ __forceinline__ void band_passes(unsigned *hist, TexSmem &S, unsigned short *clr, int b, int h, int w,
+                                            int warp, int lane, int tid, LevelFn level)
 {
+    constexpr int NT = NW * 32;
     using acc_t = typename std::conditional<STAGED, unsigned, unsigned long long>::type;
 #pragma unroll 1
     for (int a = 0; a < 4; ++a) {
@@ -95,6 +96,8 @@ __device__ __forceinline__ void band_passes(unsigned *hist, TexSmem &S, int b, i
                 } else {
                     const int sft = (bin & 1) * 16;
                     old = (atomicAdd(&hist[bin >> 1], 1u << sft) >> sft) & 0xffffu;
+                    // staged crops remember the touched word: clearing needs no second look at the levels
+                    if (STAGED) clr[r * ncw + (c - c_lo)] = (unsigned short)(bin >> 1);
                 }
                 if (d == 0)
                     sdiag += (acc_t)2 * old + 1;
@@ -136,14 +139,19 @@ __device__ __forceinline__ void band_passes(unsigned *hist, TexSmem &S, int b, i
             for (int i = 0; i < NW; ++i) t += __longlong_as_double((long long)S.red[i][7]);
             S.sums[b][a][7] = (unsigned long long)__double_as_longlong(t);
         }
-        // clear the histogram by replaying the pairs (all non-zero words were touched)
-        for (int r = warp; r < nr; r += NW)
-            for (int c = c_lo + lane; c < c_lo + ncw; c += 32) {
-                const int i = level(r, c), j = level(r + dr, c + dc);
-                const int lo = min(i, j), hi = max(i, j);
-                const int bin = hi * (hi + 1) / 2 + lo;
-                hist[WIDE ? bin : (bin >> 1)] = 0u;
-            }
+        // clear the histogram: all non-zero words were touched by this angle's pairs
+        if (STAGED) {
+            const int npairs = (nr > 0 && ncw > 0) ? nr * ncw : 0;
+            for (int t = tid; t < npairs; t += NT) hist[clr[t]] = 0u;
+        } else {
+            for (int r = warp; r < nr; r += NW)
+                for (int c = c_lo + lane; c < c_lo + ncw; c += 32) {
+                    const int i = level(r, c), j = level(r + dr, c + dc);
+                    const int lo = min(i, j), hi = max(i, j);
+                    const int bin = hi * (hi + 1) / 2 + lo;
+                    hist[WIDE ? bin : (bin >> 1)] = 0u;
+                }
+        }
         __syncthreads();   // histogram clean, S.red free
     }
 }
@@ -159,6 +167,7 @@ texture_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw
     unsigned *hist = reinterpret_cast<unsigned *>(smem);
     TexSmem &S = *reinterpret_cast<TexSmem *>(smem + (size_t)kHistWords * 4);
     unsigned char *tiles = smem + (size_t)kHistWords * 4 + sizeof(TexSmem);   // [kBC][kTile], 16-bit launch only
+    unsigned short *clr = reinterpret_cast<unsigned short *>(tiles + (size_t)kBC * kTile);   // [kTile] touched words
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < kHistWords; i += NT) hist[i] = 0u;
@@ -268,12 +277,12 @@ texture_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw
                 if (!((any_bands >> b) & 1u)) continue;   // no valid sample: NaN features (:217-231)
                 if (staged) {
                     const unsigned char *tile = tiles + b * kTile;
-                    band_passes<WIDE, true, NW>(hist, S, b, h, w, warp, lane, tid,
+                    band_passes<WIDE, true, NW>(hist, S, clr, b, h, w, warp, lane, tid,
                                                 [&](int r, int c) -> int { return tile[r * w + c]; });
                 } else {
                     const int band = tb.band[k0 + b];
                     const float lo_v = S.mn[b], hi_v = S.mx[b];
-                    band_passes<WIDE, false, NW>(hist, S, b, h, w, warp, lane, tid, [&](int r, int c) -> int {
+                    band_passes<WIDE, false, NW>(hist, S, clr, b, h, w, warp, lane, tid, [&](int r, int c) -> int {
                         const int64_t p = (int64_t)(y0 + r) * W + (x0 + c);
                         float v = (labels[p] == lab) ? raw[p * C + band] : 0.0f;
                         if (!(v == v)) v = 0.0f;
@@ -332,7 +341,7 @@ texture_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw
 template <bool WIDE, int NT> static size_t texture_smem_bytes()
 {
     const size_t hist_words = WIDE ? kBins : (kBins + 1) / 2;
-    return hist_words * 4 + sizeof(TexSmem) + (WIDE ? 16 : (size_t)kBC * kTile);
+    return hist_words * 4 + sizeof(TexSmem) + (WIDE ? 16 : (size_t)kBC * kTile + (size_t)kTile * 2);
 }
 
 }  // namespace obia
