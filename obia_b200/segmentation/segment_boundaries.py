@@ -12,9 +12,11 @@ What differs, on purpose (DESIGN.md "boundary"):
     the reference's columns (`geometry`, `segment_id`) and row order (ascending
     label, one row per 4-connected region, `segment_id = 1..N`) and carries the
     label raster as `.label_raster`.  Polygon geometries are materialised on
-    the host only on request (`polygonize=True`, needs shapely) -- the
+    the host only on request (`polygonize=True`): one vectorised outline
+    trace of the whole label raster (utils/polygonize.py; shapely Polygons
+    when shapely is installed, `SimplePolygon` otherwise) instead of the
     reference's per-label full-raster `rasterio.features.shapes` loop
-    (:62-70) is O(n_segments * H * W) and is not on the GPU path.
+    (:62-70), which is O(n_segments * H * W).
   * the reference prints the shape of the band stack (:46); this does not.
 """
 from __future__ import annotations
@@ -158,7 +160,7 @@ def create_segments(image, segmentation_bands=None, method="slic", *, mutate_ima
     :param segmentation_bands: band indices used for segmentation (None = all).
     :param method: 'slic' (the GPU hot path).  'quickshift' is not implemented.
     :param mutate_image: reproduce the reference's in-place normalisation of `image.img_data`.
-    :param polygonize: also build shapely polygons on the host (slow, optional).
+    :param polygonize: also build the polygon geometries on the host (optional; utils/polygonize.py).
     :param kwargs: skimage.segmentation.slic keyword arguments.
     :return: SegmentsFrame with columns `geometry`, `segment_id`.
     """

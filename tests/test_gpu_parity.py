@@ -539,6 +539,26 @@ def test_segment_end_to_end_columns_and_values():
     assert seg.segments[["pai", "fhd", "ch", "mean_intensity", "variance_intensity"]].isna().all().all()
 
 
+def test_create_segments_polygonize():
+    """polygonize=True: one polygon per table row, in row order, whose area is the segment's pixel
+    count and whose bounds are the segment's bounding box under the raster's affine transform."""
+    from obia_b200.handlers.geotif import Image
+    from obia_b200.segmentation.segment_boundaries import create_segments
+    from gpu_helpers import synth_raster
+    raw = synth_raster(90, 120, 4, seed=9)
+    aff = [2.0, 0.0, 0.0, -2.0, 1000.0, 5000.0]
+    seg = create_segments(Image(raw.copy(), "EPSG:32702", aff, None, None), n_segments=40, compactness=0.3,
+                          polygonize=True)
+    labels = seg.label_raster.cpu().numpy()
+    rows = np.asarray(seg.segment_labels)
+    assert len(seg) == len(rows) and seg["geometry"].notna().all()
+    for v, g in zip(rows, seg["geometry"]):
+        ys, xs = np.nonzero(labels == v)
+        assert g.area == 4.0 * ys.size                                    # 2 x 2 map units per pixel
+        assert tuple(g.bounds) == (1000.0 + 2 * xs.min(), 5000.0 - 2 * (ys.max() + 1),
+                                   1000.0 + 2 * (xs.max() + 1), 5000.0 - 2 * ys.min())
+
+
 def test_image_mutation_into_pinned_host_memory():
     """Page-locked img_data is normalised by a kernel writing straight into host memory
     (obia_b200_normalize_to); the result is bit-identical to numpy's normalize_band."""
