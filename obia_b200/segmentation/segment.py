@@ -43,10 +43,12 @@ class Segments:
         return fromarray((img * 255).astype(np.uint8))
 
     def write_segments(self, file_path):
-        if hasattr(self.segments, "to_file"):
-            self.segments.to_file(file_path)
-        else:
-            raise NotImplementedError("writing a GeoPackage needs geopandas (host step outside the GPU path)")
+        """segment.py:55-60.  Geometries are traced from the label raster on first use."""
+        if any(g is None for g in self.segments["geometry"]):
+            image_affine = getattr(self._segments, "affine_transformation", None)
+            self._segments.materialize_geometry(image_affine)
+            self.segments["geometry"] = self._segments["geometry"].to_numpy()
+        self.segments.to_file(file_path)
 
 
 def segment(image, segmentation_bands=None, statistics_bands=None,

@@ -33,11 +33,59 @@ class SegmentsFrame(pd.DataFrame):
       segment_labels  int64 numpy array: label value of each row (row i <-> segment_id i+1)
       crs, transform  copied from the Image
     """
-    _metadata = ["label_raster", "segment_labels", "crs", "transform", "slic_result"]
+    _metadata = ["label_raster", "segment_labels", "crs", "transform", "slic_result", "affine_transformation",
+                 "_pending_mutation"]
 
     @property
     def _constructor(self):
         return SegmentsFrame
+
+    def materialize_geometry(self, affine_transformation=None):
+        """Fill the `geometry` column from the label raster (host step, utils/polygonize.py)."""
+        from ..utils.polygonize import polygons_from_labels
+        self["geometry"] = polygons_from_labels(self.label_raster.cpu().numpy(), self.segment_labels,
+                                                affine_transformation)
+        return self
+
+    def to_file(self, file_path, driver=None):
+        """`GeoDataFrame.to_file` of the reference (segment.py:55-60, tiling.py:289-291).
+
+        With geopandas + shapely installed the table is handed to geopandas (GeoPackage etc.).
+        Without them only GeoJSON can be written (pure Python): `.geojson` / `.json` paths, or
+        `driver="GeoJSON"`; other formats raise NotImplementedError naming the missing library.
+        """
+        import json
+        import os
+
+        geoms = list(self["geometry"])
+        if any(g is None for g in geoms):
+            raise ValueError("to_file needs polygon geometries: call create_segments(..., polygonize=True) "
+                             "or .materialize_geometry() first")
+        ext = os.path.splitext(str(file_path))[1].lower()
+        if driver is None:
+            driver = "GeoJSON" if ext in (".geojson", ".json") else None
+        if driver != "GeoJSON":
+            try:
+                import geopandas as gpd
+            except ImportError as e:
+                raise NotImplementedError("writing this format needs geopandas (GDAL); without it only "
+                                          "GeoJSON is supported") from e
+            gpd.GeoDataFrame(pd.DataFrame(self), geometry="geometry", crs=self.crs).to_file(file_path, driver=driver)
+            return
+        cols = [c for c in self.columns if c != "geometry"]
+        feats = []
+        for i, g in enumerate(geoms):
+            props = {}
+            for c in cols:
+                v = self[c].iloc[i]
+                v = v.item() if hasattr(v, "item") else v
+                props[c] = None if (isinstance(v, float) and v != v) else v
+            feats.append({"type": "Feature", "properties": props, "geometry": g.__geo_interface__})
+        doc = {"type": "FeatureCollection", "features": feats}
+        if self.crs:
+            doc["crs"] = {"type": "name", "properties": {"name": str(self.crs)}}
+        with open(file_path, "w") as f:
+            json.dump(doc, f)
 
 
 def normalize_band(band):
@@ -150,6 +198,7 @@ def frame_from_labels(labels, start_label, n_labels, connected, image=None, poly
     gdf.segment_labels = seg_labels if raster is labels else ids
     gdf.crs = None if image is None else _epsg_string(image.crs)
     gdf.transform = None if image is None else image.transform
+    gdf.affine_transformation = None if image is None else image.affine_transformation
     return gdf
 
 

@@ -559,6 +559,27 @@ def test_create_segments_polygonize():
                                    1000.0 + 2 * (xs.max() + 1), 5000.0 - 2 * ys.min())
 
 
+def test_write_segments_geojson(tmp_path):
+    """Segments.write_segments (segment.py:55-60): without geopandas the feature table is written as
+    GeoJSON, geometries traced from the label raster on first use."""
+    import json
+    from obia_b200.handlers.geotif import Image
+    from obia_b200.segmentation.segment import segment
+    from gpu_helpers import synth_raster
+    raw = synth_raster(64, 80, 3, seed=5, quantize=True)
+    seg = segment(Image(raw.copy(), "EPSG:32702", [1, 0, 0, -1, 100, 200], None, None), n_segments=20, compactness=10)
+    path = tmp_path / "segments.geojson"
+    seg.write_segments(str(path))
+    doc = json.loads(path.read_text())
+    assert doc["type"] == "FeatureCollection" and len(doc["features"]) == len(seg.segments)
+    f0 = doc["features"][0]
+    assert f0["geometry"]["type"] == "Polygon" and f0["properties"]["segment_id"] == 1
+    assert abs(f0["properties"]["b0_mean"] - float(seg.segments["b0_mean"].iloc[0])) < 1e-12
+    assert f0["properties"]["pai"] is None                       # NaN columns become null
+    with pytest.raises(NotImplementedError):
+        seg.write_segments(str(tmp_path / "segments.gpkg"))
+
+
 def test_image_mutation_into_pinned_host_memory():
     """Page-locked img_data is normalised by a kernel writing straight into host memory
     (obia_b200_normalize_to); the result is bit-identical to numpy's normalize_band."""
