@@ -339,11 +339,13 @@ def _as_device_raster(input_raster, device):
 def create_tiled_segments(input_raster, output_dir, input_mask=None,
                           method="slic", tile_size=200, buffer=30, crown_radius=5,
                           *, device=None, segment_tile=None, distributed=None, verbose=False,
-                          return_labels=True, **kwargs):
+                          return_labels=True, polygons=False, **kwargs):
     """
     :param input_raster: path (needs rasterio), `Image`, or an (H, W, C) array / tensor.
-    :param output_dir: directory for `segments.gpkg` (needs geopandas) or, without geopandas,
-        `segments_labels.npy`; None writes nothing.
+    :param output_dir: directory for `segments_labels.npy` (the label raster); None writes nothing.
+    :param polygons: also trace the segments into polygons on the host (single rank only) and write
+        `segments.gpkg` like the reference (tiling.py:289-291) when geopandas is installed, else
+        `segments.geojson` (columns `geometry`, `segment_id`).
     :param input_mask: path / array (H, W); non-zero = segment here.
     :param method: only 'slic' (ValueError otherwise, tiling.py:76-77).
     :param kwargs: forwarded to SLIC (`n_segments`, `compactness`, `max_num_iter`, ...).
@@ -383,6 +385,18 @@ def create_tiled_segments(input_raster, output_dir, input_mask=None,
         os.makedirs(output_dir, exist_ok=True)
         suffix = "" if world == 1 else f".rank{rank}"
         np.save(os.path.join(output_dir, f"segments_labels{suffix}.npy"), labels.cpu().numpy())
+        if polygons:
+            if world != 1:
+                raise NotImplementedError("polygons=True needs the whole label raster on one rank")
+            from ..segmentation.segment_boundaries import frame_from_labels
+            image = input_raster if hasattr(input_raster, "affine_transformation") else None
+            # one row per 4-connected region, ids 1..N in ascending label order (tiling.py:286-288)
+            frame = frame_from_labels(labels, 1, n, connected=False, image=image, polygonize=True)
+            try:
+                import geopandas  # noqa: F401
+                frame.to_file(os.path.join(output_dir, "segments.gpkg"), driver="GPKG")
+            except ImportError:
+                frame.to_file(os.path.join(output_dir, "segments.geojson"))
     if return_labels:
         return labels, n, cols
     return None

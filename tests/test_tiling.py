@@ -134,3 +134,27 @@ def test_gpu_tiled_driver_vs_oracle():
         assert ((got >= 0) == (want >= 0)).mean() >= 0.995
         assert abs(n2 - n1) <= max(2, 0.02 * n1)
         assert agree >= 0.97     # ids shift when one tile's count differs by one; coverage above is the hard check
+
+
+@pytest.mark.gpu
+def test_gpu_tiled_driver_writes_polygons(tmp_path):
+    """output_dir + polygons=True: the reference's `segments.gpkg` (here GeoJSON without geopandas)."""
+    import json
+    from gpu_helpers import synth_raster
+    H, W, C = 150, 170, 3
+    raw = synth_raster(H, W, C, seed=8)
+    mask = np.ones((H, W), bool)
+    mask[:20, :30] = False
+    labels, n, _ = create_tiled_segments(raw, str(tmp_path), mask, tile_size=60, buffer=10, crown_radius=4,
+                                         distributed=False, polygons=True, compactness=0.2)
+    saved = np.load(tmp_path / "segments_labels.npy")
+    np.testing.assert_array_equal(saved, labels.cpu().numpy())
+    doc = json.loads((tmp_path / "segments.geojson").read_text())
+    assert [f["properties"]["segment_id"] for f in doc["features"]] == list(range(1, len(doc["features"]) + 1))
+    assert len(doc["features"]) >= n                   # one row per 4-connected region
+    total = 0.0
+    for f in doc["features"]:
+        rings = [np.asarray(r) for r in f["geometry"]["coordinates"]]
+        area = [abs(0.5 * np.sum(r[:-1, 0] * r[1:, 1] - r[1:, 0] * r[:-1, 1])) for r in rings]
+        total += area[0] - sum(area[1:])
+    assert total == float((saved >= 0).sum())           # the polygons tile the segmented area exactly
