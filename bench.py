@@ -352,7 +352,7 @@ def run_ours(args):
 
     # ---- CPU baseline (bounded sample) ---------------------------------------------
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:      # reported at N=1 only (rank 0's host cores)
         size = args.cpu_size
         tot, t_slic, t_stats, nseg = cpu_oracle_step(size)
         cpu = {"value": size * size / 1e6 / tot, "unit": "MP/s", "cores": 1, "kind": "port",
