@@ -190,6 +190,34 @@ def test_slic_full_agreement(H, W, C, n, compactness, kw):
         assert agree >= 0.995
 
 
+def test_skimage_known_answers_through_the_cuda_path():
+    """scikit-image's own known-answer cases (test_slic.py::test_color_2d, ::test_color_2d_mask,
+    ::test_gray_2d_mask, as recalled in tests/test_oracle_slic.py) run through the CUDA pipeline.
+    The images already span [0, 1] per band, so obia's normalisation is the identity."""
+    from obia_b200 import pipeline
+    from test_oracle_slic import _mask_cases, check_mask_case
+    msk, cases = _mask_cases()
+    for img, kw, want in cases:
+        raw = np.ascontiguousarray(img, dtype=np.float32)
+        assert raw.min() == 0.0 and raw.max() == 1.0
+        res = pipeline.slic_labels(_cuda(raw), None, mask=_cuda(msk.astype(np.uint8)), **kw)
+        seg = res.labels.cpu().numpy().copy()
+        seg[seg == -1] = 0                      # obia marks masked pixels -1 (segment_boundaries.py:55-57)
+        check_mask_case(seg, want)
+    # unmasked colour quadrants, start_label=0 (test_color_2d)
+    rng = np.random.RandomState(0)
+    img = np.zeros((20, 21, 3))
+    img[:10, :10, 0] = 1
+    img[10:, :10, 1] = 1
+    img[10:, 10:, 2] = 1
+    img = np.clip(img + 0.01 * rng.normal(size=img.shape), 0, 1).astype(np.float32)
+    seg = pipeline.slic_labels(_cuda(img), None, n_segments=4, sigma=0, enforce_connectivity=False,
+                               start_label=0).labels.cpu().numpy()
+    assert len(np.unique(seg)) == 4
+    assert (seg[:10, :10] == 0).all() and (seg[10:, :10] == 2).all()
+    assert (seg[:10, 10:] == 1).all() and (seg[10:, 10:] == 3).all()
+
+
 def test_slic_zero_pre_connectivity_and_masked():
     """SLICO (slic_zero=True): the assignment before connectivity agrees with the oracle pixel for
     pixel (>= 99.5 %), also with a mask (maskSLIC runs its spatial-only pass first)."""
