@@ -216,6 +216,15 @@ def test_skimage_known_answers_through_the_cuda_path():
     assert len(np.unique(seg)) == 4
     assert (seg[:10, :10] == 0).all() and (seg[10:, :10] == 2).all()
     assert (seg[:10, 10:] == 1).all() and (seg[10:, 10:] == 3).all()
+    # test_slic_zero, test_multichannel_2d, test_more_segments_than_pixels, test_enforce_connectivity_mask
+    from test_oracle_slic import _more_cases
+    for name, img, m, kw, want in _more_cases():
+        raw = np.ascontiguousarray(img, dtype=np.float32)
+        assert raw.min() == 0.0 and raw.max() == 1.0, name
+        res = pipeline.slic_labels(_cuda(raw), None, mask=None if m is None else _cuda(m.astype(np.uint8)), **kw)
+        seg = res.labels.cpu().numpy().copy()
+        seg[seg == -1] = 0
+        np.testing.assert_array_equal(seg, want, err_msg=name)
 
 
 def test_slic_zero_pre_connectivity_and_masked():
