@@ -357,13 +357,13 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
         // the centre records are loaded once when they all fit (the usual case)
         const bool load_chunk = !(single_chunk && sp > 0);
         if (load_chunk) __syncthreads();  // previous chunk fully consumed; s_sorted complete
-        for (int i = tid; load_chunk && i < nc * (2 + CP); i += NT) {
-            const int s = i / (2 + CP), f = i % (2 + CP);
-            const int k = s_sorted[c0 + s];
-            const float *rec = centres + (int64_t)k * (2 + Cf);
-            if (f == 0) {
+        if (load_chunk) {
+            // positions and windows: one thread per candidate
+            for (int sI = tid; sI < nc; sI += NT) {
+                const int k = s_sorted[c0 + sI];
+                const float *rec = centres + (int64_t)k * (2 + Cf);
                 const float cy = rec[0], cx = rec[1];
-                s_cyx[s] = make_float2(cy, cx);
+                s_cyx[sI] = make_float2(cy, cx);
                 // windows exactly as the reference computes them (float32, then C cast)
                 const float ylo = __fsub_rn(cy, (float)(2 * step_y));
                 const float yhi = __fadd_rn(__fadd_rn(cy, (float)(2 * step_y)), 1.0f);
@@ -374,11 +374,28 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
                 w.y = trunc_i(((float)Hg < yhi) ? (float)Hg : yhi);
                 w.z = trunc_i((0.0f > xlo) ? 0.0f : xlo);
                 w.w = trunc_i(((float)W < xhi) ? (float)W : xhi);
-                s_win[s] = w;
-                if (SZ) s_mdc[s] = maxdc[k];
-            } else if (f >= 2) {
-                const int c = f - 2;
-                s_nf[s][c] = (c < Cf) ? -rec[2 + c] : 0.0f;
+                s_win[sI] = w;
+                if (SZ) s_mdc[sI] = maxdc[k];
+            }
+            // colours: batches of independent loads (the address depends on a shared-memory
+            // look-up, so the compiler does not overlap the round trips by itself)
+            constexpr int UN = (CP >= 32) ? 8 : 2;
+            for (int i0 = tid; i0 < nc * CP; i0 += NT * UN) {
+                float v[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int i = i0 + u * NT;
+                    v[u] = 0.0f;
+                    if (i < nc * CP) {
+                        const int sI = i / CP, c = i % CP;
+                        if (c < Cf) v[u] = centres[(int64_t)s_sorted[c0 + sI] * (2 + Cf) + 2 + c];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int i = i0 + u * NT;
+                    if (i < nc * CP) (&s_nf[0][0])[i] = -v[u];
+                }
             }
         }
         if (load_chunk) __syncthreads();
