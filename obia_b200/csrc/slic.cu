@@ -212,8 +212,8 @@ __device__ __forceinline__ void eval_candidate(const u64 (&px2)[(PX + 1) / 2][CP
 template <int CP> struct Traits {
     static constexpr int kIds = 1024;   // centre ids a tile can collect
     static constexpr int kChk = (CP <= 32) ? 64 : 32;       // centre records resident at once
-    static constexpr int kAcc = (CP <= 16) ? 128 : 32;      // slots with a tile accumulator row
-    static constexpr int kRec = (CP <= 4) ? 768 : (CP == 8) ? 640 : (CP == 16) ? 288 : (CP == 32) ? 128 : 64;
+    static constexpr int kAcc = (CP <= 16) ? 128 : 64;      // slots with a tile accumulator row
+    static constexpr int kRec = (CP <= 4) ? 768 : (CP == 8) ? 640 : (CP == 16) ? 288 : (CP == 32) ? 112 : 44;
 };
 
 // Warp strip: 16 pixels wide x (32 / (16/PX)) rows; a CTA tile is 2 x 4 strips (32 px wide) times
@@ -240,6 +240,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     constexpr int NF = 3 + CP;     // accumulator fields per slot (count, sum y, sum x, colours)
     constexpr int kIds = Traits<CP>::kIds, kChk = Traits<CP>::kChk, kAcc = Traits<CP>::kAcc,
                   kRec = Traits<CP>::kRec;
+    constexpr bool kRounds = CP >= 16;   // record pool smaller than a strip phase: several fold rounds
     constexpr int NT = kWarps * 32;
     __shared__ int s_ids[kIds];      // as collected
     __shared__ int s_sorted[kIds];   // ascending centre index
@@ -492,31 +493,6 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     // fixed point in shared memory; the tile then folds them into its per-slot accumulators
     // field-parallel (integer adds: independent of scheduling) and issues one RED.64 per touched
     // (centre, field).
-    auto emit = [&](int slot, int kcur, int cnt, int sxl, const float (&fs)[CP]) {
-        int ridx = kRec;
-        if (slot >= 0 && slot < kAcc) ridx = atomicAdd(&s_nrec, 1);
-        if (ridx < kRec) {
-            int *r = s_rec[ridx];
-            r[0] = slot;
-            r[1] = cnt;
-            r[2] = cnt * (y - ty0);
-            r[3] = sxl;
-#pragma unroll
-            for (int c = 0; c < CP; ++c) r[4 + c] = __float2int_rn(fs[c] * fix_scale32);
-        } else {
-            // no tile accumulator for this centre (or record pool full): add to HBM directly
-            unsigned long long *a = acc + (int64_t)kcur * (3 + Cf);
-            atomicAdd(&a[0], (unsigned long long)cnt);
-            atomicAdd(&a[1], (unsigned long long)((long long)cnt * yg));
-            atomicAdd(&a[2], (unsigned long long)((long long)sxl + (long long)cnt * tx0));
-#pragma unroll
-            for (int c = 0; c < CP; ++c)
-                // same 32-bit quantisation as the tile path, so the sum does not depend on which
-                // contributions took this route
-                if (c < Cf)
-                    atomicAdd(&a[3 + c], (unsigned long long)((long long)__float2int_rn(fs[c] * fix_scale32) * fix_ratio));
-        }
-    };
     auto px_val = [&](int j, int c) -> float {
         if constexpr (PX == 1) {
             return px1[c];
@@ -530,45 +506,110 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
 #pragma unroll
     for (int j = PX - 1; j >= 0; --j)
         if (((vmask >> j) & 1u) && bests[j] >= 0) lead = bests[j];
-    if (lead >= 0) {
-        int cnt = 0, sxl = 0;
+    // Contributions ("items") of this lane: item PX = the pixels that share the leading winner, summed
+    // in a fixed order; item j = pixel j on its own (another winner, or it kept its previous centre).
+    // place(): into the record pool if there is room, or straight to HBM when the item's centre has no
+    // tile accumulator; returns false when the pool is full and the item has to wait for the next round.
+    auto place = [&](int item, int kcur) -> bool {
+        int slot, cnt = 0, sxl = 0;
         float fs[CP];
+        if (item == PX) {
+            slot = lead;
 #pragma unroll
-        for (int c = 0; c < CP; ++c) fs[c] = 0.0f;
+            for (int c = 0; c < CP; ++c) fs[c] = 0.0f;
 #pragma unroll
-        for (int j = 0; j < PX; ++j) {
-            if (((vmask >> j) & 1u) && bests[j] == lead) {
-                cnt += 1;
-                sxl += xb + j - tx0;
+            for (int j = 0; j < PX; ++j) {
+                if (((vmask >> j) & 1u) && bests[j] == lead) {
+                    cnt += 1;
+                    sxl += xb + j - tx0;
 #pragma unroll
-                for (int c = 0; c < CP; ++c) fs[c] = __fadd_rn(fs[c], px_val(j, c));
+                    for (int c = 0; c < CP; ++c) fs[c] = __fadd_rn(fs[c], px_val(j, c));
+                }
             }
+        } else {
+            slot = bests[item];
+            cnt = 1;
+            sxl = xb + item - tx0;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) fs[c] = px_val(item, c);
         }
-        emit(lead, s_sorted[lead], cnt, sxl, fs);
-    }
+        if (slot >= 0 && slot < kAcc) {
+            const int ridx = atomicAdd(&s_nrec, 1);
+            if (ridx < kRec) {
+                int *r = s_rec[ridx];
+                r[0] = slot;
+                r[1] = cnt;
+                r[2] = cnt * (y - ty0);
+                r[3] = sxl;
 #pragma unroll
-    for (int j = 0; j < PX; ++j) {
-        if (!((vmask >> j) & 1u) || bests[j] == lead) continue;
-        int kcur = kk[j];
-        if (kcur < 0) kcur = labels[(int64_t)y * W + xb + j] - start_label;   // kept its previous centre
-        if (kcur < 0) continue;
-        float fs[CP];
+                for (int c = 0; c < CP; ++c) r[4 + c] = __float2int_rn(fs[c] * fix_scale32);
+                return true;
+            }
+            if (kRounds) return false;            // pool full: next round
+        }
+        // no tile accumulator for this centre (or, with few channels, the rare full pool): add to
+        // HBM directly, with the SAME 32-bit quantisation as the tile path, so the sum does not
+        // depend on which contributions took this route
+        unsigned long long *a = acc + (int64_t)kcur * (3 + Cf);
+        atomicAdd(&a[0], (unsigned long long)cnt);
+        atomicAdd(&a[1], (unsigned long long)((long long)cnt * yg));
+        atomicAdd(&a[2], (unsigned long long)((long long)sxl + (long long)cnt * tx0));
 #pragma unroll
-        for (int c = 0; c < CP; ++c) fs[c] = px_val(j, c);
-        emit(bests[j], kcur, 1, xb + j - tx0, fs);
-    }
-    __syncthreads();
-    {
+        for (int c = 0; c < CP; ++c)
+            if (c < Cf)
+                atomicAdd(&a[3 + c], (unsigned long long)((long long)__float2int_rn(fs[c] * fix_scale32) * fix_ratio));
+        return true;
+    };
+    auto fold = [&]() {
         const int nrec = min(s_nrec, kRec);
         for (int e = tid; e < nrec * NF; e += NT) {
             const int r = e / NF, f = e - r * NF;
             const int v = s_rec[r][1 + f];
             if (v != 0) atomicAdd(&s_acc[s_rec[r][0]][f], v);
         }
+    };
+    if constexpr (!kRounds) {
+        // few channels: the pool holds a whole strip phase
+        if (lead >= 0) place(PX, s_sorted[lead]);
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            if (!((vmask >> j) & 1u) || bests[j] == lead) continue;
+            int kcur = kk[j];
+            if (kcur < 0) kcur = labels[(int64_t)y * W + xb + j] - start_label;   // kept its previous centre
+            if (kcur < 0) continue;
+            place(j, kcur);
+        }
+        __syncthreads();
+        fold();
+        __syncthreads();
+        if (tid == 0) s_nrec = 0;
+        __syncthreads();
+    } else {
+        // many channels: the pool (shared memory) is small against a strip phase and a direct RED.64
+        // per field would dominate the kernel -> fill the pool, fold it, repeat while items are left
+        unsigned pending = (lead >= 0) ? (1u << PX) : 0u;
+        int kc[PX];
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            kc[j] = -1;
+            if (!((vmask >> j) & 1u) || bests[j] == lead) continue;
+            kc[j] = kk[j];
+            if (kc[j] < 0) kc[j] = labels[(int64_t)y * W + xb + j] - start_label;
+            if (kc[j] >= 0) pending |= 1u << j;
+        }
+        while (true) {
+            if (((pending >> PX) & 1u) && place(PX, s_sorted[lead])) pending &= ~(1u << PX);
+#pragma unroll
+            for (int j = 0; j < PX; ++j)
+                if (((pending >> j) & 1u) && place(j, kc[j])) pending &= ~(1u << j);
+            const int more = __syncthreads_or(pending != 0);
+            fold();
+            __syncthreads();
+            if (tid == 0) s_nrec = 0;
+            __syncthreads();
+            if (!more) break;
+        }
     }
-    __syncthreads();
-    if (tid == 0) s_nrec = 0;
-    __syncthreads();
     }   // strip phases
     const int nslots = min(nids, kAcc);
     for (int i = tid; i < nslots * (3 + Cf); i += NT) {
