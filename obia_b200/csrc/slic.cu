@@ -213,7 +213,10 @@ template <int CP> struct Traits {
     static constexpr int kIds = 1024;   // centre ids a tile can collect
     static constexpr int kChk = (CP <= 32) ? 64 : 32;       // centre records resident at once
     static constexpr int kAcc = (CP <= 16) ? 128 : 64;      // slots with a tile accumulator row
-    static constexpr int kRec = (CP <= 4) ? 768 : (CP == 8) ? 640 : (CP == 16) ? 288 : (CP == 32) ? 112 : 44;
+    static constexpr int kRec = (CP <= 4) ? 768 : (CP == 8) ? 640 : (CP == 16) ? 288 : 512;
+    // >= 32 channels run one CTA per SM (registers), so the record pool can live in dynamic shared
+    // memory beyond the 48 KB static limit and hold a whole strip phase
+    static constexpr bool kDynRec = CP >= 32;
 };
 
 // Warp strip: 16 pixels wide x (32 / (16/PX)) rows; a CTA tile is 2 x 4 strips (32 px wide) times
@@ -250,7 +253,9 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
     __shared__ __align__(16) float s_nf[kChk][CP];  // negated centre colours
     __shared__ float s_mdc[SZ ? kChk : 1];          // SLICO colour-distance maxima
     __shared__ int s_acc[kAcc][NF];
-    __shared__ __align__(16) int s_rec[kRec][NF + 1];
+    extern __shared__ __align__(16) int s_dyn[];
+    __shared__ __align__(16) int s_rec_static[Traits<CP>::kDynRec ? 1 : kRec][NF + 1];
+    int(*s_rec)[NF + 1] = Traits<CP>::kDynRec ? reinterpret_cast<int(*)[NF + 1]>(s_dyn) : s_rec_static;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * (TH * NS);
@@ -645,13 +650,20 @@ static int launch_assign(const float *feat, const uint8_t *mask, const float *ce
     const float fix_scale32 = (float)ldexp(fix_scale, bits_px - 42 - lg_ns);
     const long long fix_ratio = 1LL << (42 - bits_px + lg_ns);
     dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, NS * 4 * (32 / (16 / PX))));
+    constexpr size_t dyn = Traits<CP>::kDynRec ? (size_t)Traits<CP>::kRec * (3 + CP + 1) * sizeof(int) : 0;
+    if (dyn > 0) {
+        OBIA_CUDA_CHECK(cudaFuncSetAttribute(slic_assign_update_kernel<CP, PX, NS, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        OBIA_CUDA_CHECK(cudaFuncSetAttribute(slic_assign_update_kernel<CP, PX, NS, false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    }
     prof_begin(st);
     if (slic_zero)
-        slic_assign_update_kernel<CP, PX, NS, true><<<grid, kWarps * 32, 0, st>>>(
+        slic_assign_update_kernel<CP, PX, NS, true><<<grid, kWarps * 32, dyn, st>>>(
             feat, mask, centres, w.maxdc, w.head, w.next, labels, w.acc, (int)H, (int)W, pitch, Cf, sw, step_y, step_x,
             (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, fix_scale32, fix_ratio, status, y_off, (int)Hg);
     else
-        slic_assign_update_kernel<CP, PX, NS, false><<<grid, kWarps * 32, 0, st>>>(
+        slic_assign_update_kernel<CP, PX, NS, false><<<grid, kWarps * 32, dyn, st>>>(
             feat, mask, centres, w.maxdc, w.head, w.next, labels, w.acc, (int)H, (int)W, pitch, Cf, sw, step_y, step_x,
             (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, fix_scale32, fix_ratio, status, y_off, (int)Hg);
     prof_end(st);
