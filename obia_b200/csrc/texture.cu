@@ -35,7 +35,8 @@
 namespace obia {
 
 constexpr int kBins = 256 * 257 / 2;   // unordered level pairs
-constexpr int kTile = 2048;            // crop pixels staged in shared memory as uint8, per band
+constexpr int kTileBytes = 16384;       // shared memory for the staged uint8 levels of one band chunk
+constexpr int kTileMax = 4096;          // largest staged crop (pixels); 16384 / bands-in-chunk if smaller
 constexpr int kTexFields = 6;
 
 struct TexBands {
@@ -63,7 +64,7 @@ struct TexSmem {                       // fixed-size part of the dynamic shared 
 };
 
 // The four angle passes of one band: accumulate the pair sums (and the multiplicity histogram),
-// publish them, clear the histogram by replaying the pairs.  STAGED crops (<= kTile pixels, levels
+// publish them, clear the histogram by replaying the pairs.  STAGED crops (<= kTileMax pixels, levels
 // in shared memory) keep every per-thread and per-warp sum in 32 bits.
 template <bool WIDE, bool STAGED, int NW, typename LevelFn>
 __device__ __forceinline__ void band_passes(unsigned *hist, TexSmem &S, unsigned short *clr, int b, int h, int w,
@@ -166,8 +167,8 @@ texture_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw
     constexpr int NW = NT / 32;
     unsigned *hist = reinterpret_cast<unsigned *>(smem);
     TexSmem &S = *reinterpret_cast<TexSmem *>(smem + (size_t)kHistWords * 4);
-    unsigned char *tiles = smem + (size_t)kHistWords * 4 + sizeof(TexSmem);   // [kBC][kTile], 16-bit launch only
-    unsigned short *clr = reinterpret_cast<unsigned short *>(tiles + (size_t)kBC * kTile);   // [kTile] touched words
+    unsigned char *tiles = smem + (size_t)kHistWords * 4 + sizeof(TexSmem);   // [bands in chunk][cap], 16-bit launch only
+    unsigned short *clr = reinterpret_cast<unsigned short *>(tiles + kTileBytes);   // [kTileMax] touched words
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < kHistWords; i += NT) hist[i] = 0u;
@@ -187,11 +188,13 @@ texture_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw
         const int w = bb.xmax[L] - x0 + 1, h = bb.ymax[L] - y0 + 1;
         const int64_t area = (int64_t)w * h;
         if ((area >= 65536) != WIDE) continue;   // the other launch owns this segment
-        const bool staged = !WIDE && area <= kTile;
         const int lab = (int)L;
 
         for (int k0 = 0; k0 < nb; k0 += kBC) {
             const int nbc = min(kBC, nb - k0);
+            // fewer bands in the chunk leave room for larger crops (3 bands: 4096 px, 8 bands: 2048 px)
+            const int cap = min(kTileBytes / nbc, kTileMax);
+            const bool staged = !WIDE && area <= cap;
             // ---- pass 1 over the crop: min / max of every band of this chunk ----------------------
             // sample = raster value inside the segment, 0 outside the segment and for NaN samples
             float mn[kBC], mx[kBC];
@@ -265,7 +268,7 @@ texture_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw
                             if (b < nbc) {
                                 float v = inside ? raw[p * C + tb.band[k0 + b]] : 0.0f;
                                 if (!(v == v)) v = 0.0f;
-                                tiles[b * kTile + r * w + c] = (unsigned char)quantise(v, S.mn[b], S.mx[b]);
+                                tiles[b * cap + r * w + c] = (unsigned char)quantise(v, S.mn[b], S.mx[b]);
                             }
                         }
                     }
@@ -276,7 +279,7 @@ texture_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw
             for (int b = 0; b < nbc; ++b) {
                 if (!((any_bands >> b) & 1u)) continue;   // no valid sample: NaN features (:217-231)
                 if (staged) {
-                    const unsigned char *tile = tiles + b * kTile;
+                    const unsigned char *tile = tiles + b * cap;
                     band_passes<WIDE, true, NW>(hist, S, clr, b, h, w, warp, lane, tid,
                                                 [&](int r, int c) -> int { return tile[r * w + c]; });
                 } else {
@@ -341,7 +344,7 @@ texture_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw
 template <bool WIDE, int NT> static size_t texture_smem_bytes()
 {
     const size_t hist_words = WIDE ? kBins : (kBins + 1) / 2;
-    return hist_words * 4 + sizeof(TexSmem) + (WIDE ? 16 : (size_t)kBC * kTile + (size_t)kTile * 2);
+    return hist_words * 4 + sizeof(TexSmem) + (WIDE ? 16 : (size_t)kTileBytes + (size_t)kTileMax * 2);
 }
 
 }  // namespace obia

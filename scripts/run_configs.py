@@ -62,14 +62,19 @@ def main():
             stats = pipeline.zonal_stats(res.labels, raw, None, max_label=res.n_labels)
             torch.cuda.synchronize()
             t2 = time.perf_counter()
+            tex = pipeline.texture_stats(res.labels, raw, None, max_label=res.n_labels,
+                                         quantise_f64=quant) if C <= 16 else None      # not part of mp_per_s
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
             out = dict(config=name, shape=[H, W, C], kw=kw, centres=res.n_centres, segments=res.n_labels,
                        slic_ms=1e3 * (t1 - t0), stats_ms=1e3 * (t2 - t1), mp_per_s=H * W / 1e6 / (t2 - t0),
+                       texture_ms=None if tex is None else 1e3 * (t3 - t2),
                        peak_mem_gb=torch.cuda.max_memory_allocated() / 1e9)
         cnt = stats[:, 0, 0].sum().item()
         out["pixels_counted"] = int(cnt)
         out["pixels_labelled"] = int((res.labels >= 0).sum().item())
         print(json.dumps(out), flush=True)
-        del raw, res, stats
+        del raw, res, stats, tex
         torch.cuda.empty_cache()
         torch.cuda.reset_peak_memory_stats()
 
