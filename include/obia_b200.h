@@ -141,6 +141,17 @@ int obia_b200_nearest_centroid(const double *centroids_yx, int64_t n,
                                int64_t extent_y, int64_t extent_x,
                                int32_t *closest, void *workspace, void *stream);
 
+/* HOST helper (no CUDA): the two `RandomState(123)` sample draws of skimage's
+ * `_get_mask_centroids` -- `np.sort(rng.choice(np.arange(n_coord), k, replace=False))` for
+ * k = min(n_segments, n_coord) and then k = min(100 * n_segments, n_coord) -- numpy's legacy
+ * MT19937 + masked-rejection Fisher-Yates restated bit for bit.  Thread-safe and GIL-free, so the
+ * tiled driver runs it for many tiles on host threads while the GPU segments earlier tiles.
+ *   idx        [min(n_segments, n_coord)]       int64 out (host)
+ *   idx_dense  [min(100 * n_segments, n_coord)] int64 out (host)
+ */
+int obia_b200_mask_sample_indices(int64_t n_coord, int64_t n_segments, int64_t *idx,
+                                  int64_t *idx_dense);
+
 /* ---------------------------------------------------------------- K2 ----
  * SLIC iterations: replaces Cython `_slic_cython`
  * (skimage/segmentation/_slic.pyx) reached from segment_boundaries.py:51.

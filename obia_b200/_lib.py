@@ -32,6 +32,7 @@ SIGNATURES = {
                                                  _i32, _f32, _vp]),
     "obia_b200_mask_kmeans_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "obia_b200_mask_kmeans": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _vp, _vp]),
+    "obia_b200_mask_sample_indices": (ctypes.c_int, [_i64, _i64, _vp, _vp]),
     "obia_b200_nearest_centroid": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "obia_b200_slic_workspace_bytes": (_i64, [_i64, _i64, _i32, _i64, _i32, _i32]),
     "obia_b200_slic_iterate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i64, _f32,

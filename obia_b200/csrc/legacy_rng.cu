@@ -1,0 +1,111 @@
+// Host-side helper of the maskSLIC initialisation: the two sample draws of scikit-image's
+// `_get_mask_centroids` (reached from obia/segmentation/segment_boundaries.py:51 whenever `mask=` is
+// passed, i.e. for every tile of obia/utils/tiling.py:137-143, :275-281):
+//
+//     rng = np.random.RandomState(123)
+//     idx       = np.sort(rng.choice(np.arange(n_coord), min(n_segments, n_coord), replace=False))
+//     idx_dense = np.sort(rng.choice(np.arange(n_coord), min(100 * n_segments, n_coord), replace=False))
+//
+// numpy's legacy `choice(replace=False)` is `permutation(n)[:k]`, `permutation` is `arange` + the legacy
+// `shuffle`: for i = n-1 .. 1 swap x[i] with x[random_interval(i)], where `random_interval` draws 32-bit
+// MT19937 outputs masked to the bit length of i until one is <= i (64-bit outputs beyond 2^32).  The
+// algorithm is inherently sequential in i, O(n_coord) per draw, and the result depends only on
+// (n_coord, n_segments) -- restated here in C++ so that the tiled driver can run it for many tiles in
+// parallel host threads (ctypes releases the GIL) while the GPU works on earlier tiles.  No CUDA here.
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+struct MT19937 {
+    uint32_t key[624];
+    int pos;
+    explicit MT19937(uint32_t seed)
+    {
+        // numpy `_legacy_seeding(int)` -> mt19937_seed == init_genrand
+        for (int i = 0; i < 624; ++i) {
+            key[i] = seed;
+            seed = 1812433253u * (seed ^ (seed >> 30)) + (uint32_t)i + 1u;
+        }
+        pos = 624;
+    }
+    void gen()
+    {
+        constexpr uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, A = 0x9908b0dfu;
+        int i = 0;
+        for (; i < 624 - 397; ++i) {
+            const uint32_t y = (key[i] & UPPER) | (key[i + 1] & LOWER);
+            key[i] = key[i + 397] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+        }
+        for (; i < 623; ++i) {
+            const uint32_t y = (key[i] & UPPER) | (key[i + 1] & LOWER);
+            key[i] = key[i + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+        }
+        const uint32_t y = (key[623] & UPPER) | (key[0] & LOWER);
+        key[623] = key[396] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+        pos = 0;
+    }
+    uint32_t next32()
+    {
+        if (pos == 624) gen();
+        uint32_t y = key[pos++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    uint64_t next64() { const uint64_t hi = next32(); return (hi << 32) | next32(); }
+    // numpy legacy `random_interval`: uniform integer in [0, max]
+    uint64_t interval(uint64_t max)
+    {
+        if (max == 0) return 0;
+        uint64_t mask = max;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4;
+        mask |= mask >> 8; mask |= mask >> 16; mask |= mask >> 32;
+        uint64_t v;
+        if (max <= 0xffffffffull) {
+            while ((v = (next32() & mask)) > max) {}
+        } else {
+            while ((v = (next64() & mask)) > max) {}
+        }
+        return v;
+    }
+};
+
+// first k entries of RandomState.permutation(n), sorted
+template <typename T>
+void choice_sorted(MT19937 &rng, int64_t n, int64_t k, int64_t *out)
+{
+    std::vector<T> x((size_t)n);
+    for (int64_t i = 0; i < n; ++i) x[(size_t)i] = (T)i;
+    for (int64_t i = n - 1; i >= 1; --i) {
+        const int64_t j = (int64_t)rng.interval((uint64_t)i);
+        std::swap(x[(size_t)i], x[(size_t)j]);
+    }
+    std::sort(x.begin(), x.begin() + k);
+    for (int64_t i = 0; i < k; ++i) out[i] = (int64_t)x[(size_t)i];
+}
+
+}  // namespace
+
+extern "C" int obia_b200_mask_sample_indices(int64_t n_coord, int64_t n_segments, int64_t *idx,
+                                             int64_t *idx_dense)
+{
+    if (n_coord <= 0 || n_segments <= 0 || !idx || !idx_dense)
+        return obia::set_err(OBIA_B200_ERR_ARG, "mask_sample_indices: bad argument");
+    const int64_t k1 = std::min(n_segments, n_coord);
+    const int64_t k2 = std::min((int64_t)100 * n_segments, n_coord);
+    MT19937 rng(123u);
+    if (n_coord <= 0x7fffffffLL) {
+        choice_sorted<int32_t>(rng, n_coord, k1, idx);
+        choice_sorted<int32_t>(rng, n_coord, k2, idx_dense);
+    } else {
+        choice_sorted<int64_t>(rng, n_coord, k1, idx);
+        choice_sorted<int64_t>(rng, n_coord, k2, idx_dense);
+    }
+    return OBIA_B200_OK;
+}

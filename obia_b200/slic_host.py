@@ -100,7 +100,44 @@ def mask_centroids(mask_hw, n_segments):
     return centroids[:, 1:3].copy(), steps
 
 
-_CHOICE_CACHE = {}
+_CHOICE_CACHE = {}      # (n_coord, n_segments) -> (idx, idx_dense) or a Future of it
+_CHOICE_POOL = None
+
+
+def _draw_mask_samples(n_coord, n_segments):
+    """The two RandomState(123) draws, bit for bit numpy's legacy algorithm, computed by the C++
+    restatement in the library (`obia_b200_mask_sample_indices`): ctypes releases the GIL, so
+    several draws run in parallel host threads."""
+    import ctypes
+
+    from . import _lib
+    lib = _lib.load()
+    idx = np.empty(min(n_segments, n_coord), dtype=np.int64)
+    idx_dense = np.empty(min(100 * n_segments, n_coord), dtype=np.int64)
+    _lib.check(lib.obia_b200_mask_sample_indices(int(n_coord), int(n_segments),
+                                                 idx.ctypes.data_as(ctypes.c_void_p),
+                                                 idx_dense.ctypes.data_as(ctypes.c_void_p)), "mask_sample_indices")
+    return idx, idx_dense
+
+
+def prefetch_mask_samples(keys):
+    """Start the draws for `keys` = iterable of (n_coord, n_segments) on background threads; a later
+    `mask_sample_indices` call for the same key waits for that result instead of recomputing it.
+    The legacy permutation is O(n_coord) and sequential (about 0.1 s for a 2000 x 2000 tile), which
+    would otherwise serialise with the GPU work of every tile whose mask count is new."""
+    global _CHOICE_POOL
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    if _CHOICE_POOL is None:
+        _CHOICE_POOL = ThreadPoolExecutor(max_workers=max(1, min(16, (os.cpu_count() or 2) - 1)),
+                                          thread_name_prefix="obia_b200_rng")
+    for n_coord, n_segments in keys:
+        key = (int(n_coord), int(n_segments))
+        if key[0] <= 0 or key[1] <= 0 or key in _CHOICE_CACHE:
+            continue
+        if len(_CHOICE_CACHE) > 4096:
+            _CHOICE_CACHE.clear()
+        _CHOICE_CACHE[key] = _CHOICE_POOL.submit(_draw_mask_samples, *key)
 
 
 def mask_sample_indices(n_coord, n_segments):
@@ -112,14 +149,11 @@ def mask_sample_indices(n_coord, n_segments):
     key = (int(n_coord), int(n_segments))
     hit = _CHOICE_CACHE.get(key)
     if hit is None:
-        rng = np.random.RandomState(123)
-        idx_full = np.arange(n_coord, dtype=int)
-        idx = np.sort(rng.choice(idx_full, min(n_segments, n_coord), replace=False))
-        n_dense = int((10 ** 2) * n_segments)
-        idx_dense = np.sort(rng.choice(idx_full, min(n_dense, n_coord), replace=False))
-        if len(_CHOICE_CACHE) > 256:
+        if len(_CHOICE_CACHE) > 4096:
             _CHOICE_CACHE.clear()
-        hit = _CHOICE_CACHE[key] = (idx, idx_dense)
+        hit = _CHOICE_CACHE[key] = _draw_mask_samples(*key)
+    elif not isinstance(hit, tuple):
+        hit = _CHOICE_CACHE[key] = hit.result()
     return hit
 
 

@@ -157,24 +157,53 @@ class TiledSegmenter:
             self.sizes[base + lab] = c
 
     # ------------------------------------------------------------------ passes
+    def _prefetch_samples(self, masks):
+        """Start the maskSLIC sample draws (host, O(mask pixels) each, see slic_host) of the given
+        window masks on background threads: one device reduction + one read-back for all of them."""
+        if self.segment_tile is not _default_segment_tile:
+            return
+        masks = [m for m in masks if m is not None]
+        if not masks:
+            return
+        from .. import slic_host
+        counts = torch.stack([m.sum() for m in masks]).cpu().tolist()
+        crown_area = math.pi * (self.crown_radius ** 2)
+        keys = []
+        for c in counts:
+            n = int(self.n_segments_fixed) if self.n_segments_fixed is not None else \
+                int(round(float(c) * self.pixel_area / crown_area))
+            keys.append((int(c), n))
+        slic_host.prefetch_mask_samples(keys)
+
     def run_black(self):
-        for t in self.black:
-            if not self.owns(t):
-                continue
-            m = None if self.mask is None else self.mask[t["y0"]:t["y0"] + t["h"], t["x0"]:t["x0"] + t["w"]]
+        owned = [t for t in self.black if self.owns(t)]
+        masks = [None if self.mask is None else self.mask[t["y0"]:t["y0"] + t["h"], t["x0"]:t["x0"] + t["w"]]
+                 for t in owned]
+        self._prefetch_samples(masks)
+        for t, m in zip(owned, masks):
             self._segment(t, m, 0)
         self._exchange(None)
 
     def run_white(self):
         rows = sorted({t["row"] for t in self.white})
         by_row = {r: [t for t in self.white if t["row"] == r] for r in rows}
+        # white windows of one tile-row are disjoint when tile_size > 2 * buffer: their masks can all
+        # be built first (and their sample draws started in the background) before any is segmented
+        batched = self.T > 2 * self.buffer
         for r in rows:
-            for t in by_row[r]:
-                if self.owns(t):
-                    self._white_tile(t)
+            owned = [t for t in by_row[r] if self.owns(t)]
+            if batched:
+                masks = [self._white_prepare(t) for t in owned]
+                self._prefetch_samples(masks)
+                for t, m in zip(owned, masks):
+                    self._segment(t, m, 1)
+            else:
+                for t in owned:
+                    self._segment(t, self._white_prepare(t), 1)
             self._exchange(r)
 
-    def _white_tile(self, t):
+    def _white_prepare(self, t):
+        """Delete / freeze the earlier segments around one white window; returns the window's mask."""
         y0, x0, h, w = t["y0"], t["x0"], t["h"], t["w"]
         view = self.G[y0:y0 + h, x0:x0 + w]
         inside = window_polygon_mask(h, w, self.buffer, self.device)
@@ -198,7 +227,7 @@ class TiledSegmenter:
                 m = ~excluded                                      # deviation 2 (:259-260)
         elif self.verbose:
             print(f"No overlapping black segments found for tile ({t['x0']}, {t['y0']}).")
-        self._segment(t, m, 1)
+        return m
 
     # ------------------------------------------------------------------ seam exchange
     def _exchange(self, white_row):

@@ -102,3 +102,22 @@ def test_combine_stats_matches_numpy_scipy():
             ref[5] = ref[6] = np.nan          # scipy: (nearly) constant data -> NaN
         np.testing.assert_allclose(out, ref, rtol=1e-8, atol=1e-12, equal_nan=True)
     assert split_rows(10, 3) == [(0, 4), (4, 3), (7, 3)] and split_rows(4, 4) == [(0, 1)] * 0 + [(0, 1), (1, 1), (2, 1), (3, 1)]
+
+
+def test_mask_sample_indices_equals_numpy_legacy_choice():
+    """The C++ restatement of numpy's legacy RandomState(123).choice(replace=False) (MT19937, masked
+    rejection, backward Fisher-Yates) is bit-identical to numpy, also through the background prefetch."""
+    from obia_b200 import slic_host
+    cases = [(1, 1), (2, 1), (3, 5), (10, 3), (400, 4), (1000, 7), (40000, 199), (65536, 10), (65537, 700),
+             (123457, 1000)]
+    slic_host._CHOICE_CACHE.clear()
+    slic_host.prefetch_mask_samples(cases[::2] + [(0, 3), (5, 0)])        # half of them in the background
+    for n, k in cases:
+        rng = np.random.RandomState(123)
+        full = np.arange(n, dtype=int)
+        want = (np.sort(rng.choice(full, min(k, n), replace=False)),
+                np.sort(rng.choice(full, min(100 * k, n), replace=False)))
+        got = slic_host.mask_sample_indices(n, k)
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+        assert slic_host.mask_sample_indices(n, k) is got                  # cached
