@@ -129,8 +129,10 @@ def prefetch_mask_samples(keys):
     import os
     from concurrent.futures import ThreadPoolExecutor
     if _CHOICE_POOL is None:
-        _CHOICE_POOL = ThreadPoolExecutor(max_workers=max(1, min(16, (os.cpu_count() or 2) - 1)),
-                                          thread_name_prefix="obia_b200_rng")
+        # one process per GPU under torchrun: share the host cores between the local ranks
+        local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1))
+        workers = max(1, min(8, ((os.cpu_count() or 2) - 1) // local))
+        _CHOICE_POOL = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="obia_b200_rng")
     for n_coord, n_segments in keys:
         key = (int(n_coord), int(n_segments))
         if key[0] <= 0 or key[1] <= 0 or key in _CHOICE_CACHE:
