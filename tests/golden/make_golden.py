@@ -75,6 +75,23 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), raw=raw, bands=np.asarray(bands),
                             labels=labels.astype(np.int32), ids=ids, stats=stats, counts=counts, **save)
         print(name, raw.shape, raw.dtype, "labels", len(ids))
+    make_texture_golden()
+
+
+def make_texture_golden():
+    """GLCM texture features (oracle/texture_oracle.py) of the segments of two fixtures: a float32
+    raster (float32 quantisation) and the uint8 raster (float64 quantisation, like the reference's
+    masked crop of an integer raster)."""
+    import texture_oracle
+    for src, bands in (("slic_ms8_96", [0, 3, 7]), ("slic_rgb_64", [0, 1, 2])):
+        z = np.load(os.path.join(HERE, src + ".npz"))
+        raw, labels, ids = z["raw"], z["labels"], z["ids"]
+        f64 = raw.dtype != np.float32
+        tex = texture_oracle.textural_stats(labels, raw.astype(np.float32), bands, ids,
+                                            compute_dtype=np.float64 if f64 else np.float32)
+        np.savez_compressed(os.path.join(HERE, "texture_" + src[5:] + ".npz"), source=np.asarray(src),
+                            bands=np.asarray(bands), ids=ids, texture=tex, quantise_f64=np.asarray(f64))
+        print("texture", src, tex.shape)
 
 
 if __name__ == "__main__":

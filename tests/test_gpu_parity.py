@@ -532,6 +532,39 @@ def test_texture_stats_edge_cases():
     np.testing.assert_array_equal(got, again)
 
 
+# --------------------------------------------------------- golden fixtures ---
+@pytest.mark.parametrize("name", ["slic_rgb_64", "slic_ms8_96", "slic_masked_80"])
+def test_golden_fixtures_through_the_cuda_path(name):
+    """The committed fixtures of tests/golden (oracle outputs, script committed): SLIC labels >= 99.5 %,
+    statistics on the fixture's own labels (counts / min / max exact, moments 1e-5), texture 1e-9."""
+    import os
+    from obia_b200 import pipeline
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    z = np.load(os.path.join(gold, name + ".npz"), allow_pickle=False)
+    kw = {k[3:]: z[k].item() for k in z.files if k.startswith("kw_")}
+    raw = z["raw"].astype(np.float32)
+    mask = z["mask"].astype(bool) if "mask" in z.files else None
+    res = pipeline.slic_labels(_cuda(raw), z["bands"].tolist(), mask=None if mask is None else _cuda(mask), **kw)
+    agree = float((res.labels.cpu().numpy() == z["labels"]).mean())
+    assert agree >= 0.995, agree
+    labels, ids = z["labels"].astype(np.int32), z["ids"]
+    f64 = z["raw"].dtype != np.float32
+    got = pipeline.zonal_stats(_cuda(labels), _cuda(raw), None,
+                               resolution=1e-15 if f64 else 1e-6).cpu().numpy()[ids]
+    want = z["stats"]
+    np.testing.assert_array_equal(got[:, 0, 0], z["counts"])
+    np.testing.assert_allclose(got[:, :, 1], want[:, :, 0], rtol=1e-5)
+    np.testing.assert_allclose(got[:, :, 2], want[:, :, 1], rtol=1e-5, atol=1e-12)
+    np.testing.assert_array_equal(got[:, :, 3], want[:, :, 2])
+    np.testing.assert_array_equal(got[:, :, 4], want[:, :, 3])
+    tname = os.path.join(gold, "texture_" + name[5:] + ".npz")
+    if os.path.exists(tname):
+        t = np.load(tname)
+        tex = pipeline.texture_stats(_cuda(labels), _cuda(raw), t["bands"].tolist(),
+                                     quantise_f64=bool(t["quantise_f64"])).cpu().numpy()[t["ids"]]
+        np.testing.assert_allclose(tex, t["texture"], rtol=1e-9, atol=1e-12)
+
+
 # ------------------------------------------------------------- end to end ---
 def test_segment_end_to_end_columns_and_values():
     import slic_oracle as so

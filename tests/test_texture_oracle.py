@@ -103,3 +103,15 @@ def test_textural_stats_per_label_and_nan_band():
     assert np.isnan(out[list(ids).index(4), 1]).all() and not np.isnan(out[list(ids).index(4), 0]).any()
     assert ((out[:, 0, 3] > 0) & (out[:, 0, 3] <= 1)).all()                  # ASM in (0, 1]
     np.testing.assert_allclose(out[:, 0, 4] <= np.sqrt(out[:, 0, 3]) + 1e-12, True)   # mean sqrt <= sqrt mean
+
+
+@pytest.mark.parametrize("name", ["texture_ms8_96", "texture_rgb_64"])
+def test_texture_golden_fixtures(name):
+    """Regression pins generated by tests/golden/make_golden.py (oracle output, see its header)."""
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    z = np.load(os.path.join(gold, name + ".npz"))
+    src = np.load(os.path.join(gold, str(z["source"]) + ".npz"))
+    got = T.textural_stats(src["labels"], src["raw"].astype(np.float32), z["bands"].tolist(), z["ids"],
+                           compute_dtype=np.float64 if bool(z["quantise_f64"]) else np.float32)
+    np.testing.assert_array_equal(got, z["texture"])
