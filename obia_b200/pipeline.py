@@ -105,7 +105,8 @@ def mask_centroids_device(mask_dev, n_segments):
 
     Host part: the two RandomState(123) draws (cached per mask size) and the mean of the
     nearest-centroid offsets; device part: `obia_b200_mask_kmeans` (bit-identical to scipy's
-    kmeans2 on pixel coordinates) and, beyond 2048 centroids, `obia_b200_nearest_centroid`.  Returns (yx float64 (n, 2) numpy, steps (3,)).
+    kmeans2 on pixel coordinates) and, beyond 64 centroids, `obia_b200_nearest_centroid`.
+    Returns (yx float64 (n, 2) numpy, steps (3,), number of mask pixels).
     """
     lib = _lib.load()
     coord = torch.nonzero(mask_dev)                 # row-major, like np.nonzero
@@ -124,16 +125,18 @@ def mask_centroids_device(mask_dev, n_segments):
     ws = torch.empty((lib.obia_b200_mask_kmeans_workspace_bytes(n, H, W),), dtype=torch.uint8, device=dev)
     _lib.check(lib.obia_b200_mask_kmeans(_p(pts), int(pts.shape[0]), _p(cent), n, 5, H, W, _p(ws), _stream_ptr()),
                "mask_kmeans")
-    if n <= 2048:
+    if n <= 64:
         yx = cent.cpu().numpy()
-        return yx, slic_host.steps_from_centroids(yx)
-    # many centroids: the nearest-other-centroid search runs on the device as well (the host
-    # version needs scipy's n x n pdist matrix, or a k-d tree that breaks ties differently)
+        return yx, slic_host.steps_from_centroids(yx), n_coord
+    # the nearest-other-centroid search runs on the device as well (the host version needs scipy's
+    # n x n pdist matrix -- 0.4 ms for a 200-pixel tile -- or a k-d tree that breaks ties differently)
     closest = torch.empty((n,), dtype=torch.int32, device=dev)
     _lib.check(lib.obia_b200_nearest_centroid(_p(cent), n, H, W, _p(closest), _p(ws), _stream_ptr()),
                "nearest_centroid")
-    yx = cent.cpu().numpy()
-    return yx, slic_host.steps_from_centroids(yx, closest=closest.cpu().numpy())
+    # one read-back for both results
+    packed = torch.cat([cent.reshape(-1), closest.to(torch.float64)]).cpu().numpy()
+    yx = packed[:2 * n].reshape(n, 2).copy()
+    return yx, slic_host.steps_from_centroids(yx, closest=packed[2 * n:].astype(np.int64)), n_coord
 
 
 @dataclass
@@ -225,11 +228,12 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
     Cf = 3 if to_lab else Cs
 
     # ---- centres --------------------------------------------------------------
+    n_mask = None      # number of mask pixels, when already known
     if init_centroids is not None or mask_dev is not None:
         if init_centroids is not None:
             yx, steps = init_centroids
         else:
-            yx, steps = mask_centroids_device(mask_dev, int(n_segments))
+            yx, steps, n_mask = mask_centroids_device(mask_dev, int(n_segments))
         n = int(yx.shape[0])
         centres_np = np.zeros((n, 2 + Cf), dtype=np.float32)
         centres_np[:, :2] = yx.astype(np.float32)
@@ -302,7 +306,7 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
     n_labels = n
     if enforce_connectivity:
         if mask_dev is not None:
-            segment_size = float(mask_dev.sum().item()) / n
+            segment_size = float(n_mask if n_mask is not None else mask_dev.sum().item()) / n
         else:
             segment_size = float(H * W) / n
         min_size = int(min_size_factor * segment_size)

@@ -311,7 +311,8 @@ def test_mask_centroids_bitexact_vs_scipy(n):
     yy, xx = np.mgrid[:170, :230]
     mask = (((yy - 80) ** 2 / 70.0 ** 2 + (xx - 120) ** 2 / 100.0 ** 2) < 1.0) & ((yy + xx) % 7 != 0)
     want_c, want_steps = so._get_mask_centroids(mask[np.newaxis].astype(np.uint8), n, True)
-    yx, steps = pipeline.mask_centroids_device(_cuda(mask.astype(np.uint8)), n)
+    yx, steps, n_mask = pipeline.mask_centroids_device(_cuda(mask.astype(np.uint8)), n)
+    assert n_mask == int(mask.sum())
     np.testing.assert_array_equal(yx, want_c[:, 1:])
     np.testing.assert_array_equal(steps, want_steps)
 
@@ -326,7 +327,8 @@ def test_mask_centroids_grid_search_bitexact_vs_scipy(n):
     mask = (((yy - 200) ** 2 / 190.0 ** 2 + (xx - 260) ** 2 / 240.0 ** 2) < 1.0) & ((yy * 3 + xx) % 11 != 0)
     mask[100:140, 200:330] = False                       # a hole: empty grid cells inside the support
     want_c, want_steps = so._get_mask_centroids(mask[np.newaxis].astype(np.uint8), n, True)
-    yx, steps = pipeline.mask_centroids_device(_cuda(mask.astype(np.uint8)), n)
+    yx, steps, n_mask = pipeline.mask_centroids_device(_cuda(mask.astype(np.uint8)), n)
+    assert n_mask == int(mask.sum())
     np.testing.assert_array_equal(yx, want_c[:, 1:])
     np.testing.assert_array_equal(steps, want_steps)
 
