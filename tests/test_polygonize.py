@@ -100,3 +100,45 @@ def test_affine_and_missing_values():
     assert q is None
     assert tuple(p.bounds) == (500.0, 880.0, 530.0, 900.0) and p.area == 600.0
     assert p.wkt.startswith("POLYGON ((") and p.__geo_interface__["type"] == "Polygon"
+
+
+def test_segments_frame_geojson_roundtrip_on_cpu(tmp_path):
+    """SegmentsFrame.materialize_geometry + to_file (GeoJSON, no geopandas) from a CPU label raster."""
+    import json
+    import pandas as pd
+    import torch
+    from obia_b200.segmentation.segment_boundaries import SegmentsFrame
+    lab = np.zeros((6, 8), np.int32)
+    lab[:, 4:] = 1
+    lab[2:4, 1:3] = 2
+    f = SegmentsFrame({"geometry": None, "segment_id": [1, 2, 3]}, index=pd.RangeIndex(3))
+    f.label_raster = torch.from_numpy(lab)
+    f.segment_labels = np.array([0, 1, 2])
+    f.crs = "EPSG:32702"
+    with pytest.raises(ValueError):
+        f.to_file(str(tmp_path / "x.geojson"))                 # no geometries yet
+    f.materialize_geometry([1.0, 0.0, 0.0, -1.0, 10.0, 20.0])
+    f["b0_mean"] = [1.5, float("nan"), 3.0]
+    f.to_file(str(tmp_path / "x.geojson"))
+    doc = json.loads((tmp_path / "x.geojson").read_text())
+    assert doc["crs"]["properties"]["name"] == "EPSG:32702" and len(doc["features"]) == 3
+    assert doc["features"][1]["properties"] == {"segment_id": 2, "b0_mean": None}
+    assert len(doc["features"][0]["geometry"]["coordinates"]) == 2            # label 0 has a hole (label 2)
+    assert [g.area for g in f["geometry"]] == [20.0, 24.0, 4.0]
+    with pytest.raises(NotImplementedError):
+        f.to_file(str(tmp_path / "x.gpkg"))
+
+
+def test_image_stats_dtype_rule():
+    """Image.stats_in_float64: integer rasters are reduced in float64 by the reference (utils.py:64)."""
+    import torch
+    from obia_b200.handlers.geotif import Image
+    assert not Image(np.zeros((2, 2, 1), np.float32), None, None, None, None).stats_in_float64()
+    assert Image(np.zeros((2, 2, 1), np.uint8), None, None, None, None).stats_in_float64()
+    assert Image(np.zeros((2, 2, 1), np.float64), None, None, None, None).stats_in_float64()
+    assert not Image(torch.zeros((2, 2, 1)), None, None, None, None).stats_in_float64()
+    assert Image(torch.zeros((2, 2, 1), dtype=torch.int16), None, None, None, None).stats_in_float64()
+
+    class _File:           # rasterio dataset stand-in: the FILE dtype decides, not img_data (always float32)
+        dtypes = ("uint8", "uint8")
+    assert Image(np.zeros((2, 2, 2), np.float32), None, None, None, _File()).stats_in_float64()
