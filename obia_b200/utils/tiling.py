@@ -95,13 +95,36 @@ def _default_segment_tile(raw_tile, mask_tile, n_segments, slic_kwargs):
     return res.labels
 
 
+def block_columns(width, tile_size, world):
+    """Column blocks of whole tile columns: (col_lo, col_hi) tile-column ranges per rank."""
+    n_tile_cols = (width + tile_size - 1) // tile_size
+    per = (n_tile_cols + world - 1) // world
+    return ([min(n_tile_cols, r * per) for r in range(world)],
+            [min(n_tile_cols, (r + 1) * per) for r in range(world)])
+
+
+def local_columns(width, tile_size, buffer, world, rank):
+    """Pixel columns [xa, xb) a rank has to hold: its block plus `buffer` columns on either side (the
+    reach of its white windows and of the seam bands it exchanges)."""
+    col_lo, col_hi = block_columns(width, tile_size, world)
+    if col_lo[rank] >= col_hi[rank]:
+        return width, width
+    return max(0, col_lo[rank] * tile_size - buffer), min(width, col_hi[rank] * tile_size + buffer)
+
+
 class TiledSegmenter:
-    """State of one rank: its column block of the raster (plus halo) and the global-id label raster."""
+    """State of one rank: its column block of the raster (plus halo) and the global-id label raster.
+
+    `raw` / `mask` hold the pixel columns [x_origin, x_origin + raw.shape[1]) of a raster that is
+    `width_total` wide (default: the whole raster); all tile coordinates are global.
+    """
 
     def __init__(self, raw, mask, tile_size, buffer, crown_radius, pixel_area, slic_kwargs,
-                 segment_tile=None, rank=0, world=1, dist=None, verbose=False):
+                 segment_tile=None, rank=0, world=1, dist=None, verbose=False, x_origin=0, width_total=None):
         self.raw, self.mask = raw, mask
-        self.H, self.W = int(raw.shape[0]), int(raw.shape[1])
+        self.xo = int(x_origin)
+        self.Wl = int(raw.shape[1])
+        self.H, self.W = int(raw.shape[0]), int(width_total if width_total is not None else raw.shape[1])
         self.T, self.buffer, self.crown_radius, self.pixel_area = int(tile_size), int(buffer), crown_radius, pixel_area
         self.kw = dict(slic_kwargs)
         self.n_segments_fixed = self.kw.pop("n_segments", None)      # deviation 1
@@ -111,17 +134,18 @@ class TiledSegmenter:
         self.device = raw.device
         self.n_tile_cols = (self.W + self.T - 1) // self.T
         self.n_tile_rows = (self.H + self.T - 1) // self.T
-        # column blocks of whole tile columns
-        per = (self.n_tile_cols + world - 1) // world
-        self.col_lo = [min(self.n_tile_cols, r * per) for r in range(world)]
-        self.col_hi = [min(self.n_tile_cols, (r + 1) * per) for r in range(world)]
-        self.G = torch.full((self.H, self.W), -1, dtype=torch.int64, device=self.device)
+        self.col_lo, self.col_hi = block_columns(self.W, self.T, world)
+        self.G = torch.full((self.H, self.Wl), -1, dtype=torch.int64, device=self.device)
         self.sizes = {}        # creation key -> pixel count (every segment this rank knows about)
         if world > 1 and self.T <= 2 * self.buffer:
             raise ValueError("multi-GPU tiling needs tile_size > 2 * buffer")
         self.black, self.white = plan_tiles(self.H, self.W, self.T, self.buffer)
 
     # ------------------------------------------------------------------ helpers
+    def _win(self, arr, y0, x0, h, w):
+        """Window [y0, y0+h) x [x0, x0+w) (global coordinates) of a locally stored array."""
+        return arr[y0:y0 + h, x0 - self.xo:x0 - self.xo + w]
+
     def owns(self, tile):
         return self.col_lo[self.rank] <= tile["col"] < self.col_hi[self.rank]
 
@@ -140,7 +164,7 @@ class TiledSegmenter:
             n = self._n_segments(mask_tile)
             if n <= 0:
                 raise ValueError("n_segments must be positive")
-            local = self.segment_tile(self.raw[y0:y0 + h, x0:x0 + w], mask_tile, n, self.kw)
+            local = self.segment_tile(self._win(self.raw, y0, x0, h, w), mask_tile, n, self.kw)
         except ValueError:
             if self.verbose:
                 print(f"empty tile: ({t['y0']}) ({t['x0']})")          # :149-150, :283-284
@@ -151,7 +175,7 @@ class TiledSegmenter:
             return
         uniq, counts = torch.unique(local[valid], return_counts=True)
         base = creation_key(pass_idx, t["row"], t["col"])
-        view = self.G[y0:y0 + h, x0:x0 + w]
+        view = self._win(self.G, y0, x0, h, w)
         view[valid] = local[valid] + base
         for lab, c in zip(uniq.tolist(), counts.tolist()):
             self.sizes[base + lab] = c
@@ -177,7 +201,7 @@ class TiledSegmenter:
 
     def run_black(self):
         owned = [t for t in self.black if self.owns(t)]
-        masks = [None if self.mask is None else self.mask[t["y0"]:t["y0"] + t["h"], t["x0"]:t["x0"] + t["w"]]
+        masks = [None if self.mask is None else self._win(self.mask, t["y0"], t["x0"], t["h"], t["w"])
                  for t in owned]
         self._prefetch_samples(masks)
         for t, m in zip(owned, masks):
@@ -205,9 +229,9 @@ class TiledSegmenter:
     def _white_prepare(self, t):
         """Delete / freeze the earlier segments around one white window; returns the window's mask."""
         y0, x0, h, w = t["y0"], t["x0"], t["h"], t["w"]
-        view = self.G[y0:y0 + h, x0:x0 + w]
+        view = self._win(self.G, y0, x0, h, w)
         inside = window_polygon_mask(h, w, self.buffer, self.device)
-        m = None if self.mask is None else self.mask[y0:y0 + h, x0:x0 + w].clone()
+        m = None if self.mask is None else self._win(self.mask, y0, x0, h, w).clone()
         ids_in, cnt_in = torch.unique(view[inside & (view >= 0)], return_counts=True)
         if ids_in.numel() > 0:
             total = torch.tensor([self.sizes[i] for i in ids_in.tolist()], device=self.device)
@@ -269,7 +293,7 @@ class TiledSegmenter:
                 sx0, sx1 = xa_, xb_
                 rx0, rx1 = xa_, xb_
             if i_send:
-                band = self.G[ya:yb, sx0:sx1].contiguous()
+                band = self.G[ya:yb, sx0 - self.xo:sx1 - self.xo].contiguous()
                 ids = torch.unique(band[band >= 0])
                 table = torch.tensor([[i, self.sizes.get(i, 0)] for i in ids.tolist()], dtype=torch.int64,
                                      device=self.device).reshape(-1, 2)
@@ -292,7 +316,7 @@ class TiledSegmenter:
                 band = torch.empty((rb - ra, rx1 - rx0), dtype=torch.int64, device=self.device)
                 self.dist.recv(band, nb)
                 n = int(meta.item())
-                old = self.G[ra:rb, rx0:rx1]
+                old = self.G[ra:rb, rx0 - self.xo:rx1 - self.xo]
                 gone = set(torch.unique(old[old >= 0]).tolist())
                 if n:
                     table = torch.empty((n, 2), dtype=torch.int64, device=self.device)
@@ -300,7 +324,7 @@ class TiledSegmenter:
                     for i, s in table.tolist():
                         self.sizes[i] = s
                         gone.discard(i)
-                self.G[ra:rb, rx0:rx1] = band
+                self.G[ra:rb, rx0 - self.xo:rx1 - self.xo] = band
                 # segments that vanished from the band were deleted by the neighbour; they lay
                 # entirely inside its window, i.e. entirely inside this band
                 if white_row is not None:
@@ -317,9 +341,9 @@ class TiledSegmenter:
     # ------------------------------------------------------------------ result
     def finalize(self):
         """Final 1..N numbering: black survivors then white, in creation order (:289-290)."""
-        x0 = self.col_lo[self.rank] * self.T
-        x1 = min(self.W, self.col_hi[self.rank] * self.T)
-        own = self.G[:, x0:x1]
+        x0 = min(self.W, self.col_lo[self.rank] * self.T)
+        x1 = max(x0, min(self.W, self.col_hi[self.rank] * self.T))
+        own = self.G[:, x0 - self.xo:x1 - self.xo] if x1 > x0 else self.G[:, :0]
         keys = torch.unique(own[own >= 0])
         if self.world > 1:
             n_loc = torch.tensor([keys.numel()], dtype=torch.int64, device=self.device)
@@ -340,8 +364,10 @@ class TiledSegmenter:
         return final, int(allk.numel()), (x0, x1)
 
 
-def _as_device_raster(input_raster, device):
-    """(raw (H, W, C) float32 tensor, pixel_area, Image-or-None) from a path / Image / array."""
+def _as_device_raster(input_raster, device, columns=None):
+    """(raw (H, W_local, C) float32 tensor, pixel_area, Image-or-None, total width) from a path / Image /
+    array.  `columns(width) -> (xa, xb)`: only those pixel columns are uploaded (multi-GPU: a rank
+    keeps its block plus halo, not the whole raster)."""
     from ..handlers.geotif import Image
     pixel_area, image = 1.0, None
     if isinstance(input_raster, (str, os.PathLike)):
@@ -356,13 +382,18 @@ def _as_device_raster(input_raster, device):
             pixel_area = abs(tr.a) * abs(tr.e)             # :128-131
     else:
         data = input_raster
-    if isinstance(data, torch.Tensor):
-        raw = data.to(device=device, dtype=torch.float32)
-    else:
-        raw = torch.from_numpy(np.ascontiguousarray(np.asarray(data), dtype=np.float32)).to(device)
-    if raw.dim() != 3:
+    if not isinstance(data, torch.Tensor):
+        data = np.asarray(data)
+    if data.ndim != 3:
         raise ValueError(f"Unable to open {input_raster}")
-    return raw, pixel_area, image
+    width = int(data.shape[1])
+    xa, xb = (0, width) if columns is None else columns(width)
+    data = data[:, xa:xb]
+    if isinstance(data, torch.Tensor):
+        raw = data.to(device=device, dtype=torch.float32).contiguous()
+    else:
+        raw = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(device)
+    return raw, pixel_area, image, width, xa
 
 
 def create_tiled_segments(input_raster, output_dir, input_mask=None,
@@ -393,19 +424,21 @@ def create_tiled_segments(input_raster, output_dir, input_mask=None,
         dist, rank, world = tdist, tdist.get_rank(), tdist.get_world_size()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
-    raw, pixel_area, _ = _as_device_raster(input_raster, device)
+    raw, pixel_area, _, width, xa = _as_device_raster(
+        input_raster, device, columns=lambda w: local_columns(w, int(tile_size), int(buffer), world, rank))
     mask = None
     if input_mask is not None:
         if isinstance(input_mask, (str, os.PathLike)):
             raise ValueError(f"Unable to open {input_mask}") if not os.path.exists(str(input_mask)) else \
                 NotImplementedError("reading a mask file needs rasterio; pass the array instead")
         m = input_mask if isinstance(input_mask, torch.Tensor) else torch.from_numpy(np.asarray(input_mask))
-        mask = (m != 0).to(device)
-        if tuple(mask.shape) != tuple(raw.shape[:2]):
+        if tuple(m.shape) != (int(raw.shape[0]), width):
             raise ValueError("image and mask should have the same shape.")
+        mask = (m[:, xa:xa + int(raw.shape[1])] != 0).to(device).contiguous()
 
     seg = TiledSegmenter(raw, mask, tile_size, buffer, crown_radius, pixel_area, kwargs,
-                         segment_tile=segment_tile, rank=rank, world=world, dist=dist, verbose=verbose)
+                         segment_tile=segment_tile, rank=rank, world=world, dist=dist, verbose=verbose,
+                         x_origin=xa, width_total=width)
     seg.run_black()
     seg.run_white()
     labels, n, cols = seg.finalize()
