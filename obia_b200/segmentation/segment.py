@@ -51,26 +51,39 @@ class Segments:
         self.segments.to_file(file_path)
 
 
-def segment(image, segmentation_bands=None, statistics_bands=None,
-            method="slic", calc_mean=True, calc_variance=True,
-            calc_skewness=True, calc_kurtosis=True, calc_contrast=True,
-            calc_dissimilarity=True, calc_homogeneity=True, calc_ASM=True,
-            calc_energy=True, calc_correlation=True, **kwargs):
+def segment(
+    image,
+    segmentation_bands=None,
+    statistics_bands=None,
+    method="slic",
+    calc_mean=True,
+    calc_variance=True,
+    calc_skewness=True,
+    calc_kurtosis=True,
+    calc_contrast=True,
+    calc_dissimilarity=True,
+    calc_homogeneity=True,
+    calc_ASM=True,
+    calc_energy=True,
+    calc_correlation=True,
+    **kwargs,
+):
+    """`create_segments` then `create_objects` (reference segment.py:63-93: same positional order,
+    names and defaults; `calc_min` / `calc_max` cannot be switched off here, as in the reference)."""
+    column_flags = dict(calc_mean=calc_mean, calc_variance=calc_variance, calc_skewness=calc_skewness,
+                        calc_kurtosis=calc_kurtosis, calc_contrast=calc_contrast,
+                        calc_dissimilarity=calc_dissimilarity, calc_homogeneity=calc_homogeneity,
+                        calc_ASM=calc_ASM, calc_energy=calc_energy, calc_correlation=calc_correlation)
     # the in-place normalisation of image.img_data (a side effect of create_segments) is written back
     # on a side stream; inside segment() it only has to be complete when segment() returns
-    segments_gdf = create_segments(image, segmentation_bands=segmentation_bands, method=method,
-                                   _defer_mutation_sync=True, **kwargs)
-    pending = getattr(segments_gdf, "_pending_mutation", None)
+    boundaries = create_segments(image, segmentation_bands=segmentation_bands, method=method,
+                                 _defer_mutation_sync=True, **kwargs)
+    pending = getattr(boundaries, "_pending_mutation", None)
     try:
-        slic_kwargs = {k: v for k, v in kwargs.items() if k not in ("mutate_image", "polygonize")}
-        objects_gdf = create_objects(segments_gdf, image, spectral_bands=statistics_bands, calc_mean=calc_mean,
-                                     calc_variance=calc_variance, calc_skewness=calc_skewness,
-                                     calc_kurtosis=calc_kurtosis,
-                                     calc_contrast=calc_contrast, calc_dissimilarity=calc_dissimilarity,
-                                     calc_homogeneity=calc_homogeneity, calc_ASM=calc_ASM, calc_energy=calc_energy,
-                                     calc_correlation=calc_correlation)
+        features = create_objects(boundaries, image, spectral_bands=statistics_bands, **column_flags)
     finally:
         if pending is not None:
             pending.synchronize()
-            segments_gdf._pending_mutation = None
-    return Segments(segments_gdf, objects_gdf, method, **slic_kwargs)
+            boundaries._pending_mutation = None
+    slic_kwargs = {k: v for k, v in kwargs.items() if k not in ("mutate_image", "polygonize")}
+    return Segments(boundaries, features, method, **slic_kwargs)
