@@ -62,7 +62,8 @@ def test_hole_and_corner_touching_pixels():
     assert pe.area == 14.0 and len(_rings(pe)[1]) == 2
 
 
-@pytest.mark.parametrize("seed,shape", [(0, (40, 50)), (1, (64, 64)), (2, (17, 90))])
+@pytest.mark.parametrize("seed,shape", [(0, (40, 50)), (1, (64, 64)), (2, (17, 90)), (3, (1, 1)), (4, (1, 23)),
+                                        (5, (31, 2)), (6, (5, 5)), (7, (128, 96))])
 def test_random_regions_fill_back_exactly(seed, shape):
     """Every 4-connected region of a random label raster: polygon area == pixel count, the
     polygon rasterises back to exactly the region, rings are closed and axis-aligned."""
