@@ -207,6 +207,32 @@ int obia_b200_slic_sweep(const float *features, const uint8_t *mask, const float
 int obia_b200_slic_finish_sweep(float *centres, void *workspace, int64_t H_total, int64_t W,
                                 int32_t Cf, int64_t n, int32_t step_y, int32_t step_x,
                                 double fix_scale, void *stream);
+/* Tolerance mode of the two calls above (same arguments, same workspace, same fused deterministic
+ * centre update): the squared distance is expanded so that one fused multiply-add per channel
+ * ranks a candidate centre (see csrc/slic_fast.cu); every tile works in local coordinates and
+ * colours relative to one of its candidate centres, so the float32 result differs from the
+ * reference's operation order only between candidates that are within rounding of each other.
+ * This is the mode north_star's ">= 99.5 % label agreement" tolerance allows and the default of
+ * the Python host (`exact=False`); the exact calls above reproduce `_slic_cython` bit for bit
+ * given the centres.  slic_zero != 0 falls through to the exact kernel.  For a sharded run to be
+ * bit-identical to the single-GPU one, y_offset must be a multiple of 64 (tile height).
+ * `obia_b200_slic_fast_variant(warps)` selects the CTA shape (8 or 4 warps; tuning knob). */
+int obia_b200_slic_iterate_fast(const float *features, const uint8_t *mask,
+                                float *centres, int32_t *labels, void *workspace,
+                                int64_t H, int64_t W, int64_t pitch, int32_t Cf,
+                                int64_t n, float step, int32_t step_y,
+                                int32_t step_x, int32_t max_num_iter,
+                                int32_t start_label, int32_t ignore_color,
+                                int32_t slic_zero, double fix_scale, int32_t *status,
+                                void *stream);
+int obia_b200_slic_sweep_fast(const float *features, const uint8_t *mask, const float *centres,
+                              int32_t *labels, void *workspace, int64_t H, int64_t W, int64_t pitch,
+                              int32_t Cf, int64_t n, float step, int32_t step_y, int32_t step_x,
+                              int32_t start_label, int32_t ignore_color, int32_t slic_zero,
+                              double fix_scale, int64_t y_offset, int64_t H_total, int32_t *status,
+                              void *stream);
+int obia_b200_slic_fast_variant(int32_t warps_per_cta);
+
 /* slic_zero (SLICO, `_slic.pyx` "update the color distance maxima"): with slic_zero != 0 a sweep
  * divides every colour distance by the centre's running maximum (initialised to 1 by slic_begin);
  * after finish_sweep this call raises each centre's maximum to the largest colour distance of the

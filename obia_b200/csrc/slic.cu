@@ -17,44 +17,9 @@
 //     fixed point and added with one coalesced RED.64 per field, so sums are
 //     independent of scheduling.
 // Features are band-planar so each lane streams 128-bit loads (4 pixels).
-#include "common.cuh"
-
-#ifndef OBIA_NS
-#define OBIA_NS 2   // strip phases per CTA tile (32 x (32*NS) pixels for 4 px / lane)
-#endif
+#include "slic_common.cuh"
 
 namespace obia {
-
-constexpr int kWarps = 8;
-
-// workspace layout (all 16-byte aligned)
-struct SlicWs {
-    unsigned long long *acc;  // [n][3+Cf] count, sum y, sum x, fixed-point colour sums
-    int32_t *head;            // [ncy*ncx] cell -> first centre
-    int32_t *next;            // [n]
-    float *maxdc;             // [n] SLICO: largest colour distance seen per centre (slic_zero)
-    int64_t ncy, ncx;
-    int64_t bytes;
-};
-
-static SlicWs slic_ws_layout(void *base, int64_t H, int64_t W, int Cf, int64_t n, int step_y, int step_x)
-{
-    SlicWs w;
-    w.ncy = ceil_div(H, step_y);
-    w.ncx = ceil_div(W, step_x);
-    char *p = (char *)base;
-    int64_t off = 0;
-    w.acc = (unsigned long long *)(p + off);
-    off += round_up(n * (3 + Cf) * 8, 256);
-    w.head = (int32_t *)(p + off);
-    off += round_up(w.ncy * w.ncx * 4, 256);
-    w.next = (int32_t *)(p + off);
-    off += round_up(n * 4, 256);
-    w.maxdc = (float *)(p + off);
-    off += round_up(n * 4, 256);
-    w.bytes = off;
-    return w;
-}
 
 // ------------------------------------------------------------------------
 // centres: finalise the means of the previous iteration (if from_acc) and
@@ -93,15 +58,6 @@ slic_centres_kernel(float *centres, unsigned long long *acc, int32_t *head, int3
     gx = max((int64_t)0, min(ncx - 1, gx));
     next[k] = atomicExch(&head[gy * ncx + gx], (int32_t)k);
 }
-
-__device__ __forceinline__ int floordiv_i(int a, int b)
-{
-    int q = a / b;
-    return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
-}
-
-// C cast float -> integer as the Cython code does (`<Py_ssize_t>`): truncation
-__device__ __forceinline__ int trunc_i(float v) { return (int)v; }
 
 // ---- packed fp32x2 arithmetic (sm_100a FADD2 / FFMA2): two pixels per instruction ------
 typedef unsigned long long u64;
@@ -711,6 +667,13 @@ __global__ void fill_f32_kernel(float *p, int64_t n, float v)
 
 }  // namespace obia
 
+namespace obia {
+// slic_fast.cu
+int launch_assign_fast(const float *feat, const uint8_t *mask, const float *centres, const SlicWs &w, int32_t *labels,
+                       int64_t H, int64_t W, int64_t pitch, int Cf, float sw, int step_y, int step_x, int start_label,
+                       int ignore_color, double fix_scale, int32_t *status, int y_off, int64_t Hg, cudaStream_t st);
+}
+
 using namespace obia;
 
 extern "C" int64_t obia_b200_slic_workspace_bytes(int64_t H, int64_t W, int32_t Cf, int64_t n,
@@ -755,12 +718,12 @@ extern "C" int obia_b200_slic_begin(int32_t *labels, void *workspace, int64_t H,
     return OBIA_B200_OK;
 }
 
-extern "C" int obia_b200_slic_sweep(const float *features, const uint8_t *mask, const float *centres,
-                                    int32_t *labels, void *workspace, int64_t H, int64_t W, int64_t pitch,
-                                    int32_t Cf, int64_t n, float step, int32_t step_y, int32_t step_x,
-                                    int32_t start_label, int32_t ignore_color, int32_t slic_zero,
-                                    double fix_scale, int64_t y_offset, int64_t H_total, int32_t *status,
-                                    void *stream)
+static int slic_sweep_impl(const float *features, const uint8_t *mask, const float *centres,
+                           int32_t *labels, void *workspace, int64_t H, int64_t W, int64_t pitch,
+                           int32_t Cf, int64_t n, float step, int32_t step_y, int32_t step_x,
+                           int32_t start_label, int32_t ignore_color, int32_t slic_zero,
+                           double fix_scale, int64_t y_offset, int64_t H_total, int32_t *status,
+                           void *stream, int fast)
 {
     int rc = slic_check_args(features, centres, labels, workspace, status, H, W, pitch, Cf, n, step, step_y, step_x,
                              start_label, fix_scale);
@@ -776,6 +739,10 @@ extern "C" int obia_b200_slic_sweep(const float *features, const uint8_t *mask, 
         const_cast<float *>(centres), w.acc, w.head, w.next, n, Cf, 0, 1.0 / fix_scale, step_y, step_x, w.ncy, w.ncx);
     OBIA_LAUNCH_CHECK();
     const int yo = (int)y_offset;
+    // tolerance mode (slic_fast.cu); SLICO divides the colour term per centre and stays on the exact kernel
+    if (fast && !slic_zero)
+        return launch_assign_fast(features, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x, start_label,
+                                  ignore_color, fix_scale, status, yo, H_total, st);
     if (Cf <= 4)
         rc = launch_assign<4, 4, OBIA_NS>(features, mask, centres, slic_zero, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                           start_label, ignore_color, fix_scale, status, yo, H_total, st);
@@ -792,6 +759,28 @@ extern "C" int obia_b200_slic_sweep(const float *features, const uint8_t *mask, 
         rc = launch_assign<64, 2, OBIA_NS>(features, mask, centres, slic_zero, w, labels, H, W, pitch, Cf, sw, step_y, step_x,
                                            start_label, ignore_color, fix_scale, status, yo, H_total, st);
     return rc;
+}
+
+extern "C" int obia_b200_slic_sweep(const float *features, const uint8_t *mask, const float *centres,
+                                    int32_t *labels, void *workspace, int64_t H, int64_t W, int64_t pitch,
+                                    int32_t Cf, int64_t n, float step, int32_t step_y, int32_t step_x,
+                                    int32_t start_label, int32_t ignore_color, int32_t slic_zero,
+                                    double fix_scale, int64_t y_offset, int64_t H_total, int32_t *status,
+                                    void *stream)
+{
+    return slic_sweep_impl(features, mask, centres, labels, workspace, H, W, pitch, Cf, n, step, step_y, step_x,
+                           start_label, ignore_color, slic_zero, fix_scale, y_offset, H_total, status, stream, 0);
+}
+
+extern "C" int obia_b200_slic_sweep_fast(const float *features, const uint8_t *mask, const float *centres,
+                                         int32_t *labels, void *workspace, int64_t H, int64_t W, int64_t pitch,
+                                         int32_t Cf, int64_t n, float step, int32_t step_y, int32_t step_x,
+                                         int32_t start_label, int32_t ignore_color, int32_t slic_zero,
+                                         double fix_scale, int64_t y_offset, int64_t H_total, int32_t *status,
+                                         void *stream)
+{
+    return slic_sweep_impl(features, mask, centres, labels, workspace, H, W, pitch, Cf, n, step, step_y, step_x,
+                           start_label, ignore_color, slic_zero, fix_scale, y_offset, H_total, status, stream, 1);
 }
 
 extern "C" int obia_b200_slic_finish_sweep(float *centres, void *workspace, int64_t H_total, int64_t W, int32_t Cf,
@@ -826,12 +815,12 @@ extern "C" int obia_b200_slic_update_max_color(const float *features, const uint
     return OBIA_B200_OK;
 }
 
-extern "C" int obia_b200_slic_iterate(const float *features, const uint8_t *mask, float *centres,
-                                      int32_t *labels, void *workspace, int64_t H, int64_t W,
-                                      int64_t pitch, int32_t Cf, int64_t n, float step, int32_t step_y,
-                                      int32_t step_x, int32_t max_num_iter, int32_t start_label,
-                                      int32_t ignore_color, int32_t slic_zero, double fix_scale,
-                                      int32_t *status, void *stream)
+static int slic_iterate_impl(const float *features, const uint8_t *mask, float *centres,
+                             int32_t *labels, void *workspace, int64_t H, int64_t W,
+                             int64_t pitch, int32_t Cf, int64_t n, float step, int32_t step_y,
+                             int32_t step_x, int32_t max_num_iter, int32_t start_label,
+                             int32_t ignore_color, int32_t slic_zero, double fix_scale,
+                             int32_t *status, void *stream, int fast)
 {
     int rc = slic_check_args(features, centres, labels, workspace, status, H, W, pitch, Cf, n, step, step_y, step_x,
                              start_label, fix_scale);
@@ -839,8 +828,8 @@ extern "C" int obia_b200_slic_iterate(const float *features, const uint8_t *mask
     if (max_num_iter < 0) return set_err(OBIA_B200_ERR_ARG, "slic_iterate: bad argument");
     rc = obia_b200_slic_begin(labels, workspace, H, W, H, Cf, n, step_y, step_x, start_label, status, stream);
     for (int it = 0; it < max_num_iter && !rc; ++it) {
-        rc = obia_b200_slic_sweep(features, mask, centres, labels, workspace, H, W, pitch, Cf, n, step, step_y,
-                                  step_x, start_label, ignore_color, slic_zero, fix_scale, 0, H, status, stream);
+        rc = slic_sweep_impl(features, mask, centres, labels, workspace, H, W, pitch, Cf, n, step, step_y,
+                             step_x, start_label, ignore_color, slic_zero, fix_scale, 0, H, status, stream, fast);
         // the reference updates the centres after every sweep, the last one included
         if (!rc) rc = obia_b200_slic_finish_sweep(centres, workspace, H, W, Cf, n, step_y, step_x, fix_scale, stream);
         if (!rc && slic_zero)
@@ -848,4 +837,26 @@ extern "C" int obia_b200_slic_iterate(const float *features, const uint8_t *mask
                                                  step_y, step_x, start_label, stream);
     }
     return rc;
+}
+
+extern "C" int obia_b200_slic_iterate(const float *features, const uint8_t *mask, float *centres,
+                                      int32_t *labels, void *workspace, int64_t H, int64_t W,
+                                      int64_t pitch, int32_t Cf, int64_t n, float step, int32_t step_y,
+                                      int32_t step_x, int32_t max_num_iter, int32_t start_label,
+                                      int32_t ignore_color, int32_t slic_zero, double fix_scale,
+                                      int32_t *status, void *stream)
+{
+    return slic_iterate_impl(features, mask, centres, labels, workspace, H, W, pitch, Cf, n, step, step_y, step_x,
+                             max_num_iter, start_label, ignore_color, slic_zero, fix_scale, status, stream, 0);
+}
+
+extern "C" int obia_b200_slic_iterate_fast(const float *features, const uint8_t *mask, float *centres,
+                                           int32_t *labels, void *workspace, int64_t H, int64_t W,
+                                           int64_t pitch, int32_t Cf, int64_t n, float step, int32_t step_y,
+                                           int32_t step_x, int32_t max_num_iter, int32_t start_label,
+                                           int32_t ignore_color, int32_t slic_zero, double fix_scale,
+                                           int32_t *status, void *stream)
+{
+    return slic_iterate_impl(features, mask, centres, labels, workspace, H, W, pitch, Cf, n, step, step_y, step_x,
+                             max_num_iter, start_label, ignore_color, slic_zero, fix_scale, status, stream, 1);
 }

@@ -158,7 +158,7 @@ class SlicResult:
 def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.0, max_num_iter=10,
                 sigma=0, spacing=None, convert2lab=None, enforce_connectivity=True,
                 min_size_factor=0.5, max_size_factor=3, slic_zero=False, start_label=1, mask=None,
-                channel_axis=-1, keep_intermediates=False, init_centroids=None, minmax=None):
+                channel_axis=-1, keep_intermediates=False, init_centroids=None, minmax=None, exact=False):
     """SLIC label raster of `raw[:, :, segmentation_bands]` with obia's wrapper semantics.
 
     Equivalent of segment_boundaries.py:31-57 up to the label raster: every band
@@ -166,6 +166,10 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
     selected bands go through skimage's slic() semantics, masked pixels get -1.
 
     kwargs are skimage.segmentation.slic's (obia forwards **kwargs verbatim).
+
+    `exact=False` (default) runs the tolerance-mode assignment kernel (one FMA per channel, see
+    csrc/slic_fast.cu: north_star's ">= 99.5 % label agreement" bar); `exact=True` the kernel that
+    reproduces `_slic_cython`'s float32 operation order bit for bit given the centres.
     """
     lib = _lib.load()
     _require_cuda(raw, "raw", torch.float32)
@@ -289,7 +293,8 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
     status = torch.zeros((4,), dtype=torch.int32, device=dev)
 
     def run(ignore_color):
-        _lib.check(lib.obia_b200_slic_iterate(
+        iterate = lib.obia_b200_slic_iterate if exact else lib.obia_b200_slic_iterate_fast
+        _lib.check(iterate(
             _p(feats), _p(mask_dev), _p(centres), _p(labels), _p(ws), H, W, pitch, Cf, n, step,
             step_y, step_x, int(max_num_iter), int(start_label), int(ignore_color), int(bool(slic_zero)),
             fix_scale, _p(status), _stream_ptr()), "slic_iterate")

@@ -35,7 +35,7 @@ def to_planar(features_hwc):
 
 
 def run_slic_iterate(features_hwc, mask, centres_yxc, step, iters, start_label=1, ignore_color=False, slic_zero=False,
-                     fix_scale=None):
+                     fix_scale=None, fast=False):
     """Run obia_b200_slic_iterate on oracle-prepared features/centres.
 
     centres_yxc: (n, 2 + C) float32 rows (cy, cx, colour...).  Returns (labels, centres_out)."""
@@ -53,7 +53,8 @@ def run_slic_iterate(features_hwc, mask, centres_yxc, step, iters, start_label=1
     ws = torch.empty((lib.obia_b200_slic_workspace_bytes(H, W, C, n, step_y, step_x),), dtype=torch.uint8,
                      device="cuda")
     p = pipeline._p
-    _lib.check(lib.obia_b200_slic_iterate(p(feats), p(mask_t), p(centres), p(labels), p(ws), H, W, pitch, C, n,
+    iterate = lib.obia_b200_slic_iterate_fast if fast else lib.obia_b200_slic_iterate
+    _lib.check(iterate(p(feats), p(mask_t), p(centres), p(labels), p(ws), H, W, pitch, C, n,
                                           float(step), step_y, step_x, int(iters), int(start_label),
                                           int(ignore_color), int(slic_zero), float(fix_scale), p(status),
                                           pipeline._stream_ptr()), "slic_iterate")
