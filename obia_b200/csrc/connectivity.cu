@@ -21,18 +21,26 @@
 
 namespace obia {
 
-constexpr int kScanChunk = 2048;
 constexpr int32_t kTInf = 0x7fffffff;
+constexpr int kBitChunk = 1024;    // bitmap words per numbering block (32768 pixels)
 
+// Workspace.  `T` is the union-find parent array first and the piece-start array afterwards (every
+// pixel points at the first raster pixel of its piece); `psize` is only meaningful at piece starts;
+// `fin` (final label per piece start) shares memory with the BFS queue, which is idle by then;
+// `roots` (list of component roots, consumed by the classification) shares it as well.
 struct CcWs {
-    int32_t *parent, *T, *psize, *adj, *aux, *queue, *list, *blocksum, *ctr, *stamp, *dirty0, *dirty1;
-    uint8_t *visit;
-    int64_t nblocks;
+    int32_t *T, *psize, *adj, *aux, *queue, *list, *ctr, *stamp, *dirty0, *dirty1;
+    uint32_t *bits;       // kept-piece starts, one bit per pixel
+    int32_t *chunksum;    // per kBitChunk words
+    uint8_t *visit, *flag;
+    int64_t nwords, nchunks;
     int64_t bytes;
 };
 // ctr words
 enum { CTR_NSMALL = 0, CTR_NOVER = 1, CTR_CURSOR = 2, CTR_CHANGED = 3, CTR_NKEPT = 4, CTR_ERR = 5, CTR_NDIRTY0 = 6,
-       CTR_NDIRTY1 = 7, CTR_ROUNDS = 8, CTR_WORDS = 12 };
+       CTR_NDIRTY1 = 7, CTR_ROUNDS = 8, CTR_NROOTS = 9, CTR_KBEFORE = 10, CTR_KCORE = 11, CTR_FAIL = 12, CTR_WORDS = 16 };
+// flag bits (strip mode: which results depend on pixels outside the strip)
+enum { FLAG_CUT = 1, FLAG_ADJ_UNKNOWN = 2, FLAG_TFIX_UNKNOWN = 4, FLAG_LABEL_UNKNOWN = 8 };
 
 static CcWs cc_ws_layout(void *base, int64_t N)
 {
@@ -44,17 +52,19 @@ static CcWs cc_ws_layout(void *base, int64_t N)
         off += round_up(bytes, 256);
         return r;
     };
-    w.parent = (int32_t *)take(N * 4);
     w.T = (int32_t *)take(N * 4);
     w.psize = (int32_t *)take(N * 4);
     w.adj = (int32_t *)take(N * 4);
     w.aux = (int32_t *)take(N * 4);
     w.queue = (int32_t *)take(2 * N * 4);
     w.list = (int32_t *)take(N * 4);
-    w.nblocks = ceil_div(N, kScanChunk);
-    w.blocksum = (int32_t *)take((w.nblocks + 1) * 4);
+    w.nwords = ceil_div(N, 32);
+    w.nchunks = ceil_div(w.nwords, kBitChunk);
+    w.bits = (uint32_t *)take(w.nchunks * kBitChunk * 4);
+    w.chunksum = (int32_t *)take((w.nchunks + 1) * 4);
     w.ctr = (int32_t *)take(CTR_WORDS * 4);
     w.visit = (uint8_t *)take(N);
+    w.flag = (uint8_t *)take(N);
     w.stamp = (int32_t *)take(N * 4);    // round in which a piece was last queued for re-evaluation
     w.dirty0 = (int32_t *)take(N * 4);   // ping-pong lists of pieces to re-evaluate
     w.dirty1 = (int32_t *)take(N * 4);
@@ -130,10 +140,12 @@ __device__ __forceinline__ void uf_union_s(int *parent, int a, int b)
 
 __global__ void __launch_bounds__(256)
 cc_local_kernel(const int32_t *__restrict__ lab, int32_t *__restrict__ parent, int32_t *__restrict__ psize,
-                uint8_t *__restrict__ visit, int32_t *__restrict__ stamp, int H, int W, int32_t mask_label)
+                int H, int W, int32_t mask_label)
 {
     __shared__ int32_t s_lab[kTile * kTile];
     __shared__ int s_par[kTile * kTile];
+    __shared__ int s_cnt[kTile * kTile];   // pixels per tile-local root
+    __shared__ unsigned char s_len[kTile * kTile];   // run length at run heads
     const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // a warp = one tile row: every pixel is linked to the first pixel of its horizontal run
@@ -145,8 +157,11 @@ cc_local_kernel(const int32_t *__restrict__ lab, int32_t *__restrict__ parent, i
         const bool head = (lane == 0) || (l != lp) || (l == mask_label);
         const unsigned heads = __ballot_sync(0xffffffffu, head);
         const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+        const unsigned later = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
         s_lab[ly * kTile + lane] = l;
         s_par[ly * kTile + lane] = ly * kTile + start;
+        s_cnt[ly * kTile + lane] = 0;
+        s_len[ly * kTile + lane] = (unsigned char)((later ? (__ffs(later) - 1) : 32) - lane);
     }
     __syncthreads();
     // vertical joins, once per pair of overlapping runs (at the first column of the overlap)
@@ -172,8 +187,12 @@ cc_local_kernel(const int32_t *__restrict__ lab, int32_t *__restrict__ parent, i
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < kTile * kTile / 256; ++k)
-        if (head_root[k] >= 0) s_par[threadIdx.x + k * 256] = head_root[k];
+    for (int k = 0; k < kTile * kTile / 256; ++k) {
+        if (head_root[k] >= 0) {
+            s_par[threadIdx.x + k * 256] = head_root[k];
+            atomicAdd(&s_cnt[head_root[k]], (int)s_len[threadIdx.x + k * 256]);   // one add per run
+        }
+    }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kTile * kTile / 256; ++k) {
@@ -182,11 +201,14 @@ cc_local_kernel(const int32_t *__restrict__ lab, int32_t *__restrict__ parent, i
         const int y = y0 + ly, x = x0 + lx;
         if (y >= H || x >= W) continue;
         const int64_t g = (int64_t)y * W + x;
+        if (s_lab[i] == mask_label) {
+            parent[g] = -1;
+            psize[g] = 0;
+            continue;
+        }
         const int r = s_par[s_par[i]];
         parent[g] = (int32_t)((int64_t)(y0 + r / kTile) * W + x0 + r % kTile);
-        psize[g] = 0;
-        visit[g] = 0;
-        stamp[g] = 0;
+        psize[g] = (r == i) ? s_cnt[i] : 0;    // tile-local component size at its tile-local root
     }
 }
 
@@ -224,42 +246,55 @@ cc_border_kernel(const int32_t *__restrict__ lab, int32_t *parent, int H, int W,
     }
 }
 
-// phase 1c: flatten, T = root, component sizes (one atomic per run of equal
-// roots inside a warp)
+// phase 1c: every pixel points at its component root (T = root, written over the parent array: a
+// concurrent find that reads the new value just skips part of its chain); tile-local sizes are summed
+// into the root (one atomic per tile-local component); roots are appended to a compact list.
 __global__ void __launch_bounds__(256)
-cc_flatten_kernel(const int32_t *__restrict__ lab, int32_t *parent, int32_t *__restrict__ T,
-                  int32_t *psize, int64_t N, int32_t mask_label)
+cc_flatten_kernel(int32_t *T, int32_t *psize, int32_t *roots, int32_t *ctr, int64_t N)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    int32_t root = -1;
-    if (i < N && lab[i] != mask_label) {
-        root = uf_find(parent, (int32_t)i);
-        parent[i] = root;
-        T[i] = root;
-    } else if (i < N) {
-        T[i] = -1;
+    bool is_root = false;
+    if (i < N) {
+        const int32_t p = __ldcg(T + i);
+        if (p >= 0) {
+            const int32_t root = uf_find(T, p);
+            if (root != p) T[i] = root;
+            const int32_t mine = psize[i];
+            if (mine > 0 && root != (int32_t)i) atomicAdd(psize + root, mine);
+            is_root = root == (int32_t)i;
+        }
     }
-    const int32_t prev = __shfl_up_sync(0xffffffffu, root, 1);
-    const bool is_head = (lane == 0) || (prev != root);
-    const unsigned heads = __ballot_sync(0xffffffffu, is_head);
-    if (is_head && root >= 0) {
-        const unsigned later = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
-        const int end = later ? (__ffs(later) - 1) : 32;
-        atomicAdd(psize + root, end - lane);
+    const unsigned m = __ballot_sync(0xffffffffu, is_root);
+    if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(ctr + CTR_NROOTS, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (is_root) roots[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
     }
 }
 
-// phase 2 list: roots of components larger than max_size
+// phase 2/3 lists: classify the components by size (over the compact root list): larger than
+// max_size -> split list (grows from the end of `list`), smaller than min_size -> small list,
+// otherwise kept: its start pixel is marked in the bitmap.
 __global__ void __launch_bounds__(256)
-cc_list_over_kernel(const int32_t *__restrict__ T, const int32_t *__restrict__ psize, int32_t *list,
-                    int32_t *ctr, int64_t N, int64_t max_size)
+cc_classify_kernel(const int32_t *__restrict__ roots, const int32_t *__restrict__ psize, int32_t *list,
+                   int32_t *adj, int32_t *aux, uint32_t *bits, int32_t *ctr, int64_t N, int64_t min_size,
+                   int64_t max_size)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    if (T[i] == (int32_t)i && (int64_t)psize[i] > max_size) {
-        const int e = atomicAdd(ctr + CTR_NOVER, 1);
-        list[N - 1 - e] = (int32_t)i;  // oversized list grows from the end of `list`
+    const int n_roots = ctr[CTR_NROOTS];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_roots; e += gridDim.x * blockDim.x) {
+        const int32_t i = roots[e];
+        const int64_t sz = psize[i];
+        if (sz > max_size) {
+            list[N - 1 - atomicAdd(ctr + CTR_NOVER, 1)] = i;
+        } else if (sz < min_size) {
+            list[atomicAdd(ctr + CTR_NSMALL, 1)] = i;
+            adj[i] = -1;
+            aux[i] = i;  // tfix: optimistic "labelled at its own time"
+        } else {
+            atomicOr(bits + (i >> 5), 1u << (i & 31));
+        }
     }
 }
 

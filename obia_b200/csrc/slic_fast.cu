@@ -15,6 +15,10 @@
 // truncated +-2*step windows), ascending-index tie rule, exact spatial pruning, the deterministic
 // fixed-point centre update and the strip addressing (y_off / Hg) are those of the exact kernel;
 // sums are taken over f - o and the tile adds count * o back in 64-bit fixed point.
+// The score is kept in units of 1/w (the colour side is scaled by step^2 instead of the spatial side
+// by w): with integer pixel and centre coordinates -- the first sweep, when all centre colours are
+// still zero -- the spatial part is exact integer arithmetic, so the exact ties of the regular grid
+// (pixels half-way between two centres) go to the lowest centre index exactly as in the reference.
 // Results differ from the exact kernel only where two candidates are within float32 rounding of
 // each other (tests: >= 99.9 % agreement per sweep, ARI reported).
 #include "slic_common.cuh"
@@ -24,15 +28,18 @@ namespace obia {
 template <int CP, int NW> struct FastTraits {
     static constexpr int CR = (3 + CP + 3) / 4 * 4;          // floats per candidate record
     static constexpr int kIds = 1024;
-    static constexpr int kChk = (CP <= 32) ? 64 : 32;
-    static constexpr int kAcc = (CP <= 16) ? 128 : 64;
-    static constexpr int kRecFull = (CP <= 4) ? 768 : (CP == 8) ? 608 : (CP == 16) ? 272 : 512;
-    static constexpr int kRec = kRecFull * NW / 8;
-    static constexpr bool kDynRec = CP >= 32;
+    static constexpr int kChk = (CP <= 32) ? 64 : 32;        // candidate records resident at once (<= 64)
+    static constexpr int kAcc = (CP <= 16) ? 128 : 64;       // slots with a tile accumulator row
+    static constexpr int PX = (CP <= 8) ? 4 : 2;             // pixels per lane
+    static constexpr int kRecW = 32 * PX;                    // records per warp and phase: one per pixel at most
+    static constexpr int kRec = NW * kRecW;
+    static constexpr int NFR = 2 + CP;                       // words per record / accumulator row
+    static constexpr int RS = NFR | 1;                       // record stride in words (odd: conflict-free stores)
+    static constexpr size_t kDyn = ((size_t)kRec * RS + (size_t)kAcc * NFR) * sizeof(int);
 };
 
 // Score of the PX pixels of this lane against one candidate record (see the header):
-//   rec[0] = B_k, rec[1] = -2 w cy', rec[2] = -2 w cx', rec[3 + c] = -2 m'_c.
+//   rec[0] = B_k / w, rec[1] = -2 cy', rec[2] = -2 cx', rec[3 + c] = -2 m'_c / w.
 template <int CP, int PX, int CR, bool CHECK>
 __device__ __forceinline__ void eval_fast(const float (&pf)[PX][CP], float yr, float xbr, const float *__restrict__ cand,
                                           const int4 w, int y, int xb, int slot, float (&best)[PX],
@@ -63,36 +70,43 @@ __device__ __forceinline__ void eval_fast(const float (&pf)[PX][CP], float yr, f
     }
 }
 
+// Tile accumulator / record layout (NFR = 2 + CP 32-bit words, field-major records):
+//   word 0 = count | (sum of tile-local rows << 13)     (tile <= 4096 pixels, <= 128 rows: 13 + 19 bits, unsigned)
+//   word 1 = sum of tile-local columns                 (records carry their slot in bits 16..)
+//   word 2 + c = 32-bit fixed-point sum of (f_c - o_c)
 template <int CP, int PX, int NS, int NW>
 __global__ void __launch_bounds__(NW * 32, (CP <= 16) ? (24 / NW) : 1)
 slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restrict__ mask,
                         const float *__restrict__ centres, const int32_t *__restrict__ head,
                         const int32_t *__restrict__ next, int32_t *__restrict__ labels,
                         unsigned long long *__restrict__ acc, int H, int W, int64_t pitch, int Cf,
-                        float spatial_weight, int step_y, int step_x, int ncy, int ncx, int start_label,
-                        int ignore_color, double fix_scale, float fix_scale32, long long fix_ratio,
-                        int32_t *status, int y_off, int Hg)
+                        float spatial_weight, float inv_weight, int step_y, int step_x, int ncy, int ncx,
+                        int start_label, int ignore_color, double fix_scale, float fix_scale32,
+                        long long fix_ratio, int32_t *status, int y_off, int Hg, int dbg)
 {
     using T = FastTraits<CP, NW>;
+    static_assert(PX == T::PX, "pixels per lane");
     constexpr int LPR = 16 / PX;         // lanes per strip row
     constexpr int RW = 32 / LPR;         // rows per warp strip
     constexpr int TH = (NW / 2) * RW;    // rows per phase (two strips side by side)
-    constexpr int NF = 3 + CP;
+    constexpr int NFR = T::NFR;
     constexpr int CR = T::CR, kIds = T::kIds, kChk = T::kChk, kAcc = T::kAcc, kRec = T::kRec;
-    constexpr bool kRounds = CP >= 16;
     constexpr int NT = NW * 32;
+    static_assert(TH * NS <= 128 && 32 * TH * NS <= 4096 && kChk <= 64, "packed record fields");
     __shared__ int s_ids[kIds];
     __shared__ int s_sorted[kIds];
-    __shared__ int s_nids, s_nrec;
+    __shared__ int s_nids;
+    __shared__ int s_cells[4];
     __shared__ int4 s_win[kChk];
     __shared__ float2 s_cyx[kChk];
     __shared__ __align__(16) float s_cand[kChk][CR];
+    __shared__ unsigned short s_wl[NW][kChk];    // per-warp list of surviving candidates (slot | full << 15)
     __shared__ float s_off[CP];
     __shared__ long long s_off64[CP];
-    __shared__ int s_acc[kAcc][NF];
     extern __shared__ __align__(16) int s_dyn[];
-    __shared__ __align__(16) int s_rec_static[T::kDynRec ? 1 : kRec][NF + 1];
-    int(*s_rec)[NF + 1] = T::kDynRec ? reinterpret_cast<int(*)[NF + 1]>(s_dyn) : s_rec_static;
+    constexpr int RS = T::RS;
+    int(*s_rec)[RS] = reinterpret_cast<int(*)[RS]>(s_dyn);                      // [kRec][RS]
+    int(*s_acc)[NFR] = reinterpret_cast<int(*)[NFR]>(s_dyn + RS * kRec);        // [kAcc][NFR]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * (TH * NS);
@@ -101,17 +115,18 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
     const int X0 = tx0 + 16, Y0 = ty0 + y_off + (TH * NS) / 2;
 
     // ---- collect candidate centre ids (as in the exact kernel) --------------------------------
-    if (tid == 0) {
-        s_nids = 0;
-        s_nrec = 0;
+    if (tid < 4) {
+        // cell range whose centres can reach the tile: a centre at cy reaches rows y with
+        // y - 2s <= cy < y + 1 + 2s; two pixels of slack absorb the float rounding of the cell index
+        const int lo = (tid & 1) ? tx0 : ty0 + y_off, hi = (tid & 1) ? tx1 : ty1 + y_off;
+        const int st = (tid & 1) ? step_x : step_y, nc = (tid & 1) ? ncx : ncy;
+        s_cells[tid] = (tid < 2) ? max(0, floordiv_i(lo - 2 * st - 2, st)) : min(nc - 1, floordiv_i(hi + 2 * st + 2, st));
+        if (tid == 0) s_nids = 0;
     }
-    for (int i = tid; i < kAcc * NF; i += NT) (&s_acc[0][0])[i] = 0;
+    for (int i = tid; i < kAcc * NFR; i += NT) (&s_acc[0][0])[i] = 0;
     __syncthreads();
     {
-        const int gy_lo = max(0, floordiv_i(ty0 + y_off - 2 * step_y - 2, step_y));
-        const int gy_hi = min(ncy - 1, floordiv_i(ty1 + y_off + 2 * step_y + 2, step_y));
-        const int gx_lo = max(0, floordiv_i(tx0 - 2 * step_x - 2, step_x));
-        const int gx_hi = min(ncx - 1, floordiv_i(tx1 + 2 * step_x + 2, step_x));
+        const int gy_lo = s_cells[0], gx_lo = s_cells[1], gy_hi = s_cells[2], gx_hi = s_cells[3];
         const int ny = gy_hi - gy_lo + 1, nx = gx_hi - gx_lo + 1;
         for (int i = tid; i < ny * nx; i += NT) {
             const int gy = gy_lo + i / nx, gx = gx_lo + i % nx;
@@ -148,54 +163,45 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
 
     const bool single_chunk = nids <= kChk;
     const float INF = __int_as_float(0x7f800000);
+    const int64_t plane = (int64_t)H * pitch;
     for (int sp = 0; sp < NS; ++sp) {
         // ---- this lane's pixels ------------------------------------------------------------
         const int sx0 = tx0 + (warp & 1) * 16, sy0 = ty0 + sp * TH + (warp >> 1) * RW;
         const int y = sy0 + lane / LPR;
         const int xb = sx0 + (lane % LPR) * PX;
-        const bool row_ok = y < H;
+        const bool ld_ok = y < H && xb < W;
         float pf[PX][CP];
         unsigned vmask = 0;
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
-            bool v = row_ok && (xb + j) < W;
+            bool v = ld_ok && (xb + j) < W;
             if (v && mask) v = mask[(int64_t)y * W + xb + j] != 0;
             vmask |= (v ? 1u : 0u) << j;
         }
+        {
+            const float *src = feat + (int64_t)y * pitch + xb;
 #pragma unroll
-        for (int c = 0; c < CP; ++c) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c < Cf && row_ok && xb < W) {
-                const float *src = feat + (int64_t)c * H * pitch + (int64_t)y * pitch + xb;
-                if constexpr (PX == 4) {
-                    v = *reinterpret_cast<const float4 *>(src);
-                } else {
-                    const float2 t = *reinterpret_cast<const float2 *>(src);
-                    v.x = t.x; v.y = t.y;
+            for (int c = 0; c < CP; ++c) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ld_ok && c < Cf) {
+                    if constexpr (PX == 4) {
+                        v = ldg_stream_f4(reinterpret_cast<const float4 *>(src + c * plane));
+                    } else {
+                        const float2 t = *reinterpret_cast<const float2 *>(src + c * plane);
+                        v.x = t.x; v.y = t.y;
+                    }
                 }
-            }
-            const float o = s_off[c];
-            pf[0][c] = v.x - o;
-            pf[1][c] = v.y - o;
-            if constexpr (PX == 4) {
-                pf[2][c] = v.z - o;
-                pf[3][c] = v.w - o;
+                const float o = s_off[c];
+                pf[0][c] = v.x - o;
+                pf[1][c] = v.y - o;
+                if constexpr (PX == 4) {
+                    pf[2][c] = v.z - o;
+                    pf[3][c] = v.w - o;
+                }
             }
         }
         const int yg = y + y_off;
         const float yr = (float)(yg - Y0), xbr = (float)(xb - X0);
-        // candidate-independent part of the distance (needed for the pruning bound only)
-        float A[PX];
-#pragma unroll
-        for (int j = 0; j < PX; ++j) {
-            const float xr = xbr + (float)j;
-            float a = spatial_weight * (yr * yr + xr * xr);
-            if (!ignore_color) {
-#pragma unroll
-                for (int c = 0; c < CP; ++c) a = fmaf(pf[j][c], pf[j][c], a);
-            }
-            A[j] = ((vmask >> j) & 1u) ? a : 0.0f;
-        }
 
         float best[PX];
         int bests[PX];
@@ -232,17 +238,18 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
                     w.w = trunc_i(((float)W < xhi) ? (float)W : xhi);
                     s_win[sI] = w;
                     const float cyr = cy - (float)Y0, cxr = cx - (float)X0;
-                    float B = spatial_weight * (cyr * cyr + cxr * cxr);
+                    float Bc = 0.0f;
                     float *cr = s_cand[sI];
-                    cr[1] = -2.0f * spatial_weight * cyr;
-                    cr[2] = -2.0f * spatial_weight * cxr;
+                    cr[1] = -2.0f * cyr;
+                    cr[2] = -2.0f * cxr;
 #pragma unroll
                     for (int c = 0; c < CP; ++c) {
                         const float mc = (c < Cf && !ignore_color) ? m[c] - s_off[c] : 0.0f;
-                        B = fmaf(mc, mc, B);
-                        cr[3 + c] = -2.0f * mc;
+                        Bc = fmaf(mc, mc, Bc);
+                        cr[3 + c] = -2.0f * inv_weight * mc;
                     }
-                    cr[0] = B;
+                    // integer-valued (exact) while the centres sit on the pixel grid and Bc == 0
+                    cr[0] = fmaf(cyr, cyr, cxr * cxr) + inv_weight * Bc;
 #pragma unroll
                     for (int c = 3 + CP; c < CR; ++c) cr[c] = 0.0f;
                 }
@@ -273,7 +280,11 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
                 }
                 fullbits[half] = __ballot_sync(0xffffffffu, full);
             }
+            // Seed the pruning bound with the nearest candidate: its distances bound every pixel's final
+            // minimum from above.  Skipped when its spatial bound alone says nothing can be pruned
+            // (colour-dominated runs: the bound would exceed every candidate's spatial term anyway).
             seedkey = __reduce_min_sync(0xffffffffu, seedkey);
+            if (dbg & 4) seedkey = 0xffffffffu;
             if (seedkey != 0xffffffffu && __uint_as_float(seedkey & ~63u) < wbound) {
                 const int s = (int)(seedkey & 63u);
                 float tb[PX];
@@ -284,27 +295,44 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
                     ts[j] = -1;
                 }
                 eval_fast<CP, PX, CR, true>(pf, yr, xbr, s_cand[s], s_win[s], yg, xb, 0, tb, ts);
-                float m = tb[0] + A[0];
+                // true distance = w * score + A, A = candidate-independent part
+                float m = 0.0f;
 #pragma unroll
-                for (int j = 1; j < PX; ++j) m = fmaxf(m, tb[j] + A[j]);
+                for (int j = 0; j < PX; ++j) {
+                    const float xr = xbr + (float)j;
+                    float a = spatial_weight * (yr * yr + xr * xr);
+                    if (!ignore_color) {
+#pragma unroll
+                        for (int c = 0; c < CP; ++c) a = fmaf(pf[j][c], pf[j][c], a);
+                    }
+                    if ((vmask >> j) & 1u) m = fmaxf(m, fmaf(tb[j], spatial_weight, a));
+                }
                 m = fmaxf(m, 0.0f) * 1.0001f + 1e-30f;   // rounding slack of the expanded form
                 wbound = fminf(wbound, __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m))));
             }
+            // survivors, ascending slot order, compacted into the warp's list
+            int wcnt = 0;
 #pragma unroll
             for (int half = 0; half < kChk / 32; ++half) {
-                unsigned m = __ballot_sync(0xffffffffu, hit[half] && lb[half] <= wbound);
-                const unsigned fb = fullbits[half];
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int s = half * 32 + b;
-                    if ((fb >> b) & 1u)
-                        eval_fast<CP, PX, CR, false>(pf, yr, xbr, s_cand[s], make_int4(0, 0, 0, 0), yg, xb, c0 + s,
-                                                     best, bests);
-                    else
-                        eval_fast<CP, PX, CR, true>(pf, yr, xbr, s_cand[s], s_win[s], yg, xb, c0 + s, best, bests);
-                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit[half] && lb[half] <= wbound);
+                if ((m >> lane) & 1u)
+                    s_wl[warp][wcnt + __popc(m & ((1u << lane) - 1u))] =
+                        (unsigned short)((half * 32 + lane) | (((fullbits[half] >> lane) & 1u) << 15));
+                wcnt += __popc(m);
             }
+            if (dbg & 2) wcnt = min(wcnt, 1);
+            __syncwarp();
+            const unsigned short *wl = s_wl[warp];
+            for (int i = 0; i < wcnt; ++i) {
+                const unsigned e = wl[i];
+                const int s = (int)(e & 0x7fffu);
+                const float *cand = &s_cand[0][0] + s * CR;
+                if (e & 0x8000u)
+                    eval_fast<CP, PX, CR, false>(pf, yr, xbr, cand, make_int4(0, 0, 0, 0), yg, xb, c0 + s, best, bests);
+                else
+                    eval_fast<CP, PX, CR, true>(pf, yr, xbr, cand, s_win[s], yg, xb, c0 + s, best, bests);
+            }
+            __syncwarp();
         }
 
         // ---- labels --------------------------------------------------------------------------
@@ -326,48 +354,14 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
                 if (kk[j] >= 0) labels[(int64_t)y * W + xb + j] = kk[j] + start_label;
         }
 
-        // ---- fused centre update (records -> tile accumulators -> RED.64), sums of f - o ----------
-        int lead = -1;
-#pragma unroll
-        for (int j = PX - 1; j >= 0; --j)
-            if (((vmask >> j) & 1u) && bests[j] >= 0) lead = bests[j];
-        auto place = [&](int item, int kcur) -> bool {
-            int slot, cnt = 0, sxl = 0;
-            float fs[CP];
-            if (item == PX) {
-                slot = lead;
-#pragma unroll
-                for (int c = 0; c < CP; ++c) fs[c] = 0.0f;
-#pragma unroll
-                for (int j = 0; j < PX; ++j) {
-                    if (((vmask >> j) & 1u) && bests[j] == lead) {
-                        cnt += 1;
-                        sxl += xb + j - tx0;
-#pragma unroll
-                        for (int c = 0; c < CP; ++c) fs[c] = __fadd_rn(fs[c], pf[j][c]);
-                    }
-                }
-            } else {
-                slot = bests[item];
-                cnt = 1;
-                sxl = xb + item - tx0;
-#pragma unroll
-                for (int c = 0; c < CP; ++c) fs[c] = pf[item % PX][c];
-            }
-            if (slot >= 0 && slot < kAcc) {
-                const int ridx = atomicAdd(&s_nrec, 1);
-                if (ridx < kRec) {
-                    int *r = s_rec[ridx];
-                    r[0] = slot;
-                    r[1] = cnt;
-                    r[2] = cnt * (y - ty0);
-                    r[3] = sxl;
-#pragma unroll
-                    for (int c = 0; c < CP; ++c) r[4 + c] = __float2int_rn(fs[c] * fix_scale32);
-                    return true;
-                }
-                if (kRounds) return false;
-            }
+        // ---- fused centre update -----------------------------------------------------------------
+        // Per lane: the pixels that share the lane's leading winner are summed (fixed order) into one
+        // record, every other pixel is a record of its own; records sit in shared memory at an odd
+        // stride (conflict-free stores), the tile folds them into its per-slot accumulators with lanes
+        // across fields and issues one RED.64 per touched (centre, field) at the end.  Integer sums of
+        // f - o: independent of scheduling.  Pixels that kept their previous centre (no candidate) and
+        // slots beyond the accumulator rows go to HBM directly with the same quantisation.
+        auto direct = [&](int kcur, int cnt, int sxl, const float (&fs)[CP]) {
             unsigned long long *a = acc + (int64_t)kcur * (3 + Cf);
             atomicAdd(&a[0], (unsigned long long)cnt);
             atomicAdd(&a[1], (unsigned long long)((long long)cnt * yg));
@@ -377,72 +371,115 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
                 if (c < Cf)
                     atomicAdd(&a[3 + c], (unsigned long long)((long long)__float2int_rn(fs[c] * fix_scale32) * fix_ratio +
                                                               (long long)cnt * s_off64[c]));
-            return true;
         };
-        auto fold = [&]() {
-            const int nrec = min(s_nrec, kRec);
-            for (int e = tid; e < nrec * NF; e += NT) {
-                const int r = e / NF, f = e - r * NF;
-                const int v = s_rec[r][1 + f];
-                if (v != 0) atomicAdd(&s_acc[s_rec[r][0]][f], v);
-            }
-        };
-        if constexpr (!kRounds) {
-            if (lead >= 0) place(PX, s_sorted[lead]);
+        int lead = -1;
+#pragma unroll
+        for (int j = PX - 1; j >= 0; --j)
+            if (((vmask >> j) & 1u) && bests[j] >= 0) lead = bests[j];
+        // number of records of this lane: the lead group + every other assigned pixel
+        int nrec_l = 0;
+        if (lead >= 0 && lead < kAcc) nrec_l = 1;
+#pragma unroll
+        for (int j = 0; j < PX; ++j)
+            if (((vmask >> j) & 1u) && bests[j] >= 0 && bests[j] != lead && bests[j] < kAcc) ++nrec_l;
+        int incl = nrec_l;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int nrec_w = __shfl_sync(0xffffffffu, incl, 31);   // records of this warp in this phase
+        int(*w_rec)[RS] = s_rec + warp * T::kRecW;               // the warp's own record region: no CTA barrier
+        int rbase = incl - nrec_l;
+        if (lead >= 0) {
+            int cnt = 0, sxl = 0;
+            float fs[CP];
+#pragma unroll
+            for (int c = 0; c < CP; ++c) fs[c] = 0.0f;
 #pragma unroll
             for (int j = 0; j < PX; ++j) {
-                if (!((vmask >> j) & 1u) || bests[j] == lead) continue;
-                int kcur = kk[j];
-                if (kcur < 0) kcur = labels[(int64_t)y * W + xb + j] - start_label;
-                if (kcur < 0) continue;
-                place(j, kcur);
-            }
-            __syncthreads();
-            fold();
-            __syncthreads();
-            if (tid == 0) s_nrec = 0;
-            __syncthreads();
-        } else {
-            unsigned pending = (lead >= 0) ? (1u << PX) : 0u;
-            int kc[PX];
+                if (((vmask >> j) & 1u) && bests[j] == lead) {
+                    cnt += 1;
+                    sxl += xb + j - tx0;
 #pragma unroll
-            for (int j = 0; j < PX; ++j) {
-                kc[j] = -1;
-                if (!((vmask >> j) & 1u) || bests[j] == lead) continue;
-                kc[j] = kk[j];
-                if (kc[j] < 0) kc[j] = labels[(int64_t)y * W + xb + j] - start_label;
-                if (kc[j] >= 0) pending |= 1u << j;
+                    for (int c = 0; c < CP; ++c) fs[c] = __fadd_rn(fs[c], pf[j][c]);
+                }
             }
-            while (true) {
-                if (((pending >> PX) & 1u) && place(PX, s_sorted[lead])) pending &= ~(1u << PX);
+            if (lead < kAcc) {
+                int *r = w_rec[rbase];
+                r[0] = cnt | ((cnt * (y - ty0)) << 13);
+                r[1] = sxl | (lead << 16);
 #pragma unroll
-                for (int j = 0; j < PX; ++j)
-                    if (((pending >> j) & 1u) && place(j, kc[j])) pending &= ~(1u << j);
-                const int more = __syncthreads_or(pending != 0);
-                fold();
-                __syncthreads();
-                if (tid == 0) s_nrec = 0;
-                __syncthreads();
-                if (!more) break;
+                for (int c = 0; c < CP; ++c) r[2 + c] = __float2int_rn(fs[c] * fix_scale32);
+                ++rbase;
+            } else {
+                direct(s_sorted[lead], cnt, sxl, fs);
             }
         }
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            if (!((vmask >> j) & 1u) || (bests[j] == lead && lead >= 0)) continue;
+            if (bests[j] >= 0 && bests[j] < kAcc) {
+                int *r = w_rec[rbase];
+                r[0] = 1 | ((y - ty0) << 13);
+                r[1] = (xb + j - tx0) | (bests[j] << 16);
+#pragma unroll
+                for (int c = 0; c < CP; ++c) r[2 + c] = __float2int_rn(pf[j][c] * fix_scale32);
+                ++rbase;
+            } else {
+                int kcur = kk[j];
+                if (kcur < 0) kcur = labels[(int64_t)y * W + xb + j] - start_label;   // kept its previous centre
+                if (kcur < 0) continue;
+                float fs[CP];
+#pragma unroll
+                for (int c = 0; c < CP; ++c) fs[c] = pf[j][c];
+                direct(kcur, 1, xb + j - tx0, fs);
+            }
+        }
+        __syncwarp();
+        {
+            // lanes across FIELDS (RPW records per warp instruction): the atomics of one instruction go to
+            // different words unless two of its records share a slot.  Each warp folds its own records.
+            constexpr int RPW = (NFR <= 10) ? 3 : (NFR <= 16) ? 2 : 1;   // records per warp pass
+            constexpr int FPL = (NFR + 31) / 32;                           // fields per lane when NFR > 32
+            const int rr = (RPW > 1) ? lane / NFR : 0, f0 = (RPW > 1) ? lane - rr * NFR : lane;
+            if (rr < RPW) {
+                for (int r = rr; r < nrec_w; r += RPW) {
+                    const int *rec = w_rec[r];
+                    const int w1 = rec[1];
+                    int *a = s_acc[w1 >> 16];
+#pragma unroll
+                    for (int q = 0; q < FPL; ++q) {
+                        const int f = f0 + 32 * q;
+                        if (f < NFR) {
+                            const int v = (f == 1) ? (w1 & 0xffff) : rec[f];
+                            atomicAdd(&a[f], v);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
     }   // strip phases
+    __syncthreads();
     const int nslots = min(nids, kAcc);
-    for (int i = tid; i < nslots * (3 + Cf); i += NT) {
-        const int slot = i / (3 + Cf), f = i % (3 + Cf);
-        const int cnt = s_acc[slot][0];
+    for (int i = tid; i < nslots * (3 + CP); i += NT) {
+        const int slot = i / (3 + CP), f = i - slot * (3 + CP);
+        if (f >= 3 + Cf) continue;
+        const unsigned w0 = (unsigned)s_acc[slot][0];
+        const int cnt = (int)(w0 & 0x1fffu);
         if (cnt == 0) continue;
-        const long long v = s_acc[slot][f];
         long long g;
-        if (f == 0) g = v;
-        else if (f == 1) g = v + (long long)cnt * (ty0 + y_off);
-        else if (f == 2) g = v + (long long)cnt * tx0;
-        else g = v * fix_ratio + (long long)cnt * s_off64[f - 3];
+        if (f == 0) g = cnt;
+        else if (f == 1) g = (long long)(w0 >> 13) + (long long)cnt * (ty0 + y_off);
+        else if (f == 2) g = (long long)s_acc[slot][1] + (long long)cnt * tx0;
+        else g = (long long)s_acc[slot][f - 1] * fix_ratio + (long long)cnt * s_off64[f - 3];
         if (g != 0) atomicAdd(&acc[(int64_t)s_sorted[slot] * (3 + Cf) + f], (unsigned long long)g);
     }
 }
 
 static int g_fast_warps = 8;   // tuning knob (obia_b200_slic_fast_variant): warps per CTA, 8 or 4
+static int g_fast_dbg = 0;     // ablation switches (bits 8.. of the same call): 2 one candidate per chunk, 4 no seed
 
 template <int CP, int PX, int NS, int NW>
 static int launch_fast_t(const float *feat, const uint8_t *mask, const float *centres, const SlicWs &w, int32_t *labels,
@@ -462,14 +499,13 @@ static int launch_fast_t(const float *feat, const uint8_t *mask, const float *ce
     const float fix_scale32 = (float)ldexp(fix_scale, bits_px - 42 - lg_ns);
     const long long fix_ratio = 1LL << (42 - bits_px + lg_ns);
     dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, NS * TH));
-    constexpr size_t dyn = T::kDynRec ? (size_t)T::kRec * (3 + CP + 1) * sizeof(int) : 0;
+    constexpr size_t dyn = T::kDyn;
     auto kern = slic_assign_fast_kernel<CP, PX, NS, NW>;
-    if (dyn > 0)
-        OBIA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    OBIA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     prof_begin(st);
     kern<<<grid, NW * 32, dyn, st>>>(feat, mask, centres, w.head, w.next, labels, w.acc, (int)H, (int)W, pitch, Cf, sw,
-                                     step_y, step_x, (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale,
-                                     fix_scale32, fix_ratio, status, y_off, (int)Hg);
+                                     1.0f / sw, step_y, step_x, (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale,
+                                     fix_scale32, fix_ratio, status, y_off, (int)Hg, g_fast_dbg);
     prof_end(st);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
@@ -482,12 +518,12 @@ int launch_assign_fast(const float *feat, const uint8_t *mask, const float *cent
 #define OBIA_FAST_ARGS feat, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x, start_label, ignore_color, \
                        fix_scale, status, y_off, Hg, st
     if (Cf <= 4) {
-        if (g_fast_warps == 4) return launch_fast_t<4, 4, 4, 4>(OBIA_FAST_ARGS);
-        return launch_fast_t<4, 4, 2, 8>(OBIA_FAST_ARGS);
+        if (g_fast_warps == 4) return launch_fast_t<4, 4, 8, 4>(OBIA_FAST_ARGS);
+        return launch_fast_t<4, 4, 4, 8>(OBIA_FAST_ARGS);
     }
     if (Cf <= 8) {
-        if (g_fast_warps == 4) return launch_fast_t<8, 4, 4, 4>(OBIA_FAST_ARGS);
-        return launch_fast_t<8, 4, 2, 8>(OBIA_FAST_ARGS);
+        if (g_fast_warps == 4) return launch_fast_t<8, 4, 8, 4>(OBIA_FAST_ARGS);
+        return launch_fast_t<8, 4, 4, 8>(OBIA_FAST_ARGS);
     }
     if (Cf <= 16) return launch_fast_t<16, 2, 2, 8>(OBIA_FAST_ARGS);
     if (Cf <= 32) return launch_fast_t<32, 2, 2, 8>(OBIA_FAST_ARGS);
@@ -499,7 +535,9 @@ int launch_assign_fast(const float *feat, const uint8_t *mask, const float *cent
 
 extern "C" int obia_b200_slic_fast_variant(int32_t warps_per_cta)
 {
-    if (warps_per_cta != 4 && warps_per_cta != 8) return obia::set_err(OBIA_B200_ERR_ARG, "slic_fast_variant: 4 or 8");
-    obia::g_fast_warps = warps_per_cta;
+    const int warps = warps_per_cta & 0xff;
+    if (warps != 4 && warps != 8) return obia::set_err(OBIA_B200_ERR_ARG, "slic_fast_variant: 4 or 8");
+    obia::g_fast_warps = warps;
+    obia::g_fast_dbg = (warps_per_cta >> 8) & 0xff;
     return OBIA_B200_OK;
 }

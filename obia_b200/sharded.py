@@ -28,7 +28,8 @@ from .pipeline import _i32_array, _p, _require_cuda, _stream_ptr
 class ShardedSlic:
     def __init__(self, raw_strip, row0, H_total, segmentation_bands=None, *, n_segments=100, compactness=10.0,
                  max_num_iter=10, sigma=0, convert2lab=None, enforce_connectivity=True, min_size_factor=0.5,
-                 max_size_factor=3, slic_zero=False, start_label=1, mask=None, spacing=None):
+                 max_size_factor=3, slic_zero=False, start_label=1, mask=None, spacing=None, exact=False):
+        self.exact = bool(exact)
         _require_cuda(raw_strip, "raw_strip", torch.float32)
         if mask is not None:
             raise NotImplementedError("sharded global SLIC supports unmasked rasters (use the tiled driver for masks)")
@@ -98,7 +99,8 @@ class ShardedSlic:
 
     # -- step 3 (x max_num_iter): sweep -> reduce acc over strips -> finish ----------------------------
     def sweep(self):
-        _lib.check(self.lib.obia_b200_slic_sweep(
+        sweep = self.lib.obia_b200_slic_sweep if self.exact else self.lib.obia_b200_slic_sweep_fast
+        _lib.check(sweep(
             _p(self.feats), None, _p(self.centres), _p(self.labels), _p(self.ws), self.h, self.W, self.pitch, self.Cf,
             self.n, self.step, self.step_y, self.step_x, self.start_label, 0, 0, self.fix_scale, self.row0, self.H,
             _p(self.status), _stream_ptr()), "slic_sweep")
