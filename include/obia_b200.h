@@ -233,6 +233,16 @@ int obia_b200_slic_sweep_fast(const float *features, const uint8_t *mask, const 
                               void *stream);
 int obia_b200_slic_fast_variant(int32_t warps_per_cta);
 
+/* Sharded runs may exchange only the BANDS of the accumulator table whose centres can receive pixels
+ * from two ranks (centre indices [up_lo, up_hi) at the upper strip boundary, [down_lo, down_hi) at the
+ * lower one) instead of all-reducing the whole table.  After finish_sweep this check raises status[1]
+ * when a live centre outside those bands has a window that reaches beyond rows [row_lo, row_hi) of
+ * this rank (a centre drifted further than the band allows): the caller then repeats the run with
+ * the full all-reduce.  Asynchronous. */
+int obia_b200_slic_band_check(const float *centres, int64_t n, int32_t Cf, int64_t row_lo, int64_t row_hi,
+                              int64_t H_total, int64_t up_lo, int64_t up_hi, int64_t down_lo,
+                              int64_t down_hi, int32_t step_y, int32_t *status, void *stream);
+
 /* slic_zero (SLICO, `_slic.pyx` "update the color distance maxima"): with slic_zero != 0 a sweep
  * divides every colour distance by the centre's running maximum (initialised to 1 by slic_begin);
  * after finish_sweep this call raises each centre's maximum to the largest colour distance of the
@@ -248,8 +258,8 @@ int obia_b200_slic_update_max_color(const float *features, const uint8_t *mask, 
  * (sequential raster-scan BFS) reached from segment_boundaries.py:51.
  * Union-find connected components + exact data-parallel replay of the
  * reference's small-segment merge, BFS size cap and raster-order numbering
- * (see DESIGN.md, K3).  Synchronises the stream internally (a few 4-byte
- * read-backs drive the fixed-point loop).
+ * (see DESIGN.md, K3).  Synchronises the stream once at the end (the read-back
+ * of the segment count; more only when the rare label-0 chains need extra rounds).
  *   labels_in  [H][W] int32 (values start_label-1 = masked)
  *   labels_out [H][W] int32
  *   n_labels_host  out: number of kept segments (labels are
@@ -261,6 +271,36 @@ int obia_b200_enforce_connectivity(const int32_t *labels_in,
                                    int64_t H, int64_t W, int64_t min_size,
                                    int64_t max_size, int32_t start_label,
                                    int64_t *n_labels_host, void *stream);
+
+/* The same, for ONE raster sharded by row strips across GPUs (no reference counterpart: the reference is
+ * single-process; result = the rows the single-raster call above would give, bit for bit).
+ * `labels_ext` holds the rank's core rows [core_row0, core_row0 + core_rows) preceded / followed by halo
+ * rows of its neighbours' SLIC labels (H_ext rows in all; `top_open` / `bottom_open` = the halo edge is
+ * not the raster edge).  SLIC components are bounded by the +-2*step windows, so with a halo of a few
+ * window heights every piece that reaches the core is complete inside the strip.
+ *   strip_begin   components, size-cap split, small-piece merge targets; returns on the host
+ *                 counts[0] = kept pieces that start above the core rows (inside the strip),
+ *                 counts[1] = kept pieces that start in the core rows, counts[2] = all kept pieces.
+ *                 The caller all-gathers counts[1] over the ranks; `label_offset` of this rank is the
+ *                 exclusive prefix sum minus its counts[0] (north_star: "exclusive scan of per-tile
+ *                 label offsets").
+ *   strip_finish  numbers the pieces (start_label + label_offset + local rank) and writes
+ *                 the core rows.  `incomplete_host[0]` != 0 when a core pixel's label depends on pixels
+ *                 outside the strip (cut component or unknown merge chain): the caller retries with a
+ *                 taller halo (or gathers the whole raster); `incomplete_host[1]` != 0 when label 0
+ *                 occurs in the core rows (start_label 1 only: merged pieces without an earlier
+ *                 neighbour, SURVEY.md defect 7).  Both calls synchronise the stream.
+ * workspace: obia_b200_connectivity_workspace_bytes(H_ext, W), unchanged between the two calls. */
+int obia_b200_connectivity_strip_begin(const int32_t *labels_ext, void *workspace, int64_t H_ext,
+                                       int64_t W, int64_t core_row0, int64_t core_rows,
+                                       int32_t top_open, int32_t bottom_open, int64_t min_size,
+                                       int64_t max_size, int32_t start_label, int64_t *counts_host,
+                                       void *stream);
+int obia_b200_connectivity_strip_finish(const int32_t *labels_ext, int32_t *labels_out_core,
+                                        void *workspace, int64_t H_ext, int64_t W, int64_t core_row0,
+                                        int64_t core_rows, int64_t min_size, int64_t max_size,
+                                        int32_t start_label, int64_t label_offset,
+                                        int32_t *incomplete_host, void *stream);
 
 /* ---------------------------------------------------------------- K4 ----
  * Per-segment, per-band zonal statistics in one pass over the raster:
@@ -277,13 +317,24 @@ int obia_b200_enforce_connectivity(const int32_t *labels_in,
  *              scipy returns NaN skew/kurtosis when m2 <= (resolution*mean)^2
  *   stats      [max_label+1][Cz][8] float64 out:
  *              count, mean, variance, min, max, skewness, kurtosis, sum
- *              (count==0 -> NaN statistics)
+ *              NaN samples are dropped per band like `band_data[~np.isnan(band_data)]`
+ *              (:144-147): count = valid samples of that band; count==0 -> NaN statistics
  */
 int64_t obia_b200_zonal_workspace_bytes(int64_t max_label, int32_t Cz);
 int obia_b200_zonal_stats(const int32_t *labels, const float *raw, int64_t H,
                           int64_t W, int32_t C, const int32_t *bands_host,
                           int32_t Cz, int64_t max_label, double resolution,
                           double *stats, void *workspace, void *stream);
+
+/* Same statistics over the label range [label_lo, label_lo + n_rows): row r of `stats` = label
+ * label_lo + r, every other label is skipped.  Used by the sharded path, where a rank's strip holds a
+ * contiguous range of the raster-order label numbering.
+ * workspace: obia_b200_zonal_workspace_bytes(n_rows - 1, Cz). */
+int obia_b200_zonal_stats_range(const int32_t *labels, const float *raw, int64_t H,
+                                int64_t W, int32_t C, const int32_t *bands_host,
+                                int32_t Cz, int64_t label_lo, int64_t n_rows,
+                                double resolution, double *stats, void *workspace,
+                                void *stream);
 
 /* ---------------------------------------------------------------- K5 ----
  * Per-segment GLCM texture features: replaces calculate_textural_stats

@@ -45,15 +45,23 @@ SIGNATURES = {
     "obia_b200_slic_begin": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i32, _i64, _i32, _i32, _i32, _vp, _vp]),
     "obia_b200_slic_sweep": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i64, _f32, _i32,
                                             _i32, _i32, _i32, _i32, _f64, _i64, _i64, _vp, _vp]),
+    "obia_b200_slic_band_check": (ctypes.c_int, [_vp, _i64, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i32,
+                                                 _vp, _vp]),
     "obia_b200_slic_update_max_color": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32,
                                                        _i64, _i32, _i32, _i32, _vp]),
     "obia_b200_slic_finish_sweep": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _i64, _i32, _i32, _f64, _vp]),
     "obia_b200_connectivity_workspace_bytes": (_i64, [_i64, _i64]),
     "obia_b200_enforce_connectivity": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp,
                                                       _vp]),
+    "obia_b200_connectivity_strip_begin": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i64, _i64,
+                                                          _i32, _vp, _vp]),
+    "obia_b200_connectivity_strip_finish": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32,
+                                                           _i64, _vp, _vp]),
     "obia_b200_zonal_workspace_bytes": (_i64, [_i64, _i32]),
     "obia_b200_zonal_stats": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _i64, _f64, _vp, _vp,
                                              _vp]),
+    "obia_b200_zonal_stats_range": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _i64, _i64, _f64, _vp,
+                                                   _vp, _vp]),
     "obia_b200_texture_workspace_bytes": (_i64, [_i64]),
     "obia_b200_texture_stats": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _i64, _i32, _vp, _vp,
                                                _vp]),

@@ -38,15 +38,17 @@ static __global__ void zonal_init_kernel(ZonalWs w, int64_t n)
 }
 
 static __global__ void __launch_bounds__(256)
-zonal_bbox_kernel(const int32_t *__restrict__ labels, ZonalWs w, int64_t N, int W, int64_t max_label)
+zonal_bbox_kernel(const int32_t *__restrict__ labels, ZonalWs w, int64_t N, int W, int64_t max_label,
+                  int32_t label_lo = 0)
 {
+    // table row = label - label_lo (label_lo != 0: the rank-local label range of a sharded raster)
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int32_t l = -1;
     int x = 0, y = 0;
     if (i < N) {
         l = labels[i];
-        if (l < 0 || (int64_t)l > max_label) l = -1;
+        if (l < 0 || l < label_lo || (int64_t)l - label_lo > max_label) l = -1;
         y = (int)(i / W);
         x = (int)(i - (int64_t)y * W);
     }
@@ -57,13 +59,14 @@ zonal_bbox_kernel(const int32_t *__restrict__ labels, ZonalWs w, int64_t N, int 
         const unsigned later = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
         const int end = later ? (__ffs(later) - 1) : 32;
         const int len = end - lane;
-        atomicMin(w.xmin + l, x);
-        atomicMax(w.xmax + l, x + len - 1);
+        const int32_t r = l - label_lo;
+        atomicMin(w.xmin + r, x);
+        atomicMax(w.xmax + r, x + len - 1);
         // a row can only be the label's first / last one if the pixel above / below the run head
         // carries another label (otherwise a smaller / larger y is reported by that row)
-        if (y == 0 || labels[i - W] != l) atomicMin(w.ymin + l, y);
-        if (i + W >= N || labels[i + W] != l) atomicMax(w.ymax + l, y);
-        atomicAdd(w.count + l, len);
+        if (y == 0 || labels[i - W] != l) atomicMin(w.ymin + r, y);
+        if (i + W >= N || labels[i + W] != l) atomicMax(w.ymax + r, y);
+        atomicAdd(w.count + r, len);
     }
 }
 

@@ -38,7 +38,8 @@ struct CcWs {
 };
 // ctr words
 enum { CTR_NSMALL = 0, CTR_NOVER = 1, CTR_CURSOR = 2, CTR_CHANGED = 3, CTR_NKEPT = 4, CTR_ERR = 5, CTR_NDIRTY0 = 6,
-       CTR_NDIRTY1 = 7, CTR_ROUNDS = 8, CTR_NROOTS = 9, CTR_KBEFORE = 10, CTR_KCORE = 11, CTR_FAIL = 12, CTR_WORDS = 16 };
+       CTR_NDIRTY1 = 7, CTR_ROUNDS = 8, CTR_NROOTS = 9, CTR_KBEFORE = 10, CTR_KCORE = 11, CTR_FAIL = 12, CTR_HASZERO = 13,
+       CTR_WORDS = 16 };
 // flag bits (strip mode: which results depend on pixels outside the strip)
 enum { FLAG_CUT = 1, FLAG_ADJ_UNKNOWN = 2, FLAG_TFIX_UNKNOWN = 4, FLAG_LABEL_UNKNOWN = 8 };
 
@@ -279,8 +280,8 @@ cc_flatten_kernel(int32_t *T, int32_t *psize, int32_t *roots, int32_t *ctr, int6
 // otherwise kept: its start pixel is marked in the bitmap.
 __global__ void __launch_bounds__(256)
 cc_classify_kernel(const int32_t *__restrict__ roots, const int32_t *__restrict__ psize, int32_t *list,
-                   int32_t *adj, int32_t *aux, uint32_t *bits, int32_t *ctr, int64_t N, int64_t min_size,
-                   int64_t max_size)
+                   int32_t *adj, int32_t *aux, int32_t *stamp, uint32_t *bits, int32_t *ctr, int64_t N,
+                   int64_t min_size, int64_t max_size)
 {
     const int n_roots = ctr[CTR_NROOTS];
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_roots; e += gridDim.x * blockDim.x) {
@@ -292,6 +293,7 @@ cc_classify_kernel(const int32_t *__restrict__ roots, const int32_t *__restrict_
             list[atomicAdd(ctr + CTR_NSMALL, 1)] = i;
             adj[i] = -1;
             aux[i] = i;  // tfix: optimistic "labelled at its own time"
+            stamp[i] = 0;
         } else {
             atomicOr(bits + (i >> 5), 1u << (i & 31));
         }
@@ -311,17 +313,19 @@ __device__ __forceinline__ bool nbr(int dir, int py, int px, int H, int W, int32
     return true;
 }
 
-// phase 2: replay the BFS cap on oversized components, one thread each
+// phase 2: replay the BFS cap on oversized components, one thread each.  T still holds the component
+// root for every unassigned member; every piece is classified as it is created (small list / kept bit).
 __global__ void __launch_bounds__(128)
-cc_split_kernel(const int32_t *__restrict__ lab, const int32_t *__restrict__ parent, int32_t *T,
-                int32_t *psize, int32_t *queue, const int32_t *__restrict__ list, int32_t *ctr,
-                uint8_t *visit, int64_t N, int H, int W, int64_t max_size)
+cc_split_kernel(const int32_t *__restrict__ lab, int32_t *T, int32_t *psize, int32_t *queue, int32_t *list,
+                int32_t *adj, int32_t *aux, int32_t *stamp, uint32_t *bits, uint8_t *flag, int32_t *ctr,
+                uint8_t *visit, int64_t N, int H, int W, int64_t min_size, int64_t max_size)
 {
     const int n_over = ctr[CTR_NOVER];
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_over; e += gridDim.x * blockDim.x) {
         const int32_t r = list[N - 1 - e];
         const int32_t L = lab[r];
         const int32_t n = psize[r];
+        const uint8_t cut = flag ? (flag[r] & FLAG_CUT) : 0;
         int32_t *qu = queue + atomicAdd(ctr + CTR_CURSOR, n);
         // uncapped BFS: mark members (visit = 2), bounding box
         int cnt = 1, head = 0;
@@ -347,7 +351,7 @@ cc_split_kernel(const int32_t *__restrict__ lab, const int32_t *__restrict__ par
         for (int y = ymin; y <= ymax; ++y) {
             for (int x = xmin; x <= xmax; ++x) {
                 const int32_t s = y * W + x;
-                if (parent[s] != r || visit[s] != 2) continue;
+                if (visit[s] != 2 || T[s] != r) continue;
                 int pc = 1, ph = 0;
                 qu[0] = s;
                 visit[s] = 1;
@@ -365,44 +369,24 @@ cc_split_kernel(const int32_t *__restrict__ lab, const int32_t *__restrict__ par
                     }
                     ++ph;
                 }
+                // (members still marked 2 keep T == r until their own piece is formed, so the
+                //  membership test above stays valid while T is rewritten piece by piece)
                 for (int i = 0; i < pc; ++i) {
                     T[qu[i]] = s;
                     visit[qu[i]] = 0;
                 }
                 psize[s] = pc;
+                if (flag) flag[s] = cut;
+                if ((int64_t)pc < min_size) {
+                    list[atomicAdd(ctr + CTR_NSMALL, 1)] = s;
+                    adj[s] = -1;
+                    aux[s] = s;
+                    stamp[s] = 0;
+                } else {
+                    atomicOr(bits + (s >> 5), 1u << (s & 31));
+                }
             }
         }
-    }
-}
-
-// phase 3 list: starts of pieces smaller than min_size (one global atomic per CTA)
-__global__ void __launch_bounds__(256)
-cc_list_small_kernel(const int32_t *__restrict__ T, const int32_t *__restrict__ psize, int32_t *list,
-                     int32_t *adj, int32_t *aux, int32_t *ctr, int64_t N, int64_t min_size)
-{
-    __shared__ int s_warp[8];
-    __shared__ int s_base;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool is_small = (i < N) && T[i] == (int32_t)i && (int64_t)psize[i] < min_size;
-    const unsigned m = __ballot_sync(0xffffffffu, is_small);
-    if (lane == 0) s_warp[warp] = __popc(m);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int tot = 0;
-        for (int w = 0; w < 8; ++w) {
-            const int c = s_warp[w];
-            s_warp[w] = tot;
-            tot += c;
-        }
-        s_base = tot ? atomicAdd(ctr + CTR_NSMALL, tot) : 0;
-    }
-    __syncthreads();
-    if (is_small) {
-        const int e = s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u));
-        list[e] = (int32_t)i;
-        adj[i] = -1;
-        aux[i] = (int32_t)i;  // tfix: optimistic "labelled at its own time"
     }
 }
 
@@ -413,60 +397,66 @@ struct CcParams {
     int32_t optimistic;   // round 1: every piece counts as labelled from its own start pixel
 };
 
+struct CcArrays {
+    const int32_t *lab, *T, *psize, *list;
+    int32_t *adj, *aux, *queue, *ctr, *stamp;
+    uint8_t *visit;
+    uint8_t *flag;        // strip mode only (else NULL): FLAG_* per piece start
+};
+
 // Scan position at which pixel q (not in piece t) receives a label > mask label, kTInf if never:
 // kept pieces at their start; merged pieces at their start for start_label 0 (they always carry
 // a label >= 0), at `tfix` for start_label 1 (label 0 == mask label until a later re-scan).
-__device__ __forceinline__ int32_t label_time(const int32_t *lab, const int32_t *T, const int32_t *psize,
-                                              const int32_t *aux, const CcParams &P, int32_t q, int32_t t)
+// Strip mode: `unk` is raised when that time is not known inside the strip (the neighbour's component
+// is cut by the strip edge, or it is a merged piece whose own re-scan time is unknown).
+__device__ __forceinline__ int32_t label_time(const CcArrays &A, const CcParams &P, int32_t q, int32_t t, bool &unk)
 {
-    if (P.optimistic) {
-        // one load per neighbour: T is -1 on masked pixels, and in round 1 both kept and merged
-        // pieces are taken as labelled from their start (merged ones are re-checked in round 2)
-        const int32_t tq = T[q];
-        return (tq < 0 || tq == t) ? kTInf : tq;
+    const int32_t tq = A.T[q];       // -1 on masked pixels
+    if (tq < 0 || tq == t) return kTInf;
+    if (A.flag) {
+        const uint8_t f = A.flag[tq];
+        if (f & FLAG_CUT) unk = true;
+        else if ((f & FLAG_TFIX_UNKNOWN) && P.start_label == 1) unk = true;
     }
-    if (lab[q] == P.mask_label) return kTInf;
-    const int32_t tq = T[q];
-    if (tq == t) return kTInf;
-    if ((int64_t)psize[tq] >= P.min_size) return tq;
+    if (P.optimistic) return tq;     // round 1: merged pieces count as labelled from their start
+    if ((int64_t)A.psize[tq] >= P.min_size) return tq;
     if (P.start_label == 0) return tq;
-    return __ldcg(aux + tq);
+    return __ldcg(A.aux + tq);
 }
 
-__device__ __forceinline__ bool labelled_at(const int32_t *lab, const int32_t *T, const int32_t *psize,
-                                            const int32_t *aux, const CcParams &P, int32_t q, int32_t t,
-                                            int32_t now)
-{
-    return label_time(lab, T, psize, aux, P, q, t) < now;
-}
-
-// replay of the reference BFS restricted to piece t, started at pixel s
-__device__ int bfs_piece(const int32_t *lab, const int32_t *T, const int32_t *psize, const int32_t *aux,
-                         uint8_t *visit, int32_t *qu, const CcParams &P, int32_t t, int32_t s,
-                         int32_t L, int32_t &adj_out, int32_t &first_time)
+// replay of the reference BFS restricted to piece t, started at pixel s.  `unk_any`: some examined
+// neighbour has an unknown labelling time; `known_before`: some examined neighbour is known to be
+// labelled before s.
+__device__ int bfs_piece(const CcArrays &A, int32_t *qu, const CcParams &P, int32_t t, int32_t s,
+                         int32_t &adj_out, int32_t &first_time, bool &unk_any, bool &known_before)
 {
     int cnt = 1, head = 0;
     int32_t adjq = -1;
     int32_t tmin = kTInf;   // earliest scan position at which any examined neighbour is labelled
     qu[0] = s;
-    visit[s] = 1;
+    A.visit[s] = 1;
     while (head < cnt && (int64_t)cnt < P.max_size) {
         const int32_t p = qu[head];
         const int py = p / P.W, px = p % P.W;
         for (int d = 0; d < 4; ++d) {
             int32_t q;
             if (!nbr(d, py, px, P.H, P.W, q)) continue;
-            const bool same = T[q] == t;   // a piece is a set of equal-label pixels: T alone identifies it
+            const bool same = A.T[q] == t;   // a piece is a set of equal-label pixels: T alone identifies it
             if (same) {
-                if (!visit[q]) {
-                    visit[q] = 1;
+                if (!A.visit[q]) {
+                    A.visit[q] = 1;
                     qu[cnt++] = q;
                     if ((int64_t)cnt >= P.max_size) break;
                 }
             } else {
-                const int32_t lt = label_time(lab, T, psize, aux, P, q, t);
+                bool unk = false;
+                const int32_t lt = label_time(A, P, q, t, unk);
+                if (unk) unk_any = true;
                 tmin = min(tmin, lt);
-                if (lt < s) adjq = q;
+                if (lt < s) {
+                    adjq = q;
+                    if (!unk) known_before = true;
+                }
             }
         }
         ++head;
@@ -475,12 +465,6 @@ __device__ int bfs_piece(const int32_t *lab, const int32_t *T, const int32_t *ps
     first_time = tmin;
     return cnt;
 }
-
-struct CcArrays {
-    const int32_t *lab, *T, *psize, *list;
-    int32_t *adj, *aux, *queue, *ctr, *stamp;
-    uint8_t *visit;
-};
 
 // A small piece that touches pixel p of a piece whose `tfix` just changed may have relied on the
 // old value -- later pieces at their start, EARLIER pieces at one of their re-scan times -- so
@@ -492,9 +476,8 @@ __device__ __forceinline__ void push_dependents(const CcArrays &A, const CcParam
     for (int d = 0; d < 4; ++d) {
         int32_t q;
         if (!nbr(d, py, px, P.H, P.W, q)) continue;
-        if (A.lab[q] == P.mask_label) continue;
         const int32_t tq = A.T[q];
-        if (tq == t || (int64_t)A.psize[tq] >= P.min_size) continue;
+        if (tq < 0 || tq == t || (int64_t)A.psize[tq] >= P.min_size) continue;
         if (atomicExch(A.stamp + tq, round_id) != round_id) dirty_next[atomicAdd(n_next, 1)] = tq;
     }
 }
@@ -505,11 +488,11 @@ __device__ __forceinline__ void push_dependents(const CcArrays &A, const CcParam
 __device__ bool small_piece_adjacent(const CcArrays &A, const CcParams &P, int32_t t, int32_t *qu,
                                      int round_id, int32_t *dirty_next, int32_t *n_next)
 {
-    const int32_t L = A.lab[t];
     const int32_t n = A.psize[t];
     int32_t a = -1;
     int32_t fix = t;
     int cnt = 1;
+    bool unk_any = false, known_before = false;
     const int32_t *members = qu;   // pixels of the first BFS
     if (n == 1) {
         const int py = t / P.W, px = t % P.W;
@@ -517,13 +500,18 @@ __device__ bool small_piece_adjacent(const CcArrays &A, const CcParams &P, int32
         for (int d = 0; d < 4 && P.max_size > 1; ++d) {
             int32_t q;
             if (!nbr(d, py, px, P.H, P.W, q)) continue;
-            if (labelled_at(A.lab, A.T, A.psize, A.aux, P, q, t, t)) a = q;
+            bool unk = false;
+            if (label_time(A, P, q, t, unk) < t) {
+                a = q;
+                if (!unk) known_before = true;
+            }
+            if (unk) unk_any = true;
         }
         if (a < 0 && P.start_label == 1) fix = kTInf;  // stays label 0: no later pixel to re-enter at
         qu[0] = t;
     } else {
         int32_t tmin;
-        cnt = bfs_piece(A.lab, A.T, A.psize, A.aux, A.visit, qu, P, t, t, L, a, tmin);
+        cnt = bfs_piece(A, qu, P, t, t, a, tmin, unk_any, known_before);
         for (int i = 0; i < cnt; ++i) A.visit[qu[i]] = 0;
         if (a < 0 && P.start_label == 1) {
             // Merged to 0 == mask label: the raster scan re-enters the piece at each of its later
@@ -534,6 +522,7 @@ __device__ bool small_piece_adjacent(const CcArrays &A, const CcParams &P, int32
             int32_t *qu2 = qu;
             for (int i = 0; i < cnt; ++i) cand[i] = qu[i];
             members = cand;
+            bool u2 = false, k2 = false;
             if ((int64_t)n < P.max_size) {
                 // The BFS is not cut by the size cap, so from ANY start it examines every
                 // neighbour of the piece: the first successful re-scan is at the first member
@@ -544,7 +533,7 @@ __device__ bool small_piece_adjacent(const CcArrays &A, const CcParams &P, int32
                         if (cand[i] > tmin && cand[i] < s) s = cand[i];
                 if (s != kTInf) {
                     int32_t a2, tm2;
-                    const int c2 = bfs_piece(A.lab, A.T, A.psize, A.aux, A.visit, qu2, P, t, s, L, a2, tm2);
+                    const int c2 = bfs_piece(A, qu2, P, t, s, a2, tm2, u2, k2);
                     for (int i = 0; i < c2; ++i) A.visit[qu2[i]] = 0;
                     a = a2;
                     fix = (a2 >= 0) ? s : kTInf;
@@ -559,7 +548,7 @@ __device__ bool small_piece_adjacent(const CcArrays &A, const CcParams &P, int32
                     if (s == kTInf) break;
                     last = s;
                     int32_t a2, tm2;
-                    const int c2 = bfs_piece(A.lab, A.T, A.psize, A.aux, A.visit, qu2, P, t, s, L, a2, tm2);
+                    const int c2 = bfs_piece(A, qu2, P, t, s, a2, tm2, u2, k2);
                     for (int i = 0; i < c2; ++i) A.visit[qu2[i]] = 0;
                     if (a2 >= 0) {
                         a = a2;
@@ -571,7 +560,19 @@ __device__ bool small_piece_adjacent(const CcArrays &A, const CcParams &P, int32
         }
     }
     A.adj[t] = a;
-    if (A.aux[t] == fix) return false;
+    bool flag_changed = false;
+    if (A.flag && unk_any) {
+        // conservative: any unknown neighbour makes `adjacent` unknown; the re-scan time stays known
+        // when a KNOWN neighbour is labelled before the piece's own start (then tfix == start)
+        uint8_t f = A.flag[t];
+        uint8_t nf = f | FLAG_ADJ_UNKNOWN;
+        if (!known_before && P.start_label == 1) nf |= FLAG_TFIX_UNKNOWN;
+        if (nf != f) {
+            A.flag[t] = nf;
+            flag_changed = ((nf ^ f) & FLAG_TFIX_UNKNOWN) != 0;
+        }
+    }
+    if (A.aux[t] == fix && !flag_changed) return false;
     A.aux[t] = fix;
     if (P.start_label == 0) return true;   // no label-0 ambiguity: nobody depends on tfix
     // tell later small neighbours of the piece to look again
@@ -620,6 +621,7 @@ cc_small_round_kernel(CcArrays A, CcParams P, const int32_t *__restrict__ cur, i
                       int nxt_ctr, int round_id)
 {
     const int n = A.ctr[cur_ctr];
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.ctr[CTR_ROUNDS] = round_id;
     const int lane = threadIdx.x & 31;
     const int stride = gridDim.x * blockDim.x;
     for (int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); e0 < n; e0 += stride) {
@@ -645,30 +647,50 @@ cc_small_round_kernel(CcArrays A, CcParams P, const int32_t *__restrict__ cur, i
     }
 }
 
-// phase 4a/b/c: rank of kept piece starts (chunked prefix sum)
-__device__ __forceinline__ bool is_kept_start(const int32_t *T, const int32_t *psize, int64_t i,
-                                              int64_t min_size)
+__global__ void cc_reset_round_kernel(int32_t *ctr, int nxt_ctr)
 {
-    return T[i] == (int32_t)i && (int64_t)psize[i] >= min_size;
+    ctr[nxt_ctr] = 0;
+    ctr[CTR_CURSOR] = 0;   // queue space is recycled
 }
 
+// phase 4a/b/c: kept pieces are numbered by the rank of their start pixel = prefix population count
+// of the start-pixel bitmap (N / 8 bytes instead of two passes over T and psize)
 __global__ void __launch_bounds__(256)
-cc_count_kernel(const int32_t *__restrict__ T, const int32_t *__restrict__ psize, int32_t *blocksum,
-                int64_t N, int64_t min_size)
+cc_bits_count_kernel(const uint32_t *__restrict__ bits, int32_t *chunksum, int64_t core_lo, int64_t core_hi,
+                     int32_t *ctr)
 {
-    __shared__ int s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
+    __shared__ int s_cnt[3];
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * kScanChunk;
-    int c = 0;
-    for (int j = threadIdx.x; j < kScanChunk; j += 256) {
-        const int64_t i = base + j;
-        if (i < N && is_kept_start(T, psize, i, min_size)) ++c;
+    const int64_t w0 = (int64_t)blockIdx.x * kBitChunk;
+    int c = 0, before = 0, core = 0;
+    for (int j = threadIdx.x; j < kBitChunk; j += 256) {
+        const uint32_t v = bits[w0 + j];
+        c += __popc(v);
+        // kept pieces that start before / inside the core rows of a strip (pixel range [core_lo, core_hi))
+        const int64_t p0 = (w0 + j) * 32;
+        if (v) {
+            for (uint32_t m = v; m; m &= m - 1) {
+                const int64_t px = p0 + __ffs(m) - 1;
+                before += px < core_lo;
+                core += (px >= core_lo && px < core_hi);
+            }
+        }
     }
     c = __reduce_add_sync(0xffffffffu, c);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    before = __reduce_add_sync(0xffffffffu, before);
+    core = __reduce_add_sync(0xffffffffu, core);
+    if ((threadIdx.x & 31) == 0) {
+        if (c) atomicAdd(&s_cnt[0], c);
+        if (before) atomicAdd(&s_cnt[1], before);
+        if (core) atomicAdd(&s_cnt[2], core);
+    }
     __syncthreads();
-    if (threadIdx.x == 0) blocksum[blockIdx.x] = s_cnt;
+    if (threadIdx.x == 0) {
+        chunksum[blockIdx.x] = s_cnt[0];
+        if (s_cnt[1]) atomicAdd(ctr + CTR_KBEFORE, s_cnt[1]);
+        if (s_cnt[2]) atomicAdd(ctr + CTR_KCORE, s_cnt[2]);
+    }
 }
 
 __global__ void __launch_bounds__(1024)
@@ -710,68 +732,109 @@ cc_scan_blocks_kernel(int32_t *blocksum, int64_t nblocks, int32_t *ctr)
     if (threadIdx.x == 0) ctr[CTR_NKEPT] = s_carry;
 }
 
+// label of every kept piece: start_label + label_offset + rank of its start pixel (label_offset != 0
+// only for strips: global rank of the strip's first core piece minus its local rank)
 __global__ void __launch_bounds__(256)
-cc_number_kernel(const int32_t *__restrict__ T, const int32_t *__restrict__ psize,
-                 const int32_t *__restrict__ blocksum, int32_t *aux, int64_t N, int64_t min_size,
-                 int32_t start_label)
+cc_bits_number_kernel(const uint32_t *__restrict__ bits, const int32_t *__restrict__ chunksum, int32_t *fin,
+                      int32_t label_base)
 {
     __shared__ int s_warp[8];
-    __shared__ int s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_base = blocksum[blockIdx.x];
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * kScanChunk;
-    for (int j0 = 0; j0 < kScanChunk; j0 += 256) {
-        const int64_t i = base + j0 + threadIdx.x;
-        const bool k = (i < N) && is_kept_start(T, psize, i, min_size);
-        const unsigned m = __ballot_sync(0xffffffffu, k);
-        if (lane == 0) s_warp[warp] = __popc(m);
-        __syncthreads();
-        int before = s_base;
-        for (int w = 0; w < warp; ++w) before += s_warp[w];
-        if (k) aux[i] = start_label + before + __popc(m & ((1u << lane) - 1u));
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int tot = 0;
-            for (int w = 0; w < 8; ++w) tot += s_warp[w];
-            s_base += tot;
+    const int64_t w0 = (int64_t)blockIdx.x * kBitChunk;
+    int running = chunksum[blockIdx.x];
+    for (int j0 = 0; j0 < kBitChunk; j0 += 256) {
+        const uint32_t v = bits[w0 + j0 + threadIdx.x];
+        const int c = __popc(v);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int before = running + incl - c;
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) {
+            if (w < warp) before += s_warp[w];
+            tot += s_warp[w];
+        }
+        const int64_t p0 = (w0 + j0 + threadIdx.x) * 32;
+        int k = 0;
+        for (uint32_t m = v; m; m &= m - 1) fin[p0 + __ffs(m) - 1] = label_base + before + k++;
+        running += tot;
         __syncthreads();
     }
 }
 
-// phase 4d: final labels
+// phase 4d: merged pieces follow their adjacent chain to a kept piece (or to 0, the initial value of
+// `adjacent`); strip mode also records whether anything on the chain is unknown inside the strip
 __global__ void __launch_bounds__(256)
-cc_resolve_kernel(const int32_t *__restrict__ lab, const int32_t *__restrict__ T,
-                  const int32_t *__restrict__ psize, const int32_t *__restrict__ adj,
-                  const int32_t *__restrict__ aux, int32_t *__restrict__ out, int32_t *ctr, int64_t N,
-                  int64_t min_size, int32_t mask_label)
+cc_small_final_kernel(CcArrays A, const uint32_t *__restrict__ bits, int32_t *fin, int max_hops)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    if (lab[i] == mask_label) {
-        out[i] = mask_label;
-        return;
-    }
-    int32_t t = T[i];
-    int32_t r = mask_label;
-    bool done = false;
-    for (int hop = 0; hop < (1 << 24) && !done; ++hop) {   // chains are short; never spin
-        if ((int64_t)psize[t] >= min_size) {
-            r = aux[t];
-            done = true;
-        } else {
-            const int32_t a = adj[t];
-            if (a < 0) {
-                r = 0;  // `adjacent` initial value
+    const int n_small = A.ctr[CTR_NSMALL];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_small; e += gridDim.x * blockDim.x) {
+        const int32_t t0 = A.list[e];
+        int32_t t = t0, r = 0;
+        bool unk = false, done = false;
+        for (int hop = 0; hop < max_hops && !done; ++hop) {   // chains are short; never spin
+            if ((bits[t >> 5] >> (t & 31)) & 1u) {
+                r = fin[t];
+                if (A.flag && (A.flag[t] & FLAG_CUT)) unk = true;
                 done = true;
             } else {
-                t = T[a];
+                if (A.flag && (A.flag[t] & (FLAG_CUT | FLAG_ADJ_UNKNOWN))) unk = true;
+                const int32_t a = A.adj[t];
+                if (a < 0) {
+                    r = 0;  // `adjacent` initial value
+                    done = true;
+                } else {
+                    t = A.T[a];
+                }
             }
         }
+        if (!done) atomicExch(A.ctr + CTR_ERR, 2);
+        fin[t0] = r;            // kept and merged piece starts are disjoint: one table for both
+        if (unk) A.flag[t0] |= FLAG_LABEL_UNKNOWN;
     }
-    if (!done) atomicExch(ctr + CTR_ERR, 2);
-    out[i] = r;
+}
+
+// phase 4e: final labels of rows [row_lo, row_hi) of the strip, written to `out` (row 0 of out = row_lo)
+__global__ void __launch_bounds__(256)
+cc_resolve_kernel(const int32_t *__restrict__ T, const uint32_t *__restrict__ bits, const int32_t *__restrict__ fin,
+                  const uint8_t *__restrict__ flag, int32_t *__restrict__ out, int32_t *ctr, int64_t p_lo,
+                  int64_t p_hi, int32_t mask_label)
+{
+    const int64_t i = p_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p_hi) return;
+    const int32_t t = T[i];
+    int32_t r = mask_label;
+    if (t >= 0) {
+        r = fin[t];
+        if (r == 0 && mask_label == 0) ctr[CTR_HASZERO] = 1;   // label 0 on an unmasked pixel (benign race)
+        if (flag) {
+            const bool kept = (bits[t >> 5] >> (t & 31)) & 1u;
+            const uint8_t f = flag[t];
+            if (kept ? (f & FLAG_CUT) : (f & (FLAG_CUT | FLAG_LABEL_UNKNOWN))) atomicExch(ctr + CTR_FAIL, 1);
+        }
+    }
+    out[i - p_lo] = r;
+}
+
+// strip mode: components that touch an open edge of the strip may continue outside it
+__global__ void __launch_bounds__(256)
+cc_mark_cut_kernel(const int32_t *__restrict__ T, uint8_t *flag, int64_t N, int W, int top_open, int bottom_open)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    if (top_open) {
+        const int32_t t = T[x];
+        if (t >= 0) flag[t] = FLAG_CUT;
+    }
+    if (bottom_open) {
+        const int32_t t = T[N - W + x];
+        if (t >= 0) flag[t] = FLAG_CUT;
+    }
 }
 
 }  // namespace obia
@@ -784,6 +847,126 @@ extern "C" int64_t obia_b200_connectivity_workspace_bytes(int64_t H, int64_t W)
     return cc_ws_layout(nullptr, H * W).bytes;
 }
 
+namespace {
+
+struct CcRun {
+    const int32_t *lab;
+    CcWs w;
+    CcParams P;
+    int64_t N;
+    int32_t *fin;
+    bool strip;
+    cudaStream_t st;
+};
+
+// phases 1-3: components, split, small-piece adjacency (round 1 + two speculative rounds), counts
+int cc_phase_a(CcRun &R, int top_open, int bottom_open, int64_t core_lo, int64_t core_hi)
+{
+    const CcWs &w = R.w;
+    const CcParams &P0 = R.P;
+    const int64_t N = R.N;
+    cudaStream_t st = R.st;
+    const int H = P0.H, W = P0.W;
+    const unsigned gridN = (unsigned)ceil_div(N, 256);
+    OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr, 0, CTR_WORDS * 4, st));
+    OBIA_CUDA_CHECK(cudaMemsetAsync(w.visit, 0, (size_t)N, st));
+    OBIA_CUDA_CHECK(cudaMemsetAsync(w.bits, 0, (size_t)w.nchunks * kBitChunk * 4, st));
+    if (R.strip) OBIA_CUDA_CHECK(cudaMemsetAsync(w.flag, 0, (size_t)N, st));
+    {
+        dim3 tiles((unsigned)ceil_div(W, kTile), (unsigned)ceil_div(H, kTile));
+        cc_local_kernel<<<tiles, 256, 0, st>>>(R.lab, w.T, w.psize, H, W, P0.mask_label);
+        OBIA_LAUNCH_CHECK();
+        const int64_t nborder = (int64_t)((W - 1) / kTile) * H + (int64_t)((H - 1) / kTile) * W;
+        if (nborder > 0) {
+            cc_border_kernel<<<(unsigned)ceil_div(nborder, 256), 256, 0, st>>>(R.lab, w.T, H, W, P0.mask_label);
+            OBIA_LAUNCH_CHECK();
+        }
+    }
+    int32_t *roots = w.queue;   // idle until the split / adjacency kernels
+    cc_flatten_kernel<<<gridN, 256, 0, st>>>(w.T, w.psize, roots, w.ctr, N);
+    OBIA_LAUNCH_CHECK();
+    if (R.strip && (top_open || bottom_open)) {
+        cc_mark_cut_kernel<<<(unsigned)ceil_div(W, 256), 256, 0, st>>>(w.T, w.flag, N, W, top_open, bottom_open);
+        OBIA_LAUNCH_CHECK();
+    }
+    cc_classify_kernel<<<kNumSMs * 8, 256, 0, st>>>(roots, w.psize, w.list, w.adj, w.aux, w.stamp, w.bits, w.ctr, N,
+                                                    P0.min_size, P0.max_size);
+    OBIA_LAUNCH_CHECK();
+    cc_split_kernel<<<kNumSMs * 2, 128, 0, st>>>(R.lab, w.T, w.psize, w.queue, w.list, w.adj, w.aux, w.stamp, w.bits,
+                                                 R.strip ? w.flag : nullptr, w.ctr, w.visit, N, H, W, P0.min_size,
+                                                 P0.max_size);
+    OBIA_LAUNCH_CHECK();
+
+    CcArrays A;
+    A.lab = R.lab; A.T = w.T; A.psize = w.psize; A.list = w.list;
+    A.adj = w.adj; A.aux = w.aux; A.queue = w.queue; A.ctr = w.ctr; A.stamp = w.stamp; A.visit = w.visit;
+    A.flag = R.strip ? w.flag : nullptr;
+    CcParams P = P0;
+    cc_reset_round_kernel<<<1, 1, 0, st>>>(w.ctr, CTR_NDIRTY0);
+    OBIA_LAUNCH_CHECK();
+    P.optimistic = 1;
+    cc_small_adjacent_kernel<<<kNumSMs * 8, 128, 0, st>>>(A, P, w.dirty0);
+    OBIA_LAUNCH_CHECK();
+    return OBIA_B200_OK;
+}
+
+// rounds 2..: `n` launches without a host round trip (an empty round costs a few microseconds);
+// `cur` = index of the dirty list written last
+int cc_rounds(CcRun &R, int n, int &round_id, int &cur)
+{
+    const CcWs &w = R.w;
+    CcArrays A;
+    A.lab = R.lab; A.T = w.T; A.psize = w.psize; A.list = w.list;
+    A.adj = w.adj; A.aux = w.aux; A.queue = w.queue; A.ctr = w.ctr; A.stamp = w.stamp; A.visit = w.visit;
+    A.flag = R.strip ? w.flag : nullptr;
+    CcParams P = R.P;
+    P.optimistic = 0;
+    for (int b = 0; b < n; ++b) {
+        ++round_id;
+        const int cur_ctr = cur ? CTR_NDIRTY1 : CTR_NDIRTY0, nxt_ctr = cur ? CTR_NDIRTY0 : CTR_NDIRTY1;
+        cc_reset_round_kernel<<<1, 1, 0, R.st>>>(w.ctr, nxt_ctr);
+        OBIA_LAUNCH_CHECK();
+        cc_small_round_kernel<<<kNumSMs * 4, 128, 0, R.st>>>(A, P, cur ? w.dirty1 : w.dirty0,
+                                                             cur ? w.dirty0 : w.dirty1, cur_ctr, nxt_ctr, round_id);
+        OBIA_LAUNCH_CHECK();
+        cur ^= 1;
+    }
+    return OBIA_B200_OK;
+}
+
+int cc_count(CcRun &R, int64_t core_lo, int64_t core_hi)
+{
+    const CcWs &w = R.w;
+    OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + CTR_KBEFORE, 0, 8, R.st));
+    cc_bits_count_kernel<<<(unsigned)w.nchunks, 256, 0, R.st>>>(w.bits, w.chunksum, core_lo, core_hi, w.ctr);
+    OBIA_LAUNCH_CHECK();
+    cc_scan_blocks_kernel<<<1, 1024, 0, R.st>>>(w.chunksum, w.nchunks, w.ctr);
+    OBIA_LAUNCH_CHECK();
+    return OBIA_B200_OK;
+}
+
+// phase 4: numbering + final labels of pixel range [p_lo, p_hi)
+int cc_phase_b(CcRun &R, int32_t label_base, int32_t *out, int64_t p_lo, int64_t p_hi, int max_hops)
+{
+    const CcWs &w = R.w;
+    OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + CTR_ERR, 0, 4, R.st));
+    OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + CTR_FAIL, 0, 8, R.st));   // CTR_FAIL, CTR_HASZERO
+    CcArrays A;
+    A.lab = R.lab; A.T = w.T; A.psize = w.psize; A.list = w.list;
+    A.adj = w.adj; A.aux = w.aux; A.queue = w.queue; A.ctr = w.ctr; A.stamp = w.stamp; A.visit = w.visit;
+    A.flag = R.strip ? w.flag : nullptr;
+    cc_bits_number_kernel<<<(unsigned)w.nchunks, 256, 0, R.st>>>(w.bits, w.chunksum, R.fin, label_base);
+    OBIA_LAUNCH_CHECK();
+    cc_small_final_kernel<<<kNumSMs * 4, 256, 0, R.st>>>(A, w.bits, R.fin, max_hops);
+    OBIA_LAUNCH_CHECK();
+    cc_resolve_kernel<<<(unsigned)ceil_div(p_hi - p_lo, 256), 256, 0, R.st>>>(
+        w.T, w.bits, R.fin, R.strip ? w.flag : nullptr, out, w.ctr, p_lo, p_hi, R.P.mask_label);
+    OBIA_LAUNCH_CHECK();
+    return OBIA_B200_OK;
+}
+
+}  // namespace
+
 extern "C" int obia_b200_enforce_connectivity(const int32_t *labels_in, int32_t *labels_out,
                                               void *workspace, int64_t H, int64_t W, int64_t min_size,
                                               int64_t max_size, int32_t start_label,
@@ -795,91 +978,136 @@ extern "C" int obia_b200_enforce_connectivity(const int32_t *labels_in, int32_t 
     if (start_label != 0 && start_label != 1) return set_err(OBIA_B200_ERR_ARG, "start_label should be 0 or 1.");
     const int64_t N = H * W;
     if (N >= 0x7fffffffLL) return set_err(OBIA_B200_ERR_UNSUPPORTED, "enforce_connectivity: H*W exceeds int32");
-    cudaStream_t st = (cudaStream_t)stream;
-    CcWs w = cc_ws_layout(workspace, N);
-    const int32_t mask_label = start_label - 1;
-    const unsigned gridN = (unsigned)ceil_div(N, 256);
-
-    OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr, 0, CTR_WORDS * 4, st));
-    {
-        dim3 tiles((unsigned)ceil_div(W, kTile), (unsigned)ceil_div(H, kTile));
-        cc_local_kernel<<<tiles, 256, 0, st>>>(labels_in, w.parent, w.psize, w.visit, w.stamp, (int)H, (int)W,
-                                               mask_label);
-        OBIA_LAUNCH_CHECK();
-        const int64_t nborder = ((W - 1) / kTile) * H + ((H - 1) / kTile) * W;
-        if (nborder > 0) {
-            cc_border_kernel<<<(unsigned)ceil_div(nborder, 256), 256, 0, st>>>(labels_in, w.parent, (int)H, (int)W,
-                                                                              mask_label);
-            OBIA_LAUNCH_CHECK();
-        }
-    }
-    cc_flatten_kernel<<<gridN, 256, 0, st>>>(labels_in, w.parent, w.T, w.psize, N, mask_label);
-    OBIA_LAUNCH_CHECK();
-    cc_list_over_kernel<<<gridN, 256, 0, st>>>(w.T, w.psize, w.list, w.ctr, N, max_size);
-    OBIA_LAUNCH_CHECK();
-    cc_split_kernel<<<kNumSMs * 2, 128, 0, st>>>(labels_in, w.parent, w.T, w.psize, w.queue, w.list, w.ctr,
-                                                 w.visit, N, (int)H, (int)W, max_size);
-    OBIA_LAUNCH_CHECK();
-    cc_list_small_kernel<<<gridN, 256, 0, st>>>(w.T, w.psize, w.list, w.adj, w.aux, w.ctr, N, min_size);
-    OBIA_LAUNCH_CHECK();
-
-    CcParams P;
-    P.H = (int)H; P.W = (int)W; P.min_size = min_size; P.max_size = max_size;
-    P.mask_label = mask_label; P.start_label = start_label; P.optimistic = 0;
+    CcRun R;
+    R.lab = labels_in;
+    R.w = cc_ws_layout(workspace, N);
+    R.N = N;
+    R.fin = R.w.queue + N;   // second half of the queue: only the re-scan copies of a later round reach it
+    R.strip = false;
+    R.st = (cudaStream_t)stream;
+    R.P.H = (int)H; R.P.W = (int)W; R.P.min_size = min_size; R.P.max_size = max_size;
+    R.P.mask_label = start_label - 1; R.P.start_label = start_label; R.P.optimistic = 0;
+    int rc = cc_phase_a(R, 0, 0, 0, N);
+    if (rc) return rc;
+    // Rounds 2.. exist only for start_label 1 (label-0 chains) and are almost always empty: two are
+    // enqueued speculatively and the result is finished without a host round trip (merge chains walked
+    // for at most kSpecHops hops); the single read-back at the end tells whether more rounds, or a
+    // second finish with unbounded chains, are needed.
+    constexpr int kSpecHops = 256, kAllHops = 1 << 30;
+    int round_id = 1, cur = 0;
     int32_t hctr[CTR_WORDS];
-    {
-        CcArrays A;
-        A.lab = labels_in; A.T = w.T; A.psize = w.psize; A.list = w.list;
-        A.adj = w.adj; A.aux = w.aux; A.queue = w.queue; A.ctr = w.ctr; A.stamp = w.stamp; A.visit = w.visit;
-        OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + CTR_CURSOR, 0, 4, st));
-        P.optimistic = 1;
-        cc_small_adjacent_kernel<<<kNumSMs * 8, 128, 0, st>>>(A, P, w.dirty0);
-        OBIA_LAUNCH_CHECK();
-        P.optimistic = 0;
-        if (start_label == 1) {   // start_label 0 has no label-0 ambiguity: round 1 is exact
-            int round_id = 1;
-            int cur = 0;   // dirty list written by the previous round
-            while (true) {
-                OBIA_CUDA_CHECK(cudaMemcpyAsync(hctr, w.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, st));
-                OBIA_CUDA_CHECK(cudaStreamSynchronize(st));
-                const int n_dirty = hctr[cur ? CTR_NDIRTY1 : CTR_NDIRTY0];
-                if (getenv("OBIA_B200_DEBUG"))
-                    fprintf(stderr, "[obia_b200] connectivity: round %d, %d small pieces, %d queued\n", round_id,
-                            hctr[CTR_NSMALL], n_dirty);
-                if (n_dirty == 0) break;
-                if (round_id > (1 << 28)) return set_err(OBIA_B200_ERR_CUDA, "enforce_connectivity: no fixed point");
-                // a batch of rounds without host round trips (an empty round costs a few microseconds)
-                const int batch = 16;
-                for (int b = 0; b < batch; ++b) {
-                    ++round_id;
-                    const int cur_ctr = cur ? CTR_NDIRTY1 : CTR_NDIRTY0, nxt_ctr = cur ? CTR_NDIRTY0 : CTR_NDIRTY1;
-                    OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + nxt_ctr, 0, 4, st));
-                    OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + CTR_CURSOR, 0, 4, st));   // queue space is recycled
-                    cc_small_round_kernel<<<kNumSMs * 4, 128, 0, st>>>(A, P, cur ? w.dirty1 : w.dirty0,
-                                                                       cur ? w.dirty0 : w.dirty1, cur_ctr, nxt_ctr,
-                                                                       round_id);
-                    OBIA_LAUNCH_CHECK();
-                    cur ^= 1;
-                }
-            }
-        }
+    auto read_back = [&]() -> int {
+        OBIA_CUDA_CHECK(cudaMemcpyAsync(hctr, R.w.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, R.st));
+        OBIA_CUDA_CHECK(cudaStreamSynchronize(R.st));
+        return OBIA_B200_OK;
+    };
+    if (start_label == 1) {
+        rc = cc_rounds(R, 2, round_id, cur);
+        if (rc) return rc;
     }
-
-    cc_count_kernel<<<(unsigned)w.nblocks, 256, 0, st>>>(w.T, w.psize, w.blocksum, N, min_size);
-    OBIA_LAUNCH_CHECK();
-    cc_scan_blocks_kernel<<<1, 1024, 0, st>>>(w.blocksum, w.nblocks, w.ctr);
-    OBIA_LAUNCH_CHECK();
-    cc_number_kernel<<<(unsigned)w.nblocks, 256, 0, st>>>(w.T, w.psize, w.blocksum, w.aux, N, min_size,
-                                                          start_label);
-    OBIA_LAUNCH_CHECK();
-    cc_resolve_kernel<<<gridN, 256, 0, st>>>(labels_in, w.T, w.psize, w.adj, w.aux, labels_out, w.ctr, N,
-                                             min_size, mask_label);
-    OBIA_LAUNCH_CHECK();
-    OBIA_CUDA_CHECK(cudaMemcpyAsync(hctr, w.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, st));
-    OBIA_CUDA_CHECK(cudaStreamSynchronize(st));
+    rc = cc_count(R, 0, N);
+    if (!rc) rc = cc_phase_b(R, start_label, labels_out, 0, N, kSpecHops);
+    if (!rc) rc = read_back();
+    if (rc) return rc;
+    bool dirty = start_label == 1 && hctr[cur ? CTR_NDIRTY1 : CTR_NDIRTY0] != 0;
+    if (dirty || hctr[CTR_ERR]) {
+        while (dirty) {   // label times were still changing: rounds in batches until the list is empty
+            rc = cc_rounds(R, 16, round_id, cur);
+            if (!rc) rc = read_back();
+            if (rc) return rc;
+            dirty = hctr[cur ? CTR_NDIRTY1 : CTR_NDIRTY0] != 0;
+            if (round_id > (1 << 28)) return set_err(OBIA_B200_ERR_CUDA, "enforce_connectivity: no fixed point");
+        }
+        rc = cc_count(R, 0, N);
+        if (!rc) rc = cc_phase_b(R, start_label, labels_out, 0, N, kAllHops);
+        if (!rc) rc = read_back();
+        if (rc) return rc;
+    }
     if (n_labels_host) *n_labels_host = hctr[CTR_NKEPT];
     if (hctr[CTR_ERR])
         return set_err(OBIA_B200_ERR_CUDA, "enforce_connectivity: internal consistency check failed (%d)",
                        hctr[CTR_ERR]);
+    return OBIA_B200_OK;
+}
+
+// ---- strip mode (one raster sharded by row strips across GPUs) ----------------------------------------
+static int cc_strip_setup(CcRun &R, const int32_t *labels_ext, void *workspace, int64_t H_ext, int64_t W,
+                          int64_t core_row0, int64_t core_rows, int64_t min_size, int64_t max_size,
+                          int32_t start_label, void *stream)
+{
+    if (!labels_ext || !workspace || H_ext <= 0 || W <= 0 || core_row0 < 0 || core_rows <= 0 ||
+        core_row0 + core_rows > H_ext)
+        return set_err(OBIA_B200_ERR_ARG, "connectivity_strip: bad argument");
+    if (max_size < 1) return set_err(OBIA_B200_ERR_ARG, "connectivity_strip: max_size must be >= 1");
+    if (start_label != 0 && start_label != 1) return set_err(OBIA_B200_ERR_ARG, "start_label should be 0 or 1.");
+    const int64_t N = H_ext * W;
+    if (N >= 0x7fffffffLL) return set_err(OBIA_B200_ERR_UNSUPPORTED, "connectivity_strip: H_ext*W exceeds int32");
+    R.lab = labels_ext;
+    R.w = cc_ws_layout(workspace, N);
+    R.N = N;
+    R.fin = R.w.queue + N;
+    R.strip = true;
+    R.st = (cudaStream_t)stream;
+    R.P.H = (int)H_ext; R.P.W = (int)W; R.P.min_size = min_size; R.P.max_size = max_size;
+    R.P.mask_label = start_label - 1; R.P.start_label = start_label; R.P.optimistic = 0;
+    return OBIA_B200_OK;
+}
+
+extern "C" int obia_b200_connectivity_strip_begin(const int32_t *labels_ext, void *workspace, int64_t H_ext,
+                                                  int64_t W, int64_t core_row0, int64_t core_rows,
+                                                  int32_t top_open, int32_t bottom_open, int64_t min_size,
+                                                  int64_t max_size, int32_t start_label, int64_t *counts_host,
+                                                  void *stream)
+{
+    CcRun R;
+    int rc = cc_strip_setup(R, labels_ext, workspace, H_ext, W, core_row0, core_rows, min_size, max_size,
+                            start_label, stream);
+    if (rc) return rc;
+    if (!counts_host) return set_err(OBIA_B200_ERR_ARG, "connectivity_strip_begin: bad argument");
+    const int64_t core_lo = core_row0 * W, core_hi = (core_row0 + core_rows) * W;
+    rc = cc_phase_a(R, top_open, bottom_open, core_lo, core_hi);
+    if (rc) return rc;
+    int round_id = 1, cur = 0;
+    int32_t hctr[CTR_WORDS];
+    while (true) {
+        if (start_label == 1) {
+            rc = cc_rounds(R, round_id == 1 ? 2 : 16, round_id, cur);
+            if (rc) return rc;
+        }
+        rc = cc_count(R, core_lo, core_hi);
+        if (rc) return rc;
+        OBIA_CUDA_CHECK(cudaMemcpyAsync(hctr, R.w.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, R.st));
+        OBIA_CUDA_CHECK(cudaStreamSynchronize(R.st));
+        if (start_label == 0 || hctr[cur ? CTR_NDIRTY1 : CTR_NDIRTY0] == 0) break;
+        if (round_id > (1 << 28)) return set_err(OBIA_B200_ERR_CUDA, "connectivity_strip: no fixed point");
+    }
+    counts_host[0] = hctr[CTR_KBEFORE];
+    counts_host[1] = hctr[CTR_KCORE];
+    counts_host[2] = hctr[CTR_NKEPT];
+    return OBIA_B200_OK;
+}
+
+extern "C" int obia_b200_connectivity_strip_finish(const int32_t *labels_ext, int32_t *labels_out_core,
+                                                   void *workspace, int64_t H_ext, int64_t W, int64_t core_row0,
+                                                   int64_t core_rows, int64_t min_size, int64_t max_size,
+                                                   int32_t start_label, int64_t label_offset,
+                                                   int32_t *incomplete_host, void *stream)
+{
+    CcRun R;
+    int rc = cc_strip_setup(R, labels_ext, workspace, H_ext, W, core_row0, core_rows, min_size, max_size,
+                            start_label, stream);
+    if (rc) return rc;
+    if (!labels_out_core || !incomplete_host)
+        return set_err(OBIA_B200_ERR_ARG, "connectivity_strip_finish: bad argument");
+    const int64_t core_lo = core_row0 * W, core_hi = (core_row0 + core_rows) * W;
+    rc = cc_phase_b(R, (int32_t)(start_label + label_offset), labels_out_core, core_lo, core_hi, 1 << 30);
+    if (rc) return rc;
+    int32_t hctr[CTR_WORDS];
+    OBIA_CUDA_CHECK(cudaMemcpyAsync(hctr, R.w.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, R.st));
+    OBIA_CUDA_CHECK(cudaStreamSynchronize(R.st));
+    incomplete_host[0] = hctr[CTR_FAIL];
+    incomplete_host[1] = hctr[CTR_HASZERO];
+    if (hctr[CTR_ERR])
+        return set_err(OBIA_B200_ERR_CUDA, "connectivity_strip: internal consistency check failed (%d)", hctr[CTR_ERR]);
     return OBIA_B200_OK;
 }

@@ -659,6 +659,23 @@ slic_max_color_kernel(const float *__restrict__ feat, const uint8_t *__restrict_
     if (acc == acc && acc > maxdc[k]) atomicMax(reinterpret_cast<unsigned *>(maxdc + k), __float_as_uint(acc));
 }
 
+// Sharded runs that exchange only the boundary bands of the centre sums: a live centre outside the
+// bands whose window reaches beyond this rank's rows would need sums from (or be a candidate on) the
+// neighbour -> status[1] = 1, the caller falls back to the full all-reduce.
+__global__ void __launch_bounds__(256)
+slic_band_check_kernel(const float *__restrict__ centres, int64_t n, int Cf, int row_lo, int row_hi, int H_total,
+                       int64_t up_lo, int64_t up_hi, int64_t down_lo, int64_t down_hi, int step_y, int32_t *status)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float cy = centres[k * (2 + Cf)];
+    if (!(cy == cy)) return;
+    const float reach = (float)(2 * step_y + 3);
+    const bool in_up = k >= up_lo && k < up_hi, in_down = k >= down_lo && k < down_hi;
+    if (row_lo > 0 && !in_up && cy - reach < (float)row_lo) atomicExch(status + 1, 1);
+    if (row_hi < H_total && !in_down && cy + reach > (float)row_hi) atomicExch(status + 1, 1);
+}
+
 __global__ void fill_f32_kernel(float *p, int64_t n, float v)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -795,6 +812,18 @@ extern "C" int obia_b200_slic_finish_sweep(float *centres, void *workspace, int6
     OBIA_CUDA_CHECK(cudaMemsetAsync(w.head, 0xff, (size_t)(w.ncy * w.ncx) * 4, st));
     slic_centres_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(centres, w.acc, w.head, w.next, n, Cf, 1,
                                                                    1.0 / fix_scale, step_y, step_x, w.ncy, w.ncx);
+    OBIA_LAUNCH_CHECK();
+    return OBIA_B200_OK;
+}
+
+extern "C" int obia_b200_slic_band_check(const float *centres, int64_t n, int32_t Cf, int64_t row_lo, int64_t row_hi,
+                                         int64_t H_total, int64_t up_lo, int64_t up_hi, int64_t down_lo,
+                                         int64_t down_hi, int32_t step_y, int32_t *status, void *stream)
+{
+    if (!centres || !status || n <= 0 || Cf <= 0 || row_lo < 0 || row_hi <= row_lo || row_hi > H_total || step_y <= 0)
+        return set_err(OBIA_B200_ERR_ARG, "slic_band_check: bad argument");
+    slic_band_check_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        centres, n, Cf, (int)row_lo, (int)row_hi, (int)H_total, up_lo, up_hi, down_lo, down_hi, step_y, status);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
 }

@@ -518,12 +518,12 @@ int launch_assign_fast(const float *feat, const uint8_t *mask, const float *cent
 #define OBIA_FAST_ARGS feat, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x, start_label, ignore_color, \
                        fix_scale, status, y_off, Hg, st
     if (Cf <= 4) {
-        if (g_fast_warps == 4) return launch_fast_t<4, 4, 8, 4>(OBIA_FAST_ARGS);
-        return launch_fast_t<4, 4, 4, 8>(OBIA_FAST_ARGS);
+        if (g_fast_warps == 4) return launch_fast_t<4, 4, 4, 4>(OBIA_FAST_ARGS);
+        return launch_fast_t<4, 4, 2, 8>(OBIA_FAST_ARGS);
     }
     if (Cf <= 8) {
-        if (g_fast_warps == 4) return launch_fast_t<8, 4, 8, 4>(OBIA_FAST_ARGS);
-        return launch_fast_t<8, 4, 4, 8>(OBIA_FAST_ARGS);
+        if (g_fast_warps == 4) return launch_fast_t<8, 4, 4, 4>(OBIA_FAST_ARGS);
+        return launch_fast_t<8, 4, 2, 8>(OBIA_FAST_ARGS);
     }
     if (Cf <= 16) return launch_fast_t<16, 2, 2, 8>(OBIA_FAST_ARGS);
     if (Cf <= 32) return launch_fast_t<32, 2, 2, 8>(OBIA_FAST_ARGS);

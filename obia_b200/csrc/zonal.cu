@@ -42,12 +42,13 @@ template <bool VEC>
 __global__ void __launch_bounds__(256, 2)
 zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw, ZonalWs w, int W,
                     int C, ZBands zb, int Cz, int64_t max_label, double resolution,
-                    double *__restrict__ stats)
+                    double *__restrict__ stats, int32_t label_lo)
 {
     constexpr int R = 4;
     const int lane = threadIdx.x & 31;
-    const int64_t L = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t L = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // table row
     if (L > max_label) return;
+    const int32_t LV = (int32_t)L + label_lo;                                         // label value
     const int b0 = blockIdx.y * kZB;
     const int nb = min(kZB, Cz - b0);
     double *out = stats + (L * Cz + b0) * 8;
@@ -75,23 +76,38 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
         }
     };
 
-    // pivot = the segment's first pixel in its first row (row y0 holds one by construction)
+    // pivot per band = the first VALID (non-NaN) sample among the segment's pixels of the first 32-column
+    // chunk of its first row that holds one (row y0 holds a pixel by construction); 0 when they are
+    // all NaN in that band.  The pivot only conditions the power sums, any finite value is correct.
     float pivot[kZB];
     {
-        int xr = -1;
-        for (int xs = x0; xs <= x1 && xr < 0; xs += 32) {
+        bool found = false;
+#pragma unroll
+        for (int b = 0; b < kZB; ++b) pivot[b] = 0.0f;
+        for (int xs = x0; xs <= x1 && !found; xs += 32) {
             const int x = xs + lane;
-            const bool hit = (x <= x1) && (labels[(int64_t)y0 * W + x] == (int32_t)L);
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (m) xr = xs + __ffs(m) - 1;
+            const bool hit = (x <= x1) && (labels[(int64_t)y0 * W + x] == LV);
+            if (__ballot_sync(0xffffffffu, hit)) {
+                found = true;
+                float v[kZB];
+#pragma unroll
+                for (int b = 0; b < kZB; ++b) v[b] = 0.0f;
+                if (hit) load_px((int64_t)y0 * W + x, v);
+#pragma unroll
+                for (int b = 0; b < kZB; ++b) {
+                    const unsigned m = __ballot_sync(0xffffffffu, hit && v[b] == v[b]);
+                    const float pv = __shfl_sync(0xffffffffu, v[b], m ? (__ffs(m) - 1) : 0);
+                    pivot[b] = m ? pv : 0.0f;
+                }
+            }
         }
-        load_px((int64_t)y0 * W + xr, pivot);
     }
 
     const float INF = __int_as_float(0x7f800000);
     // ps[m*8 + b] = float32 partial of the (m+1)-th pivot-shifted power sum of band b (this lane's
     // pixels since the last fold); `tot` = float64 running total of ps[lane] over the whole warp.
     float ps[4 * kZB], mn[kZB], mx[kZB];
+    int nvalid[kZB];   // NaN samples are dropped per band (segment_statistics.py:144-147)
     double tot = 0.0;
 #pragma unroll
     for (int i = 0; i < 4 * kZB; ++i) ps[i] = 0.0f;
@@ -99,6 +115,7 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
     for (int b = 0; b < kZB; ++b) {
         mn[b] = INF;
         mx[b] = -INF;
+        nvalid[b] = 0;
     }
     // Fold: transposed butterfly.  At each step a lane keeps the half of the vector selected by
     // its lane bit and adds the partner's copy of that half, so after 5 steps lane l holds the
@@ -162,7 +179,7 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int y = yb + r;
-                hit[r] = (x <= x1) && (y <= y1) && (labels[(int64_t)y * W + x] == (int32_t)L);
+                hit[r] = (x <= x1) && (y <= y1) && (labels[(int64_t)y * W + x] == LV);
             }
             float v[R][kZB];
 #pragma unroll
@@ -173,13 +190,15 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
                 if (!hit[r]) continue;
 #pragma unroll
                 for (int b = 0; b < kZB; ++b) {
-                    const float d = v[r][b] - pivot[b];
+                    const bool ok = v[r][b] == v[r][b];
+                    const float d = ok ? v[r][b] - pivot[b] : 0.0f;
                     const float dd = d * d;
+                    nvalid[b] += ok;
                     ps[b] += d;
                     ps[kZB + b] += dd;
                     ps[2 * kZB + b] = fmaf(dd, d, ps[2 * kZB + b]);
                     ps[3 * kZB + b] = fmaf(dd, dd, ps[3 * kZB + b]);
-                    mn[b] = fminf(mn[b], v[r][b]);
+                    mn[b] = fminf(mn[b], v[r][b]);   // fminf / fmaxf return the non-NaN operand
                     mx[b] = fmaxf(mx[b], v[r][b]);
                 }
             }
@@ -198,6 +217,7 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
             mn[b] = fminf(mn[b], __shfl_xor_sync(0xffffffffu, mn[b], o));
             mx[b] = fmaxf(mx[b], __shfl_xor_sync(0xffffffffu, mx[b], o));
         }
+        nvalid[b] = __reduce_add_sync(0xffffffffu, nvalid[b]);
     }
     // lane m*8 + b holds the m-th power sum of band b: hand the four sums of band b to lane b
     const int bsel = lane & (kZB - 1);
@@ -209,7 +229,14 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
 #pragma unroll
     for (int b = 0; b < kZB; ++b) {
         if (lane == b && b < nb) {
-            const double n = (double)cnt_total;
+            double *o = out + b * 8;
+            if (nvalid[b] == 0) {   // every sample of the band is NaN: the reference returns NaN statistics
+                o[0] = 0.0;
+                for (int k = 1; k < 7; ++k) o[k] = NAND;
+                o[7] = 0.0;
+                continue;
+            }
+            const double n = (double)nvalid[b];
             const double md = S1 / n;
             const double e2 = S2 / n, e3 = S3 / n, e4 = S4 / n;
             const double mean = (double)pivot[b] + md;
@@ -220,7 +247,6 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
             // scipy.stats.skew/kurtosis: NaN when the data are (nearly) constant
             const double thr = resolution * mean;
             const bool degenerate = m2 <= thr * thr;
-            double *o = out + b * 8;
             o[0] = n;
             o[1] = mean;
             o[2] = m2;
@@ -241,11 +267,12 @@ template <int BPL>
 __global__ void __launch_bounds__(256)
 zonal_gather_bands_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw, ZonalWs w, int W,
                           int C, ZBands zb, int Cz, int64_t max_label, double resolution,
-                          double *__restrict__ stats)
+                          double *__restrict__ stats, int32_t label_lo)
 {
     const int lane = threadIdx.x & 31;
     const int64_t L = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (L > max_label) return;
+    const int32_t LV = (int32_t)L + label_lo;
     const int cnt_total = w.count[L];
     const double NAND = __longlong_as_double(0x7ff8000000000000LL);
     double *out = stats + L * Cz * 8;
@@ -264,6 +291,8 @@ zonal_gather_bands_kernel(const int32_t *__restrict__ labels, const float *__res
     }
     float pivot[BPL], s1[BPL], s2[BPL], s3[BPL], s4[BPL], mn[BPL], mx[BPL];
     double d1[BPL], d2[BPL], d3[BPL], d4[BPL];
+    int nvalid[BPL];
+    bool have_pivot[BPL];
     const float INF = __int_as_float(0x7f800000);
 #pragma unroll
     for (int k = 0; k < BPL; ++k) {
@@ -272,14 +301,15 @@ zonal_gather_bands_kernel(const int32_t *__restrict__ labels, const float *__res
         mn[k] = INF;
         mx[k] = -INF;
         pivot[k] = 0.0f;
+        nvalid[k] = 0;
+        have_pivot[k] = false;
     }
-    bool have_pivot = false;
     int pending = 0;
     for (int y = y0; y <= y1; ++y) {
         const int64_t row = (int64_t)y * W;
         for (int xs = x0; xs <= x1; xs += 32) {
             const int x = xs + lane;
-            const bool hit = (x <= x1) && (labels[row + x] == (int32_t)L);
+            const bool hit = (x <= x1) && (labels[row + x] == LV);
             unsigned m = __ballot_sync(0xffffffffu, hit);
             while (m) {
                 // up to four matching pixels per trip: all their loads are issued before any is used
@@ -303,17 +333,18 @@ zonal_gather_bands_kernel(const int32_t *__restrict__ labels, const float *__res
                         for (int k = 0; k < BPL; ++k) v[u][k] = bok[k] ? p[bidx[k]] : 0.0f;
                     }
                 }
-                if (!have_pivot) {
-                    have_pivot = true;
-#pragma unroll
-                    for (int k = 0; k < BPL; ++k) pivot[k] = v[0][k];
-                }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (bpos[u] < 0) continue;
 #pragma unroll
                     for (int k = 0; k < BPL; ++k) {
-                        const float d = v[u][k] - pivot[k];
+                        const bool ok = v[u][k] == v[u][k];     // NaN samples are dropped per band
+                        if (ok && !have_pivot[k]) {             // pivot = the band's first valid sample
+                            have_pivot[k] = true;
+                            pivot[k] = v[u][k];
+                        }
+                        nvalid[k] += ok;
+                        const float d = ok ? v[u][k] - pivot[k] : 0.0f;
                         const float dd = d * d;
                         s1[k] += d;
                         s2[k] += dd;
@@ -339,7 +370,14 @@ zonal_gather_bands_kernel(const int32_t *__restrict__ labels, const float *__res
 #pragma unroll
     for (int k = 0; k < BPL; ++k) {
         if (!bok[k]) continue;
-        const double n = (double)cnt_total;
+        double *o = out + (lane + 32 * k) * 8;
+        if (nvalid[k] == 0) {
+            o[0] = 0.0;
+            for (int q = 1; q < 7; ++q) o[q] = NAND;
+            o[7] = 0.0;
+            continue;
+        }
+        const double n = (double)nvalid[k];
         const double S1 = d1[k] + (double)s1[k], S2 = d2[k] + (double)s2[k];
         const double S3 = d3[k] + (double)s3[k], S4 = d4[k] + (double)s4[k];
         const double md = S1 / n, e2 = S2 / n, e3 = S3 / n, e4 = S4 / n;
@@ -350,7 +388,6 @@ zonal_gather_bands_kernel(const int32_t *__restrict__ labels, const float *__res
         const double m4 = e4 - 4.0 * md * e3 + 6.0 * md * md * e2 - 3.0 * md * md * md * md;
         const double thr = resolution * mean;
         const bool degenerate = m2 <= thr * thr;
-        double *o = out + (lane + 32 * k) * 8;
         o[0] = n;
         o[1] = mean;
         o[2] = m2;
@@ -372,17 +409,17 @@ extern "C" int64_t obia_b200_zonal_workspace_bytes(int64_t max_label, int32_t Cz
     return zonal_ws_layout(nullptr, max_label).bytes;
 }
 
-extern "C" int obia_b200_zonal_stats(const int32_t *labels, const float *raw, int64_t H, int64_t W,
-                                     int32_t C, const int32_t *bands_host, int32_t Cz, int64_t max_label,
-                                     double resolution, double *stats, void *workspace, void *stream)
+static int zonal_stats_impl(const int32_t *labels, const float *raw, int64_t H, int64_t W,
+                            int32_t C, const int32_t *bands_host, int32_t Cz, int64_t label_lo, int64_t max_label,
+                            double resolution, double *stats, void *workspace, void *stream)
 {
     if (!labels || !raw || !bands_host || !stats || !workspace || H <= 0 || W <= 0 || C <= 0 || Cz <= 0 ||
-        max_label < 0)
+        max_label < 0 || label_lo < 0)
         return set_err(OBIA_B200_ERR_ARG, "zonal_stats: bad argument");
     if (Cz > OBIA_B200_MAX_BANDS)
         return set_err(OBIA_B200_ERR_UNSUPPORTED, "zonal_stats: at most %d statistics bands per call",
                        OBIA_B200_MAX_BANDS);
-    if (H * W >= 0x7fffffffLL || max_label >= 0x7fffffffLL)
+    if (H * W >= 0x7fffffffLL || max_label + label_lo >= 0x7fffffffLL)
         return set_err(OBIA_B200_ERR_UNSUPPORTED, "zonal_stats: H*W exceeds int32");
     ZBands zb;
     memset(&zb, 0, sizeof(zb));
@@ -395,17 +432,18 @@ extern "C" int obia_b200_zonal_stats(const int32_t *labels, const float *raw, in
     ZonalWs w = zonal_ws_layout(workspace, max_label);
     const int64_t n = max_label + 1;
     const int64_t N = H * W;
+    const int32_t lo = (int32_t)label_lo;
     zonal_init_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(w, n);
     OBIA_LAUNCH_CHECK();
-    zonal_bbox_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(labels, w, N, (int)W, max_label);
+    zonal_bbox_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(labels, w, N, (int)W, max_label, lo);
     OBIA_LAUNCH_CHECK();
     if (Cz >= 24) {
         // many bands: lanes across bands, one pass over the raster for all of them
         const unsigned g = (unsigned)ceil_div(n, 8);
         if (Cz <= 32)
-            zonal_gather_bands_kernel<1><<<g, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label, resolution, stats);
+            zonal_gather_bands_kernel<1><<<g, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label, resolution, stats, lo);
         else
-            zonal_gather_bands_kernel<2><<<g, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label, resolution, stats);
+            zonal_gather_bands_kernel<2><<<g, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label, resolution, stats, lo);
         OBIA_LAUNCH_CHECK();
         return OBIA_B200_OK;
     }
@@ -416,10 +454,27 @@ extern "C" int obia_b200_zonal_stats(const int32_t *labels, const float *raw, in
         vec = (b % kZB == 0) ? (zb.band[b] % 4 == 0) : (zb.band[b] == zb.band[b - 1] + 1);
     if (vec)
         zonal_gather_kernel<true><<<grid, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label,
-                                                        resolution, stats);
+                                                        resolution, stats, lo);
     else
         zonal_gather_kernel<false><<<grid, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label,
-                                                         resolution, stats);
+                                                         resolution, stats, lo);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
+}
+
+extern "C" int obia_b200_zonal_stats(const int32_t *labels, const float *raw, int64_t H, int64_t W,
+                                     int32_t C, const int32_t *bands_host, int32_t Cz, int64_t max_label,
+                                     double resolution, double *stats, void *workspace, void *stream)
+{
+    return zonal_stats_impl(labels, raw, H, W, C, bands_host, Cz, 0, max_label, resolution, stats, workspace, stream);
+}
+
+extern "C" int obia_b200_zonal_stats_range(const int32_t *labels, const float *raw, int64_t H, int64_t W,
+                                           int32_t C, const int32_t *bands_host, int32_t Cz, int64_t label_lo,
+                                           int64_t n_rows, double resolution, double *stats, void *workspace,
+                                           void *stream)
+{
+    if (n_rows <= 0) return set_err(OBIA_B200_ERR_ARG, "zonal_stats_range: bad argument");
+    return zonal_stats_impl(labels, raw, H, W, C, bands_host, Cz, label_lo, n_rows - 1, resolution, stats, workspace,
+                            stream);
 }

@@ -1,18 +1,32 @@
 """Global SLIC + zonal statistics on ONE raster sharded by row strips across GPUs
-("global SLIC on one huge raster").
+("global SLIC on one huge raster"; the reference itself is single-process).
 
-Every rank keeps rows [row0, row0 + h) of the raw raster in HBM.  Per sweep each rank assigns its
-own pixels against the full (replicated) centre table and accumulates its contribution to the
-centre sums; the int64 fixed-point sums are all-reduced over NCCL (integer addition: exact and
-order-independent), so every rank derives the same centres and the labels are BIT-IDENTICAL to the
-single-GPU run for any number of ranks.  Connectivity needs the whole label raster: the int32
-strips are all-gathered (4 B/pixel) and every rank runs the exact connectivity kernels on the full
-raster, keeping its strip.  Zonal statistics are computed per strip and merged with the pairwise
-moment-combination formulas (Chan et al.); counts / min / max stay exact.
+Every rank keeps rows [row0, row0 + h) of the raw raster in HBM; strips start on multiples of
+`ROW_ALIGN` rows so that the CTA tiles of the assignment kernel are the same as in a single-GPU run.
+Exchanges (NCCL over NVLink via torch.distributed, or tensor copies when several strips live on one
+GPU in the tests):
 
-`ShardedSlic` holds one strip's state and exposes the steps separately so the same code path is
-driven either by `torch.distributed` (`slic_zonal_distributed`) or, in the tests, by several strips
-living on one GPU with the reductions done by hand.
+  band ranges      one all-reduce (min / max) of C floats.
+  per sweep        every rank assigns its own pixels against the replicated centre table and sums its
+                   contribution in 64-bit fixed point; only the BANDS of the table whose centres can
+                   receive pixels from two ranks (initial grid row within `band_steps` grid steps of a
+                   strip boundary) are exchanged with the neighbour and added (integer addition: exact
+                   and order-independent), so both neighbours derive identical centres.  A centre that
+                   drifts out of its band raises a flag (`obia_b200_slic_band_check`) and the run is
+                   repeated with the full all-reduce of the table.
+  connectivity     SLIC components are bounded by the +-2*step windows, so each rank labels its strip
+                   plus `halo` rows of its neighbours' labels (`obia_b200_connectivity_strip_*`); kept
+                   pieces are counted per rank, one all-gather + exclusive prefix sum gives the label
+                   offsets (north_star: "exclusive scan of per-tile label offsets").  A strip whose
+                   result could depend on pixels outside the halo reports it; all ranks then fall back
+                   to gathering the label raster and running the single-raster kernel.
+  statistics       the raster-order numbering makes a rank's labels a contiguous range; statistics are
+                   computed over that range only (`obia_b200_zonal_stats_range`) and the rows of the
+                   segments that straddle a boundary are merged with the neighbour (pairwise moment
+                   combination; counts / min / max exact).  The table stays sharded by label range.
+
+Labels are BIT-IDENTICAL to the single-GPU run for any number of ranks (tests emulate 2-4 ranks on
+one GPU; scripts/sharded_check.py runs over NCCL).
 """
 from __future__ import annotations
 
@@ -24,7 +38,99 @@ import torch
 from . import _lib, pipeline, slic_host
 from .pipeline import _i32_array, _p, _require_cuda, _stream_ptr
 
+ROW_ALIGN = 128     # strips start on multiples of the tallest CTA tile of the assignment kernels
 
+
+def split_rows(H_total, world, align=ROW_ALIGN):
+    """Contiguous row strips, as equal as possible, every strip starting on a multiple of `align`."""
+    units = -(-H_total // align)
+    base, extra = divmod(units, world)
+    rows, r = [], 0
+    for k in range(world):
+        h = (base + (1 if k < extra else 0)) * align
+        h = max(0, min(h, H_total - r))
+        rows.append((r, h))
+        r += h
+    if any(h == 0 for _, h in rows):
+        raise ValueError(f"raster of {H_total} rows is too small for {world} strips of {align}-row tiles")
+    return rows
+
+
+# ------------------------------------------------------------------ communication ---
+class DistComm:
+    """torch.distributed (NCCL on GPUs): this process holds one strip."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.local = [self.rank]
+
+    def all_reduce(self, tensors, op):
+        ops = {"min": self.dist.ReduceOp.MIN, "max": self.dist.ReduceOp.MAX, "sum": self.dist.ReduceOp.SUM}
+        self.dist.all_reduce(tensors[0], op=ops[op])
+
+    def all_gather_host(self, values):
+        """values: one list of python ints per local strip -> list over all ranks."""
+        t = torch.tensor(values[0], dtype=torch.int64, device="cuda")
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [o.tolist() for o in torch.stack(out).cpu()]
+
+    def all_gather(self, tensors):
+        out = [torch.empty_like(tensors[0]) for _ in range(self.world)]
+        self.dist.all_gather(out, tensors[0].contiguous())
+        return [out]
+
+    def neighbour_exchange(self, send_up, send_down, recv_up_like, recv_down_like):
+        """send_up[i] goes to rank-1, send_down[i] to rank+1; returns what the upper / lower neighbour
+        sent here (None at the raster edges).  `*_like`: (shape, dtype) of the expected messages."""
+        dist, r = self.dist, self.rank
+        ops, ru, rd = [], None, None
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if r > 0 and recv_up_like[0] is not None:
+            ru = torch.empty(recv_up_like[0][0], dtype=recv_up_like[0][1], device=dev)
+            ops.append(dist.P2POp(dist.irecv, ru, r - 1))
+        if r < self.world - 1 and recv_down_like[0] is not None:
+            rd = torch.empty(recv_down_like[0][0], dtype=recv_down_like[0][1], device=dev)
+            ops.append(dist.P2POp(dist.irecv, rd, r + 1))
+        if r > 0 and send_up[0] is not None:
+            ops.append(dist.P2POp(dist.isend, send_up[0].contiguous(), r - 1))
+        if r < self.world - 1 and send_down[0] is not None:
+            ops.append(dist.P2POp(dist.isend, send_down[0].contiguous(), r + 1))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return [ru], [rd]
+
+
+class LocalComm:
+    """All strips live in this process (tests: several ranks emulated on one GPU)."""
+
+    def __init__(self, world):
+        self.world, self.rank = world, 0
+        self.local = list(range(world))
+
+    def all_reduce(self, tensors, op):
+        st = torch.stack(tensors)
+        red = {"min": st.amin(0), "max": st.amax(0), "sum": st.sum(0)}[op]
+        for t in tensors:
+            t.copy_(red)
+
+    def all_gather_host(self, values):
+        return [list(v) for v in values]
+
+    def all_gather(self, tensors):
+        return [[t.clone() for t in tensors] for _ in tensors]
+
+    def neighbour_exchange(self, send_up, send_down, recv_up_like, recv_down_like):
+        n = self.world
+        ru = [None if i == 0 or send_down[i - 1] is None else send_down[i - 1].clone() for i in range(n)]
+        rd = [None if i == n - 1 or send_up[i + 1] is None else send_up[i + 1].clone() for i in range(n)]
+        return ru, rd
+
+
+# ------------------------------------------------------------------ one strip ---
 class ShardedSlic:
     def __init__(self, raw_strip, row0, H_total, segmentation_bands=None, *, n_segments=100, compactness=10.0,
                  max_num_iter=10, sigma=0, convert2lab=None, enforce_connectivity=True, min_size_factor=0.5,
@@ -36,7 +142,7 @@ class ShardedSlic:
         if np.any(np.asarray(sigma) > 0):
             raise NotImplementedError("sigma > 0 needs a halo exchange of the features: not implemented for strips")
         if slic_zero or spacing is not None:
-            raise NotImplementedError("slic_zero / spacing are not implemented on the B200 path")
+            raise NotImplementedError("slic_zero / spacing are not implemented on the sharded path")
         if start_label not in (0, 1):
             raise ValueError("start_label should be 0 or 1.")
         self.lib = _lib.load()
@@ -57,6 +163,7 @@ class ShardedSlic:
         self.to_lab = Cs == 3 and (convert2lab or convert2lab is None)
         self.Cf = 3 if self.to_lab else Cs
         self.dev = raw_strip.device
+        self.top_open, self.bottom_open = self.row0 > 0, self.row0 + self.h < self.H
 
     # -- step 1: band ranges of this strip, to be min/max-reduced over the strips ----------------
     def local_minmax(self):
@@ -64,17 +171,24 @@ class ShardedSlic:
         return mm, fl          # (C, 4) float32: min, max, ., . ; (C,) int32 flags
 
     # -- step 2: features + replicated centres -----------------------------------------------------
-    def prepare(self, minmax_global, flags_global):
+    def prepare(self, minmax_global, flags_global, band_steps=4):
         mm = minmax_global.cpu().numpy()
         fl = flags_global.cpu().numpy()
         f32 = np.float32
         for b in self.bands:
             if fl[b] or not np.isfinite(mm[b, 0]) or not np.isfinite(mm[b, 1]) or mm[b, 1] == mm[b, 0]:
                 raise ValueError("unmasked NaN values in image are not supported")
-        yx, steps = slic_host.grid_centroids(self.H, self.W, self.n_segments)
-        self.n = int(yx.shape[0])
-        self.step = float(max(steps))
+        starts, isteps = slic_host.regular_grid_steps((1, self.H, self.W), self.n_segments)
+        sy, sx = isteps[1] or 1, isteps[2] or 1
+        ys = torch.arange(starts[1], self.H, sy, device=self.dev, dtype=torch.float32)
+        xs = torch.arange(starts[2], self.W, sx, device=self.dev, dtype=torch.float32)
+        self.ny, self.nx = int(ys.numel()), int(xs.numel())
+        self.n = self.ny * self.nx
+        self.step = float(max(1.0 if s is None else float(s) for s in isteps))
         self.step_y, self.step_x = slic_host.window_steps(self.H, self.W, self.n)
+        self.centres = torch.zeros((self.n, 2 + self.Cf), dtype=torch.float32, device=self.dev)
+        self.centres[:, 0] = ys.repeat_interleave(self.nx)
+        self.centres[:, 1] = xs.repeat(self.ny)
         ratio = f32(1.0 / self.compactness)
         self.pitch = (self.W + 31) // 32 * 32
         self.feats = torch.empty((self.Cf, self.h, self.pitch), dtype=torch.float32, device=self.dev)
@@ -84,9 +198,6 @@ class ShardedSlic:
             _p(self.raw), self.h, self.W, self.C, _i32_array(self.bands), len(self.bands),
             bmin.ctypes.data_as(ctypes.c_void_p), bmax.ctypes.data_as(ctypes.c_void_p), 0.0, 1.0,
             int(self.to_lab), float(ratio), _p(self.feats), self.pitch, _stream_ptr()), "slic_features")
-        c = np.zeros((self.n, 2 + self.Cf), dtype=np.float32)
-        c[:, :2] = yx.astype(np.float32)
-        self.centres = torch.from_numpy(c).to(self.dev)
         self.fix_scale = slic_host.fixed_point_scale(float(ratio) * (256.0 if self.to_lab else 4.0), self.H, self.W,
                                                      self.step_y, self.step_x)
         nbytes = self.lib.obia_b200_slic_workspace_bytes(self.H, self.W, self.Cf, self.n, self.step_y, self.step_x)
@@ -96,8 +207,16 @@ class ShardedSlic:
         _lib.check(self.lib.obia_b200_slic_begin(_p(self.labels), _p(self.ws), self.h, self.W, self.H, self.Cf, self.n,
                                                  self.step_y, self.step_x, self.start_label, _p(self.status),
                                                  _stream_ptr()), "slic_begin")
+        # centre-index bands at the strip boundaries: grid rows within `band_steps` steps of the boundary
+        def band(yb):
+            lo = int(np.ceil((yb - band_steps * sy - starts[1]) / sy))
+            hi = int(np.floor((yb + band_steps * sy - starts[1]) / sy))
+            lo, hi = max(lo, 0), min(hi, self.ny - 1)
+            return (lo * self.nx, (hi + 1) * self.nx) if hi >= lo else (0, 0)
+        self.band_up = band(self.row0) if self.top_open else (0, 0)
+        self.band_down = band(self.row0 + self.h) if self.bottom_open else (0, 0)
 
-    # -- step 3 (x max_num_iter): sweep -> reduce acc over strips -> finish ----------------------------
+    # -- step 3 (x max_num_iter): sweep -> combine acc over strips -> finish ---------------------------
     def sweep(self):
         sweep = self.lib.obia_b200_slic_sweep if self.exact else self.lib.obia_b200_slic_sweep_fast
         _lib.check(sweep(
@@ -109,29 +228,81 @@ class ShardedSlic:
         """This strip's centre sums: int64 view (n, 3 + Cf) of the head of the workspace."""
         return self.ws[: self.n * (3 + self.Cf) * 8].view(torch.int64).view(self.n, 3 + self.Cf)
 
-    def finish_sweep(self):
+    def finish_sweep(self, check_bands=False):
         _lib.check(self.lib.obia_b200_slic_finish_sweep(_p(self.centres), _p(self.ws), self.H, self.W, self.Cf, self.n,
                                                         self.step_y, self.step_x, self.fix_scale, _stream_ptr()),
                    "slic_finish_sweep")
+        if check_bands:
+            _lib.check(self.lib.obia_b200_slic_band_check(
+                _p(self.centres), self.n, self.Cf, self.row0, self.row0 + self.h, self.H, self.band_up[0],
+                self.band_up[1], self.band_down[0], self.band_down[1], self.step_y, _p(self.status), _stream_ptr()),
+                "slic_band_check")
 
-    def check_status(self):
-        if int(self.status[0].item()) != 0:
-            raise _lib.ObiaB200Error("slic_sweep: a tile collected more than 1024 candidate centres")
-
-    # -- step 4: connectivity on the gathered raster, keep the strip ------------------------------------
-    def connect(self, full_labels):
-        if not self.enforce:
-            self.final = self.labels
-            self.n_labels = self.n
-            return
+    def sizes(self):
         seg = float(self.H * self.W) / self.n
-        min_size, max_size = int(self.min_size_factor * seg), int(self.max_size_factor * seg)
-        out, self.n_labels = pipeline.enforce_connectivity(full_labels, min_size, max_size, self.start_label)
-        self.final = out[self.row0:self.row0 + self.h].contiguous()
+        return int(self.min_size_factor * seg), int(self.max_size_factor * seg)
 
-    # -- step 5: per-strip statistics (merged by combine_stats) -----------------------------------------
-    def strip_stats(self, bands=None):
-        return pipeline.zonal_stats(self.final, self.raw, bands, max_label=self.n_labels + 1, resolution=1e-6)
+    def default_halo(self):
+        """Rows of neighbour labels on each side: two window heights (a SLIC component spans at most
+        4*step+1 rows), so the pieces that reach the core and the pieces they can merge into are whole."""
+        return 8 * self.step_y + 8
+
+    # -- step 4a: connectivity on the gathered raster (fallback) ----------------------------------------
+    def connect_full(self, full_labels):
+        min_size, max_size = self.sizes()
+        out, n_labels = pipeline.enforce_connectivity(full_labels, min_size, max_size, self.start_label)
+        self.final = out[self.row0:self.row0 + self.h].contiguous()
+        self.n_labels = n_labels
+        self.has_zero = None
+
+    # -- step 4b: connectivity on the strip + halo ---------------------------------------------------
+    def strip_begin(self, halo_up, halo_down):
+        parts = [t for t in (halo_up, self.labels, halo_down) if t is not None]
+        self.ext = torch.cat(parts, dim=0).contiguous() if len(parts) > 1 else self.labels
+        self.core_row0 = 0 if halo_up is None else int(halo_up.shape[0])
+        H_ext = int(self.ext.shape[0])
+        self.cc_ws = torch.empty((self.lib.obia_b200_connectivity_workspace_bytes(H_ext, self.W),),
+                                 dtype=torch.uint8, device=self.dev)
+        counts = (ctypes.c_int64 * 3)()
+        min_size, max_size = self.sizes()
+        _lib.check(self.lib.obia_b200_connectivity_strip_begin(
+            _p(self.ext), _p(self.cc_ws), H_ext, self.W, self.core_row0, self.h, int(halo_up is not None),
+            int(halo_down is not None), min_size, max_size, self.start_label, counts, _stream_ptr()),
+            "connectivity_strip_begin")
+        self.k_before, self.k_core = int(counts[0]), int(counts[1])
+        return self.k_core
+
+    def strip_finish(self, labels_before):
+        """labels_before = number of kept pieces that start in the core rows of the ranks above."""
+        self.label_base = int(labels_before)
+        out = torch.empty((self.h, self.W), dtype=torch.int32, device=self.dev)
+        flags = (ctypes.c_int32 * 2)()
+        min_size, max_size = self.sizes()
+        _lib.check(self.lib.obia_b200_connectivity_strip_finish(
+            _p(self.ext), _p(out), _p(self.cc_ws), int(self.ext.shape[0]), self.W, self.core_row0, self.h, min_size,
+            max_size, self.start_label, self.label_base - self.k_before, flags, _stream_ptr()),
+            "connectivity_strip_finish")
+        self.final = out
+        self.has_zero = bool(flags[1])
+        del self.cc_ws, self.ext
+        return int(flags[0])
+
+    # -- step 5: statistics over this rank's label range -------------------------------------------------
+    def range_stats(self, bands=None, resolution=1e-6):
+        """Rows = labels [start_label + label_base - k_before, start_label + label_base + k_core)."""
+        bands = list(range(self.C)) if bands is None else [int(b) for b in bands]
+        n_rows = max(1, self.k_before + self.k_core)
+        lo = self.start_label + self.label_base - self.k_before
+        stats = torch.empty((n_rows, len(bands), 8), dtype=torch.float64, device=self.dev)
+        ws = torch.empty((self.lib.obia_b200_zonal_workspace_bytes(n_rows - 1, 8),), dtype=torch.uint8, device=self.dev)
+        _lib.check(self.lib.obia_b200_zonal_stats_range(_p(self.final), _p(self.raw), self.h, self.W, self.C,
+                                                        _i32_array(bands), len(bands), lo, n_rows, float(resolution),
+                                                        _p(stats), _p(ws), _stream_ptr()), "zonal_stats_range")
+        return stats
+
+    def zero_stats(self, bands=None, resolution=1e-6):
+        """Row of label 0 (start_label 1 only; pieces merged into nothing, SURVEY.md defect 7)."""
+        return pipeline.zonal_stats(self.final, self.raw, bands, max_label=0, resolution=resolution)
 
 
 def combine_stats(tables, resolution=1e-6):
@@ -179,49 +350,183 @@ def combine_stats(tables, resolution=1e-6):
     return out
 
 
-def split_rows(H_total, world):
-    """Contiguous row strips, as equal as possible."""
-    base, extra = divmod(H_total, world)
-    rows, r = [], 0
-    for k in range(world):
-        h = base + (1 if k < extra else 0)
-        rows.append((r, h))
-        r += h
-    return rows
+# ------------------------------------------------------------------ driver ---
+class ShardedResult:
+    """Per local strip: final labels (core rows), the rank's slice of the statistics table (rows =
+    labels [label_lo, label_lo + rows)), the statistics of label 0 (or None), the global segment count."""
+
+    def __init__(self):
+        self.labels, self.stats, self.label_lo, self.zero_row = [], [], [], None
+        self.n_labels, self.timings, self.mode = 0, {}, {}
 
 
-def slic_zonal_distributed(raw_strip, row0, H_total, segmentation_bands=None, statistics_bands=None, **slic_kwargs):
+def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None, timings=False, stats=True):
+    """Drive the strips held by this process (`comm.local`) through the sharded path.
+
+    exchange: "band" (neighbour exchange of the boundary bands of the centre sums, falls back to
+    "allreduce" when a centre leaves its band) or "allreduce" (whole table every sweep)."""
+    res = ShardedResult()
+    ev = []
+
+    def mark(name):
+        if timings:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append((name, e))
+
+    mark("start")
+    mms = [s.local_minmax() for s in strips]
+    lo = [m[0][:, 0].clone() for m in mms]
+    hi = [m[0][:, 1].clone() for m in mms]
+    fl = [m[1] for m in mms]
+    comm.all_reduce(lo, "min")
+    comm.all_reduce(hi, "max")
+    comm.all_reduce(fl, "max")
+    for i, s in enumerate(strips):
+        s.prepare(torch.stack([lo[i], hi[i], lo[i], hi[i]], dim=1), fl[i])
+    mark("preprocess")
+
+    def slic(mode):
+        for it in range(strips[0].max_num_iter):
+            for s in strips:
+                s.sweep()
+            if mode == "allreduce" or comm.world == 1:
+                comm.all_reduce([s.acc() for s in strips], "sum")
+            else:
+                up = [s.acc()[s.band_up[0]:s.band_up[1]] if s.top_open else None for s in strips]
+                down = [s.acc()[s.band_down[0]:s.band_down[1]] if s.bottom_open else None for s in strips]
+                like_u = [None if u is None else (tuple(u.shape), u.dtype) for u in up]
+                like_d = [None if d is None else (tuple(d.shape), d.dtype) for d in down]
+                ru, rd = comm.neighbour_exchange(up, down, like_u, like_d)
+                for s, u, d, a, b in zip(strips, up, down, ru, rd):
+                    if a is not None:
+                        u += a
+                    if b is not None:
+                        d += b
+            for s in strips:
+                s.finish_sweep(check_bands=(mode == "band" and comm.world > 1))
+        st = [s.status.clone() for s in strips]
+        comm.all_reduce(st, "max")
+        flags = st[0].cpu().tolist()
+        if flags[0]:
+            raise _lib.ObiaB200Error("slic_sweep: a tile collected more than 1024 candidate centres")
+        return flags[1]
+
+    mode = exchange
+    if slic(mode):
+        # a centre left its band: redo with the whole table (prepare() resets centres, labels, sums)
+        mode = "allreduce"
+        for i, s in enumerate(strips):
+            s.prepare(torch.stack([lo[i], hi[i], lo[i], hi[i]], dim=1), fl[i])
+        slic(mode)
+    res.mode["exchange"] = mode
+    mark("slic")
+
+    s0 = strips[0]
+    if not s0.enforce:
+        for s in strips:
+            s.final, s.k_before, s.k_core, s.label_base, s.has_zero = s.labels, 0, s.n, 0, False
+        res.n_labels = s0.n
+        res.mode["connectivity"] = "none"
+        kcores = None
+    else:
+        h_rows = int(halo) if halo is not None else s0.default_halo()
+        incomplete = 1
+        rows_all = comm.all_gather_host([[s.h] for s in strips])
+        if comm.world > 1 and min(r[0] for r in rows_all) >= h_rows:
+            up = [s.labels[:h_rows] if s.top_open else None for s in strips]
+            down = [s.labels[s.h - h_rows:] if s.bottom_open else None for s in strips]
+            like = ((h_rows, s0.W), torch.int32)
+            ru, rd = comm.neighbour_exchange(up, down, [like if s.top_open else None for s in strips],
+                                             [like if s.bottom_open else None for s in strips])
+            kc = [[s.strip_begin(a, b)] for s, a, b in zip(strips, ru, rd)]
+            kcores = [k[0] for k in comm.all_gather_host(kc)]
+            prefix = np.concatenate([[0], np.cumsum(kcores)])
+            inc = [torch.tensor([s.strip_finish(int(prefix[r]))], dtype=torch.int32, device=s.dev)
+                   for s, r in zip(strips, comm.local)]
+            comm.all_reduce(inc, "max")
+            incomplete = int(inc[0].item())
+            res.n_labels = int(prefix[-1])
+            res.mode["connectivity"] = "strip+halo"
+        elif comm.world == 1:
+            s0.strip_begin(None, None)
+            incomplete = s0.strip_finish(0)
+            res.n_labels = s0.k_core
+            kcores = [s0.k_core]
+            res.mode["connectivity"] = "strip+halo"
+        if incomplete:
+            # some strip's result could depend on pixels outside its halo (or the strips are thinner than
+            # the halo): gather the label raster, every rank runs the single-raster kernel
+            hmax = max(r[0] for r in rows_all)
+            pads = []
+            for s in strips:
+                pad = torch.full((hmax, s.W), s.start_label - 1, dtype=torch.int32, device=s.dev)
+                pad[:s.h] = s.labels
+                pads.append(pad)
+            gathered = comm.all_gather(pads)
+            for s, g in zip(strips, gathered):
+                full = torch.cat([t[:r[0]] for t, r in zip(g, rows_all)], dim=0).contiguous()
+                s.connect_full(full)
+            res.n_labels = s0.n_labels
+            res.mode["connectivity"] = "gathered"
+            kcores = None
+    mark("connectivity")
+
+    res.labels = [s.final for s in strips]
+    if stats:
+        if kcores is None:
+            # labels are not a contiguous range per rank: whole-table statistics merged over all ranks
+            tabs = [pipeline.zonal_stats(s.final, s.raw, statistics_bands, max_label=res.n_labels + 1) for s in strips]
+            allt = comm.all_gather(tabs)
+            merged = [combine_stats(list(g)) for g in allt]
+            res.stats, res.label_lo = merged, [0 for _ in strips]
+            res.mode["stats"] = "replicated"
+        else:
+            tabs = [s.range_stats(statistics_bands) for s in strips]
+            kb = comm.all_gather_host([[s.k_before] for s in strips])
+            # rows of pieces that start above the core go UP to their owner
+            up = [t[:s.k_before] if s.top_open and s.k_before > 0 else None for s, t in zip(strips, tabs)]
+            Cz = int(tabs[0].shape[1])
+            like_d = []
+            for s, r in zip(strips, comm.local):
+                nb = kb[r + 1][0] if r + 1 < comm.world else 0
+                like_d.append(((nb, Cz, 8), torch.float64) if nb > 0 else None)
+            _, rd = comm.neighbour_exchange(up, [None] * len(strips), [None] * len(strips), like_d)
+            out = []
+            for s, t, b in zip(strips, tabs, rd):
+                own = t[s.k_before:s.k_before + s.k_core]
+                if b is not None and b.shape[0] > 0:
+                    nb = int(b.shape[0])
+                    if nb > own.shape[0]:
+                        raise _lib.ObiaB200Error("a segment spans more than two strips: strips are too thin")
+                    tail = combine_stats([own[own.shape[0] - nb:], b])
+                    own = torch.cat([own[:own.shape[0] - nb], tail], dim=0)
+                out.append(own)
+            res.stats = out
+            res.label_lo = [s.start_label + s.label_base for s in strips]
+            res.mode["stats"] = "label-range"
+            hz = [torch.tensor([int(bool(s.has_zero))], dtype=torch.int32, device=s.dev) for s in strips]
+            comm.all_reduce(hz, "max")
+            if int(hz[0].item()):
+                z = [s.zero_stats(statistics_bands) for s in strips]
+                res.zero_row = combine_stats(list(comm.all_gather(z)[0]))
+    mark("stats")
+    if timings:
+        torch.cuda.synchronize()
+        res.timings = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(ev[:-1], ev[1:])}
+    return res
+
+
+def slic_zonal_distributed(raw_strip, row0, H_total, segmentation_bands=None, statistics_bands=None,
+                           exchange="band", halo=None, timings=False, stats=True, **slic_kwargs):
     """Run the sharded path with torch.distributed (one process per GPU, NCCL).
 
-    Every rank passes its own strip.  Returns (final labels of the strip, number of segments,
-    statistics table (n_segments + 2, Cz, 8) of the WHOLE raster, identical on every rank).
-    """
-    import torch.distributed as dist
-    world, rank = dist.get_world_size(), dist.get_rank()
+    Every rank passes its own strip (`split_rows(H_total, world)`).  Returns a ShardedResult whose
+    lists hold this rank's single entry: final labels of the strip, the rank's rows of the statistics
+    table and the label of its first row."""
+    comm = DistComm()
+    rows = split_rows(H_total, comm.world)
+    if (int(row0), int(raw_strip.shape[0])) != rows[comm.rank]:
+        raise ValueError("strips must be the aligned contiguous split of split_rows()")
     s = ShardedSlic(raw_strip, row0, H_total, segmentation_bands, **slic_kwargs)
-    mm, fl = s.local_minmax()
-    lo, hi = mm[:, 0].clone(), mm[:, 1].clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    dist.all_reduce(fl, op=dist.ReduceOp.MAX)
-    mm = torch.stack([lo, hi, lo, hi], dim=1)
-    s.prepare(mm, fl)
-    for _ in range(s.max_num_iter):
-        s.sweep()
-        dist.all_reduce(s.acc(), op=dist.ReduceOp.SUM)      # the one exchange per iteration (int64: exact)
-        s.finish_sweep()
-    s.check_status()
-    rows = split_rows(H_total, world)
-    if (row0, s.h) != rows[rank]:
-        raise ValueError("strips must be the contiguous equal split of split_rows()")
-    hmax = max(h for _, h in rows)
-    pad = torch.full((hmax, s.W), s.start_label - 1, dtype=torch.int32, device=s.dev)
-    pad[:s.h] = s.labels
-    gathered = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(gathered, pad)
-    full = torch.cat([g[:h] for g, (_, h) in zip(gathered, rows)], dim=0).contiguous()
-    s.connect(full)
-    st = s.strip_stats(statistics_bands)
-    tables = [torch.empty_like(st) for _ in range(world)]
-    dist.all_gather(tables, st.contiguous())
-    return s.final, s.n_labels, combine_stats(tables)
+    return run_sharded([s], comm, statistics_bands, exchange=exchange, halo=halo, timings=timings, stats=stats)

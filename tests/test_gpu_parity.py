@@ -573,6 +573,61 @@ def test_zonal_stats_edge_cases():
     assert np.isnan(want[[0, 2], :, 4]).all()
 
 
+@pytest.mark.parametrize("C,bands", [(8, None), (5, [4, 1, 2]), (40, None)])
+def test_zonal_stats_drop_nan_per_band(C, bands):
+    """NaN nodata in a statistics band (not a segmentation band): the reference drops NaN samples per band
+    (`band_data[~np.isnan(band_data)]`, segment_statistics.py:144-147) and uses the per-band valid count;
+    a band with no valid sample in a segment gives NaN statistics.  Both gather kernels."""
+    import stats_oracle
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    H, W = 90, 120
+    rng = np.random.RandomState(C)
+    raw = synth_raster(H, W, C, seed=C) * 50 + 100
+    yy, xx = np.mgrid[:H, :W]
+    labels = ((yy // 15) * 8 + xx // 15).astype(np.int32)
+    nan_band = 2
+    raw[rng.rand(H, W) < 0.2, nan_band] = np.nan            # scattered nodata
+    raw[:15, :15, nan_band] = np.nan                         # label 0: the whole band is nodata
+    raw[15, 0, nan_band] = np.nan                            # label 8: its first pixel is nodata (pivot choice)
+    raw[0, 15, 1] = np.nan                                   # first pixel of label 1 in another band
+    ids = np.unique(labels)
+    sel = list(range(C)) if bands is None else bands
+    want, counts = stats_oracle.zonal_stats(labels, raw, sel, ids)
+    got = pipeline.zonal_stats(_cuda(labels), _cuda(raw), bands, resolution=1e-6).cpu().numpy()[ids]
+    for j, b in enumerate(sel):
+        valid = np.array([np.isfinite(raw[:, :, b][labels == l]).sum() for l in ids])
+        np.testing.assert_array_equal(got[:, j, 0], valid)
+    np.testing.assert_allclose(got[:, :, 1], want[:, :, 0], rtol=1e-5, equal_nan=True)
+    np.testing.assert_allclose(got[:, :, 2], want[:, :, 1], rtol=2e-5, atol=1e-9, equal_nan=True)
+    np.testing.assert_array_equal(got[:, :, 3], want[:, :, 2])
+    np.testing.assert_array_equal(got[:, :, 4], want[:, :, 3])
+    np.testing.assert_allclose(got[:, :, 5], want[:, :, 4], rtol=1e-4, atol=1e-4, equal_nan=True)
+    np.testing.assert_allclose(got[:, :, 6], want[:, :, 5], rtol=1e-4, atol=1e-4, equal_nan=True)
+    if nan_band in sel:
+        assert np.isnan(got[0, sel.index(nan_band), 1:7]).all() and got[0, sel.index(nan_band), 0] == 0
+
+
+def test_zonal_stats_label_range():
+    """obia_b200_zonal_stats_range: rows = labels [lo, lo + n); everything else is skipped."""
+    import ctypes
+    from obia_b200 import _lib, pipeline
+    from gpu_helpers import synth_raster
+    lib = _lib.load()
+    H, W, C = 64, 96, 4
+    raw = _cuda(synth_raster(H, W, C, seed=3))
+    yy, xx = np.mgrid[:H, :W]
+    labels = _cuda(((yy // 8) * 12 + xx // 8 + 1).astype(np.int32))          # 1..96
+    full = pipeline.zonal_stats(labels, raw, None, max_label=96)
+    lo, n = 30, 25
+    out = torch.empty((n, C, 8), dtype=torch.float64, device="cuda")
+    ws = torch.empty((lib.obia_b200_zonal_workspace_bytes(n - 1, 8),), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.obia_b200_zonal_stats_range(pipeline._p(labels), pipeline._p(raw), H, W, C,
+                                               pipeline._i32_array(range(C)), C, lo, n, 1e-6, pipeline._p(out),
+                                               pipeline._p(ws), pipeline._stream_ptr()), "zonal_stats_range")
+    assert torch.equal(out, full[lo:lo + n])
+
+
 # ------------------------------------------------------------------ K5 ------
 @pytest.mark.parametrize("C,bands,f64,quantize", [(3, None, True, True), (8, [7, 0, 3], False, False),
                                                   (4, [2], False, False)])
@@ -874,44 +929,125 @@ def test_misaligned_views_are_handled():
 
 
 # ------------------------------------------------ sharded (multi-GPU) path, emulated on one GPU ---
-@pytest.mark.parametrize("world,C,n,compactness", [(2, 4, 300, 0.2), (3, 3, 150, 10.0), (4, 8, 500, 0.1)])
-def test_sharded_global_slic_is_bit_identical(world, C, n, compactness):
-    """Row strips + summed int64 centre sums give exactly the single-GPU labels; merged strip
-    statistics equal the one-pass statistics (the NCCL all-reduce is replaced by a tensor sum)."""
+def _run_local_shards(raw, world, kw, stat_bands=None, **run_kw):
+    from obia_b200.sharded import LocalComm, ShardedSlic, run_sharded, split_rows
+    H = int(raw.shape[0])
+    strips = [ShardedSlic(raw[r0:r0 + h].contiguous(), r0, H, None, **kw) for r0, h in split_rows(H, world)]
+    return strips, run_sharded(strips, LocalComm(world), stat_bands, **run_kw)
+
+
+def _check_sharded_against_single(res, ref, ref_stats, start_label):
+    got = torch.cat(res.labels, dim=0)
+    assert torch.equal(got, ref.labels)
+    assert res.n_labels == ref.n_labels
+    b = ref_stats.cpu().numpy()
+    if res.mode["stats"] == "label-range":
+        a = torch.cat(res.stats, dim=0).cpu().numpy()
+        assert res.label_lo[0] == start_label and a.shape[0] == ref.n_labels
+        b_rows = b[start_label:start_label + ref.n_labels]
+        if res.zero_row is not None:
+            a = np.concatenate([res.zero_row.cpu().numpy()[:1], a])
+            b_rows = np.concatenate([b[:1], b_rows])
+        else:
+            assert start_label == 0 or b[0, 0, 0] == 0
+    else:
+        a, b_rows = res.stats[0].cpu().numpy(), b
+    np.testing.assert_array_equal(a[:, :, 0], b_rows[:, :, 0])
+    np.testing.assert_array_equal(a[:, :, 3:5], b_rows[:, :, 3:5])
+    np.testing.assert_allclose(a[:, :, 1:3], b_rows[:, :, 1:3], rtol=1e-6, atol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(a[:, :, 5], b_rows[:, :, 5], rtol=1e-5, atol=1e-5, equal_nan=True)
+    np.testing.assert_allclose(a[:, :, 6] + 3, b_rows[:, :, 6] + 3, rtol=1e-5, equal_nan=True)
+
+
+@pytest.mark.parametrize("world,C,n,compactness,exact,start_label", [
+    (2, 4, 1500, 0.2, True, 1), (3, 3, 900, 10.0, False, 1), (4, 8, 2500, 0.1, False, 1), (4, 5, 2000, 0.05, True, 0),
+    (2, 8, 1200, 1.0, False, 0)])
+def test_sharded_global_slic_is_bit_identical(world, C, n, compactness, exact, start_label):
+    """Row strips (aligned to the kernel tiles) + neighbour exchange of the boundary bands of the int64
+    centre sums + strip connectivity with label halos + label-range statistics give exactly the
+    single-GPU labels and (merged) statistics; the NCCL exchanges are replaced by tensor copies."""
     from obia_b200 import pipeline
-    from obia_b200.sharded import ShardedSlic, combine_stats, split_rows
     from gpu_helpers import synth_raster
-    H, W = 270, 333
+    H, W = 128 * world + 77, 333
     raw = _cuda(synth_raster(H, W, C, seed=world, quantize=(C == 3)))
-    kw = dict(n_segments=n, compactness=compactness, max_num_iter=6, exact=True)
+    kw = dict(n_segments=n, compactness=compactness, max_num_iter=6, exact=exact, start_label=start_label)
     ref = pipeline.slic_labels(raw, None, **kw)
     ref_stats = pipeline.zonal_stats(ref.labels, raw, None, max_label=ref.n_labels + 1)
-    strips = [ShardedSlic(raw[r0:r0 + h].contiguous(), r0, H, None, **kw) for r0, h in split_rows(H, world)]
-    mms = [s.local_minmax() for s in strips]
-    lo = torch.stack([m[0][:, 0] for m in mms]).amin(0)
-    hi = torch.stack([m[0][:, 1] for m in mms]).amax(0)
-    fl = torch.stack([m[1] for m in mms]).amax(0)
-    mm = torch.stack([lo, hi, lo, hi], dim=1)
-    for s in strips:
-        s.prepare(mm, fl)
-    for _ in range(kw["max_num_iter"]):
-        for s in strips:
-            s.sweep()
-        total = torch.stack([s.acc() for s in strips]).sum(0)          # == all_reduce(SUM)
-        for s in strips:
-            s.acc().copy_(total)
-            s.finish_sweep()
-    full = torch.cat([s.labels for s in strips], dim=0).contiguous()    # == all_gather
-    for s in strips:
-        s.check_status()
-        s.connect(full)
-    got = torch.cat([s.final for s in strips], dim=0)
-    assert torch.equal(got, ref.labels)
-    assert all(s.n_labels == ref.n_labels for s in strips)
-    merged = combine_stats([s.strip_stats() for s in strips])
-    a, b = merged.cpu().numpy(), ref_stats.cpu().numpy()
-    np.testing.assert_array_equal(a[:, :, 0], b[:, :, 0])
-    np.testing.assert_array_equal(a[:, :, 3:5], b[:, :, 3:5])
-    np.testing.assert_allclose(a[:, :, 1:3], b[:, :, 1:3], rtol=1e-6, atol=1e-9, equal_nan=True)
-    np.testing.assert_allclose(a[:, :, 5], b[:, :, 5], rtol=1e-5, atol=1e-5, equal_nan=True)
-    np.testing.assert_allclose(a[:, :, 6] + 3, b[:, :, 6] + 3, rtol=1e-5, equal_nan=True)
+    strips, res = _run_local_shards(raw, world, kw)
+    assert res.mode == {"exchange": "band", "connectivity": "strip+halo", "stats": "label-range"}, res.mode
+    _check_sharded_against_single(res, ref, ref_stats, start_label)
+    # the fallbacks give the same result: whole-table all-reduce, gathered connectivity (halo too short)
+    strips, res2 = _run_local_shards(raw, world, kw, exchange="allreduce", halo=2)
+    assert res2.mode["exchange"] == "allreduce"
+    if res2.mode["connectivity"] == "gathered":
+        assert res2.mode["stats"] == "replicated"
+    _check_sharded_against_single(res2, ref, ref_stats, start_label)
+
+
+def test_sharded_band_fallback_when_centres_leave_their_band():
+    """band_steps too small for the drift: obia_b200_slic_band_check raises the flag and the driver
+    repeats the run with the whole-table all-reduce -- same labels as the single-GPU run."""
+    from obia_b200 import pipeline
+    from obia_b200.sharded import LocalComm, ShardedSlic, run_sharded, split_rows
+    from gpu_helpers import synth_raster
+    H, W, C = 384, 300, 4
+    raw = _cuda(synth_raster(H, W, C, seed=11))
+    kw = dict(n_segments=600, compactness=0.05, max_num_iter=5)
+    ref = pipeline.slic_labels(raw, None, **kw)
+    strips = [ShardedSlic(raw[r0:r0 + h].contiguous(), r0, H, None, **kw) for r0, h in split_rows(H, 3)]
+    orig = ShardedSlic.prepare
+    try:
+        ShardedSlic.prepare = lambda self, mm, fl, band_steps=0: orig(self, mm, fl, band_steps=0)
+        res = run_sharded(strips, LocalComm(3))
+    finally:
+        ShardedSlic.prepare = orig
+    assert res.mode["exchange"] == "allreduce"
+    assert torch.equal(torch.cat(res.labels, dim=0), ref.labels)
+
+
+@pytest.mark.parametrize("seed,start_label", [(0, 1), (1, 0), (2, 1)])
+def test_connectivity_strip_mode_matches_full_raster(seed, start_label):
+    """obia_b200_connectivity_strip_* on strips of a noisy label raster: whenever a strip reports its
+    result complete, the core rows are bit-identical to the single-raster kernel (numbering included);
+    with a generous halo every strip is complete."""
+    import ctypes
+    from obia_b200 import _lib, pipeline
+    from gpu_helpers import synth_raster
+    lib = _lib.load()
+    H, W = 600, 257
+    raw = _cuda(synth_raster(H, W, 5, seed=seed, noise=0.12))
+    pre = pipeline.slic_labels(raw, None, n_segments=900, compactness=0.04, max_num_iter=4,
+                               enforce_connectivity=False, start_label=start_label).labels
+    seg = float(H * W) / 900
+    min_size, max_size = int(0.5 * seg), int(3 * seg)
+    full, n_full = pipeline.enforce_connectivity(pre, min_size, max_size, start_label)
+    p, sp = pipeline._p, pipeline._stream_ptr
+    bounds = [0, 150, 290, 470, H]
+    for halo in (4, 40, 130):
+        begun, kcore = [], []
+        for r in range(4):
+            c0, c1 = bounds[r], bounds[r + 1]
+            e0, e1 = max(0, c0 - halo), min(H, c1 + halo)
+            ext = pre[e0:e1].contiguous()
+            ws = torch.empty((lib.obia_b200_connectivity_workspace_bytes(e1 - e0, W),), dtype=torch.uint8, device="cuda")
+            counts = (ctypes.c_int64 * 3)()
+            _lib.check(lib.obia_b200_connectivity_strip_begin(p(ext), p(ws), e1 - e0, W, c0 - e0, c1 - c0, int(e0 > 0),
+                                                              int(e1 < H), min_size, max_size, start_label, counts, sp()),
+                       "strip_begin")
+            begun.append((ext, ws, e0, e1, c0, c1, int(counts[0])))
+            kcore.append(int(counts[1]))
+        prefix = np.concatenate([[0], np.cumsum(kcore)])
+        n_complete = 0
+        for r, (ext, ws, e0, e1, c0, c1, kb) in enumerate(begun):
+            out = torch.empty((c1 - c0, W), dtype=torch.int32, device="cuda")
+            flags = (ctypes.c_int32 * 2)()
+            _lib.check(lib.obia_b200_connectivity_strip_finish(p(ext), p(out), p(ws), e1 - e0, W, c0 - e0, c1 - c0,
+                                                               min_size, max_size, start_label, int(prefix[r]) - kb,
+                                                               flags, sp()), "strip_finish")
+            if not flags[0]:
+                n_complete += 1
+                assert torch.equal(out, full[c0:c1]), f"halo {halo}, strip {r}: complete but different"
+                assert bool(flags[1]) == bool((out == 0).any().item()) or start_label == 0
+        print(f"halo {halo}: {n_complete}/4 strips complete, kept per strip {kcore} (total {n_full})")
+        if halo == 130:
+            assert n_complete == 4 and int(prefix[-1]) == n_full
