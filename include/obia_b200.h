@@ -287,9 +287,10 @@ int obia_b200_enforce_connectivity(const int32_t *labels_in,
  *   strip_finish  numbers the pieces (start_label + label_offset + local rank) and writes
  *                 the core rows.  `incomplete_host[0]` != 0 when a core pixel's label depends on pixels
  *                 outside the strip (cut component or unknown merge chain): the caller retries with a
- *                 taller halo (or gathers the whole raster); `incomplete_host[1]` != 0 when label 0
- *                 occurs in the core rows (start_label 1 only: merged pieces without an earlier
- *                 neighbour, SURVEY.md defect 7).  Both calls synchronise the stream.
+ *                 taller halo (or gathers the whole raster); `incomplete_host[1]` != 0 when the strip
+ *                 holds a merged piece without an earlier neighbour: it carries label 0 whatever the
+ *                 rank (SURVEY.md defect 7), outside the rank's label range.  Both calls synchronise
+ *                 the stream.
  * workspace: obia_b200_connectivity_workspace_bytes(H_ext, W), unchanged between the two calls. */
 int obia_b200_connectivity_strip_begin(const int32_t *labels_ext, void *workspace, int64_t H_ext,
                                        int64_t W, int64_t core_row0, int64_t core_rows,

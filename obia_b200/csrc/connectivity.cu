@@ -788,6 +788,7 @@ cc_small_final_kernel(CcArrays A, const uint32_t *__restrict__ bits, int32_t *fi
                 if (a < 0) {
                     r = 0;  // `adjacent` initial value
                     done = true;
+                    A.ctr[CTR_HASZERO] = 1;   // a leftover piece carries label 0 (benign race: same value)
                 } else {
                     t = A.T[a];
                 }
@@ -811,7 +812,6 @@ cc_resolve_kernel(const int32_t *__restrict__ T, const uint32_t *__restrict__ bi
     int32_t r = mask_label;
     if (t >= 0) {
         r = fin[t];
-        if (r == 0 && mask_label == 0) ctr[CTR_HASZERO] = 1;   // label 0 on an unmasked pixel (benign race)
         if (flag) {
             const bool kept = (bits[t >> 5] >> (t & 31)) & 1u;
             const uint8_t f = flag[t];

@@ -301,8 +301,15 @@ class ShardedSlic:
         return stats
 
     def zero_stats(self, bands=None, resolution=1e-6):
-        """Row of label 0 (start_label 1 only; pieces merged into nothing, SURVEY.md defect 7)."""
-        return pipeline.zonal_stats(self.final, self.raw, bands, max_label=0, resolution=resolution)
+        """Row of label 0 from this strip's pixels when label 0 lies outside the rank's label range
+        (pieces merged into nothing carry label 0 on any rank, SURVEY.md defect 7); an empty row otherwise."""
+        if self.start_label + self.label_base - self.k_before > 0:
+            return pipeline.zonal_stats(self.final, self.raw, bands, max_label=0, resolution=resolution)
+        Cz = self.C if bands is None else len(bands)
+        row = torch.full((1, Cz, 8), float("nan"), dtype=torch.float64, device=self.dev)
+        row[..., 0] = 0.0
+        row[..., 7] = 0.0
+        return row
 
 
 def combine_stats(tables, resolution=1e-6):
@@ -509,7 +516,14 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
             comm.all_reduce(hz, "max")
             if int(hz[0].item()):
                 z = [s.zero_stats(statistics_bands) for s in strips]
-                res.zero_row = combine_stats(list(comm.all_gather(z)[0]))
+                zero = combine_stats(list(comm.all_gather(z)[0]))
+                if s0.start_label == 1:
+                    res.zero_row = zero
+                else:
+                    # start_label 0: label 0 is also the first kept segment, owned by the first rank
+                    for s, t in zip(strips, res.stats):
+                        if s.row0 == 0 and t.shape[0] > 0:
+                            t[:1] = combine_stats([t[:1], zero])
     mark("stats")
     if timings:
         torch.cuda.synchronize()
