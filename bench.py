@@ -9,6 +9,13 @@ HBM -> SLIC label raster -> per-segment per-band statistics table in HBM.  Workl
 BASELINE.json configs[1]: 8-band float32 10000x10000, n_segments=200000 (3.2 GB, far larger
 than the 126 MB L2, so no L2 flush is needed between steps).
 
+N > 1: ONE raster of N x 10000 rows x 10000 columns (same grid step, n_segments = N x 200000: 20000 x
+10000 for N=2, BASELINE config 5's 20000 x 20000 pixel count for N=4, half of the 40000 x 40000 raster
+for N=8) sharded by row strips, one strip per GPU ("weak": per-GPU work fixed).  The data path has real
+exchanges (obia_b200/sharded.py): neighbour exchange of the boundary bands of the centre sums every
+sweep, label halos + an all-gather of per-rank segment counts for connectivity, boundary rows of the
+statistics table.  `split_ms` gives the per-stage timing of a step on rank 0.
+
 One JSON line is printed by rank 0 (see the task contract): `value` = whole-job MP/s with inputs
 resident in HBM; `e2e` = the same metric through the public API `segment()` with pinned HOST
 buffers (H2D of the raster and D2H of the results inside the timed region); `roofline` for the
@@ -184,12 +191,66 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------ our arm ---
+def synth_strip_cuda(row0, h, W, C, seed, device):
+    """Rows [row0, row0 + h) of the synthetic raster (same surface formula as synth_raster_cuda on
+    global row numbers; noise from a per-strip generator)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    yy = torch.arange(row0, row0 + h, device=device, dtype=torch.float32)[:, None]
+    xx = torch.arange(W, device=device, dtype=torch.float32)[None, :]
+    out = torch.empty((h, W, C), dtype=torch.float32, device=device)
+    for c in range(C):
+        fy, fx = 0.004 * (c + 1), 0.003 * (c + 2)
+        surf = 0.5 + 0.25 * torch.sin(yy * fy + c) + 0.25 * torch.cos(xx * fx - c)
+        noise = torch.randn((h, W), generator=g, device=device, dtype=torch.float32) * 0.05
+        out[:, :, c] = (0.6 + 0.05 * c) * surf + noise
+    return out
+
+
+def parity_block(size, seed=2):
+    """Label agreement / ARI of the CUDA path (tolerance mode, the one timed) and of the exact mode
+    against the CPU oracle on a size x size crop of the workload (north_star: >= 99.5 %, ARI reported)."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import slic_oracle as so
+    from obia_b200 import pipeline
+    from sklearn.metrics import adjusted_rand_score
+    wl = WORKLOAD
+    raw = synth_raster_np(size, size, wl["C"], seed)
+    n = max(1, int(round(wl["n_segments"] * (size / wl["H"]) * (size / wl["W"]))))
+    kw = dict(n_segments=n, compactness=wl["compactness"], max_num_iter=wl["max_num_iter"])
+    so.USE_FMA = True
+    try:
+        want = so.create_segments_labels(raw.copy(), None, **kw)
+    finally:
+        so.USE_FMA = False
+    out = {"crop": f"{size}x{size}x{wl['C']}", "n_segments": n, "oracle_segments": int(want.max())}
+    dev_raw = torch.from_numpy(raw).cuda()
+    for name, exact in (("tolerance_mode", False), ("exact_mode", True)):
+        got = pipeline.slic_labels(dev_raw, None, exact=exact, **kw).labels.cpu().numpy()
+        key = got.astype(np.int64).ravel() * (int(want.max()) + 2) + want.astype(np.int64).ravel()
+        pairs, cnt = np.unique(key, return_counts=True)
+        pg, pw = pairs // (int(want.max()) + 2), pairs % (int(want.max()) + 2)
+        bg = np.zeros(int(got.max()) + 1, np.int64)
+        np.maximum.at(bg, pg, cnt)
+        bw = np.zeros(int(want.max()) + 2, np.int64)
+        np.maximum.at(bw, pw, cnt)
+        out[name] = {"agreement": float((got == want).mean()),
+                     "matched_agreement": float(min(bg.sum(), bw.sum())) / got.size,
+                     "ari": float(adjusted_rand_score(want.ravel(), got.ravel())), "segments": int(got.max())}
+    return out
+
+
 def run_ours(args):
+    import ctypes
+
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    from obia_b200 import _lib, pipeline
+    from obia_b200 import _lib, pipeline, sharded
     from obia_b200.handlers.geotif import Image
     from obia_b200.segmentation.segment import segment
 
@@ -213,16 +274,27 @@ def run_ours(args):
         wl["H"] = wl["W"] = args.size
         wl["n_segments"] = max(1, int(round(WORKLOAD["n_segments"] * (args.size / WORKLOAD["H"]) ** 2)))
     H, W, C = wl["H"], wl["W"], wl["C"]
-    slic_kw = dict(n_segments=wl["n_segments"], compactness=wl["compactness"], max_num_iter=wl["max_num_iter"])
-    # weak scaling: every rank owns one raster of the workload shape (independent units, no
-    # data-path collective); seeds differ per rank
-    raw = synth_raster_cuda(H, W, C, seed=2 + rank, device=dev)
+    H_total = H * world                          # one raster, `world` strips
+    n_total = wl["n_segments"] * world           # same grid step for every N
+    slic_kw = dict(n_segments=n_total, compactness=wl["compactness"], max_num_iter=wl["max_num_iter"],
+                   exact=bool(args.exact))
+    if world == 1:
+        row0, h = 0, H
+        raw = synth_raster_cuda(H, W, C, seed=2, device=dev)
+    else:
+        row0, h = sharded.split_rows(H_total, world)[rank]
+        raw = synth_strip_cuda(row0, h, W, C, seed=2 + rank, device=dev)
     torch.cuda.synchronize()
+    comm = sharded.DistComm() if world > 1 else None
 
-    def step():
-        res = pipeline.slic_labels(raw, None, **slic_kw)
-        stats = pipeline.zonal_stats(res.labels, raw, None, max_label=res.n_labels)
-        return res, stats
+    def step(timings=False):
+        if world == 1:
+            res = pipeline.slic_labels(raw, None, **slic_kw)
+            stats = pipeline.zonal_stats(res.labels, raw, None, max_label=res.n_labels)
+            return res.n_labels, stats, None
+        s = sharded.ShardedSlic(raw, row0, H_total, None, **slic_kw)
+        r = sharded.run_sharded([s], comm, None, timings=timings)
+        return r.n_labels, r.stats[0], r
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,7 +303,7 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        res, stats = step()
+        n_out, stats, _ = step()
     barrier()
 
     sampler = ClockSampler(local_rank)
@@ -242,13 +314,12 @@ def run_ours(args):
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        res, stats = step()
+        n_out, stats, shard_res = step()
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = lib.obia_b200_launch_count() - launches0
     lib.obia_b200_profile_enable(0)
-    import ctypes
     k_ms, k_n = ctypes.c_double(0), ctypes.c_int64(0)
     lib.obia_b200_profile_read(ctypes.byref(k_ms), ctypes.byref(k_n))
     clocks = sampler.stop()
@@ -257,13 +328,31 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    mpx = H * W / 1e6
-    value = world * mpx * args.steps / (ms_total / 1e3)
+    mpx = H_total * W / 1e6
+    value = mpx * args.steps / (ms_total / 1e3)
+
+    # ---- per-stage split of one step (outside the timed region; CUDA events per stage) ----------
+    split = None
+    if world > 1:
+        _, _, r = step(timings=True)
+        split = dict(r.timings, **{"mode": r.mode})
+    else:
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        res1 = pipeline.slic_labels(raw, None, **slic_kw)
+        e[1].record()
+        pipeline.zonal_stats(res1.labels, raw, None, max_label=res1.n_labels)
+        e[2].record()
+        torch.cuda.synchronize()
+        split = {"slic_labels (preprocess + sweeps + connectivity)": e[0].elapsed_time(e[1]),
+                 "zonal_stats": e[1].elapsed_time(e[2])}
+        del res1
+    barrier()
 
     # ---- same workload at skimage's default compactness (10): spatially dominated, so the exact
     # candidate pruning of the SLIC kernel applies (reported beside the headline, not instead) ----
     alt = None
-    if not args.no_alt:
+    if not args.no_alt and world == 1:
         kw10 = dict(slic_kw, compactness=10.0)
         for _ in range(2):
             r10 = pipeline.slic_labels(raw, None, **kw10)
@@ -281,48 +370,63 @@ def run_ours(args):
         k10_ms, k10_n = ctypes.c_double(0), ctypes.c_int64(0)
         lib.obia_b200_profile_read(ctypes.byref(k10_ms), ctypes.byref(k10_n))
         ms10 = a0.elapsed_time(a1) / 3
-        alt = {"compactness": 10.0, "ms_per_step": ms10, "value": world * mpx / (ms10 / 1e3), "unit": "MP/s",
+        alt = {"compactness": 10.0, "ms_per_step": ms10, "value": mpx / (ms10 / 1e3), "unit": "MP/s",
                "assign_kernel_avg_ms": k10_ms.value / max(1, k10_n.value), "segments_out": int(r10.n_labels),
-               "note": "rank-0 timing, 3 steps"}
+               "note": "3 steps"}
+        del r10
 
     # ---- e2e through the public API with pinned host buffers -------------------
     e2e = None
     if not args.no_e2e:
-        pristine = torch.empty((H, W, C), dtype=torch.float32, pin_memory=True)
+        pristine = torch.empty((h, W, C), dtype=torch.float32, pin_memory=True)
         pristine.copy_(raw)
-        work = torch.empty((H, W, C), dtype=torch.float32, pin_memory=True)
+        work = torch.empty((h, W, C), dtype=torch.float32, pin_memory=True)
         e2e_steps = min(args.steps, args.e2e_steps)
         t_e2e, d2h, t_tex = 0.0, 0, None
         # the metric is SLIC + zonal (spectral) statistics: the GLCM texture columns of the default
         # `segment()` call are switched off for the timed steps and reported once, separately
         tex_off = dict(calc_contrast=False, calc_dissimilarity=False, calc_homogeneity=False, calc_ASM=False,
                        calc_energy=False, calc_correlation=False)
-        for i in range(2 + e2e_steps):     # first one is a warm-up, last one the full default column set
-            full = i == 1 + e2e_steps
+        kw_api = {k: v for k, v in slic_kw.items()}
+        n_iters = (2 + e2e_steps) if world == 1 else (1 + e2e_steps)
+        for i in range(n_iters):     # first one is a warm-up; N=1: the last one has the full default column set
+            full = world == 1 and i == 1 + e2e_steps
             work.copy_(pristine)            # restore the input buffer (not part of the path)
-            torch.cuda.synchronize()
+            barrier()
             t0 = time.perf_counter()
-            img = Image(work.numpy(), "EPSG:32702", [1, 0, 0, -1, 0, 0], None, None)
-            # H2D upload + kernels + D2H table
-            seg = segment(img, None, None, "slic", **({} if full else tex_off), **slic_kw)
+            if world == 1:
+                img = Image(work.numpy(), "EPSG:32702", [1, 0, 0, -1, 0, 0], None, None)
+                # H2D upload + kernels + D2H table
+                seg = segment(img, None, None, "slic", **({} if full else tex_off), **kw_api)
+                n_rows = len(seg.segments)
+                d2h_i = work.numel() * 4 + n_rows * C * 6 * 8     # normalised img_data write-back + stats rows
+                del img, seg
+            else:
+                # sharded public entry: host strip -> device, sharded path, this rank's rows of the table -> host
+                dev_strip = work.to(dev, non_blocking=True)
+                s = sharded.ShardedSlic(dev_strip, row0, H_total, None, **slic_kw)
+                r = sharded.run_sharded([s], comm, None)
+                table = r.stats[0].cpu()
+                d2h_i = table.numel() * 8
+                del dev_strip, s, r, table
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if full:
                 t_tex = dt
             elif i > 0:
                 t_e2e += dt
-            n_rows = len(seg.segments)
-            if not full:
-                d2h = work.numel() * 4 + n_rows * C * 6 * 8     # normalised img_data write-back + stats rows
-            del img, seg
+                d2h = d2h_i
         t2 = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * mpx * e2e_steps / float(t2.item()), "unit": "MP/s",
-               "h2d_bytes_per_step": H * W * C * 4, "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-               "api": "obia_b200.segmentation.segment.segment(Image(host ndarray), method='slic', ...)",
-               "with_texture_columns": {"value": mpx / t_tex, "unit": "MP/s", "steps": 1,
-                                        "note": "rank-local, default segment() column set incl. GLCM texture"}}
+        e2e = {"value": mpx * e2e_steps / float(t2.item()), "unit": "MP/s",
+               "h2d_bytes_per_step": h * W * C * 4, "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "bytes_are": "per rank" if world > 1 else "whole job",
+               "api": ("obia_b200.segmentation.segment.segment(Image(host ndarray), method='slic', ...)" if world == 1 else
+                       "obia_b200.sharded.slic_zonal_distributed(host strip -> device, ...) + table rows to host")}
+        if t_tex is not None:
+            e2e["with_texture_columns"] = {"value": mpx / t_tex, "unit": "MP/s", "steps": 1,
+                                           "note": "default segment() column set incl. GLCM texture"}
         del pristine, work
 
     if rank != 0:
@@ -334,28 +438,30 @@ def run_ours(args):
     peak, peak_kind = load_peak_hbm()
     Cf = C
     I = wl["max_num_iter"]
-    alg_bytes = (4.0 * Cf + 4.0 / I) * H * W          # SURVEY.md 8(d) stage B per launch
+    alg_bytes = (4.0 * Cf + 4.0 / I) * h * W          # SURVEY.md 8(d) stage B per launch (this rank's strip)
     k_avg_ms = k_ms.value / max(1, k_n.value)
     achieved = alg_bytes / (k_avg_ms / 1e3) / 1e9 if k_avg_ms > 0 else None
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tpath) and world == 1:
         with open(tpath) as f:
             tj = json.load(f)
         if tj["workload"] == {"H": H, "W": W, "C": C}:
-            k = tj["slic_assign_update_kernel"]
+            k = tj["slic_assign_fast_kernel" if not args.exact else "slic_assign_update_kernel"]
             traffic = k["dram_bytes_read"] + k["dram_bytes_write"]     # per launch, from the ncu capture
-    roofline = {"bound": "hbm", "kernel": "slic_assign_update_kernel", "achieved": achieved, "peak": peak,
+    kname = "slic_assign_update_kernel (exact)" if args.exact else "slic_assign_fast_kernel (tolerance mode)"
+    bytes_px = 2 * 4 * C + 4 * Cf * (1 + I) + 16 + 4 * C
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "avg_launch_ms": k_avg_ms, "launches_timed": int(k_n.value),
                 "kernel_share_of_step": (k_ms.value / ms_total) if ms_total else None,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "pipeline_bytes_per_px": 2 * 4 * C + 4 * Cf * (1 + I) + 16 + 4 * C,
-                "pipeline_frac_of_hbm_roofline": ((2 * 4 * C + 4 * Cf * (1 + I) + 16 + 4 * C) * H * W
+                "pipeline_bytes_per_px": bytes_px,
+                "pipeline_frac_of_hbm_roofline": (bytes_px * H_total * W / world
                                                   / (ms_total / args.steps / 1e3) / 1e9 / peak)}
 
-    # ---- CPU baseline (bounded sample) ---------------------------------------------
-    cpu = None
+    # ---- CPU baseline (bounded sample) + parity of the timed mode against it --------------------
+    cpu, parity = None, None
     if not args.no_cpu and world == 1:      # reported at N=1 only (rank 0's host cores)
         size = args.cpu_size
         tot, t_slic, t_stats, nseg = cpu_oracle_step(size)
@@ -363,18 +469,24 @@ def run_ours(args):
                "sample": (f"{size}x{size}x{C} crop, n_segments scaled by area (same grid step), one pass: "
                           f"slic {t_slic:.1f}s + per-segment numpy/scipy stats {t_stats:.1f}s over {nseg} segments"),
                "host_cores_available": os.cpu_count()}
+        parity = parity_block(args.parity_size)
 
+    if world == 1:
+        wname = (f"c2: {C}-band float32 {H}x{W}, slic n_segments={wl['n_segments']} + zonal stats on all bands")
+    else:
+        wname = (f"c2 per GPU: ONE {C}-band float32 {H_total}x{W} raster sharded by row strips over {world} GPUs, "
+                 f"slic n_segments={n_total} (same grid step as c2) + zonal stats on all bands")
     line = {
         "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"c2: {C}-band float32 {H}x{W}, slic n_segments={wl['n_segments']} + zonal stats "
-                               f"on all bands, one raster per GPU",
-                   "compactness": wl["compactness"], "max_num_iter": I,
-                   "l2": "inputs (3.2 GB/step) are larger than the 126 MB L2; no flush between steps",
-                   "segments_out": int(res.n_labels)},
+        "config": {"workload": wname, "compactness": wl["compactness"], "max_num_iter": I,
+                   "slic_mode": "exact (bit-exact _slic_cython arithmetic)" if args.exact else
+                                "tolerance (exact=False: one FMA per channel, >= 99.5 % label agreement bar)",
+                   "l2": "inputs (3.2 GB/step/GPU) are larger than the 126 MB L2; no flush between steps",
+                   "segments_out": int(n_out)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "cpu_baseline": cpu, "also": alt,
+        "cpu_baseline": cpu, "parity": parity, "split_ms": split, "also": alt,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -393,6 +505,8 @@ def main():
     ap.add_argument("--no-alt", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-size", type=int, default=768)
+    ap.add_argument("--parity-size", type=int, default=768, help="crop side of the oracle-vs-CUDA parity block")
+    ap.add_argument("--exact", action="store_true", help="time the exact-mode SLIC kernel instead of the tolerance mode")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

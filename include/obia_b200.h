@@ -337,6 +337,23 @@ int obia_b200_zonal_stats_range(const int32_t *labels, const float *raw, int64_t
                                 double resolution, double *stats, void *workspace,
                                 void *stream);
 
+/* Polygons -> label raster, pixel-centre rule: replaces the per-segment
+ * `rasterio.features.geometry_mask([polygon], transform, invert=True)` of
+ * obia/utils/utils.py:53-67 (create_objects, segment_statistics.py:479-484) and
+ * `rasterio.features.rasterize` of obia/utils/tiling.py:248-255.  All pointers are device pointers.
+ *   xy              [n_vertices][2] float64 vertex (x, y) in PIXEL coordinates (column, row; pixel
+ *                   (r, c) covers [c, c+1) x [r, r+1)); rings need not repeat their first vertex
+ *   ring_start      [n_rings + 1] first vertex of every ring
+ *   poly_ring_start [n_polygons + 1] first ring of every polygon (exterior, holes, further parts:
+ *                   even-odd over all of them)
+ *   poly_label      [n_polygons] label written for the polygon's pixels (larger label wins overlaps)
+ *   bbox            [n_polygons][4] int32 x0, y0, x1, y1 (inclusive, clipped to the raster)
+ *   labels          [H][W] int32 in/out, pre-filled by the caller (-1 = no polygon) */
+int obia_b200_rasterize_polygons(const double *xy, const int32_t *ring_start,
+                                 const int32_t *poly_ring_start, const int32_t *poly_label,
+                                 const int32_t *bbox, int64_t n_polygons, int32_t *labels,
+                                 int64_t H, int64_t W, void *stream);
+
 /* ---------------------------------------------------------------- K5 ----
  * Per-segment GLCM texture features: replaces calculate_textural_stats
  * (obia/segmentation/segment_statistics.py:179-298) as create_objects calls it

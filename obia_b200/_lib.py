@@ -62,6 +62,7 @@ SIGNATURES = {
                                              _vp]),
     "obia_b200_zonal_stats_range": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _i64, _i64, _f64, _vp,
                                                    _vp, _vp]),
+    "obia_b200_rasterize_polygons": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp]),
     "obia_b200_texture_workspace_bytes": (_i64, [_i64]),
     "obia_b200_texture_stats": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _i64, _i32, _vp, _vp,
                                                _vp]),
@@ -72,6 +73,12 @@ _LIB = None
 
 class ObiaB200Error(RuntimeError):
     pass
+
+
+class CandidateOverflowError(ObiaB200Error, ValueError):
+    """A SLIC tile exceeded the 1024 candidate centres the kernels stage per tile.  A ValueError like
+    the errors scikit-image raises for unusable inputs, so `create_tiled_segments` skips the tile
+    (obia/utils/tiling.py:149-150) instead of aborting."""
 
 
 def load():

@@ -55,7 +55,8 @@ class Image:
         import torch
 
         cached = getattr(self, "_obia_b200_raw", None)
-        if cached is not None and not refresh:
+        key = self._raw_key()
+        if cached is not None and not refresh and getattr(self, "_obia_b200_raw_key", None) == key:
             return cached
         data = self.img_data
         if isinstance(data, torch.Tensor):
@@ -70,7 +71,24 @@ class Image:
         if raw.dim() != 3:
             raise ValueError("img_data must be (H, W, C)")
         self._obia_b200_raw = raw
+        self._obia_b200_raw_key = key
         return raw
+
+    def _raw_key(self):
+        """Identity of `img_data` the cached raw raster belongs to: object id, shape, dtype and, for
+        torch tensors, the in-place version counter.  Assigning a new array to `img_data` (a crop,
+        band maths, another tile) or editing a tensor in place invalidates the cache; in-place edits
+        of a numpy array cannot be detected (pass `refresh=True`).  "Raw" = the values at first use:
+        the reference normalises `img_data` in place and re-reads the file for the statistics."""
+        data = self.img_data
+        ver = getattr(data, "_version", None)
+        return (id(data), tuple(getattr(data, "shape", ())), str(getattr(data, "dtype", None)), ver)
+
+    def _note_mutation(self):
+        """Called after obia_b200 itself has normalised `img_data` in place (the reference's side
+        effect): the cached raw values stay the ones to use."""
+        if getattr(self, "_obia_b200_raw", None) is not None:
+            self._obia_b200_raw_key = self._raw_key()
 
 
 def open_geotiff(image_path, bands=None):

@@ -88,6 +88,20 @@ def normalize_to_host(raw, host, minmax_dev, max_ctas=16):
                                           int(max_ctas), _stream_ptr()), "normalize_to")
 
 
+def normalize_to(raw, out, minmax_dev):
+    """Normalised copy of `raw` into the CUDA tensor `out` (same shape, float32, contiguous, 16-byte
+    aligned).  `raw` is left untouched."""
+    lib = _lib.load()
+    _require_cuda(raw, "raw", torch.float32)
+    _require_cuda(out, "out", torch.float32)
+    H, W, C = raw.shape
+    if tuple(out.shape) != tuple(raw.shape) or out.data_ptr() % 16:
+        raise ValueError("normalize_to needs an aligned output of raw's shape")
+    work = _aligned(raw)
+    _lib.check(lib.obia_b200_normalize_to(_p(work), _p(out), H * W, C, _p(minmax_dev), 0, _stream_ptr()),
+               "normalize_to")
+
+
 def normalize_inplace(raw, minmax_dev):
     """`img_data[:, :, i] = normalize_band(...)` for every band (segment_boundaries.py:31-33)."""
     lib = _lib.load()
@@ -299,8 +313,10 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
             step_y, step_x, int(max_num_iter), int(start_label), int(ignore_color), int(bool(slic_zero)),
             fix_scale, _p(status), _stream_ptr()), "slic_iterate")
         if int(status[0].item()) != 0:
-            raise _lib.ObiaB200Error("slic_iterate: a tile collected more than 1024 candidate centres "
-                                     "(degenerate centre distribution)")
+            raise _lib.CandidateOverflowError(
+                "slic_iterate: a 32 x 64 pixel tile collected more than 1024 candidate centres -- the centre "
+                "density is beyond what the kernels stage per tile (n_segments above about one centre per 2 "
+                "pixels, or a mask that packs all centres into a small part of the raster)")
 
     if mask_dev is not None:
         run(True)   # maskSLIC step 2: spatial-only k-means moves the centres first

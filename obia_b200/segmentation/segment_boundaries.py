@@ -116,7 +116,16 @@ def _apply_image_mutation(image, raw, minmax_dev, stream=None, after=None):
 
     data = image.img_data
     if isinstance(data, torch.Tensor) and data.is_cuda and data.dtype == torch.float32 and data.is_contiguous():
-        pipeline.normalize_inplace(data, minmax_dev)
+        # always derived from the cached RAW values (never img_data in place: a second call would
+        # rescale the already normalised raster with the raw range)
+        if data.data_ptr() % 16 == 0 and tuple(data.shape) == tuple(raw.shape):
+            pipeline.normalize_to(raw, data, minmax_dev)
+        else:
+            tmp = raw.clone()
+            pipeline.normalize_inplace(tmp, minmax_dev)
+            data.copy_(tmp)
+        if hasattr(image, "_note_mutation"):
+            image._note_mutation()
         return
     with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
         if stream is not None and after is not None:
@@ -133,6 +142,8 @@ def _apply_image_mutation(image, raw, minmax_dev, stream=None, after=None):
             # page-locked img_data: the kernel streams the normalised raster straight into it over
             # PCIe (no staging copy; the copy engine stays free for the SLIC path's small read-backs)
             pipeline.normalize_to_host(raw, host, minmax_dev)
+            if hasattr(image, "_note_mutation"):
+                image._note_mutation()
             return
         tmp = raw.clone()
         pipeline.normalize_inplace(tmp, minmax_dev)
@@ -142,6 +153,8 @@ def _apply_image_mutation(image, raw, minmax_dev, stream=None, after=None):
             host.copy_(tmp)
         else:
             arr[...] = tmp.cpu().numpy()
+    if hasattr(image, "_note_mutation"):
+        image._note_mutation()
 
 
 def frame_from_labels(labels, start_label, n_labels, connected, image=None, polygonize=False):

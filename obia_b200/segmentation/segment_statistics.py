@@ -48,14 +48,33 @@ def _create_empty_stats_columns(spectral_bands, textural_bands, calc_mean, calc_
     return columns
 
 
-def _labels_of(segments):
-    """(label raster CUDA int32, label value per row) of a segments table."""
+def _labels_of(segments, image, raw):
+    """(label raster CUDA int32, label value per row) of a segments table.
+
+    Tables made by obia_b200 `create_segments` carry their label raster; the label of a row follows its
+    `segment_id` (1..N), so filtered / reordered rows keep their own segment.  Any other table with
+    `geometry` + `segment_id` columns (a GeoDataFrame read from a GeoPackage, polygons edited by the
+    user: what the reference accepts, segment_statistics.py:475-484) is burnt into a label raster with
+    the pixel-centre rule of `mask_image_with_polygon` (utils.py:53-67) by the CUDA scanline kernel."""
     raster = getattr(segments, "label_raster", None)
-    if raster is None:
-        raise TypeError(
-            "create_objects needs the table returned by obia_b200 create_segments (it carries the label "
-            "raster); rasterising arbitrary polygon GeoDataFrames is a host step outside the GPU path")
-    return raster, np.asarray(segments.segment_labels, dtype=np.int64)
+    all_labels = getattr(segments, "segment_labels", None)
+    if raster is not None and all_labels is not None:
+        all_labels = np.asarray(all_labels, dtype=np.int64)
+        ids = np.asarray(segments["segment_id"], dtype=np.int64)
+        if len(ids) == len(all_labels) and np.array_equal(ids, np.arange(1, len(ids) + 1)):
+            return raster, all_labels
+        if len(ids) and (ids.min() < 1 or ids.max() > len(all_labels)):
+            raise ValueError("segment_id values do not belong to the label raster this table carries")
+        return raster, all_labels[ids - 1]
+    if "geometry" not in segments or "segment_id" not in segments:
+        raise TypeError("create_objects needs a table with 'geometry' and 'segment_id' columns")
+    from ..utils.rasterize import rasterize_polygons
+    geoms = list(segments["geometry"])
+    if any(g is None for g in geoms):
+        raise ValueError("create_objects needs polygon geometries (or the table returned by create_segments)")
+    H, W = int(raw.shape[0]), int(raw.shape[1])
+    raster = rasterize_polygons(geoms, H, W, getattr(image, "affine_transformation", None), device=raw.device)
+    return raster, np.arange(1, len(geoms) + 1, dtype=np.int64)
 
 
 def create_objects(
@@ -93,7 +112,7 @@ def create_objects(
         calc_pai, calc_fhd, calc_ch, calc_mean_intensity, calc_variance_intensity
     )
 
-    raster, row_labels = _labels_of(segments)
+    raster, row_labels = _labels_of(segments, image, raw)
     n_rows = len(row_labels)
     float_cols = columns[1:-1]
     # one (n_columns, n_rows) float64 block, column-major for pandas (zero-copy): the spectral

@@ -60,11 +60,14 @@ def split_rows(H_total, world, align=ROW_ALIGN):
 class DistComm:
     """torch.distributed (NCCL on GPUs): this process holds one strip."""
 
-    def __init__(self):
+    def __init__(self, device=None):
         import torch.distributed as dist
         self.dist = dist
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         self.local = [self.rank]
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())   # (gloo tests pass "cpu")
+        self.device = torch.device(device)
 
     def all_reduce(self, tensors, op):
         ops = {"min": self.dist.ReduceOp.MIN, "max": self.dist.ReduceOp.MAX, "sum": self.dist.ReduceOp.SUM}
@@ -72,7 +75,7 @@ class DistComm:
 
     def all_gather_host(self, values):
         """values: one list of python ints per local strip -> list over all ranks."""
-        t = torch.tensor(values[0], dtype=torch.int64, device="cuda")
+        t = torch.tensor(values[0], dtype=torch.int64, device=self.device)
         out = [torch.empty_like(t) for _ in range(self.world)]
         self.dist.all_gather(out, t)
         return [o.tolist() for o in torch.stack(out).cpu()]
@@ -87,7 +90,7 @@ class DistComm:
         sent here (None at the raster edges).  `*_like`: (shape, dtype) of the expected messages."""
         dist, r = self.dist, self.rank
         ops, ru, rd = [], None, None
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev = self.device
         if r > 0 and recv_up_like[0] is not None:
             ru = torch.empty(recv_up_like[0][0], dtype=recv_up_like[0][1], device=dev)
             ops.append(dist.P2POp(dist.irecv, ru, r - 1))

@@ -101,7 +101,15 @@ def test_combine_stats_matches_numpy_scipy():
         if len(allx) and allx.var() == 0:
             ref[5] = ref[6] = np.nan          # scipy: (nearly) constant data -> NaN
         np.testing.assert_allclose(out, ref, rtol=1e-8, atol=1e-12, equal_nan=True)
-    assert split_rows(10, 3) == [(0, 4), (4, 3), (7, 3)] and split_rows(4, 4) == [(0, 1)] * 0 + [(0, 1), (1, 1), (2, 1), (3, 1)]
+    # strips start on multiples of the kernels' tile height and cover the raster exactly
+    assert split_rows(10, 3, align=1) == [(0, 4), (4, 3), (7, 3)]
+    assert split_rows(20000, 2) == [(0, 10112), (10112, 9888)]
+    for H, world in ((80000, 8), (1101, 4), (40000, 8), (512, 4)):
+        rows = split_rows(H, world)
+        assert rows[0][0] == 0 and sum(h for _, h in rows) == H and all(r % 128 == 0 for r, _ in rows)
+        assert all(rows[i][0] + rows[i][1] == rows[i + 1][0] for i in range(world - 1))
+    with pytest.raises(ValueError):
+        split_rows(300, 4)
 
 
 def test_mask_sample_indices_equals_numpy_legacy_choice():
