@@ -93,7 +93,6 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
     constexpr int CR = T::CR, kIds = T::kIds, kChk = T::kChk, kAcc = T::kAcc, kRec = T::kRec;
     constexpr int NT = NW * 32;
     static_assert(TH * NS <= 128 && 32 * TH * NS <= 4096 && kChk <= 64, "packed record fields");
-    __shared__ int s_ids[kIds];
     __shared__ int s_sorted[kIds];
     __shared__ int s_nids;
     __shared__ int s_cells[4];
@@ -105,6 +104,8 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
     __shared__ long long s_off64[CP];
     extern __shared__ __align__(16) int s_dyn[];
     constexpr int RS = T::RS;
+    static_assert((size_t)T::kRec * RS >= (size_t)kIds, "candidate ids share the record region");
+    int *s_ids = s_dyn;                                                          // as collected; dead after the sort
     int(*s_rec)[RS] = reinterpret_cast<int(*)[RS]>(s_dyn);                      // [kRec][RS]
     int(*s_acc)[NFR] = reinterpret_cast<int(*)[NFR]>(s_dyn + RS * kRec);        // [kAcc][NFR]
 

@@ -171,4 +171,6 @@ def create_objects(
     out.segment_labels = row_labels
     out.crs = getattr(segments, "crs", None)
     out.transform = getattr(segments, "transform", None)
+    aff = getattr(segments, "affine_transformation", None)
+    out.affine_transformation = aff if aff is not None else getattr(image, "affine_transformation", None)
     return out

@@ -114,7 +114,7 @@ def test_label_segments_and_classify_shaped_consumer():
     raw = synth_raster(120, 120, 3, seed=2, quantize=True)
     aff = [1.0, 0.0, 0.0, -1.0, 300.0, 900.0]
     img = Image(raw.copy(), "EPSG:32702", aff, None, None)
-    seg = segment(img, [0, 1, 2], None, "slic", n_segments=80, compactness=10, calc_contrast=False,
+    seg = segment(img, [0, 1, 2], None, "slic", n_segments=300, compactness=10, calc_contrast=False,
                   calc_dissimilarity=False, calc_homogeneity=False, calc_ASM=False, calc_energy=False,
                   calc_correlation=False)
     table = seg.segments
