@@ -280,7 +280,11 @@ int obia_b200_enforce_connectivity(const int32_t *labels_in,
  * window heights every piece that reaches the core is complete inside the strip.
  *   strip_begin   components, size-cap split, small-piece merge targets; returns on the host
  *                 counts[0] = kept pieces that start above the core rows (inside the strip),
- *                 counts[1] = kept pieces that start in the core rows, counts[2] = all kept pieces.
+ *                 counts[1] = kept pieces that start in the core rows, counts[2] = all kept pieces,
+ *                 counts[3] = rounds of the small-piece fixed point that were launched (diagnostic),
+ *                 counts[4] = kept pieces that start above the core rows but below the outer third of the
+ *                 upper halo, which the kernel books unknown (the rows of the statistics table a rank
+ *                 shares with the rank above).  `counts_host` holds 5 values.
  *                 The caller all-gathers counts[1] over the ranks; `label_offset` of this rank is the
  *                 exclusive prefix sum minus its counts[0] (north_star: "exclusive scan of per-tile
  *                 label offsets").

@@ -17,6 +17,8 @@
 //      merged pieces follow their adjacent chain.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace obia {
@@ -39,7 +41,7 @@ struct CcWs {
 // ctr words
 enum { CTR_NSMALL = 0, CTR_NOVER = 1, CTR_CURSOR = 2, CTR_CHANGED = 3, CTR_NKEPT = 4, CTR_ERR = 5, CTR_NDIRTY0 = 6,
        CTR_NDIRTY1 = 7, CTR_ROUNDS = 8, CTR_NROOTS = 9, CTR_KBEFORE = 10, CTR_KCORE = 11, CTR_FAIL = 12, CTR_HASZERO = 13,
-       CTR_WORDS = 16 };
+       CTR_CUTMIN = 14, CTR_KVALID = 15, CTR_WORDS = 16 };
 // flag bits (strip mode: which results depend on pixels outside the strip)
 enum { FLAG_CUT = 1, FLAG_ADJ_UNKNOWN = 2, FLAG_TFIX_UNKNOWN = 4, FLAG_LABEL_UNKNOWN = 8 };
 
@@ -307,8 +309,8 @@ cc_flatten_kernel(int32_t *T, int32_t *psize, int32_t *roots, int32_t *ctr, int6
 // otherwise kept: its start pixel is marked in the bitmap.
 __global__ void __launch_bounds__(256)
 cc_classify_kernel(const int32_t *__restrict__ roots, const int32_t *__restrict__ psize, int32_t *list,
-                   int32_t *adj, int32_t *aux, int32_t *stamp, uint32_t *bits, int32_t *ctr, int64_t N,
-                   int64_t min_size, int64_t max_size)
+                   int32_t *adj, int32_t *aux, int32_t *stamp, uint32_t *bits, const uint8_t *__restrict__ flag,
+                   int32_t *ctr, int64_t N, int64_t min_size, int64_t max_size)
 {
     const int n_roots = ctr[CTR_NROOTS];
     const int lane = threadIdx.x & 31;
@@ -321,8 +323,13 @@ cc_classify_kernel(const int32_t *__restrict__ roots, const int32_t *__restrict_
         if (e < n_roots) {
             i = roots[e];
             sz = psize[i];
+            // Strip mode: a component cut by an open strip edge is unknown anyway (FLAG_CUT: every result
+            // that depends on it is reported incomplete).  It is booked as ONE kept piece -- the fragments
+            // along an edge row would otherwise form long chains of "small pieces without an earlier
+            // neighbour" whose fixed point needs hundreds of rounds.
+            if (flag && (flag[i] & FLAG_CUT)) sz = min_size > max_size ? max_size : min_size;
         }
-        const bool small = i >= 0 && sz < min_size;
+        const bool small = i >= 0 && sz <= max_size && sz < min_size;   // (oversized components are split first)
         const unsigned m = __ballot_sync(0xffffffffu, small);
         int base = 0;
         if (lane == 0 && m) base = atomicAdd(ctr + CTR_NSMALL, __popc(m));
@@ -697,23 +704,25 @@ __global__ void cc_reset_round_kernel(int32_t *ctr, int nxt_ctr)
 // phase 4a/b/c: kept pieces are numbered by the rank of their start pixel = prefix population count
 // of the start-pixel bitmap (N / 8 bytes instead of two passes over T and psize)
 __global__ void __launch_bounds__(256)
-cc_bits_count_kernel(const uint32_t *__restrict__ bits, int32_t *chunksum, int64_t core_lo, int64_t core_hi,
-                     int32_t *ctr)
+cc_bits_count_kernel(const uint32_t *__restrict__ bits, int32_t *chunksum, int64_t valid_lo, int64_t core_lo,
+                     int64_t core_hi, int32_t *ctr)
 {
-    __shared__ int s_cnt[3];
-    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    __shared__ int s_cnt[4];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const int64_t w0 = (int64_t)blockIdx.x * kBitChunk;
-    int c = 0, before = 0, core = 0;
+    int c = 0, before = 0, core = 0, valid = 0;
     for (int j = threadIdx.x; j < kBitChunk; j += 256) {
         const uint32_t v = bits[w0 + j];
         c += __popc(v);
-        // kept pieces that start before / inside the core rows of a strip (pixel range [core_lo, core_hi))
+        // kept pieces that start before / inside the core rows of a strip (pixel range [core_lo, core_hi));
+        // `valid`: before the core but below the unknown band of the upper halo
         const int64_t p0 = (w0 + j) * 32;
         if (v) {
             for (uint32_t m = v; m; m &= m - 1) {
                 const int64_t px = p0 + __ffs(m) - 1;
                 before += px < core_lo;
+                valid += (px >= valid_lo && px < core_lo);
                 core += (px >= core_lo && px < core_hi);
             }
         }
@@ -721,16 +730,19 @@ cc_bits_count_kernel(const uint32_t *__restrict__ bits, int32_t *chunksum, int64
     c = __reduce_add_sync(0xffffffffu, c);
     before = __reduce_add_sync(0xffffffffu, before);
     core = __reduce_add_sync(0xffffffffu, core);
+    valid = __reduce_add_sync(0xffffffffu, valid);
     if ((threadIdx.x & 31) == 0) {
         if (c) atomicAdd(&s_cnt[0], c);
         if (before) atomicAdd(&s_cnt[1], before);
         if (core) atomicAdd(&s_cnt[2], core);
+        if (valid) atomicAdd(&s_cnt[3], valid);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         chunksum[blockIdx.x] = s_cnt[0];
         if (s_cnt[1]) atomicAdd(ctr + CTR_KBEFORE, s_cnt[1]);
         if (s_cnt[2]) atomicAdd(ctr + CTR_KCORE, s_cnt[2]);
+        if (s_cnt[3]) atomicAdd(ctr + CTR_KVALID, s_cnt[3]);
     }
 }
 
@@ -821,7 +833,7 @@ cc_small_final_kernel(CcArrays A, const uint32_t *__restrict__ bits, int32_t *fi
         for (int hop = 0; hop < max_hops && !done; ++hop) {   // chains are short; never spin
             if ((bits[t >> 5] >> (t & 31)) & 1u) {
                 r = fin[t];
-                if (A.flag && (A.flag[t] & FLAG_CUT)) unk = true;
+                if (A.flag && ((A.flag[t] & FLAG_CUT) || t >= A.ctr[CTR_CUTMIN])) unk = true;
                 done = true;
             } else {
                 if (A.flag && (A.flag[t] & (FLAG_CUT | FLAG_ADJ_UNKNOWN))) unk = true;
@@ -856,27 +868,38 @@ cc_resolve_kernel(const int32_t *__restrict__ T, const uint32_t *__restrict__ bi
         if (flag) {
             const bool kept = (bits[t >> 5] >> (t & 31)) & 1u;
             const uint8_t f = flag[t];
-            if (kept ? (f & FLAG_CUT) : (f & (FLAG_CUT | FLAG_LABEL_UNKNOWN))) atomicExch(ctr + CTR_FAIL, 1);
+            if (kept ? ((f & FLAG_CUT) || t >= ctr[CTR_CUTMIN]) : (f & (FLAG_CUT | FLAG_LABEL_UNKNOWN)))
+                atomicExch(ctr + CTR_FAIL, 1);
         }
     }
     out[i - p_lo] = r;
 }
 
-// strip mode: components that touch an open edge of the strip may continue outside it
+// strip mode: components with a pixel in the outer band of an open halo (its outer third) may continue
+// outside the strip, or depend on pieces that do: they are all booked unknown (FLAG_CUT).  A band
+// instead of the edge row alone keeps the small-piece fixed point short: under a single cut row the
+// "unknown re-scan time" flag crawls from fragment to fragment across the whole strip width.
 __global__ void __launch_bounds__(256)
-cc_mark_cut_kernel(const int32_t *__restrict__ T, uint8_t *flag, int64_t N, int W, int top_open, int bottom_open)
+cc_mark_cut_kernel(const int32_t *__restrict__ T, uint8_t *flag, int32_t *ctr, int64_t N, int W, int band_top,
+                   int band_bottom)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= W) return;
-    if (top_open) {
-        const int32_t t = T[x];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_top = (int64_t)band_top * W, n_bot = (int64_t)band_bottom * W;
+    if (i < n_top) {
+        const int32_t t = T[i];
         if (t >= 0) flag[t] = FLAG_CUT;
-    }
-    if (bottom_open) {
-        const int32_t t = T[N - W + x];
-        if (t >= 0) flag[t] = FLAG_CUT;
+    } else if (i < n_top + n_bot) {
+        const int32_t t = T[N - n_bot + (i - n_top)];
+        if (t >= 0) {
+            flag[t] = FLAG_CUT;
+            // kept pieces that start after the first bottom-band component have an unreliable rank (band
+            // components are booked as kept whatever their true size)
+            atomicMin(ctr + CTR_CUTMIN, t);
+        }
     }
 }
+
+__global__ void cc_init_ctr_kernel(int32_t *ctr) { ctr[CTR_CUTMIN] = kTInf; }
 
 }  // namespace obia
 
@@ -910,6 +933,8 @@ int cc_phase_a(CcRun &R, int top_open, int bottom_open, int64_t core_lo, int64_t
     const int H = P0.H, W = P0.W;
     const unsigned gridN = (unsigned)ceil_div(N, 256);
     OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr, 0, CTR_WORDS * 4, st));
+    cc_init_ctr_kernel<<<1, 1, 0, st>>>(w.ctr);
+    OBIA_LAUNCH_CHECK();
     OBIA_CUDA_CHECK(cudaMemsetAsync(w.visit, 0, (size_t)N, st));
     OBIA_CUDA_CHECK(cudaMemsetAsync(w.bits, 0, (size_t)w.nchunks * kBitChunk * 4, st));
     if (R.strip) OBIA_CUDA_CHECK(cudaMemsetAsync(w.flag, 0, (size_t)N, st));
@@ -927,11 +952,16 @@ int cc_phase_a(CcRun &R, int top_open, int bottom_open, int64_t core_lo, int64_t
     cc_flatten_kernel<<<(unsigned)ceil_div(N, 1024), 256, 0, st>>>(w.T, w.psize, roots, w.ctr, N);
     OBIA_LAUNCH_CHECK();
     if (R.strip && (top_open || bottom_open)) {
-        cc_mark_cut_kernel<<<(unsigned)ceil_div(W, 256), 256, 0, st>>>(w.T, w.flag, N, W, top_open, bottom_open);
+        // outer third of each open halo (core rows are [core_lo / W, core_hi / W))
+        const int halo_top = (int)(core_lo / W), halo_bottom = (int)((N - core_hi) / W);
+        const int band_top = top_open ? std::max(1, halo_top / 3) : 0;
+        const int band_bottom = bottom_open ? std::max(1, halo_bottom / 3) : 0;
+        const int64_t n = (int64_t)(band_top + band_bottom) * W;
+        cc_mark_cut_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(w.T, w.flag, w.ctr, N, W, band_top, band_bottom);
         OBIA_LAUNCH_CHECK();
     }
-    cc_classify_kernel<<<kNumSMs * 8, 256, 0, st>>>(roots, w.psize, w.list, w.adj, w.aux, w.stamp, w.bits, w.ctr, N,
-                                                    P0.min_size, P0.max_size);
+    cc_classify_kernel<<<kNumSMs * 8, 256, 0, st>>>(roots, w.psize, w.list, w.adj, w.aux, w.stamp, w.bits,
+                                                    R.strip ? w.flag : nullptr, w.ctr, N, P0.min_size, P0.max_size);
     OBIA_LAUNCH_CHECK();
     cc_split_kernel<<<kNumSMs * 2, 128, 0, st>>>(R.lab, w.T, w.psize, w.queue, w.list, w.adj, w.aux, w.stamp, w.bits,
                                                  R.strip ? w.flag : nullptr, w.ctr, w.visit, N, H, W, P0.min_size,
@@ -975,11 +1005,12 @@ int cc_rounds(CcRun &R, int n, int &round_id, int &cur)
     return OBIA_B200_OK;
 }
 
-int cc_count(CcRun &R, int64_t core_lo, int64_t core_hi)
+int cc_count(CcRun &R, int64_t core_lo, int64_t core_hi, int64_t valid_lo = 0)
 {
     const CcWs &w = R.w;
     OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + CTR_KBEFORE, 0, 8, R.st));
-    cc_bits_count_kernel<<<(unsigned)w.nchunks, 256, 0, R.st>>>(w.bits, w.chunksum, core_lo, core_hi, w.ctr);
+    OBIA_CUDA_CHECK(cudaMemsetAsync(w.ctr + CTR_KVALID, 0, 4, R.st));
+    cc_bits_count_kernel<<<(unsigned)w.nchunks, 256, 0, R.st>>>(w.bits, w.chunksum, valid_lo, core_lo, core_hi, w.ctr);
     OBIA_LAUNCH_CHECK();
     cc_scan_blocks_kernel<<<1, 1024, 0, R.st>>>(w.chunksum, w.nchunks, w.ctr);
     OBIA_LAUNCH_CHECK();
@@ -1115,7 +1146,8 @@ extern "C" int obia_b200_connectivity_strip_begin(const int32_t *labels_ext, voi
             rc = cc_rounds(R, round_id == 1 ? 2 : 16, round_id, cur);
             if (rc) return rc;
         }
-        rc = cc_count(R, core_lo, core_hi);
+        // (same band as cc_phase_a marks: the outer third of an open upper halo)
+        rc = cc_count(R, core_lo, core_hi, top_open ? (int64_t)std::max<int64_t>(1, core_row0 / 3) * W : 0);
         if (rc) return rc;
         OBIA_CUDA_CHECK(cudaMemcpyAsync(hctr, R.w.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, R.st));
         OBIA_CUDA_CHECK(cudaStreamSynchronize(R.st));
@@ -1125,6 +1157,8 @@ extern "C" int obia_b200_connectivity_strip_begin(const int32_t *labels_ext, voi
     counts_host[0] = hctr[CTR_KBEFORE];
     counts_host[1] = hctr[CTR_KCORE];
     counts_host[2] = hctr[CTR_NKEPT];
+    counts_host[3] = round_id;
+    counts_host[4] = hctr[CTR_KVALID];
     return OBIA_B200_OK;
 }
 

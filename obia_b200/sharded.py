@@ -246,9 +246,10 @@ class ShardedSlic:
         return int(self.min_size_factor * seg), int(self.max_size_factor * seg)
 
     def default_halo(self):
-        """Rows of neighbour labels on each side: two window heights (a SLIC component spans at most
-        4*step+1 rows), so the pieces that reach the core and the pieces they can merge into are whole."""
-        return 8 * self.step_y + 8
+        """Rows of neighbour labels on each side: three window heights (a SLIC component spans at most
+        4*step+1 rows).  The outer third is booked unknown by the kernel, the inner two thirds hold the
+        pieces that reach the core and the pieces they can merge into."""
+        return 12 * self.step_y + 12
 
     # -- step 4a: connectivity on the gathered raster (fallback) ----------------------------------------
     def connect_full(self, full_labels):
@@ -266,13 +267,14 @@ class ShardedSlic:
         H_ext = int(self.ext.shape[0])
         self.cc_ws = torch.empty((self.lib.obia_b200_connectivity_workspace_bytes(H_ext, self.W),),
                                  dtype=torch.uint8, device=self.dev)
-        counts = (ctypes.c_int64 * 3)()
+        counts = (ctypes.c_int64 * 5)()
         min_size, max_size = self.sizes()
         _lib.check(self.lib.obia_b200_connectivity_strip_begin(
             _p(self.ext), _p(self.cc_ws), H_ext, self.W, self.core_row0, self.h, int(halo_up is not None),
             int(halo_down is not None), min_size, max_size, self.start_label, counts, _stream_ptr()),
             "connectivity_strip_begin")
-        self.k_before, self.k_core = int(counts[0]), int(counts[1])
+        self.k_before, self.k_core, self.cc_rounds = int(counts[0]), int(counts[1]), int(counts[3])
+        self.k_shared = int(counts[4])     # rows of the statistics table shared with the rank above
         return self.k_core
 
     def strip_finish(self, labels_before):
@@ -292,10 +294,10 @@ class ShardedSlic:
 
     # -- step 5: statistics over this rank's label range -------------------------------------------------
     def range_stats(self, bands=None, resolution=1e-6):
-        """Rows = labels [start_label + label_base - k_before, start_label + label_base + k_core)."""
+        """Rows = labels [start_label + label_base - k_shared, start_label + label_base + k_core)."""
         bands = list(range(self.C)) if bands is None else [int(b) for b in bands]
-        n_rows = max(1, self.k_before + self.k_core)
-        lo = self.start_label + self.label_base - self.k_before
+        n_rows = max(1, self.k_shared + self.k_core)
+        lo = self.start_label + self.label_base - self.k_shared
         stats = torch.empty((n_rows, len(bands), 8), dtype=torch.float64, device=self.dev)
         ws = torch.empty((self.lib.obia_b200_zonal_workspace_bytes(n_rows - 1, 8),), dtype=torch.uint8, device=self.dev)
         _lib.check(self.lib.obia_b200_zonal_stats_range(_p(self.final), _p(self.raw), self.h, self.W, self.C,
@@ -306,7 +308,7 @@ class ShardedSlic:
     def zero_stats(self, bands=None, resolution=1e-6):
         """Row of label 0 from this strip's pixels when label 0 lies outside the rank's label range
         (pieces merged into nothing carry label 0 on any rank, SURVEY.md defect 7); an empty row otherwise."""
-        if self.start_label + self.label_base - self.k_before > 0:
+        if self.start_label + self.label_base - self.k_shared > 0:
             return pipeline.zonal_stats(self.final, self.raw, bands, max_label=0, resolution=resolution)
         Cz = self.C if bands is None else len(bands)
         row = torch.full((1, Cz, 8), float("nan"), dtype=torch.float64, device=self.dev)
@@ -435,7 +437,7 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
     s0 = strips[0]
     if not s0.enforce:
         for s in strips:
-            s.final, s.k_before, s.k_core, s.label_base, s.has_zero = s.labels, 0, s.n, 0, False
+            s.final, s.k_before, s.k_shared, s.k_core, s.label_base, s.has_zero = s.labels, 0, 0, s.n, 0, False
         res.n_labels = s0.n
         res.mode["connectivity"] = "none"
         kcores = None
@@ -493,9 +495,9 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
             res.mode["stats"] = "replicated"
         else:
             tabs = [s.range_stats(statistics_bands) for s in strips]
-            kb = comm.all_gather_host([[s.k_before] for s in strips])
+            kb = comm.all_gather_host([[s.k_shared] for s in strips])
             # rows of pieces that start above the core go UP to their owner
-            up = [t[:s.k_before] if s.top_open and s.k_before > 0 else None for s, t in zip(strips, tabs)]
+            up = [t[:s.k_shared] if s.top_open and s.k_shared > 0 else None for s, t in zip(strips, tabs)]
             Cz = int(tabs[0].shape[1])
             like_d = []
             for s, r in zip(strips, comm.local):
@@ -504,7 +506,7 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
             _, rd = comm.neighbour_exchange(up, [None] * len(strips), [None] * len(strips), like_d)
             out = []
             for s, t, b in zip(strips, tabs, rd):
-                own = t[s.k_before:s.k_before + s.k_core]
+                own = t[s.k_shared:s.k_shared + s.k_core]
                 if b is not None and b.shape[0] > 0:
                     nb = int(b.shape[0])
                     if nb > own.shape[0]:

@@ -396,21 +396,57 @@ def _as_device_raster(input_raster, device, columns=None):
     return raw, pixel_area, image, width, xa
 
 
+def _read_mask(input_mask):
+    """Mask from a path: `.npy` arrays directly, raster files through rasterio (band 1, like
+    `gdal.Open(input_mask)` + `ReadAsArray` at tiling.py:85-88 / :43-45)."""
+    path = str(input_mask)
+    if not os.path.exists(path):
+        raise ValueError(f"Unable to open {input_mask}")
+    if path.lower().endswith(".npy"):
+        return np.load(path)
+    try:
+        import rasterio
+    except ImportError as e:
+        raise NotImplementedError("reading a raster mask file needs rasterio; pass an array or a .npy path") from e
+    with rasterio.open(path) as src:
+        return src.read(1)
+
+
+def _write_segments(output_dir, labels, n, image):
+    """`all_segments.to_file(<output_dir>/segments.gpkg, driver='GPKG')` (tiling.py:289-291): columns
+    `geometry`, `segment_id`; GeoPackage needs geopandas (GDAL), otherwise `segments.geojson`."""
+    from ..segmentation.segment_boundaries import frame_from_labels
+    # one row per 4-connected region, ids 1..N in ascending label order (tiling.py:286-288)
+    frame = frame_from_labels(labels, 1, n, connected=False, image=image, polygonize=True)
+    try:
+        import geopandas  # noqa: F401
+        path = os.path.join(output_dir, "segments.gpkg")
+        frame.to_file(path, driver="GPKG")
+    except ImportError:
+        path = os.path.join(output_dir, "segments.geojson")
+        frame.to_file(path)
+    return path
+
+
 def create_tiled_segments(input_raster, output_dir, input_mask=None,
                           method="slic", tile_size=200, buffer=30, crown_radius=5,
                           *, device=None, segment_tile=None, distributed=None, verbose=False,
-                          return_labels=True, polygons=False, **kwargs):
+                          return_labels=False, polygons=True, save_labels=False, **kwargs):
     """
+    Same call and result as the reference (tiling.py:62-291): returns None and writes
+    `<output_dir>/segments.gpkg` (`geometry`, `segment_id`) -- `segments.geojson` when geopandas /
+    GDAL are not installed.  With several ranks the label blocks are gathered on rank 0, which traces
+    and writes the polygons (host step, utils/polygonize.py).
+
     :param input_raster: path (needs rasterio), `Image`, or an (H, W, C) array / tensor.
-    :param output_dir: directory for `segments_labels.npy` (the label raster); None writes nothing.
-    :param polygons: also trace the segments into polygons on the host (single rank only) and write
-        `segments.gpkg` like the reference (tiling.py:289-291) when geopandas is installed, else
-        `segments.geojson` (columns `geometry`, `segment_id`).
-    :param input_mask: path / array (H, W); non-zero = segment here.
+    :param output_dir: output directory; None writes nothing.
+    :param input_mask: path (`.npy`, or a raster file when rasterio is installed) / array (H, W); non-zero = segment here.
     :param method: only 'slic' (ValueError otherwise, tiling.py:76-77).
+    :param polygons: False skips the host polygonisation and the vector file (label-raster users).
+    :param save_labels: also write `segments_labels[.rankN].npy` (this rank's block of the label raster).
+    :param return_labels: return (labels (H, W_block) int32 with ids 1..N and -1 elsewhere, N, (x0, x1)
+        owned columns) instead of None.
     :param kwargs: forwarded to SLIC (`n_segments`, `compactness`, `max_num_iter`, ...).
-    :return: (labels (H, W_block) int32 with ids 1..N and -1 elsewhere, N, (x0, x1) owned columns)
-        -- the reference returns None; with `return_labels=False` so does this.
     """
     if method != "slic":
         raise ValueError("Currently, only the 'slic' method is supported for segmentation.")
@@ -424,13 +460,12 @@ def create_tiled_segments(input_raster, output_dir, input_mask=None,
         dist, rank, world = tdist, tdist.get_rank(), tdist.get_world_size()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
-    raw, pixel_area, _, width, xa = _as_device_raster(
+    raw, pixel_area, image, width, xa = _as_device_raster(
         input_raster, device, columns=lambda w: local_columns(w, int(tile_size), int(buffer), world, rank))
     mask = None
     if input_mask is not None:
         if isinstance(input_mask, (str, os.PathLike)):
-            raise ValueError(f"Unable to open {input_mask}") if not os.path.exists(str(input_mask)) else \
-                NotImplementedError("reading a mask file needs rasterio; pass the array instead")
+            input_mask = _read_mask(input_mask)
         m = input_mask if isinstance(input_mask, torch.Tensor) else torch.from_numpy(np.asarray(input_mask))
         if tuple(m.shape) != (int(raw.shape[0]), width):
             raise ValueError("image and mask should have the same shape.")
@@ -445,20 +480,28 @@ def create_tiled_segments(input_raster, output_dir, input_mask=None,
 
     if output_dir is not None:
         os.makedirs(output_dir, exist_ok=True)
-        suffix = "" if world == 1 else f".rank{rank}"
-        np.save(os.path.join(output_dir, f"segments_labels{suffix}.npy"), labels.cpu().numpy())
+        if save_labels:
+            suffix = "" if world == 1 else f".rank{rank}"
+            np.save(os.path.join(output_dir, f"segments_labels{suffix}.npy"), labels.cpu().numpy())
         if polygons:
-            if world != 1:
-                raise NotImplementedError("polygons=True needs the whole label raster on one rank")
-            from ..segmentation.segment_boundaries import frame_from_labels
-            image = input_raster if hasattr(input_raster, "affine_transformation") else None
-            # one row per 4-connected region, ids 1..N in ascending label order (tiling.py:286-288)
-            frame = frame_from_labels(labels, 1, n, connected=False, image=image, polygonize=True)
-            try:
-                import geopandas  # noqa: F401
-                frame.to_file(os.path.join(output_dir, "segments.gpkg"), driver="GPKG")
-            except ImportError:
-                frame.to_file(os.path.join(output_dir, "segments.geojson"))
+            if image is None and hasattr(input_raster, "affine_transformation"):
+                image = input_raster
+            full = labels
+            if world > 1:
+                # blocks have different widths: gather (width, block) through a padded all-gather
+                wmax = torch.tensor([labels.shape[1]], dtype=torch.int64, device=labels.device)
+                widths = [torch.zeros_like(wmax) for _ in range(world)]
+                dist.all_gather(widths, wmax)
+                wpad = int(max(w.item() for w in widths))
+                pad = torch.full((labels.shape[0], wpad), -1, dtype=torch.int32, device=labels.device)
+                pad[:, :labels.shape[1]] = labels
+                blocks = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(blocks, pad)
+                full = torch.cat([b[:, :int(w.item())] for b, w in zip(blocks, widths)], dim=1).contiguous()
+            if rank == 0:
+                _write_segments(output_dir, full, n, image)
+            if world > 1:
+                dist.barrier()
     if return_labels:
         return labels, n, cols
     return None

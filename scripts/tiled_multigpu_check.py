@@ -46,7 +46,7 @@ def main():
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    labels, n, (x0, x1) = create_tiled_segments(raw, None, mask, distributed=True, **kw)
+    labels, n, (x0, x1) = create_tiled_segments(raw, None, mask, distributed=True, return_labels=True, polygons=False, **kw)
     torch.cuda.synchronize()
     t_multi = time.perf_counter() - t0
     # gather the column blocks on rank 0
@@ -56,7 +56,7 @@ def main():
     ok = True
     if rank == 0:
         t0 = time.perf_counter()
-        single, n1, _ = create_tiled_segments(raw, None, mask, distributed=False, **kw)
+        single, n1, _ = create_tiled_segments(raw, None, mask, distributed=False, return_labels=True, polygons=False, **kw)
         torch.cuda.synchronize()
         t_single = time.perf_counter() - t0
         same = bool((single == full).all().item())

@@ -968,7 +968,7 @@ def test_sharded_global_slic_is_bit_identical(world, C, n, compactness, exact, s
     single-GPU labels and (merged) statistics; the NCCL exchanges are replaced by tensor copies."""
     from obia_b200 import pipeline
     from gpu_helpers import synth_raster
-    H, W = 256 * world + 77, 333
+    H, W = 384 * world + 77, 333
     raw = _cuda(synth_raster(H, W, C, seed=world, quantize=(C == 3)))
     kw = dict(n_segments=n, compactness=compactness, max_num_iter=6, exact=exact, start_label=start_label)
     ref = pipeline.slic_labels(raw, None, **kw)
@@ -1035,7 +1035,7 @@ def test_connectivity_strip_mode_matches_full_raster(seed, start_label):
             e0, e1 = max(0, c0 - halo), min(H, c1 + halo)
             ext = pre[e0:e1].contiguous()
             ws = torch.empty((lib.obia_b200_connectivity_workspace_bytes(e1 - e0, W),), dtype=torch.uint8, device="cuda")
-            counts = (ctypes.c_int64 * 3)()
+            counts = (ctypes.c_int64 * 5)()
             _lib.check(lib.obia_b200_connectivity_strip_begin(p(ext), p(ws), e1 - e0, W, c0 - e0, c1 - c0, int(e0 > 0),
                                                               int(e1 < H), min_size, max_size, start_label, counts, sp()),
                        "strip_begin")
