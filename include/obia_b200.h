@@ -103,7 +103,11 @@ int obia_b200_slic_features(const float *raw, int64_t H, int64_t W, int32_t C,
  * mode='reflect', truncate=4; float64 accumulation, float32 storage between
  * the row and column passes, like scipy).  Output is multiplied by `ratio`.
  *   weights_host [2*radius+1] float64 normalised kernel (host)
- *   tmp, out     [Cf][H][pitch] float32 (out may alias in; tmp may not)
+ *   tmp, out     [Cf][H][pitch] float32 (tmp may not alias in or out)
+ * With out != in and radii <= 63 (sigma <= 15.8) both passes run in ONE shared-memory tiled kernel,
+ * the taps travel as kernel parameters and the call is asynchronous (tmp is not touched).  Wider
+ * kernels, or out == in, take two global passes with the taps in constant memory; that path
+ * synchronises the stream once.
  */
 int obia_b200_gaussian_planar(const float *in, float *tmp, float *out,
                               int64_t H, int64_t W, int64_t pitch, int32_t Cf,

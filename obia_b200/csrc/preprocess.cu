@@ -312,6 +312,61 @@ gaussian_pass_kernel(const float *__restrict__ in, float *__restrict__ out, int6
     out[plane + y * pitch + x] = r;
 }
 
+// Fused, shared-memory tiled version of the two passes (north_star subsystem 1): a CTA stages a
+// (TY + 2 ry) x (TX + 2 rx) window of one feature plane with coalesced loads (half-sample reflect at
+// the raster edges), runs the column pass into a second shared buffer -- rounded to float32 exactly
+// where scipy stores the intermediate array -- then the row pass, and writes the TY x TX tile once.
+// Arithmetic and order are those of gaussian_pass_kernel (float64, centre tap, pairs outermost first).
+// The taps travel as kernel parameters: no constant-memory upload, no stream synchronisation.
+constexpr int kGaussTX = 64, kGaussTY = 32, kGaussParamRadius = 63;
+struct GaussTaps {
+    double wy[kGaussParamRadius + 1], wx[kGaussParamRadius + 1];   // [0] = centre tap
+};
+
+__global__ void __launch_bounds__(256)
+gaussian_tiled_kernel(const float *__restrict__ in, float *__restrict__ out, int H, int W, int64_t pitch, int Cf,
+                      int ry, int rx, GaussTaps taps, float ratio)
+{
+    extern __shared__ float s_g[];
+    const int IW = kGaussTX + 2 * rx, IH = kGaussTY + 2 * ry;
+    float *s_in = s_g;                 // [IH][IW]
+    float *s_mid = s_g + IH * IW;      // [TY][IW] column pass, float32 like scipy's intermediate
+    const int x0 = blockIdx.x * kGaussTX, y0 = blockIdx.y * kGaussTY;
+    for (int c = 0; c < Cf; ++c) {
+        const float *src = in + (int64_t)c * H * pitch;
+        for (int i = threadIdx.x; i < IH * IW; i += 256) {
+            const int ly = i / IW, lx = i - ly * IW;
+            const int64_t gy = reflect_idx(y0 + ly - ry, H), gx = reflect_idx(x0 + lx - rx, W);
+            s_in[i] = src[gy * pitch + gx];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kGaussTY * IW; i += 256) {
+            const int ty = i / IW, lx = i - ty * IW;
+            const float *col = s_in + (ty + ry) * IW + lx;
+            double acc = __dmul_rn((double)col[0], taps.wy[0]);
+            for (int k = ry; k >= 1; --k) {
+                const double pair = __dadd_rn((double)col[-k * IW], (double)col[k * IW]);
+                acc = __dadd_rn(acc, __dmul_rn(pair, taps.wy[k]));
+            }
+            s_mid[i] = (float)acc;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kGaussTY * kGaussTX; i += 256) {
+            const int ty = i / kGaussTX, tx = i - ty * kGaussTX;
+            const int y = y0 + ty, x = x0 + tx;
+            if (y >= H || x >= W) continue;
+            const float *row = s_mid + ty * IW + tx + rx;
+            double acc = __dmul_rn((double)row[0], taps.wx[0]);
+            for (int k = rx; k >= 1; --k) {
+                const double pair = __dadd_rn((double)row[-k], (double)row[k]);
+                acc = __dadd_rn(acc, __dmul_rn(pair, taps.wx[k]));
+            }
+            out[(int64_t)c * H * pitch + (int64_t)y * pitch + x] = __fmul_rn((float)acc, ratio);
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace obia
 
 using namespace obia;
@@ -427,8 +482,27 @@ extern "C" int obia_b200_gaussian_planar(const float *in, float *tmp, float *out
         return set_err(OBIA_B200_ERR_ARG, "gaussian_planar: bad argument");
     if (radius_y > kMaxGaussRadius || radius_x > kMaxGaussRadius || radius_y < 0 || radius_x < 0)
         return set_err(OBIA_B200_ERR_UNSUPPORTED, "gaussian_planar: radius > %d", kMaxGaussRadius);
-    if (H > 65535) return set_err(OBIA_B200_ERR_UNSUPPORTED, "gaussian_planar: H > 65535 not supported yet");
     cudaStream_t st = (cudaStream_t)stream;
+    if (radius_y <= kGaussParamRadius && radius_x <= kGaussParamRadius && out != in) {
+        // fused tiled kernel; asynchronous (taps are kernel parameters)
+        GaussTaps taps;
+        memset(&taps, 0, sizeof(taps));
+        for (int k = 0; k <= radius_y; ++k) taps.wy[k] = weights_y_host[radius_y + k];
+        for (int k = 0; k <= radius_x; ++k) taps.wx[k] = weights_x_host[radius_x + k];
+        const size_t smem = ((size_t)(kGaussTY + 2 * radius_y) + kGaussTY) * (kGaussTX + 2 * radius_x) * sizeof(float);
+        if (smem <= 200 * 1024) {
+            if (smem > 48 * 1024)
+                OBIA_CUDA_CHECK(cudaFuncSetAttribute(gaussian_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)smem));
+            dim3 grid((unsigned)ceil_div(W, kGaussTX), (unsigned)ceil_div(H, kGaussTY));
+            gaussian_tiled_kernel<<<grid, 256, smem, st>>>(in, out, (int)H, (int)W, pitch, Cf, radius_y, radius_x, taps,
+                                                          ratio);
+            OBIA_LAUNCH_CHECK();
+            return OBIA_B200_OK;
+        }
+    }
+    // very wide kernels (sigma > 15) or in-place calls: two global passes, taps in constant memory
+    if (H > 65535) return set_err(OBIA_B200_ERR_UNSUPPORTED, "gaussian_planar: H > 65535 not supported by the wide path");
     // half kernels, index 0 = centre tap (weights are symmetric)
     double hw[2][kMaxGaussRadius + 1];
     memset(hw, 0, sizeof(hw));

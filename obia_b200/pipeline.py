@@ -292,11 +292,20 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
     if smooth:
         wy, ry = slic_host.gaussian_taps(sig_y) if sig_y > 0 else (np.ones(1), 0)
         wx, rx = slic_host.gaussian_taps(sig_x) if sig_x > 0 else (np.ones(1), 0)
-        tmp = torch.empty_like(feats)
-        _lib.check(lib.obia_b200_gaussian_planar(
-            _p(feats), _p(tmp), _p(feats), H, W, pitch, Cf, wy.ctypes.data_as(ctypes.c_void_p), ry,
-            wx.ctypes.data_as(ctypes.c_void_p), rx, float(ratio), _stream_ptr()), "gaussian_planar")
-        del tmp
+        smoothed = torch.empty_like(feats)
+        if max(ry, rx) <= 63:
+            # fused tiled kernel: in -> out, tmp unused (any distinct buffer satisfies the argument check)
+            unused = torch.empty((4,), dtype=torch.float32, device=dev)
+            _lib.check(lib.obia_b200_gaussian_planar(
+                _p(feats), _p(unused), _p(smoothed), H, W, pitch, Cf,
+                wy.ctypes.data_as(ctypes.c_void_p), ry, wx.ctypes.data_as(ctypes.c_void_p), rx, float(ratio),
+                _stream_ptr()), "gaussian_planar")
+            feats = smoothed
+        else:
+            _lib.check(lib.obia_b200_gaussian_planar(
+                _p(feats), _p(smoothed), _p(feats), H, W, pitch, Cf, wy.ctypes.data_as(ctypes.c_void_p), ry,
+                wx.ctypes.data_as(ctypes.c_void_p), rx, float(ratio), _stream_ptr()), "gaussian_planar")
+            del smoothed
 
     # ---- K2: iterations -----------------------------------------------------------
     max_abs = float(ratio) * (256.0 if to_lab else 4.0)

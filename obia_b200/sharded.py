@@ -142,8 +142,9 @@ class ShardedSlic:
         _require_cuda(raw_strip, "raw_strip", torch.float32)
         if mask is not None:
             raise NotImplementedError("sharded global SLIC supports unmasked rasters (use the tiled driver for masks)")
-        if np.any(np.asarray(sigma) > 0):
-            raise NotImplementedError("sigma > 0 needs a halo exchange of the features: not implemented for strips")
+        sig = np.ravel(np.asarray(sigma, dtype=np.float32))
+        self.sigma_y, self.sigma_x = (float(sig[0]), float(sig[0])) if sig.size == 1 else (float(sig[-2]), float(sig[-1]))
+        self.smooth = self.sigma_y > 0 or self.sigma_x > 0
         if slic_zero or spacing is not None:
             raise NotImplementedError("slic_zero / spacing are not implemented on the sharded path")
         if start_label not in (0, 1):
@@ -197,10 +198,14 @@ class ShardedSlic:
         self.feats = torch.empty((self.Cf, self.h, self.pitch), dtype=torch.float32, device=self.dev)
         bmin = np.ascontiguousarray(mm[:, 0], dtype=np.float32)
         bmax = np.ascontiguousarray(mm[:, 1], dtype=np.float32)
+        # with sigma > 0 the features are smoothed first and scaled by 1/compactness afterwards (slic()'s
+        # order); the driver exchanges the rows the Gaussian reaches across the strip boundaries
         _lib.check(self.lib.obia_b200_slic_features(
             _p(self.raw), self.h, self.W, self.C, _i32_array(self.bands), len(self.bands),
             bmin.ctypes.data_as(ctypes.c_void_p), bmax.ctypes.data_as(ctypes.c_void_p), 0.0, 1.0,
-            int(self.to_lab), float(ratio), _p(self.feats), self.pitch, _stream_ptr()), "slic_features")
+            int(self.to_lab), 1.0 if self.smooth else float(ratio), _p(self.feats), self.pitch, _stream_ptr()),
+            "slic_features")
+        self.ratio = float(ratio)
         self.fix_scale = slic_host.fixed_point_scale(float(ratio) * (256.0 if self.to_lab else 4.0), self.H, self.W,
                                                      self.step_y, self.step_x)
         nbytes = self.lib.obia_b200_slic_workspace_bytes(self.H, self.W, self.Cf, self.n, self.step_y, self.step_x)
@@ -218,6 +223,31 @@ class ShardedSlic:
             return (lo * self.nx, (hi + 1) * self.nx) if hi >= lo else (0, 0)
         self.band_up = band(self.row0) if self.top_open else (0, 0)
         self.band_down = band(self.row0 + self.h) if self.bottom_open else (0, 0)
+
+    # -- step 2b (sigma > 0): Gaussian over the strip extended by the neighbours' feature rows -----------
+    def smooth_radius(self):
+        return int(4.0 * self.sigma_y + 0.5) if self.sigma_y > 0 else 0
+
+    def feature_rows(self, top):
+        """The `smooth_radius()` unsmoothed feature rows next to the upper / lower strip boundary."""
+        r = self.smooth_radius()
+        return (self.feats[:, :r] if top else self.feats[:, self.h - r:]).contiguous()
+
+    def smooth_features(self, rows_up, rows_down):
+        """scipy's reflecting Gaussian on [neighbour rows, strip, neighbour rows]: the reflection only
+        reaches the rows that are cropped away again, except at the true raster edges."""
+        wy, ry = slic_host.gaussian_taps(self.sigma_y) if self.sigma_y > 0 else (np.ones(1), 0)
+        wx, rx = slic_host.gaussian_taps(self.sigma_x) if self.sigma_x > 0 else (np.ones(1), 0)
+        parts = [p for p in (rows_up, self.feats, rows_down) if p is not None]
+        ext = torch.cat(parts, dim=1).contiguous() if len(parts) > 1 else self.feats
+        He = int(ext.shape[1])
+        out = torch.empty_like(ext)
+        tmp = torch.empty_like(ext) if max(ry, rx) > 63 else torch.empty((4,), dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.obia_b200_gaussian_planar(
+            _p(ext), _p(tmp), _p(out), He, self.W, self.pitch, self.Cf, wy.ctypes.data_as(ctypes.c_void_p), ry,
+            wx.ctypes.data_as(ctypes.c_void_p), rx, self.ratio, _stream_ptr()), "gaussian_planar")
+        top = 0 if rows_up is None else int(rows_up.shape[1])
+        self.feats = out[:, top:top + self.h].contiguous()
 
     # -- step 3 (x max_num_iter): sweep -> combine acc over strips -> finish ---------------------------
     def sweep(self):
@@ -394,8 +424,22 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
     comm.all_reduce(lo, "min")
     comm.all_reduce(hi, "max")
     comm.all_reduce(fl, "max")
-    for i, s in enumerate(strips):
-        s.prepare(torch.stack([lo[i], hi[i], lo[i], hi[i]], dim=1), fl[i])
+    def prepare_all():
+        for i, s in enumerate(strips):
+            s.prepare(torch.stack([lo[i], hi[i], lo[i], hi[i]], dim=1), fl[i])
+        if strips[0].smooth:
+            r = strips[0].smooth_radius()
+            if any(s.h < r for s in strips):
+                raise ValueError("strips are thinner than the Gaussian radius")
+            up = [s.feature_rows(True) if s.top_open and r > 0 else None for s in strips]
+            down = [s.feature_rows(False) if s.bottom_open and r > 0 else None for s in strips]
+            like = ((strips[0].Cf, r, strips[0].pitch), torch.float32)
+            ru, rd = comm.neighbour_exchange(up, down, [like if u is not None else None for u in up],
+                                             [like if d is not None else None for d in down])
+            for s, a, b in zip(strips, ru, rd):
+                s.smooth_features(a, b)
+
+    prepare_all()
     mark("preprocess")
 
     def slic(mode):
@@ -428,8 +472,7 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
     if slic(mode):
         # a centre left its band: redo with the whole table (prepare() resets centres, labels, sums)
         mode = "allreduce"
-        for i, s in enumerate(strips):
-            s.prepare(torch.stack([lo[i], hi[i], lo[i], hi[i]], dim=1), fl[i])
+        prepare_all()
         slic(mode)
     res.mode["exchange"] = mode
     mark("slic")

@@ -1,83 +1,48 @@
-"""torchrun check + timing: global SLIC + zonal statistics on ONE raster sharded by row strips over N GPUs
-(NCCL all-reduce of the int64 centre sums every sweep) equals the single-GPU result bit for bit.
+"""N ranks over NCCL (torchrun): the sharded path gives, strip by strip, exactly the labels and
+statistics of the single-GPU pipeline on the same raster.  Every rank generates the whole raster
+from the same seed, runs the single-GPU reference on its own GPU and compares its strip.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        scripts/sharded_check.py [--size 10000 --bands 8 --segments 200000 --compactness 0.1]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/sharded_check.py [H] [W]
 """
-import argparse
-import os
-import sys
-import time
-
+import json, os, sys, time
 import torch
 import torch.distributed as dist
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import bench
+from obia_b200 import pipeline, sharded
 
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--size", type=int, default=10000)
-    ap.add_argument("--bands", type=int, default=8)
-    ap.add_argument("--segments", type=int, default=200000)
-    ap.add_argument("--compactness", type=float, default=0.1)
-    ap.add_argument("--reps", type=int, default=3)
-    args = ap.parse_args()
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
-    dist.init_process_group("nccl", device_id=dev)
-    import bench
-    from obia_b200 import pipeline
-    from obia_b200.sharded import slic_zonal_distributed, split_rows
-    H = W = args.size
-    full = bench.synth_raster_cuda(H, W, args.bands, seed=2, device=dev)      # same raster on every rank (seeded)
-    r0, h = split_rows(H, world)[rank]
-    strip = full[r0:r0 + h].contiguous()
-    kw = dict(n_segments=args.segments, compactness=args.compactness, max_num_iter=10)
-    if rank != 0:
-        del full
-        torch.cuda.empty_cache()
-    times = []
-    for rep in range(1 + args.reps):
-        dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        labels, n, stats = slic_zonal_distributed(strip, r0, H, None, None, **kw)
-        torch.cuda.synchronize()
-        dist.barrier()
-        if rep:
-            times.append(time.perf_counter() - t0)
-    t_multi = min(times)
-    gathered = torch.full((H, W), -9, dtype=torch.int32, device=dev)
-    gathered[r0:r0 + h] = labels
-    dist.all_reduce(gathered, op=dist.ReduceOp.MAX)
-    ok = True
-    if rank == 0:
-        ts = []
-        for rep in range(1 + args.reps):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            ref = pipeline.slic_labels(full, None, **kw)
-            ref_stats = pipeline.zonal_stats(ref.labels, full, None, max_label=ref.n_labels + 1)
-            torch.cuda.synchronize()
-            if rep:
-                ts.append(time.perf_counter() - t0)
-        same = bool(torch.equal(gathered, ref.labels))
-        cnt_same = bool(torch.equal(stats[:, :, 0], ref_stats[:, :, 0]))
-        mean_err = float((stats[:, :, 1] - ref_stats[:, :, 1]).abs().nan_to_num().max())
-        ok = same and cnt_same and n == ref.n_labels
-        mp = H * W / 1e6
-        print(f"sharded global SLIC: world={world} raster={H}x{W}x{args.bands} segments={n} labels_identical={same} "
-              f"counts_identical={cnt_same} max|mean diff|={mean_err:.2e}  "
-              f"t_sharded={t_multi * 1e3:.1f} ms ({mp / t_multi:.0f} MP/s)  t_single={min(ts) * 1e3:.1f} ms "
-              f"({mp / min(ts):.0f} MP/s)  speed-up {min(ts) / t_multi:.2f}x", flush=True)
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=dev)
+H = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+W = int(sys.argv[2]) if len(sys.argv) > 2 else 6000
+out = {}
+for name, kw in (("c0.1", dict(compactness=0.1)), ("c10", dict(compactness=10.0)),
+                 ("c1_exact_sl0", dict(compactness=1.0, exact=True, start_label=0))):
+    kw = dict(n_segments=int(round(200000 * H * W / 1e8)), max_num_iter=10, **kw)
+    raw = bench.synth_raster_cuda(H, W, 8, 7, dev)
+    ref = pipeline.slic_labels(raw, None, **kw)
+    ref_stats = pipeline.zonal_stats(ref.labels, raw, None, max_label=ref.n_labels + 1)
+    row0, h = sharded.split_rows(H, world)[rank]
+    torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()
-    if not ok:
-        sys.exit(1)
-
-
-if __name__ == "__main__":
-    main()
+    t0 = time.perf_counter()
+    res = sharded.slic_zonal_distributed(raw[row0:row0 + h].contiguous(), row0, H, None, None, **kw)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    same = bool(torch.equal(res.labels[0], ref.labels[row0:row0 + h])) and res.n_labels == ref.n_labels
+    stats_ok = True
+    if res.mode["stats"] == "label-range":
+        lo = res.label_lo[0]
+        a, b = res.stats[0], ref_stats[lo:lo + res.stats[0].shape[0]]
+        stats_ok = bool(torch.equal(a[..., 0], b[..., 0])) and bool(torch.equal(a[..., 3:5], b[..., 3:5])) and \
+            bool(torch.allclose(a[..., 1:3], b[..., 1:3], rtol=1e-6, atol=1e-9, equal_nan=True))
+    flag = torch.tensor([int(same), int(stats_ok)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out[name] = {"labels_identical_on_all_ranks": bool(flag[0].item()), "stats_match_on_all_ranks": bool(flag[1].item()),
+                 "mode": res.mode, "segments": res.n_labels, "sharded_ms_incl_first_call": round(dt * 1e3, 1)}
+if rank == 0:
+    print(json.dumps({"world": world, "raster": [H, W, 8], "checks": out}))
+dist.destroy_process_group()

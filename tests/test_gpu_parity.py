@@ -989,6 +989,19 @@ def test_sharded_global_slic_is_bit_identical(world, C, n, compactness, exact, s
     _check_sharded_against_single(res2, ref, ref_stats, start_label)
 
 
+def test_sharded_with_gaussian_presmoothing():
+    """sigma > 0 on strips: the feature rows the Gaussian reaches are exchanged with the neighbours,
+    so the smoothed features -- and the labels -- are those of the single-GPU run."""
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    H, W, C = 384 * 3 + 50, 300, 4
+    raw = _cuda(synth_raster(H, W, C, seed=21))
+    kw = dict(n_segments=1600, compactness=0.3, max_num_iter=5, sigma=1.4)
+    ref = pipeline.slic_labels(raw, None, **kw)
+    strips, res = _run_local_shards(raw, 3, kw, stats=False)
+    assert torch.equal(torch.cat(res.labels, dim=0), ref.labels) and res.n_labels == ref.n_labels
+
+
 def test_sharded_band_fallback_when_centres_leave_their_band():
     """band_steps too small for the drift: obia_b200_slic_band_check raises the flag and the driver
     repeats the run with the whole-table all-reduce -- same labels as the single-GPU run."""
