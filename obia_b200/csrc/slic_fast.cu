@@ -28,7 +28,7 @@ namespace obia {
 template <int CP, int NW> struct FastTraits {
     static constexpr int CR = (3 + CP + 3) / 4 * 4;          // floats per candidate record
     static constexpr int kIds = 1024;
-    static constexpr int kChk = (CP <= 32) ? 64 : 32;        // candidate records resident at once (<= 64)
+    static constexpr int kChk = (CP <= 8) ? 128 : (CP <= 32) ? 64 : 32;   // candidate records resident at once (<= 128)
     static constexpr int kAcc = (CP <= 16) ? 128 : 64;       // slots with a tile accumulator row
     static constexpr int PX = (CP <= 8) ? 4 : 2;             // pixels per lane
     static constexpr int kRecW = 32 * PX;                    // records per warp and phase: one per pixel at most
@@ -92,10 +92,9 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
     constexpr int NFR = T::NFR;
     constexpr int CR = T::CR, kIds = T::kIds, kChk = T::kChk, kAcc = T::kAcc, kRec = T::kRec;
     constexpr int NT = NW * 32;
-    static_assert(TH * NS <= 128 && 32 * TH * NS <= 4096 && kChk <= 64, "packed record fields");
+    static_assert(TH * NS <= 128 && 32 * TH * NS <= 4096 && kChk <= 128, "packed record fields");
     __shared__ int s_sorted[kIds];
     __shared__ int s_nids;
-    __shared__ int s_cells[4];
     __shared__ int4 s_win[kChk];
     __shared__ float2 s_cyx[kChk];
     __shared__ __align__(16) float s_cand[kChk][CR];
@@ -116,18 +115,16 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
     const int X0 = tx0 + 16, Y0 = ty0 + y_off + (TH * NS) / 2;
 
     // ---- collect candidate centre ids (as in the exact kernel) --------------------------------
-    if (tid < 4) {
-        // cell range whose centres can reach the tile: a centre at cy reaches rows y with
-        // y - 2s <= cy < y + 1 + 2s; two pixels of slack absorb the float rounding of the cell index
-        const int lo = (tid & 1) ? tx0 : ty0 + y_off, hi = (tid & 1) ? tx1 : ty1 + y_off;
-        const int st = (tid & 1) ? step_x : step_y, nc = (tid & 1) ? ncx : ncy;
-        s_cells[tid] = (tid < 2) ? max(0, floordiv_i(lo - 2 * st - 2, st)) : min(nc - 1, floordiv_i(hi + 2 * st + 2, st));
-        if (tid == 0) s_nids = 0;
-    }
+    if (tid == 0) s_nids = 0;
     for (int i = tid; i < kAcc * NFR; i += NT) (&s_acc[0][0])[i] = 0;
     __syncthreads();
     {
-        const int gy_lo = s_cells[0], gx_lo = s_cells[1], gy_hi = s_cells[2], gx_hi = s_cells[3];
+        // cell range whose centres can reach the tile: a centre at cy reaches rows y with
+        // y - 2s <= cy < y + 1 + 2s; two pixels of slack absorb the float rounding of the cell index
+        const int gy_lo = max(0, floordiv_i(ty0 + y_off - 2 * step_y - 2, step_y));
+        const int gy_hi = min(ncy - 1, floordiv_i(ty1 + y_off + 2 * step_y + 2, step_y));
+        const int gx_lo = max(0, floordiv_i(tx0 - 2 * step_x - 2, step_x));
+        const int gx_hi = min(ncx - 1, floordiv_i(tx1 + 2 * step_x + 2, step_x));
         const int ny = gy_hi - gy_lo + 1, nx = gx_hi - gx_lo + 1;
         for (int i = tid; i < ny * nx; i += NT) {
             const int gy = gy_lo + i / nx, gx = gx_lo + i % nx;
@@ -152,15 +149,13 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
         s_sorted[r] = k;
     }
     __syncthreads();
-    // colour origin of the tile: the colour of its middle candidate (live centres only are binned,
-    // so it is finite); 0 in the spatial-only pass and when the tile has no candidate
-    if (tid < CP) {
-        float o = 0.0f;
-        if (nids > 0 && tid < Cf && !ignore_color) o = centres[(int64_t)s_sorted[nids >> 1] * (2 + Cf) + 2 + tid];
-        s_off[tid] = o;
-        s_off64[tid] = __double2ll_rn((double)o * fix_scale);
+    // (the colour origin of the tile -- the colour of its middle candidate: live centres only are binned,
+    //  so it is finite; 0 in the spatial-only pass and when the tile has no candidate -- is published by
+    //  the thread that loads that candidate's record in the first chunk build)
+    if (nids == 0 && tid < CP) {
+        s_off[tid] = 0.0f;
+        s_off64[tid] = 0;
     }
-    __syncthreads();
 
     const bool single_chunk = nids <= kChk;
     const float INF = __int_as_float(0x7f800000);
@@ -192,15 +187,17 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
                         v.x = t.x; v.y = t.y;
                     }
                 }
-                const float o = s_off[c];
-                pf[0][c] = v.x - o;
-                pf[1][c] = v.y - o;
+                // raw features for now: the loads are in flight while the candidate records are built,
+                // the tile's colour origin is subtracted right after
+                pf[0][c] = v.x;
+                pf[1][c] = v.y;
                 if constexpr (PX == 4) {
-                    pf[2][c] = v.z - o;
-                    pf[3][c] = v.w - o;
+                    pf[2][c] = v.z;
+                    pf[3][c] = v.w;
                 }
             }
         }
+        bool centred = false;
         const int yg = y + y_off;
         const float yr = (float)(yg - Y0), xbr = (float)(xb - X0);
 
@@ -220,13 +217,38 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
             const bool load_chunk = !(single_chunk && sp > 0);
             if (load_chunk) {
                 __syncthreads();
-                for (int sI = tid; sI < nc; sI += NT) {
-                    const int k = s_sorted[c0 + sI];
-                    const float *rec = centres + (int64_t)k * (2 + Cf);
-                    const float cy = rec[0], cx = rec[1];
-                    float m[CP];
+                // stage A: every candidate's record into registers (one global round trip)
+                constexpr int PER = (kChk + NT - 1) / NT;
+                float rcy[PER], rcx[PER], rm[PER][CP];
 #pragma unroll
-                    for (int c = 0; c < CP; ++c) m[c] = (c < Cf && !ignore_color) ? rec[2 + c] : 0.0f;
+                for (int u = 0; u < PER; ++u) {
+                    const int sI = tid + u * NT;
+                    rcy[u] = rcx[u] = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < CP; ++c) rm[u][c] = 0.0f;
+                    if (sI < nc) {
+                        const int k = s_sorted[c0 + sI];
+                        const float *rec = centres + (int64_t)k * (2 + Cf);
+                        rcy[u] = rec[0];
+                        rcx[u] = rec[1];
+#pragma unroll
+                        for (int c = 0; c < CP; ++c) rm[u][c] = (c < Cf && !ignore_color) ? rec[2 + c] : 0.0f;
+                        if (c0 == 0 && sI == min(nids >> 1, nc - 1)) {   // the origin candidate sits in the first chunk
+#pragma unroll
+                            for (int c = 0; c < CP; ++c) {
+                                s_off[c] = rm[u][c];
+                                s_off64[c] = __double2ll_rn((double)rm[u][c] * fix_scale);
+                            }
+                        }
+                    }
+                }
+                if (c0 == 0) __syncthreads();     // s_off published
+                // stage B: windows and score records relative to the tile origin
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int sI = tid + u * NT;
+                    if (sI >= nc) continue;
+                    const float cy = rcy[u], cx = rcx[u];
                     s_cyx[sI] = make_float2(cy, cx);
                     const float ylo = __fsub_rn(cy, (float)(2 * step_y));
                     const float yhi = __fadd_rn(__fadd_rn(cy, (float)(2 * step_y)), 1.0f);
@@ -245,7 +267,7 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
                     cr[2] = -2.0f * cxr;
 #pragma unroll
                     for (int c = 0; c < CP; ++c) {
-                        const float mc = (c < Cf && !ignore_color) ? m[c] - s_off[c] : 0.0f;
+                        const float mc = (c < Cf && !ignore_color) ? rm[u][c] - s_off[c] : 0.0f;
                         Bc = fmaf(mc, mc, Bc);
                         cr[3 + c] = -2.0f * inv_weight * mc;
                     }
@@ -255,6 +277,15 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
                     for (int c = 3 + CP; c < CR; ++c) cr[c] = 0.0f;
                 }
                 __syncthreads();
+            }
+            if (!centred) {
+                centred = true;
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+                    const float o = s_off[c];
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) pf[j][c] -= o;
+                }
             }
 
             bool hit[kChk / 32];
@@ -275,7 +306,7 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
                         const float ddx = fmaxf(0.0f, fmaxf((float)wx0 - c.y, c.y - (float)wx1));
                         hit[half] = true;
                         lb[half] = (ddy * ddy + ddx * ddx) * spatial_weight * 0.9999f;
-                        seedkey = min(seedkey, (__float_as_uint(lb[half]) & ~63u) | (unsigned)sc);
+                        seedkey = min(seedkey, (__float_as_uint(lb[half]) & ~127u) | (unsigned)sc);
                         full = w.x <= wy0 && w.y > wy1 && w.z <= wx0 && w.w > wx1;
                     }
                 }
@@ -286,8 +317,8 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
             // (colour-dominated runs: the bound would exceed every candidate's spatial term anyway).
             seedkey = __reduce_min_sync(0xffffffffu, seedkey);
             if (dbg & 4) seedkey = 0xffffffffu;
-            if (seedkey != 0xffffffffu && __uint_as_float(seedkey & ~63u) < wbound) {
-                const int s = (int)(seedkey & 63u);
+            if (seedkey != 0xffffffffu && __uint_as_float(seedkey & ~127u) < wbound) {
+                const int s = (int)(seedkey & 127u);
                 float tb[PX];
                 int ts[PX];
 #pragma unroll
@@ -520,11 +551,11 @@ int launch_assign_fast(const float *feat, const uint8_t *mask, const float *cent
                        fix_scale, status, y_off, Hg, st
     if (Cf <= 4) {
         if (g_fast_warps == 4) return launch_fast_t<4, 4, 4, 4>(OBIA_FAST_ARGS);
-        return launch_fast_t<4, 4, 2, 8>(OBIA_FAST_ARGS);
+        return launch_fast_t<4, 4, 4, 8>(OBIA_FAST_ARGS);
     }
     if (Cf <= 8) {
         if (g_fast_warps == 4) return launch_fast_t<8, 4, 4, 4>(OBIA_FAST_ARGS);
-        return launch_fast_t<8, 4, 2, 8>(OBIA_FAST_ARGS);
+        return launch_fast_t<8, 4, 4, 8>(OBIA_FAST_ARGS);
     }
     if (Cf <= 16) return launch_fast_t<16, 2, 2, 8>(OBIA_FAST_ARGS);
     if (Cf <= 32) return launch_fast_t<32, 2, 2, 8>(OBIA_FAST_ARGS);
