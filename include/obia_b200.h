@@ -337,11 +337,13 @@ int obia_b200_zonal_stats(const int32_t *labels, const float *raw, int64_t H,
 
 /* Same statistics over the label range [label_lo, label_lo + n_rows): row r of `stats` = label
  * label_lo + r, every other label is skipped.  Used by the sharded path, where a rank's strip holds a
- * contiguous range of the raster-order label numbering.
+ * contiguous range of the raster-order label numbering.  zero_row = 1 (label_lo > 0): row 0 holds
+ * label 0 -- merged pieces without an earlier neighbour carry it on any rank -- and row r >= 1 holds
+ * label label_lo + r - 1 (n_rows counts the extra row).
  * workspace: obia_b200_zonal_workspace_bytes(n_rows - 1, Cz). */
 int obia_b200_zonal_stats_range(const int32_t *labels, const float *raw, int64_t H,
                                 int64_t W, int32_t C, const int32_t *bands_host,
-                                int32_t Cz, int64_t label_lo, int64_t n_rows,
+                                int32_t Cz, int64_t label_lo, int64_t n_rows, int32_t zero_row,
                                 double resolution, double *stats, void *workspace,
                                 void *stream);
 

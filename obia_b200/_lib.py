@@ -60,8 +60,8 @@ SIGNATURES = {
     "obia_b200_zonal_workspace_bytes": (_i64, [_i64, _i32]),
     "obia_b200_zonal_stats": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _i64, _f64, _vp, _vp,
                                              _vp]),
-    "obia_b200_zonal_stats_range": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _i64, _i64, _f64, _vp,
-                                                   _vp, _vp]),
+    "obia_b200_zonal_stats_range": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _i64, _i64, _i32, _f64,
+                                                   _vp, _vp, _vp]),
     "obia_b200_rasterize_polygons": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp]),
     "obia_b200_texture_workspace_bytes": (_i64, [_i64]),
     "obia_b200_texture_stats": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _i64, _i32, _vp, _vp,

@@ -39,16 +39,18 @@ static __global__ void zonal_init_kernel(ZonalWs w, int64_t n)
 
 static __global__ void __launch_bounds__(256)
 zonal_bbox_kernel(const int32_t *__restrict__ labels, ZonalWs w, int64_t N, int W, int64_t max_label,
-                  int32_t label_lo = 0)
+                  int32_t label_lo = 0, int32_t zero_row = 0)
 {
-    // table row = label - label_lo (label_lo != 0: the rank-local label range of a sharded raster)
+    // table row = label - label_lo (label_lo != 0: the rank-local label range of a sharded raster);
+    // with zero_row the table starts with one extra row for label 0: row = label - label_lo + 1
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int32_t l = -1;
     int x = 0, y = 0;
     if (i < N) {
         l = labels[i];
-        if (l < 0 || l < label_lo || (int64_t)l - label_lo > max_label) l = -1;
+        const bool is_zero = zero_row && l == 0;
+        if (!is_zero && (l < 0 || l < label_lo || (int64_t)l - label_lo + zero_row > max_label)) l = -1;
         y = (int)(i / W);
         x = (int)(i - (int64_t)y * W);
     }
@@ -59,7 +61,7 @@ zonal_bbox_kernel(const int32_t *__restrict__ labels, ZonalWs w, int64_t N, int 
         const unsigned later = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
         const int end = later ? (__ffs(later) - 1) : 32;
         const int len = end - lane;
-        const int32_t r = l - label_lo;
+        const int32_t r = (zero_row && l == 0) ? 0 : l - label_lo + zero_row;
         atomicMin(w.xmin + r, x);
         atomicMax(w.xmax + r, x + len - 1);
         // a row can only be the label's first / last one if the pixel above / below the run head

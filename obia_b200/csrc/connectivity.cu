@@ -1143,7 +1143,7 @@ extern "C" int obia_b200_connectivity_strip_begin(const int32_t *labels_ext, voi
     int32_t hctr[CTR_WORDS];
     while (true) {
         if (start_label == 1) {
-            rc = cc_rounds(R, round_id == 1 ? 2 : 16, round_id, cur);
+            rc = cc_rounds(R, round_id == 1 ? 12 : 16, round_id, cur);   // (an empty round costs a few microseconds)
             if (rc) return rc;
         }
         // (same band as cc_phase_a marks: the outer third of an open upper halo)

@@ -42,13 +42,13 @@ template <bool VEC>
 __global__ void __launch_bounds__(256, 2)
 zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw, ZonalWs w, int W,
                     int C, ZBands zb, int Cz, int64_t max_label, double resolution,
-                    double *__restrict__ stats, int32_t label_lo)
+                    double *__restrict__ stats, int32_t label_lo, int32_t zero_row)
 {
     constexpr int R = 4;
     const int lane = threadIdx.x & 31;
     const int64_t L = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // table row
     if (L > max_label) return;
-    const int32_t LV = (int32_t)L + label_lo;                                         // label value
+    const int32_t LV = (zero_row && L == 0) ? 0 : (int32_t)L + label_lo - zero_row;   // label value
     const int b0 = blockIdx.y * kZB;
     const int nb = min(kZB, Cz - b0);
     double *out = stats + (L * Cz + b0) * 8;
@@ -267,12 +267,12 @@ template <int BPL>
 __global__ void __launch_bounds__(256)
 zonal_gather_bands_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw, ZonalWs w, int W,
                           int C, ZBands zb, int Cz, int64_t max_label, double resolution,
-                          double *__restrict__ stats, int32_t label_lo)
+                          double *__restrict__ stats, int32_t label_lo, int32_t zero_row)
 {
     const int lane = threadIdx.x & 31;
     const int64_t L = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (L > max_label) return;
-    const int32_t LV = (int32_t)L + label_lo;
+    const int32_t LV = (zero_row && L == 0) ? 0 : (int32_t)L + label_lo - zero_row;
     const int cnt_total = w.count[L];
     const double NAND = __longlong_as_double(0x7ff8000000000000LL);
     double *out = stats + L * Cz * 8;
@@ -411,7 +411,7 @@ extern "C" int64_t obia_b200_zonal_workspace_bytes(int64_t max_label, int32_t Cz
 
 static int zonal_stats_impl(const int32_t *labels, const float *raw, int64_t H, int64_t W,
                             int32_t C, const int32_t *bands_host, int32_t Cz, int64_t label_lo, int64_t max_label,
-                            double resolution, double *stats, void *workspace, void *stream)
+                            double resolution, double *stats, void *workspace, void *stream, int32_t zero_row = 0)
 {
     if (!labels || !raw || !bands_host || !stats || !workspace || H <= 0 || W <= 0 || C <= 0 || Cz <= 0 ||
         max_label < 0 || label_lo < 0)
@@ -435,15 +435,15 @@ static int zonal_stats_impl(const int32_t *labels, const float *raw, int64_t H, 
     const int32_t lo = (int32_t)label_lo;
     zonal_init_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(w, n);
     OBIA_LAUNCH_CHECK();
-    zonal_bbox_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(labels, w, N, (int)W, max_label, lo);
+    zonal_bbox_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(labels, w, N, (int)W, max_label, lo, zero_row);
     OBIA_LAUNCH_CHECK();
     if (Cz >= 24) {
         // many bands: lanes across bands, one pass over the raster for all of them
         const unsigned g = (unsigned)ceil_div(n, 8);
         if (Cz <= 32)
-            zonal_gather_bands_kernel<1><<<g, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label, resolution, stats, lo);
+            zonal_gather_bands_kernel<1><<<g, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label, resolution, stats, lo, zero_row);
         else
-            zonal_gather_bands_kernel<2><<<g, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label, resolution, stats, lo);
+            zonal_gather_bands_kernel<2><<<g, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label, resolution, stats, lo, zero_row);
         OBIA_LAUNCH_CHECK();
         return OBIA_B200_OK;
     }
@@ -454,10 +454,10 @@ static int zonal_stats_impl(const int32_t *labels, const float *raw, int64_t H, 
         vec = (b % kZB == 0) ? (zb.band[b] % 4 == 0) : (zb.band[b] == zb.band[b - 1] + 1);
     if (vec)
         zonal_gather_kernel<true><<<grid, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label,
-                                                        resolution, stats, lo);
+                                                        resolution, stats, lo, zero_row);
     else
         zonal_gather_kernel<false><<<grid, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label,
-                                                         resolution, stats, lo);
+                                                         resolution, stats, lo, zero_row);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
 }
@@ -471,10 +471,11 @@ extern "C" int obia_b200_zonal_stats(const int32_t *labels, const float *raw, in
 
 extern "C" int obia_b200_zonal_stats_range(const int32_t *labels, const float *raw, int64_t H, int64_t W,
                                            int32_t C, const int32_t *bands_host, int32_t Cz, int64_t label_lo,
-                                           int64_t n_rows, double resolution, double *stats, void *workspace,
-                                           void *stream)
+                                           int64_t n_rows, int32_t zero_row, double resolution, double *stats,
+                                           void *workspace, void *stream)
 {
-    if (n_rows <= 0) return set_err(OBIA_B200_ERR_ARG, "zonal_stats_range: bad argument");
+    if (n_rows <= 0 || (zero_row != 0 && zero_row != 1) || (zero_row && label_lo <= 0))
+        return set_err(OBIA_B200_ERR_ARG, "zonal_stats_range: bad argument");
     return zonal_stats_impl(labels, raw, H, W, C, bands_host, Cz, label_lo, n_rows - 1, resolution, stats, workspace,
-                            stream);
+                            stream, zero_row);
 }

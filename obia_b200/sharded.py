@@ -323,28 +323,28 @@ class ShardedSlic:
         return int(flags[0])
 
     # -- step 5: statistics over this rank's label range -------------------------------------------------
-    def range_stats(self, bands=None, resolution=1e-6):
-        """Rows = labels [start_label + label_base - k_shared, start_label + label_base + k_core)."""
+    def range_stats(self, bands=None, resolution=1e-6, with_zero=False):
+        """Rows = labels [start_label + label_base - k_shared, start_label + label_base + k_core); with
+        `with_zero` (label 0 outside that range) one extra leading row for label 0, returned separately.
+        Returns (table, zero row or None)."""
         bands = list(range(self.C)) if bands is None else [int(b) for b in bands]
-        n_rows = max(1, self.k_shared + self.k_core)
         lo = self.start_label + self.label_base - self.k_shared
+        zero = 1 if (with_zero and lo > 0) else 0
+        n_rows = max(1, self.k_shared + self.k_core) + zero
         stats = torch.empty((n_rows, len(bands), 8), dtype=torch.float64, device=self.dev)
         ws = torch.empty((self.lib.obia_b200_zonal_workspace_bytes(n_rows - 1, 8),), dtype=torch.uint8, device=self.dev)
         _lib.check(self.lib.obia_b200_zonal_stats_range(_p(self.final), _p(self.raw), self.h, self.W, self.C,
-                                                        _i32_array(bands), len(bands), lo, n_rows, float(resolution),
-                                                        _p(stats), _p(ws), _stream_ptr()), "zonal_stats_range")
-        return stats
-
-    def zero_stats(self, bands=None, resolution=1e-6):
-        """Row of label 0 from this strip's pixels when label 0 lies outside the rank's label range
-        (pieces merged into nothing carry label 0 on any rank, SURVEY.md defect 7); an empty row otherwise."""
-        if self.start_label + self.label_base - self.k_shared > 0:
-            return pipeline.zonal_stats(self.final, self.raw, bands, max_label=0, resolution=resolution)
-        Cz = self.C if bands is None else len(bands)
-        row = torch.full((1, Cz, 8), float("nan"), dtype=torch.float64, device=self.dev)
-        row[..., 0] = 0.0
-        row[..., 7] = 0.0
-        return row
+                                                        _i32_array(bands), len(bands), lo, n_rows, zero,
+                                                        float(resolution), _p(stats), _p(ws), _stream_ptr()),
+                   "zonal_stats_range")
+        if zero:
+            return stats[1:], stats[:1]
+        if with_zero:      # label 0 lies inside the rank's own range (first rank): nothing extra to report
+            empty = torch.full((1, len(bands), 8), float("nan"), dtype=torch.float64, device=self.dev)
+            empty[..., 0] = 0.0
+            empty[..., 7] = 0.0
+            return stats, empty
+        return stats, None
 
 
 def combine_stats(tables, resolution=1e-6):
@@ -483,31 +483,34 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
             s.final, s.k_before, s.k_shared, s.k_core, s.label_base, s.has_zero = s.labels, 0, 0, s.n, 0, False
         res.n_labels = s0.n
         res.mode["connectivity"] = "none"
-        kcores = None
+        kcores, kshared, any_zero = None, None, 0
     else:
         h_rows = int(halo) if halo is not None else s0.default_halo()
         incomplete = 1
-        rows_all = comm.all_gather_host([[s.h] for s in strips])
+        rows_all = [[h] for _, h in split_rows(s0.H, comm.world)] if comm.world > 1 else [[s0.h]]
         if comm.world > 1 and min(r[0] for r in rows_all) >= h_rows:
             up = [s.labels[:h_rows] if s.top_open else None for s in strips]
             down = [s.labels[s.h - h_rows:] if s.bottom_open else None for s in strips]
             like = ((h_rows, s0.W), torch.int32)
             ru, rd = comm.neighbour_exchange(up, down, [like if s.top_open else None for s in strips],
                                              [like if s.bottom_open else None for s in strips])
-            kc = [[s.strip_begin(a, b)] for s, a, b in zip(strips, ru, rd)]
-            kcores = [k[0] for k in comm.all_gather_host(kc)]
+            for s, a, b in zip(strips, ru, rd):
+                s.strip_begin(a, b)
+            counts = comm.all_gather_host([[s.k_core, s.k_shared] for s in strips])   # one exchange for both
+            kcores, kshared = [c[0] for c in counts], [c[1] for c in counts]
             prefix = np.concatenate([[0], np.cumsum(kcores)])
-            inc = [torch.tensor([s.strip_finish(int(prefix[r]))], dtype=torch.int32, device=s.dev)
-                   for s, r in zip(strips, comm.local)]
+            inc = [torch.tensor([s.strip_finish(int(prefix[r])), int(bool(s.has_zero))], dtype=torch.int32,
+                                device=s.dev) for s, r in zip(strips, comm.local)]
             comm.all_reduce(inc, "max")
-            incomplete = int(inc[0].item())
+            inc_host = inc[0].cpu().tolist()
+            incomplete, any_zero = int(inc_host[0]), int(inc_host[1])
             res.n_labels = int(prefix[-1])
             res.mode["connectivity"] = "strip+halo"
         elif comm.world == 1:
             s0.strip_begin(None, None)
             incomplete = s0.strip_finish(0)
             res.n_labels = s0.k_core
-            kcores = [s0.k_core]
+            kcores, kshared, any_zero = [s0.k_core], [0], int(bool(s0.has_zero))
             res.mode["connectivity"] = "strip+halo"
         if incomplete:
             # some strip's result could depend on pixels outside its halo (or the strips are thinner than
@@ -537,8 +540,9 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
             res.stats, res.label_lo = merged, [0 for _ in strips]
             res.mode["stats"] = "replicated"
         else:
-            tabs = [s.range_stats(statistics_bands) for s in strips]
-            kb = comm.all_gather_host([[s.k_shared] for s in strips])
+            both = [s.range_stats(statistics_bands, with_zero=bool(any_zero)) for s in strips]
+            tabs = [b[0] for b in both]
+            kb = [[k] for k in kshared]
             # rows of pieces that start above the core go UP to their owner
             up = [t[:s.k_shared] if s.top_open and s.k_shared > 0 else None for s, t in zip(strips, tabs)]
             Cz = int(tabs[0].shape[1])
@@ -560,11 +564,8 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
             res.stats = out
             res.label_lo = [s.start_label + s.label_base for s in strips]
             res.mode["stats"] = "label-range"
-            hz = [torch.tensor([int(bool(s.has_zero))], dtype=torch.int32, device=s.dev) for s in strips]
-            comm.all_reduce(hz, "max")
-            if int(hz[0].item()):
-                z = [s.zero_stats(statistics_bands) for s in strips]
-                zero = combine_stats(list(comm.all_gather(z)[0]))
+            if any_zero:
+                zero = combine_stats(list(comm.all_gather([b[1] for b in both])[0]))
                 if s0.start_label == 1:
                     res.zero_row = zero
                 else:

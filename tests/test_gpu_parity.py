@@ -621,9 +621,19 @@ def test_zonal_stats_label_range():
     out = torch.empty((n, C, 8), dtype=torch.float64, device="cuda")
     ws = torch.empty((lib.obia_b200_zonal_workspace_bytes(n - 1, 8),), dtype=torch.uint8, device="cuda")
     _lib.check(lib.obia_b200_zonal_stats_range(pipeline._p(labels), pipeline._p(raw), H, W, C,
-                                               pipeline._i32_array(range(C)), C, lo, n, 1e-6, pipeline._p(out),
+                                               pipeline._i32_array(range(C)), C, lo, n, 0, 1e-6, pipeline._p(out),
                                                pipeline._p(ws), pipeline._stream_ptr()), "zonal_stats_range")
     assert torch.equal(out, full[lo:lo + n])
+    # with the extra row for label 0
+    labels0 = labels.clone()
+    labels0[:3, :5] = 0
+    full0 = pipeline.zonal_stats(labels0, raw, None, max_label=96)
+    out0 = torch.empty((n + 1, C, 8), dtype=torch.float64, device="cuda")
+    ws0 = torch.empty((lib.obia_b200_zonal_workspace_bytes(n, 8),), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.obia_b200_zonal_stats_range(pipeline._p(labels0), pipeline._p(raw), H, W, C,
+                                               pipeline._i32_array(range(C)), C, lo, n + 1, 1, 1e-6, pipeline._p(out0),
+                                               pipeline._p(ws0), pipeline._stream_ptr()), "zonal_stats_range")
+    assert torch.equal(out0[1:], full0[lo:lo + n]) and torch.equal(out0[:1], full0[:1])
 
 
 # ------------------------------------------------------------------ K5 ------
