@@ -118,7 +118,10 @@ def create_objects(
     # one (n_columns, n_rows) float64 block, column-major for pandas (zero-copy): the spectral
     # statistics, then the texture features, in the reference's order; point-cloud columns stay NaN
     import torch
-    block = np.empty((len(float_cols), n_rows), dtype=np.float64)
+    # (page-locked: the device-to-host copy of the table runs at PCIe speed instead of through the
+    #  pageable staging path -- 80 MB for c2: 2 ms instead of 20; torch caches the pinned allocation)
+    block_t = torch.empty((len(float_cols), n_rows), dtype=torch.float64, pin_memory=raw.is_cuda)
+    block = block_t.numpy()
     # the reference computes in the dtype of its masked crop: float32 for float32 rasters,
     # float64 for integer rasters (np.where(mask, crop, nan), utils.py:64)
     in_f64 = bool(getattr(image, "stats_in_float64", lambda: False)())
@@ -148,7 +151,7 @@ def create_objects(
             sel = stats.index_select(0, rows)[:, :, fields]                  # (rows, Cz, nstat)
             sel = sel.permute(1, 2, 0).reshape(n_spec, n_rows).contiguous()
             assert float_cols[:n_spec] == [f"b{b}_{name}" for b in spectral_bands for name, on in want if on]
-            torch.from_numpy(block[:n_spec]).copy_(sel)
+            block_t[:n_spec].copy_(sel, non_blocking=True)
             filled[:n_spec] = True
         if calculate_textural and n_tex > 0:                                 # (:494-506)
             feats = pipeline.texture_stats(raster, raw, textural_bands, max_label=max_label,
@@ -159,8 +162,10 @@ def create_objects(
             sel = sel.permute(1, 2, 0).reshape(n_tex, n_rows).contiguous()
             assert float_cols[n_spec:n_spec + n_tex] == [f"b{b}_{name}" for b in textural_bands
                                                          for name, on in tex_want if on]
-            torch.from_numpy(block[n_spec:n_spec + n_tex]).copy_(sel)
+            block_t[n_spec:n_spec + n_tex].copy_(sel, non_blocking=True)
             filled[n_spec:n_spec + n_tex] = True
+    if raw.is_cuda:
+        torch.cuda.current_stream(raw.device).synchronize()     # the asynchronous table copies above
     block[~filled] = np.nan
     out = pd.DataFrame(block.T, columns=float_cols, copy=False)
     out.insert(0, "segment_id", np.asarray(segments["segment_id"]))
