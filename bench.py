@@ -435,7 +435,8 @@ def run_ours(args):
                 dev_strip = work.to(dev, non_blocking=True)
                 s = sharded.ShardedSlic(dev_strip, row0, H_total, None, **slic_kw)
                 r = sharded.run_sharded([s], comm, None)
-                table = r.stats[0].cpu()
+                table = torch.empty(r.stats[0].shape, dtype=torch.float64, pin_memory=True)
+                table.copy_(r.stats[0])                    # page-locked: PCIe speed, like the H2D of the strip
                 d2h_i = table.numel() * 8
                 del dev_strip, s, r, table
             torch.cuda.synchronize()

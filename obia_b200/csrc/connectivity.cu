@@ -1141,9 +1141,16 @@ extern "C" int obia_b200_connectivity_strip_begin(const int32_t *labels_ext, voi
     if (rc) return rc;
     int round_id = 1, cur = 0;
     int32_t hctr[CTR_WORDS];
+    const bool debug = getenv("OBIA_B200_DEBUG") != nullptr;   // read once per call, outside the round loop
     while (true) {
+        if (debug) {
+            OBIA_CUDA_CHECK(cudaMemcpyAsync(hctr, R.w.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, R.st));
+            OBIA_CUDA_CHECK(cudaStreamSynchronize(R.st));
+            fprintf(stderr, "[obia_b200] strip connectivity: round %d, %d small pieces, %d over, dirty %d / %d, roots %d\n",
+                    round_id, hctr[CTR_NSMALL], hctr[CTR_NOVER], hctr[CTR_NDIRTY0], hctr[CTR_NDIRTY1], hctr[CTR_NROOTS]);
+        }
         if (start_label == 1) {
-            rc = cc_rounds(R, round_id == 1 ? 12 : 16, round_id, cur);   // (an empty round costs a few microseconds)
+            rc = cc_rounds(R, round_id == 1 ? 12 : (debug ? 1 : 16), round_id, cur);   // (an empty round costs a few microseconds)
             if (rc) return rc;
         }
         // (same band as cc_phase_a marks: the outer third of an open upper halo)
