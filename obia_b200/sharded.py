@@ -145,8 +145,9 @@ class ShardedSlic:
         sig = np.ravel(np.asarray(sigma, dtype=np.float32))
         self.sigma_y, self.sigma_x = (float(sig[0]), float(sig[0])) if sig.size == 1 else (float(sig[-2]), float(sig[-1]))
         self.smooth = self.sigma_y > 0 or self.sigma_x > 0
-        if slic_zero or spacing is not None:
-            raise NotImplementedError("slic_zero / spacing are not implemented on the sharded path")
+        if spacing is not None:
+            raise NotImplementedError("anisotropic spacing is not implemented on the B200 path")
+        self.slic_zero = bool(slic_zero)
         if start_label not in (0, 1):
             raise ValueError("start_label should be 0 or 1.")
         self.lib = _lib.load()
@@ -210,6 +211,7 @@ class ShardedSlic:
                                                      self.step_y, self.step_x)
         nbytes = self.lib.obia_b200_slic_workspace_bytes(self.H, self.W, self.Cf, self.n, self.step_y, self.step_x)
         self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.dev)
+        self._maxdc_tail = (self.n * 4 + 255) // 256 * 256      # workspace layout: ..., maxdc [n] float32 (256-byte blocks)
         self.labels = torch.empty((self.h, self.W), dtype=torch.int32, device=self.dev)
         self.status = torch.zeros((4,), dtype=torch.int32, device=self.dev)
         _lib.check(self.lib.obia_b200_slic_begin(_p(self.labels), _p(self.ws), self.h, self.W, self.H, self.Cf, self.n,
@@ -254,8 +256,18 @@ class ShardedSlic:
         sweep = self.lib.obia_b200_slic_sweep if self.exact else self.lib.obia_b200_slic_sweep_fast
         _lib.check(sweep(
             _p(self.feats), None, _p(self.centres), _p(self.labels), _p(self.ws), self.h, self.W, self.pitch, self.Cf,
-            self.n, self.step, self.step_y, self.step_x, self.start_label, 0, 0, self.fix_scale, self.row0, self.H,
-            _p(self.status), _stream_ptr()), "slic_sweep")
+            self.n, self.step, self.step_y, self.step_x, self.start_label, 0, int(self.slic_zero), self.fix_scale,
+            self.row0, self.H, _p(self.status), _stream_ptr()), "slic_sweep")
+
+    def maxdc(self):
+        """SLICO: the per-centre running maxima of the colour distance (float32 view (n,), the last table
+        of the workspace); the strips' tables are combined with an element-wise maximum."""
+        return self.ws[self.ws.numel() - self._maxdc_tail:][: self.n * 4].view(torch.float32)
+
+    def update_max_color(self):
+        _lib.check(self.lib.obia_b200_slic_update_max_color(
+            _p(self.feats), None, _p(self.centres), _p(self.labels), _p(self.ws), self.h, self.W, self.H, self.pitch,
+            self.Cf, self.n, self.step_y, self.step_x, self.start_label, _stream_ptr()), "slic_update_max_color")
 
     def acc(self):
         """This strip's centre sums: int64 view (n, 3 + Cf) of the head of the workspace."""
@@ -461,6 +473,24 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
                         d += b
             for s in strips:
                 s.finish_sweep(check_bands=(mode == "band" and comm.world > 1))
+            if strips[0].slic_zero:
+                # SLICO: every strip raises the maxima of the centres its pixels belong to; the band
+                # centres take the larger of the two ranks' values (max is exact and order-free)
+                for s in strips:
+                    s.update_max_color()
+                if comm.world > 1 and mode == "allreduce":
+                    comm.all_reduce([s.maxdc() for s in strips], "max")
+                elif comm.world > 1:
+                    up = [s.maxdc()[s.band_up[0]:s.band_up[1]] if s.top_open else None for s in strips]
+                    down = [s.maxdc()[s.band_down[0]:s.band_down[1]] if s.bottom_open else None for s in strips]
+                    like_u = [None if u is None else (tuple(u.shape), u.dtype) for u in up]
+                    like_d = [None if d is None else (tuple(d.shape), d.dtype) for d in down]
+                    ru, rd = comm.neighbour_exchange(up, down, like_u, like_d)
+                    for u, d, a, b in zip(up, down, ru, rd):
+                        if a is not None:
+                            torch.maximum(u, a, out=u)
+                        if b is not None:
+                            torch.maximum(d, b, out=d)
         st = [s.status.clone() for s in strips]
         comm.all_reduce(st, "max")
         flags = st[0].cpu().tolist()

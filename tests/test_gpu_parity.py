@@ -1010,6 +1010,21 @@ def test_sharded_with_gaussian_presmoothing():
     assert torch.equal(torch.cat(res.labels, dim=0), ref.labels) and res.n_labels == ref.n_labels
 
 
+@pytest.mark.parametrize("exchange", ["band", "allreduce"])
+def test_sharded_slic_zero(exchange):
+    """SLICO on strips: the per-centre colour-distance maxima are combined with an element-wise maximum
+    (band exchange with the neighbour, or all-reduce of the table)."""
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    H, W, C = 384 * 2 + 100, 280, 5
+    raw = _cuda(synth_raster(H, W, C, seed=33))
+    kw = dict(n_segments=900, compactness=0.5, max_num_iter=6, slic_zero=True)
+    ref = pipeline.slic_labels(raw, None, **kw)
+    strips, res = _run_local_shards(raw, 2, kw, stats=False, exchange=exchange)
+    assert res.mode["exchange"] == exchange
+    assert torch.equal(torch.cat(res.labels, dim=0), ref.labels) and res.n_labels == ref.n_labels
+
+
 def test_sharded_band_fallback_when_centres_leave_their_band():
     """band_steps too small for the drift: obia_b200_slic_band_check raises the flag and the driver
     repeats the run with the whole-table all-reduce -- same labels as the single-GPU run."""
