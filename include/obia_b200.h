@@ -257,6 +257,22 @@ int obia_b200_slic_update_max_color(const float *features, const uint8_t *mask, 
                                     int64_t H_total, int64_t pitch, int32_t Cf, int64_t n,
                                     int32_t step_y, int32_t step_x, int32_t start_label, void *stream);
 
+/* method="quickshift": replaces `skimage.segmentation.quickshift(img_to_segment, **kwargs)`
+ * (obia/segmentation/segment_boundaries.py:48-49; scikit-image's `_quickshift_cython`): density of every
+ * pixel over its clipped (2w+1)^2 window, w = ceil(3 * kernel_size) (float32 distances, double exp, float32
+ * running sum, row-major order), + `noise`; parent = window pixel of strictly higher density at the smallest
+ * distance, cut at `max_dist`; labels = raster-order rank of every pixel's root, 0..n-1.
+ *   features  [Cf][H][pitch] float32 from obia_b200_slic_features (imin = 0, imax = 1: no global rescale;
+ *             to_lab = convert2lab; ratio = quickshift's `ratio`), smoothed first when sigma > 0
+ *   noise     [H][W] float64: numpy `default_rng(rng).normal(scale=1e-5, size=(H, W))`, drawn on the host
+ *   labels    [H][W] int32 out
+ *   n_labels_host  optional out (synchronises the stream when given)
+ * workspace: obia_b200_quickshift_workspace_bytes(H, W). */
+int64_t obia_b200_quickshift_workspace_bytes(int64_t H, int64_t W);
+int obia_b200_quickshift(const float *features, const double *noise, int32_t *labels, void *workspace,
+                         int64_t H, int64_t W, int64_t pitch, int32_t Cf, float kernel_size, float max_dist,
+                         int64_t *n_labels_host, void *stream);
+
 /* ---------------------------------------------------------------- K3 ----
  * Enforce connectivity: replaces Cython `_enforce_label_connectivity_cython`
  * (sequential raster-scan BFS) reached from segment_boundaries.py:51.

@@ -50,6 +50,8 @@ SIGNATURES = {
     "obia_b200_slic_update_max_color": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32,
                                                        _i64, _i32, _i32, _i32, _vp]),
     "obia_b200_slic_finish_sweep": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _i64, _i32, _i32, _f64, _vp]),
+    "obia_b200_quickshift_workspace_bytes": (_i64, [_i64, _i64]),
+    "obia_b200_quickshift": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _f32, _vp, _vp]),
     "obia_b200_connectivity_workspace_bytes": (_i64, [_i64, _i64]),
     "obia_b200_enforce_connectivity": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp,
                                                       _vp]),

@@ -362,6 +362,61 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
                       pre_connectivity=pre_cc, features=feats if keep_intermediates else None)
 
 
+def quickshift_labels(raw, segmentation_bands=None, *, ratio=1.0, kernel_size=5, max_dist=10, return_tree=False,
+                      sigma=0, convert2lab=True, rng=42, random_seed=None, channel_axis=-1):
+    """`skimage.segmentation.quickshift` on `raw[:, :, segmentation_bands]` with obia's wrapper semantics
+    (segment_boundaries.py:31-49: every band min-max normalised first).  kwargs are scikit-image's
+    (`random_seed` is the pre-0.21 name of `rng`).  Returns (labels (H, W) int32 on the device, 0..n-1; n)."""
+    lib = _lib.load()
+    _require_cuda(raw, "raw", torch.float32)
+    raw = _aligned(raw)
+    if channel_axis not in (-1, 2):
+        raise NotImplementedError("only channel_axis=-1 (obia always passes H, W, C)")
+    if return_tree:
+        raise NotImplementedError("return_tree=True returns a tuple obia's create_segments cannot use")
+    if random_seed is not None:
+        rng = random_seed
+    H, W, C = (int(v) for v in raw.shape)
+    dev = raw.device
+    bands = list(range(C)) if segmentation_bands is None else [int(b) for b in segmentation_bands]
+    for band in bands:
+        if band >= C or band < 0:
+            raise IndexError(f"Band index {band} out of range. Available bands indices: 0 to {C - 1}.")
+    if convert2lab and len(bands) != 3:
+        raise ValueError("Only RGB images can be converted to Lab space.")
+    if kernel_size < 1:
+        raise ValueError("`kernel_size` should be >= 1.")
+    minmax, flags = band_minmax(raw)
+    mm = minmax.cpu().numpy()
+    Cf = len(bands)
+    pitch = (W + 31) // 32 * 32
+    feats = torch.empty((Cf, H, pitch), dtype=torch.float32, device=dev)
+    bmin = np.ascontiguousarray(mm[:, 0], dtype=np.float32)
+    bmax = np.ascontiguousarray(mm[:, 1], dtype=np.float32)
+    smooth = float(sigma) > 0
+    f32 = np.float32
+    _lib.check(lib.obia_b200_slic_features(
+        _p(raw), H, W, C, _i32_array(bands), Cf, bmin.ctypes.data_as(ctypes.c_void_p),
+        bmax.ctypes.data_as(ctypes.c_void_p), 0.0, 1.0, int(bool(convert2lab)), 1.0 if smooth else float(f32(ratio)),
+        _p(feats), pitch, _stream_ptr()), "slic_features")
+    if smooth:
+        w, r = slic_host.gaussian_taps(f32(sigma))
+        out = torch.empty_like(feats)
+        tmp = torch.empty_like(feats) if r > 63 else torch.empty((4,), dtype=torch.float32, device=dev)
+        _lib.check(lib.obia_b200_gaussian_planar(
+            _p(feats), _p(tmp), _p(out), H, W, pitch, Cf, w.ctypes.data_as(ctypes.c_void_p), r,
+            w.ctypes.data_as(ctypes.c_void_p), r, float(f32(ratio)), _stream_ptr()), "gaussian_planar")
+        feats = out
+    # tie-breaking noise of `_quickshift_cython`: numpy's Generator stream, drawn on the host
+    noise = torch.from_numpy(np.random.default_rng(rng).normal(scale=0.00001, size=(H, W))).to(dev)
+    labels = torch.empty((H, W), dtype=torch.int32, device=dev)
+    ws = torch.empty((lib.obia_b200_quickshift_workspace_bytes(H, W),), dtype=torch.uint8, device=dev)
+    n = ctypes.c_int64(0)
+    _lib.check(lib.obia_b200_quickshift(_p(feats), _p(noise), _p(labels), _p(ws), H, W, pitch, Cf, float(kernel_size),
+                                        float(max_dist), ctypes.byref(n), _stream_ptr()), "quickshift")
+    return labels, int(n.value)
+
+
 def enforce_connectivity(labels, min_size, max_size, start_label=1):
     """K3 on its own: (labels_out int32 (H, W), number of kept segments)."""
     lib = _lib.load()

@@ -215,12 +215,35 @@ def frame_from_labels(labels, start_label, n_labels, connected, image=None, poly
     return gdf
 
 
+def _create_segments_quickshift(image, segmentation_bands, mutate_image, polygonize, kwargs):
+    """`method="quickshift"` (segment_boundaries.py:48-49): same normalisation side effect and band
+    validation as the slic branch, then `skimage.segmentation.quickshift(img, **kwargs)` on the GPU
+    (csrc/quickshift.cu).  Labels start at 0; one table row per 4-connected region of a label, in
+    ascending label order, like `np.unique` + `rasterio.features.shapes` (:59-70)."""
+    from .. import pipeline
+    raw = image.device_raw()
+    num_bands = int(raw.shape[2])
+    if segmentation_bands is None:
+        segmentation_bands = list(range(num_bands))
+    if mutate_image:
+        minmax, _ = pipeline.band_minmax(raw)
+        _apply_image_mutation(image, raw, minmax)
+    for band in segmentation_bands:
+        if band >= num_bands or band < 0:
+            raise IndexError(f"Band index {band} out of range. Available bands indices: 0 to {num_bands - 1}.")
+    labels, n = pipeline.quickshift_labels(raw, segmentation_bands, **kwargs)
+    gdf = frame_from_labels(labels, 0, n, connected=False, image=image, polygonize=polygonize)
+    gdf.slic_result = None
+    gdf._pending_mutation = None
+    return gdf
+
+
 def create_segments(image, segmentation_bands=None, method="slic", *, mutate_image=True,
                     polygonize=False, _defer_mutation_sync=False, **kwargs):
     """
     :param image: Image (obia_b200.handlers.geotif.Image) -- `img_data` (H, W, C) float32.
     :param segmentation_bands: band indices used for segmentation (None = all).
-    :param method: 'slic' (the GPU hot path).  'quickshift' is not implemented.
+    :param method: 'slic' (the GPU hot path) or 'quickshift'.
     :param mutate_image: reproduce the reference's in-place normalisation of `image.img_data`.
     :param polygonize: also build the polygon geometries on the host (optional; utils/polygonize.py).
     :param kwargs: skimage.segmentation.slic keyword arguments.
@@ -229,7 +252,7 @@ def create_segments(image, segmentation_bands=None, method="slic", *, mutate_ima
     from .. import pipeline
 
     if method == "quickshift":
-        raise NotImplementedError("method='quickshift' is not part of the B200 hot path")
+        return _create_segments_quickshift(image, segmentation_bands, mutate_image, polygonize, kwargs)
     if method != "slic":
         raise Exception('An unknown segmentation method was requested.')
 

@@ -189,3 +189,45 @@ def test_candidate_overflow_is_a_value_error():
     from obia_b200 import _lib
     assert issubclass(_lib.CandidateOverflowError, ValueError) and issubclass(_lib.CandidateOverflowError,
                                                                               _lib.ObiaB200Error)
+
+
+@pytest.mark.parametrize("C,bands,kw", [
+    (3, None, dict(kernel_size=3, max_dist=6)),                                       # Lab path (skimage default)
+    (4, [0, 2], dict(kernel_size=2, max_dist=5, convert2lab=False, ratio=0.5)),
+    (5, None, dict(kernel_size=3, max_dist=8, convert2lab=False, sigma=1.0, rng=7)),
+    (3, None, dict(kernel_size=1, max_dist=2, ratio=0.2, random_seed=3)),
+])
+def test_quickshift_against_the_oracle(C, bands, kw):
+    """method="quickshift" (segment_boundaries.py:48-49): densities, parents and the raster-order root
+    numbering of scikit-image's `_quickshift_cython` as restated in oracle/quickshift_oracle.py."""
+    import quickshift_oracle as qo
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    H, W = 57, 83
+    raw = synth_raster(H, W, C, seed=C, quantize=(C == 3))
+    okw = {("rng" if k == "random_seed" else k): v for k, v in kw.items()}
+    want = qo.create_segments_labels(raw, bands, **okw)
+    got, n = pipeline.quickshift_labels(_cuda(raw), bands, **kw)
+    got = got.cpu().numpy()
+    agree = float((got == want).mean())
+    print(f"quickshift agreement {agree:.5f}, segments gpu={n} oracle={want.max() + 1}")
+    assert agree >= 0.995 and abs(n - (want.max() + 1)) <= max(1, 0.01 * n)
+
+
+def test_create_segments_quickshift_table():
+    from obia_b200.handlers.geotif import Image
+    from obia_b200.segmentation.segment_boundaries import create_segments
+    from gpu_helpers import synth_raster
+    raw = synth_raster(60, 70, 3, seed=5, quantize=True)
+    img = Image(raw.copy(), "EPSG:32702", [1, 0, 0, -1, 0, 0], None, None)
+    segs = create_segments(img, None, "quickshift", kernel_size=3, max_dist=6, ratio=0.5)
+    assert list(segs["segment_id"]) == list(range(1, len(segs) + 1)) and len(segs) >= 2
+    assert (np.diff(np.asarray(segs.segment_labels)) >= 0).all()
+    want = raw.copy()
+    for c in range(3):
+        want[:, :, c] = (raw[:, :, c] - raw[:, :, c].min()) / (raw[:, :, c].max() - raw[:, :, c].min())
+    np.testing.assert_array_equal(img.img_data, want)          # the in-place normalisation side effect
+    with pytest.raises(ValueError, match="Lab"):
+        create_segments(Image(raw[:, :, :2].copy(), "EPSG:32702", [1, 0, 0, -1, 0, 0], None, None), None, "quickshift")
+    with pytest.raises(Exception, match="unknown segmentation method"):
+        create_segments(img, None, "watershed")
