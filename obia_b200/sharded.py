@@ -140,8 +140,12 @@ class ShardedSlic:
                  max_size_factor=3, slic_zero=False, start_label=1, mask=None, spacing=None, exact=False):
         self.exact = bool(exact)
         _require_cuda(raw_strip, "raw_strip", torch.float32)
+        self.mask = None
         if mask is not None:
-            raise NotImplementedError("sharded global SLIC supports unmasked rasters (use the tiled driver for masks)")
+            m = mask if isinstance(mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(mask)))
+            self.mask = (m != 0).to(device=raw_strip.device, dtype=torch.uint8).contiguous()
+            if tuple(self.mask.shape) != tuple(raw_strip.shape[:2]):
+                raise ValueError("image and mask should have the same shape.")
         sig = np.ravel(np.asarray(sigma, dtype=np.float32))
         self.sigma_y, self.sigma_x = (float(sig[0]), float(sig[0])) if sig.size == 1 else (float(sig[-2]), float(sig[-1]))
         self.smooth = self.sigma_y > 0 or self.sigma_x > 0
@@ -172,28 +176,51 @@ class ShardedSlic:
 
     # -- step 1: band ranges of this strip, to be min/max-reduced over the strips ----------------
     def local_minmax(self):
-        mm, fl = pipeline.band_minmax(self.raw)
-        return mm, fl          # (C, 4) float32: min, max, ., . ; (C,) int32 flags
+        mm, fl = pipeline.band_minmax(self.raw, self.mask)
+        return mm, fl          # (C, 4) float32: min, max, masked min, masked max ; (C,) int32 flags
 
     # -- step 2: features + replicated centres -----------------------------------------------------
-    def prepare(self, minmax_global, flags_global, band_steps=4):
+    def prepare(self, minmax_global, flags_global, band_steps=4, mask_init=None):
+        """`mask_init` = (yx (n, 2) float64, steps (3,), number of mask pixels) of the WHOLE mask
+        (pipeline.mask_centroids_device on the gathered mask: identical on every rank)."""
         mm = minmax_global.cpu().numpy()
         fl = flags_global.cpu().numpy()
         f32 = np.float32
-        for b in self.bands:
-            if fl[b] or not np.isfinite(mm[b, 0]) or not np.isfinite(mm[b, 1]) or mm[b, 1] == mm[b, 0]:
-                raise ValueError("unmasked NaN values in image are not supported")
-        starts, isteps = slic_host.regular_grid_steps((1, self.H, self.W), self.n_segments)
-        sy, sx = isteps[1] or 1, isteps[2] or 1
-        ys = torch.arange(starts[1], self.H, sy, device=self.dev, dtype=torch.float32)
-        xs = torch.arange(starts[2], self.W, sx, device=self.dev, dtype=torch.float32)
-        self.ny, self.nx = int(ys.numel()), int(xs.numel())
-        self.n = self.ny * self.nx
-        self.step = float(max(1.0 if s is None else float(s) for s in isteps))
-        self.step_y, self.step_x = slic_host.window_steps(self.H, self.W, self.n)
-        self.centres = torch.zeros((self.n, 2 + self.Cf), dtype=torch.float32, device=self.dev)
-        self.centres[:, 0] = ys.repeat_interleave(self.nx)
-        self.centres[:, 1] = xs.repeat(self.ny)
+        imin, imax = f32(0.0), f32(1.0)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            nmin, nmax = [], []
+            for b in self.bands:
+                if fl[b] or not np.isfinite(mm[b, 0]) or not np.isfinite(mm[b, 1]) or mm[b, 1] == mm[b, 0]:
+                    raise ValueError("unmasked NaN values in image are not supported")
+                if self.mask is not None:
+                    # skimage rescales with the range of the MASKED pixels of the normalised bands
+                    d = f32(f32(mm[b, 1]) - f32(mm[b, 0]))
+                    nmin.append(f32(f32(f32(mm[b, 2]) - f32(mm[b, 0])) / d))
+                    nmax.append(f32(f32(f32(mm[b, 3]) - f32(mm[b, 0])) / d))
+            if self.mask is not None:
+                imin, imax = f32(min(nmin)), f32(max(nmax))
+        if self.mask is not None:
+            yx, steps, self.n_mask = mask_init
+            self.n = int(yx.shape[0])
+            self.ny = self.nx = 0
+            self.step = float(max(steps))
+            self.step_y, self.step_x = slic_host.window_steps(self.H, self.W, self.n)
+            c0 = np.zeros((self.n, 2 + self.Cf), dtype=np.float32)
+            c0[:, :2] = yx.astype(np.float32)
+            self.centres = torch.from_numpy(c0).to(self.dev)
+            starts, sy = (0, 0, 0), 1
+        else:
+            starts, isteps = slic_host.regular_grid_steps((1, self.H, self.W), self.n_segments)
+            sy, sx = isteps[1] or 1, isteps[2] or 1
+            ys = torch.arange(starts[1], self.H, sy, device=self.dev, dtype=torch.float32)
+            xs = torch.arange(starts[2], self.W, sx, device=self.dev, dtype=torch.float32)
+            self.ny, self.nx = int(ys.numel()), int(xs.numel())
+            self.n = self.ny * self.nx
+            self.step = float(max(1.0 if s is None else float(s) for s in isteps))
+            self.step_y, self.step_x = slic_host.window_steps(self.H, self.W, self.n)
+            self.centres = torch.zeros((self.n, 2 + self.Cf), dtype=torch.float32, device=self.dev)
+            self.centres[:, 0] = ys.repeat_interleave(self.nx)
+            self.centres[:, 1] = xs.repeat(self.ny)
         ratio = f32(1.0 / self.compactness)
         self.pitch = (self.W + 31) // 32 * 32
         self.feats = torch.empty((self.Cf, self.h, self.pitch), dtype=torch.float32, device=self.dev)
@@ -203,7 +230,7 @@ class ShardedSlic:
         # order); the driver exchanges the rows the Gaussian reaches across the strip boundaries
         _lib.check(self.lib.obia_b200_slic_features(
             _p(self.raw), self.h, self.W, self.C, _i32_array(self.bands), len(self.bands),
-            bmin.ctypes.data_as(ctypes.c_void_p), bmax.ctypes.data_as(ctypes.c_void_p), 0.0, 1.0,
+            bmin.ctypes.data_as(ctypes.c_void_p), bmax.ctypes.data_as(ctypes.c_void_p), float(imin), float(imax),
             int(self.to_lab), 1.0 if self.smooth else float(ratio), _p(self.feats), self.pitch, _stream_ptr()),
             "slic_features")
         self.ratio = float(ratio)
@@ -214,17 +241,24 @@ class ShardedSlic:
         self._maxdc_tail = (self.n * 4 + 255) // 256 * 256      # workspace layout: ..., maxdc [n] float32 (256-byte blocks)
         self.labels = torch.empty((self.h, self.W), dtype=torch.int32, device=self.dev)
         self.status = torch.zeros((4,), dtype=torch.int32, device=self.dev)
-        _lib.check(self.lib.obia_b200_slic_begin(_p(self.labels), _p(self.ws), self.h, self.W, self.H, self.Cf, self.n,
-                                                 self.step_y, self.step_x, self.start_label, _p(self.status),
-                                                 _stream_ptr()), "slic_begin")
+        self.begin()
         # centre-index bands at the strip boundaries: grid rows within `band_steps` steps of the boundary
+        # (masked runs place their centres by k-means, not on a grid: they exchange the whole table)
         def band(yb):
+            if self.mask is not None:
+                return (0, 0)
             lo = int(np.ceil((yb - band_steps * sy - starts[1]) / sy))
             hi = int(np.floor((yb + band_steps * sy - starts[1]) / sy))
             lo, hi = max(lo, 0), min(hi, self.ny - 1)
             return (lo * self.nx, (hi + 1) * self.nx) if hi >= lo else (0, 0)
         self.band_up = band(self.row0) if self.top_open else (0, 0)
         self.band_down = band(self.row0 + self.h) if self.bottom_open else (0, 0)
+
+    def begin(self):
+        """Start of a run of sweeps (`_slic_cython` entry): labels = mask label, sums and maxima reset."""
+        _lib.check(self.lib.obia_b200_slic_begin(_p(self.labels), _p(self.ws), self.h, self.W, self.H, self.Cf, self.n,
+                                                 self.step_y, self.step_x, self.start_label, _p(self.status),
+                                                 _stream_ptr()), "slic_begin")
 
     # -- step 2b (sigma > 0): Gaussian over the strip extended by the neighbours' feature rows -----------
     def smooth_radius(self):
@@ -252,12 +286,12 @@ class ShardedSlic:
         self.feats = out[:, top:top + self.h].contiguous()
 
     # -- step 3 (x max_num_iter): sweep -> combine acc over strips -> finish ---------------------------
-    def sweep(self):
+    def sweep(self, ignore_color=False):
         sweep = self.lib.obia_b200_slic_sweep if self.exact else self.lib.obia_b200_slic_sweep_fast
         _lib.check(sweep(
-            _p(self.feats), None, _p(self.centres), _p(self.labels), _p(self.ws), self.h, self.W, self.pitch, self.Cf,
-            self.n, self.step, self.step_y, self.step_x, self.start_label, 0, int(self.slic_zero), self.fix_scale,
-            self.row0, self.H, _p(self.status), _stream_ptr()), "slic_sweep")
+            _p(self.feats), _p(self.mask), _p(self.centres), _p(self.labels), _p(self.ws), self.h, self.W, self.pitch,
+            self.Cf, self.n, self.step, self.step_y, self.step_x, self.start_label, int(ignore_color),
+            int(self.slic_zero), self.fix_scale, self.row0, self.H, _p(self.status), _stream_ptr()), "slic_sweep")
 
     def maxdc(self):
         """SLICO: the per-centre running maxima of the colour distance (float32 view (n,), the last table
@@ -266,7 +300,7 @@ class ShardedSlic:
 
     def update_max_color(self):
         _lib.check(self.lib.obia_b200_slic_update_max_color(
-            _p(self.feats), None, _p(self.centres), _p(self.labels), _p(self.ws), self.h, self.W, self.H, self.pitch,
+            _p(self.feats), _p(self.mask), _p(self.centres), _p(self.labels), _p(self.ws), self.h, self.W, self.H, self.pitch,
             self.Cf, self.n, self.step_y, self.step_x, self.start_label, _stream_ptr()), "slic_update_max_color")
 
     def acc(self):
@@ -284,7 +318,7 @@ class ShardedSlic:
                 "slic_band_check")
 
     def sizes(self):
-        seg = float(self.H * self.W) / self.n
+        seg = float(self.n_mask if self.mask is not None else self.H * self.W) / self.n
         return int(self.min_size_factor * seg), int(self.max_size_factor * seg)
 
     def default_halo(self):
@@ -429,16 +463,40 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
             ev.append((name, e))
 
     mark("start")
+    masked = strips[0].mask is not None
     mms = [s.local_minmax() for s in strips]
     lo = [m[0][:, 0].clone() for m in mms]
     hi = [m[0][:, 1].clone() for m in mms]
+    mlo = [torch.nan_to_num(m[0][:, 2], nan=float("inf")) for m in mms]     # masked range (NaN: no mask pixel here)
+    mhi = [torch.nan_to_num(m[0][:, 3], nan=float("-inf")) for m in mms]
     fl = [m[1] for m in mms]
     comm.all_reduce(lo, "min")
     comm.all_reduce(hi, "max")
     comm.all_reduce(fl, "max")
+    mask_init = [None] * len(strips)
+    if masked:
+        comm.all_reduce(mlo, "min")
+        comm.all_reduce(mhi, "max")
+        # maskSLIC initialisation needs the whole mask (RandomState(123) sample of its pixels + k-means):
+        # 1 byte per pixel is gathered and every rank derives the same centres
+        rows_m = [h for _, h in split_rows(strips[0].H, comm.world)] if comm.world > 1 else [strips[0].h]
+        hmax = max(rows_m)
+        pads = []
+        for s in strips:
+            pad = torch.zeros((hmax, s.W), dtype=torch.uint8, device=s.dev)
+            pad[:s.h] = s.mask
+            pads.append(pad)
+        gathered = comm.all_gather(pads)
+        for i, (s, g) in enumerate(zip(strips, gathered)):
+            full = torch.cat([t[:h] for t, h in zip(g, rows_m)], dim=0).contiguous()
+            if i == 0 or len(strips) == 1:
+                init = pipeline.mask_centroids_device(full, int(s.n_segments))
+            mask_init[i] = init
+            del full
+
     def prepare_all():
         for i, s in enumerate(strips):
-            s.prepare(torch.stack([lo[i], hi[i], lo[i], hi[i]], dim=1), fl[i])
+            s.prepare(torch.stack([lo[i], hi[i], mlo[i], mhi[i]], dim=1), fl[i], mask_init=mask_init[i])
         if strips[0].smooth:
             r = strips[0].smooth_radius()
             if any(s.h < r for s in strips):
@@ -454,10 +512,10 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
     prepare_all()
     mark("preprocess")
 
-    def slic(mode):
+    def slic(mode, ignore_color=False):
         for it in range(strips[0].max_num_iter):
             for s in strips:
-                s.sweep()
+                s.sweep(ignore_color)
             if mode == "allreduce" or comm.world == 1:
                 comm.all_reduce([s.acc() for s in strips], "sum")
             else:
@@ -498,7 +556,11 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
             raise _lib.ObiaB200Error("slic_sweep: a tile collected more than 1024 candidate centres")
         return flags[1]
 
-    mode = exchange
+    mode = "allreduce" if masked else exchange
+    if masked:
+        slic(mode, ignore_color=True)     # maskSLIC step 2: spatial-only k-means moves the centres first
+        for s in strips:
+            s.begin()
     if slic(mode):
         # a centre left its band: redo with the whole table (prepare() resets centres, labels, sums)
         mode = "allreduce"
@@ -560,6 +622,9 @@ def run_sharded(strips, comm, statistics_bands=None, exchange="band", halo=None,
             kcores = None
     mark("connectivity")
 
+    if masked:
+        for s in strips:
+            s.final.masked_fill_(s.mask == 0, -1)      # segment_boundaries.py:55-57
     res.labels = [s.final for s in strips]
     if stats:
         if kcores is None:

@@ -1010,6 +1010,32 @@ def test_sharded_with_gaussian_presmoothing():
     assert torch.equal(torch.cat(res.labels, dim=0), ref.labels) and res.n_labels == ref.n_labels
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_masked_slic(world):
+    """maskSLIC on strips: the mask is gathered (1 byte per pixel) so that every rank derives the same
+    k-means initialisation; the spatial-only pass and the colour pass all-reduce the whole centre table."""
+    from obia_b200 import pipeline
+    from gpu_helpers import synth_raster
+    H, W, C = 384 * world + 60, 300, 4
+    raw = _cuda(synth_raster(H, W, C, seed=40 + world))
+    yy, xx = np.mgrid[:H, :W]
+    mask = ((yy - H / 2) ** 2 / (0.47 * H) ** 2 + (xx - 140) ** 2 / 150.0 ** 2) < 1.0
+    mask[H // 2 - 20:H // 2 + 20, 100:130] = False
+    kw = dict(n_segments=700, compactness=0.3, max_num_iter=5)
+    ref = pipeline.slic_labels(raw, None, mask=_cuda(mask.astype(np.uint8)), **kw)
+    ref_stats = pipeline.zonal_stats(ref.labels, raw, None, max_label=ref.n_labels + 1)
+    from obia_b200.sharded import LocalComm, ShardedSlic, run_sharded, split_rows
+    m = _cuda(mask.astype(np.uint8))
+    strips = [ShardedSlic(raw[r0:r0 + h].contiguous(), r0, H, None, mask=m[r0:r0 + h].contiguous(), **kw)
+              for r0, h in split_rows(H, world)]
+    res = run_sharded(strips, LocalComm(world))
+    assert res.mode["exchange"] == "allreduce"
+    got = torch.cat(res.labels, dim=0)
+    assert torch.equal(got, ref.labels) and res.n_labels == ref.n_labels
+    assert bool((got[~m.bool()] == -1).all())
+    _check_sharded_against_single(res, ref, ref_stats, 1)
+
+
 @pytest.mark.parametrize("exchange", ["band", "allreduce"])
 def test_sharded_slic_zero(exchange):
     """SLICO on strips: the per-centre colour-distance maxima are combined with an element-wise maximum
@@ -1038,7 +1064,7 @@ def test_sharded_band_fallback_when_centres_leave_their_band():
     strips = [ShardedSlic(raw[r0:r0 + h].contiguous(), r0, H, None, **kw) for r0, h in split_rows(H, 3)]
     orig = ShardedSlic.prepare
     try:
-        ShardedSlic.prepare = lambda self, mm, fl, band_steps=0: orig(self, mm, fl, band_steps=0)
+        ShardedSlic.prepare = lambda self, mm, fl, band_steps=0, mask_init=None: orig(self, mm, fl, band_steps=0, mask_init=mask_init)
         res = run_sharded(strips, LocalComm(3))
     finally:
         ShardedSlic.prepare = orig
