@@ -404,6 +404,72 @@ int obia_b200_texture_stats(const int32_t *labels, const float *raw, int64_t H,
                             int32_t quantise_f64, double *features,
                             void *workspace, void *stream);
 
+/* ------------------------------------------------------ tiled driver ----
+ * `create_tiled_segments` (obia/utils/tiling.py:62-291) with every window of a BATCH -- all black tiles of a
+ * chunk (:103-153) or all white windows of one tile-row (:156-287), which are independent of each other --
+ * handled by one launch per stage instead of one Python iteration per tile.  The windows of a batch are
+ * stacked into a SLAB: window i occupies slab rows [i * win_rows, i * win_rows + h_i), columns [0, w_i);
+ * win_rows = max h + 1 leaves one masked row between windows.  `descs` is a device array of B window
+ * descriptors (136 bytes each, layout in obia_b200/csrc/batch.cuh == numpy dtype WIN_DESC in
+ * obia_b200/batch.py).  Every entry is the batched form of the single-raster entry named beside it and gives,
+ * inside each window, exactly that entry's result on the window alone. */
+
+/* obia_b200_band_minmax per window.  raw (H, Wl, C) interleaved float32; out (B, C, 4) = min, max, masked
+ * min, masked max; nonfinite (B, C); mask_counts (B) = mask pixels per window (0 without mask_slab). */
+int obia_b200_window_stats(const float *raw, int64_t Wl, int32_t C, const void *descs, int64_t B, int32_t hmax,
+                           const uint8_t *mask_slab, int32_t slab_w, float *out, int32_t *nonfinite,
+                           int32_t *mask_counts, void *stream);
+/* window of a (H, Wm) uint8 mask raster -> slab (tiling.py:121-123: the mask tile of a black tile) */
+int obia_b200_window_mask_copy(const uint8_t *mask, int64_t Wm, const void *descs, int64_t B, int32_t hmax,
+                               int32_t wmax, uint8_t *mask_slab, int32_t slab_w, void *stream);
+/* obia_b200_slic_features per window: bands (device [Cs]); band_min / band_diff (device [B][Cs]); the global
+ * rescale (imin, idiff, rescale) per window from the descriptors; features (Cf, slab_rows, pitch). */
+int obia_b200_window_features(const float *raw, int64_t Wl, int32_t C, const int32_t *bands, int32_t Cs,
+                              const float *band_min, const float *band_diff, const void *descs, int64_t B,
+                              int32_t hmax, int32_t wmax, int32_t to_lab, float ratio, float *features,
+                              int64_t slab_rows, int64_t pitch, void *stream);
+/* maskSLIC initialisation per window (obia_b200_mask_kmeans + obia_b200_nearest_centroid + the `steps` mean):
+ * points_pos / seed_pos = slab pixel positions of coord[idx_dense] / coord[idx]; cwin (n_total) = window of
+ * every centroid.  Writes centroids (n_total, 2) float64, the SLIC centre rows (n_total, 2 + Cf) and, into the
+ * descriptors, sw / inv_w (valid = 0 where the step is not positive: the reference's ValueError). */
+int64_t obia_b200_mask_kmeans_batch_workspace_bytes(int64_t n_total, int64_t km_cells_total);
+int obia_b200_mask_kmeans_batch(const int32_t *points_pos, int64_t m_total, const int32_t *seed_pos,
+                                const int32_t *cwin, void *descs, int64_t B, int64_t n_total,
+                                int64_t km_cells_total, int32_t slab_w, int32_t win_rows, int32_t iters, int32_t Cf,
+                                double *centroids, float *centres, void *workspace, void *stream);
+/* obia_b200_slic_iterate_fast per window.  `prepare` fills the kernel-variant dependent fixed-point fields of
+ * HOST descriptors before upload; status: (4 + B) int32, status[4 + i] != 0 = window i overflowed the
+ * candidate staging (CandidateOverflowError of the single-raster path). */
+int64_t obia_b200_slic_batch_workspace_bytes(int64_t n_total, int64_t cells_total, int32_t Cf);
+int obia_b200_slic_batch_prepare(void *descs_host, int64_t B, int32_t Cf);
+int obia_b200_slic_iterate_batch(const float *features, const uint8_t *mask, float *centres, int32_t *labels,
+                                 void *workspace, const void *descs, const int32_t *cwin, int64_t B,
+                                 int64_t n_total, int64_t cells_total, int32_t hmax, int32_t wmax,
+                                 int64_t slab_rows, int32_t slab_w, int64_t pitch, int32_t Cf, int32_t max_num_iter,
+                                 int32_t start_label, int32_t ignore_color, int32_t *status, void *stream);
+/* obia_b200_enforce_connectivity on the slab with (min_size, max_size) per window (device int32 pairs);
+ * kept pieces are numbered start_label.. in slab raster order, i.e. window by window.
+ * workspace: obia_b200_connectivity_workspace_bytes(H, W). */
+int obia_b200_enforce_connectivity_windows(const int32_t *labels_in, int32_t *labels_out, void *workspace,
+                                           int64_t H, int64_t W, const int32_t *window_sizes, int64_t win_rows,
+                                           int32_t start_label, int64_t *n_labels_host, void *stream);
+/* Segment bookkeeping over a global handle raster G (H, GW) int32, -1 = no segment (tiled.cu).
+ * paint: slab labels of the usable windows -> handles handle_base + (label - start_label) (label 0 of
+ * start_label 1 -> handle_zero + window; the -2 marker of start_label 0 -> first_label[window], the first kept
+ * label of the window, device [B], < 0 when it kept none), pixel counts accumulated into sizes.
+ * white_prepare: tiling.py:182-260 for every white window of a tile-row: segments entirely inside the window
+ * polygon are erased from G (live = 0), segments straddling its edge and the two bottom corner squares are
+ * masked out; the windows' SLIC masks are written into mask_slab. */
+int obia_b200_tiled_paint(const int32_t *labels_slab, const uint8_t *mask_slab, int32_t slab_w, const void *descs,
+                          const uint8_t *usable, const int32_t *first_label, int64_t B, int32_t hmax, int32_t wmax,
+                          int32_t start_label, int32_t handle_base, int32_t handle_zero, int32_t *G, int64_t GW,
+                          int32_t *sizes, void *stream);
+int obia_b200_tiled_white_prepare(int32_t *G, int64_t GW, const void *descs, const uint8_t *parity, int64_t B,
+                                  int32_t hmax, int32_t wmax, int32_t corner, int32_t *counts, int64_t capacity,
+                                  const int32_t *sizes, uint8_t *live, int32_t *any_segment,
+                                  const uint8_t *user_mask, int64_t Wm, uint8_t *mask_slab, int32_t slab_w,
+                                  void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -310,7 +310,8 @@ cc_flatten_kernel(int32_t *T, int32_t *psize, int32_t *roots, int32_t *ctr, int6
 __global__ void __launch_bounds__(256)
 cc_classify_kernel(const int32_t *__restrict__ roots, const int32_t *__restrict__ psize, int32_t *list,
                    int32_t *adj, int32_t *aux, int32_t *stamp, uint32_t *bits, const uint8_t *__restrict__ flag,
-                   int32_t *ctr, int64_t N, int64_t min_size, int64_t max_size)
+                   int32_t *ctr, int64_t N, int64_t min_size, int64_t max_size, const int2 *__restrict__ wsizes,
+                   int win_px)
 {
     const int n_roots = ctr[CTR_NROOTS];
     const int lane = threadIdx.x & 31;
@@ -323,6 +324,11 @@ cc_classify_kernel(const int32_t *__restrict__ roots, const int32_t *__restrict_
         if (e < n_roots) {
             i = roots[e];
             sz = psize[i];
+            if (wsizes) {   // slab of windows (tiled driver): the sizes of the window the component lies in
+                const int2 ws = wsizes[i / win_px];
+                min_size = ws.x;
+                max_size = ws.y;
+            }
             // Strip mode: a component cut by an open strip edge is unknown anyway (FLAG_CUT: every result
             // that depends on it is reported incomplete).  It is booked as ONE kept piece -- the fragments
             // along an edge row would otherwise form long chains of "small pieces without an earlier
@@ -366,11 +372,17 @@ __device__ __forceinline__ bool nbr(int dir, int py, int px, int H, int W, int32
 __global__ void __launch_bounds__(128)
 cc_split_kernel(const int32_t *__restrict__ lab, int32_t *T, int32_t *psize, int32_t *queue, int32_t *list,
                 int32_t *adj, int32_t *aux, int32_t *stamp, uint32_t *bits, uint8_t *flag, int32_t *ctr,
-                uint8_t *visit, int64_t N, int H, int W, int64_t min_size, int64_t max_size)
+                uint8_t *visit, int64_t N, int H, int W, int64_t min_size, int64_t max_size,
+                const int2 *__restrict__ wsizes, int win_px)
 {
     const int n_over = ctr[CTR_NOVER];
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_over; e += gridDim.x * blockDim.x) {
         const int32_t r = list[N - 1 - e];
+        if (wsizes) {
+            const int2 ws = wsizes[r / win_px];
+            min_size = ws.x;
+            max_size = ws.y;
+        }
         const int32_t L = lab[r];
         const int32_t n = psize[r];
         const uint8_t cut = flag ? (flag[r] & FLAG_CUT) : 0;
@@ -443,7 +455,18 @@ struct CcParams {
     int64_t min_size, max_size;
     int32_t mask_label, start_label;
     int32_t optimistic;   // round 1: every piece counts as labelled from its own start pixel
+    const int2 *wsizes;   // slab of windows (tiled driver): (min_size, max_size) per window, else NULL
+    int32_t win_px;       // pixels per window block of the slab
 };
+
+__device__ __forceinline__ int64_t min_size_at(const CcParams &P, int32_t p)
+{
+    return P.wsizes ? (int64_t)P.wsizes[p / P.win_px].x : P.min_size;
+}
+__device__ __forceinline__ int64_t max_size_at(const CcParams &P, int32_t p)
+{
+    return P.wsizes ? (int64_t)P.wsizes[p / P.win_px].y : P.max_size;
+}
 
 struct CcArrays {
     const int32_t *lab, *T, *psize, *list;
@@ -467,7 +490,7 @@ __device__ __forceinline__ int32_t label_time(const CcArrays &A, const CcParams 
         else if ((f & FLAG_TFIX_UNKNOWN) && P.start_label == 1) unk = true;
     }
     if (P.optimistic) return tq;     // round 1: merged pieces count as labelled from their start
-    if ((int64_t)A.psize[tq] >= P.min_size) return tq;
+    if ((int64_t)A.psize[tq] >= min_size_at(P, tq)) return tq;
     if (P.start_label == 0) return tq;
     return __ldcg(A.aux + tq);
 }
@@ -481,9 +504,10 @@ __device__ int bfs_piece(const CcArrays &A, int32_t *qu, const CcParams &P, int3
     int cnt = 1, head = 0;
     int32_t adjq = -1;
     int32_t tmin = kTInf;   // earliest scan position at which any examined neighbour is labelled
+    const int64_t max_size = max_size_at(P, t);
     qu[0] = s;
     A.visit[s] = 1;
-    while (head < cnt && (int64_t)cnt < P.max_size) {
+    while (head < cnt && (int64_t)cnt < max_size) {
         const int32_t p = qu[head];
         const int py = p / P.W, px = p % P.W;
         for (int d = 0; d < 4; ++d) {
@@ -494,7 +518,7 @@ __device__ int bfs_piece(const CcArrays &A, int32_t *qu, const CcParams &P, int3
                 if (!A.visit[q]) {
                     A.visit[q] = 1;
                     qu[cnt++] = q;
-                    if ((int64_t)cnt >= P.max_size) break;
+                    if ((int64_t)cnt >= max_size) break;
                 }
             } else {
                 bool unk = false;
@@ -525,7 +549,7 @@ __device__ __forceinline__ void push_dependents(const CcArrays &A, const CcParam
         int32_t q;
         if (!nbr(d, py, px, P.H, P.W, q)) continue;
         const int32_t tq = A.T[q];
-        if (tq < 0 || tq == t || (int64_t)A.psize[tq] >= P.min_size) continue;
+        if (tq < 0 || tq == t || (int64_t)A.psize[tq] >= min_size_at(P, tq)) continue;
         if (atomicExch(A.stamp + tq, round_id) != round_id) dirty_next[atomicAdd(n_next, 1)] = tq;
     }
 }
@@ -541,11 +565,12 @@ __device__ bool small_piece_adjacent(const CcArrays &A, const CcParams &P, int32
     int32_t fix = t;
     int cnt = 1;
     bool unk_any = false, known_before = false;
+    const int64_t max_size = max_size_at(P, t);
     const int32_t *members = qu;   // pixels of the first BFS
     if (n == 1) {
         const int py = t / P.W, px = t % P.W;
         // (with max_size <= 1 the reference's BFS loop never runs: no neighbour is looked at)
-        for (int d = 0; d < 4 && P.max_size > 1; ++d) {
+        for (int d = 0; d < 4 && max_size > 1; ++d) {
             int32_t q;
             if (!nbr(d, py, px, P.H, P.W, q)) continue;
             bool unk = false;
@@ -571,7 +596,7 @@ __device__ bool small_piece_adjacent(const CcArrays &A, const CcParams &P, int32
             for (int i = 0; i < cnt; ++i) cand[i] = qu[i];
             members = cand;
             bool u2 = false, k2 = false;
-            if ((int64_t)n < P.max_size) {
+            if ((int64_t)n < max_size) {
                 // The BFS is not cut by the size cap, so from ANY start it examines every
                 // neighbour of the piece: the first successful re-scan is at the first member
                 // pixel after the earliest labelling time among those neighbours.
@@ -823,7 +848,7 @@ cc_bits_number_kernel(const uint32_t *__restrict__ bits, const int32_t *__restri
 // phase 4d: merged pieces follow their adjacent chain to a kept piece (or to 0, the initial value of
 // `adjacent`); strip mode also records whether anything on the chain is unknown inside the strip
 __global__ void __launch_bounds__(256)
-cc_small_final_kernel(CcArrays A, const uint32_t *__restrict__ bits, int32_t *fin, int max_hops)
+cc_small_final_kernel(CcArrays A, const uint32_t *__restrict__ bits, int32_t *fin, int max_hops, int32_t leftover)
 {
     const int n_small = A.ctr[CTR_NSMALL];
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_small; e += gridDim.x * blockDim.x) {
@@ -839,7 +864,7 @@ cc_small_final_kernel(CcArrays A, const uint32_t *__restrict__ bits, int32_t *fi
                 if (A.flag && (A.flag[t] & (FLAG_CUT | FLAG_ADJ_UNKNOWN))) unk = true;
                 const int32_t a = A.adj[t];
                 if (a < 0) {
-                    r = 0;  // `adjacent` initial value
+                    r = leftover;  // `adjacent` initial value: label 0 (of the window, see the windows entry)
                     done = true;
                     A.ctr[CTR_HASZERO] = 1;   // a leftover piece carries label 0 (benign race: same value)
                 } else {
@@ -961,11 +986,12 @@ int cc_phase_a(CcRun &R, int top_open, int bottom_open, int64_t core_lo, int64_t
         OBIA_LAUNCH_CHECK();
     }
     cc_classify_kernel<<<kNumSMs * 8, 256, 0, st>>>(roots, w.psize, w.list, w.adj, w.aux, w.stamp, w.bits,
-                                                    R.strip ? w.flag : nullptr, w.ctr, N, P0.min_size, P0.max_size);
+                                                    R.strip ? w.flag : nullptr, w.ctr, N, P0.min_size, P0.max_size,
+                                                    P0.wsizes, P0.win_px);
     OBIA_LAUNCH_CHECK();
     cc_split_kernel<<<kNumSMs * 2, 128, 0, st>>>(R.lab, w.T, w.psize, w.queue, w.list, w.adj, w.aux, w.stamp, w.bits,
                                                  R.strip ? w.flag : nullptr, w.ctr, w.visit, N, H, W, P0.min_size,
-                                                 P0.max_size);
+                                                 P0.max_size, P0.wsizes, P0.win_px);
     OBIA_LAUNCH_CHECK();
 
     CcArrays A;
@@ -1029,7 +1055,10 @@ int cc_phase_b(CcRun &R, int32_t label_base, int32_t *out, int64_t p_lo, int64_t
     A.flag = R.strip ? w.flag : nullptr;
     cc_bits_number_kernel<<<(unsigned)w.nchunks, 256, 0, R.st>>>(w.bits, w.chunksum, R.fin, label_base);
     OBIA_LAUNCH_CHECK();
-    cc_small_final_kernel<<<kNumSMs * 4, 256, 0, R.st>>>(A, w.bits, R.fin, max_hops);
+    // slab of windows with start_label 0: "label 0" is the first kept piece of the piece's own WINDOW, which the
+    // caller resolves (marker -2); with start_label 1 it is the mask label 0 everywhere
+    const int32_t leftover = (R.P.wsizes && R.P.start_label == 0) ? -2 : 0;
+    cc_small_final_kernel<<<kNumSMs * 4, 256, 0, R.st>>>(A, w.bits, R.fin, max_hops, leftover);
     OBIA_LAUNCH_CHECK();
     cc_resolve_kernel<<<(unsigned)ceil_div(p_hi - p_lo, 256), 256, 0, R.st>>>(
         w.T, w.bits, R.fin, R.strip ? w.flag : nullptr, out, w.ctr, p_lo, p_hi, R.P.mask_label);
@@ -1039,10 +1068,9 @@ int cc_phase_b(CcRun &R, int32_t label_base, int32_t *out, int64_t p_lo, int64_t
 
 }  // namespace
 
-extern "C" int obia_b200_enforce_connectivity(const int32_t *labels_in, int32_t *labels_out,
-                                              void *workspace, int64_t H, int64_t W, int64_t min_size,
-                                              int64_t max_size, int32_t start_label,
-                                              int64_t *n_labels_host, void *stream)
+static int enforce_connectivity_impl(const int32_t *labels_in, int32_t *labels_out, void *workspace, int64_t H,
+                                     int64_t W, int64_t min_size, int64_t max_size, const int2 *wsizes,
+                                     int64_t win_rows, int32_t start_label, int64_t *n_labels_host, void *stream)
 {
     if (!labels_in || !labels_out || !workspace || H <= 0 || W <= 0)
         return set_err(OBIA_B200_ERR_ARG, "enforce_connectivity: bad argument");
@@ -1059,6 +1087,7 @@ extern "C" int obia_b200_enforce_connectivity(const int32_t *labels_in, int32_t 
     R.st = (cudaStream_t)stream;
     R.P.H = (int)H; R.P.W = (int)W; R.P.min_size = min_size; R.P.max_size = max_size;
     R.P.mask_label = start_label - 1; R.P.start_label = start_label; R.P.optimistic = 0;
+    R.P.wsizes = wsizes; R.P.win_px = (int32_t)std::max<int64_t>(1, win_rows * W);
     int rc = cc_phase_a(R, 0, 0, 0, N);
     if (rc) return rc;
     // Rounds 2.. exist only for start_label 1 (label-0 chains) and are almost always empty: two are
@@ -1102,6 +1131,31 @@ extern "C" int obia_b200_enforce_connectivity(const int32_t *labels_in, int32_t 
     return OBIA_B200_OK;
 }
 
+extern "C" int obia_b200_enforce_connectivity(const int32_t *labels_in, int32_t *labels_out,
+                                              void *workspace, int64_t H, int64_t W, int64_t min_size,
+                                              int64_t max_size, int32_t start_label,
+                                              int64_t *n_labels_host, void *stream)
+{
+    return enforce_connectivity_impl(labels_in, labels_out, workspace, H, W, min_size, max_size, nullptr, 0, start_label,
+                                     n_labels_host, stream);
+}
+
+// Slab of windows (tiled driver, batch.cuh): rows [i * win_rows, (i + 1) * win_rows) belong to window i, whose
+// (min_size, max_size) are window_sizes[i] (device, int32 pairs); windows are separated by mask-label rows, so
+// the result inside every window is the one obia_b200_enforce_connectivity gives on that window alone, with the
+// kept pieces numbered start_label.. in slab raster order (= window by window).  start_label 0: pieces the
+// reference merges into its `adjacent = 0` default (label 0 = the window's FIRST kept piece) are written as -2.
+extern "C" int obia_b200_enforce_connectivity_windows(const int32_t *labels_in, int32_t *labels_out, void *workspace,
+                                                      int64_t H, int64_t W, const int32_t *window_sizes,
+                                                      int64_t win_rows, int32_t start_label,
+                                                      int64_t *n_labels_host, void *stream)
+{
+    if (!window_sizes || win_rows <= 0 || H % win_rows)
+        return set_err(OBIA_B200_ERR_ARG, "enforce_connectivity_windows: bad argument");
+    return enforce_connectivity_impl(labels_in, labels_out, workspace, H, W, 1, 1, (const int2 *)window_sizes, win_rows,
+                                     start_label, n_labels_host, stream);
+}
+
 // ---- strip mode (one raster sharded by row strips across GPUs) ----------------------------------------
 static int cc_strip_setup(CcRun &R, const int32_t *labels_ext, void *workspace, int64_t H_ext, int64_t W,
                           int64_t core_row0, int64_t core_rows, int64_t min_size, int64_t max_size,
@@ -1122,6 +1176,7 @@ static int cc_strip_setup(CcRun &R, const int32_t *labels_ext, void *workspace, 
     R.st = (cudaStream_t)stream;
     R.P.H = (int)H_ext; R.P.W = (int)W; R.P.min_size = min_size; R.P.max_size = max_size;
     R.P.mask_label = start_label - 1; R.P.start_label = start_label; R.P.optimistic = 0;
+    R.P.wsizes = nullptr; R.P.win_px = 1;
     return OBIA_B200_OK;
 }
 

@@ -8,6 +8,7 @@
 // wins ties; `update_cluster_means`: per-cluster sums of the (integer-valued) coordinates divided
 // by the member count, empty clusters keep their previous centroid.  The sums are exact integers,
 // so 64-bit integer atomics reproduce scipy's sequential float64 sums bit for bit.
+#include "batch.cuh"
 #include "common.cuh"
 
 namespace obia {
@@ -185,6 +186,116 @@ __global__ void kmeans_update_kernel(double *cent, unsigned long long *sums, int
     sums[3 * j] = sums[3 * j + 1] = sums[3 * j + 2] = 0ull;
 }
 
+// ---- batched form (tiled driver, batch.cuh): every window of a slab at once ------------------------------
+// Points are slab pixel positions (row * slab_w + column; window = row / win_rows, its rows start at
+// win * win_rows); centroids are window-local float64 (y, x), indexed batch-wide; `head` / `next` hold
+// batch-wide centroid indices, each window owning the cells [km_cell0, km_cell0 + km_ncy * km_ncx).
+__device__ __forceinline__ KmGrid km_grid_of(const WinDesc &d, int32_t *head, int32_t *next)
+{
+    KmGrid g;
+    g.cs = d.km_cs;
+    g.ncy = d.km_ncy;
+    g.ncx = d.km_ncx;
+    g.head = head + d.km_cell0;
+    g.next = next;
+    return g;
+}
+
+__global__ void __launch_bounds__(256)
+km_batch_seed_kernel(const int32_t *__restrict__ seed_pos, const int32_t *__restrict__ cwin,
+                     const WinDesc *__restrict__ batch, int64_t n_total, int slab_w, double *__restrict__ cent)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_total) return;
+    const WinDesc &d = batch[cwin[k]];
+    const int32_t pos = seed_pos[k];
+    cent[2 * k] = (double)(pos / slab_w - d.row0);
+    cent[2 * k + 1] = (double)(pos % slab_w);
+}
+
+__global__ void __launch_bounds__(256)
+km_batch_bin_kernel(const double *__restrict__ cent, const int32_t *__restrict__ cwin, const WinDesc *__restrict__ batch,
+                    int64_t n_total, int32_t *head, int32_t *next)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_total) return;
+    const WinDesc &d = batch[cwin[k]];
+    const int gy = km_cell(cent[2 * k], d.km_cs, d.km_ncy), gx = km_cell(cent[2 * k + 1], d.km_cs, d.km_ncx);
+    next[k] = atomicExch(&head[d.km_cell0 + gy * d.km_ncx + gx], (int32_t)k);
+}
+
+__global__ void __launch_bounds__(256)
+km_batch_assign_kernel(const int32_t *__restrict__ pts_pos, int64_t m_total, const double *__restrict__ cent,
+                       const WinDesc *__restrict__ batch, int slab_w, int win_rows, int32_t *head, int32_t *next,
+                       unsigned long long *__restrict__ sums)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m_total) return;
+    const int32_t pos = pts_pos[i];
+    const int row = pos / slab_w, ix = pos - row * slab_w;
+    const WinDesc &d = batch[row / win_rows];
+    if (!d.valid || d.n <= 0) return;
+    const int iy = row - d.row0;
+    const KmGrid g = km_grid_of(d, head, next);
+    const int bestj = km_nearest<false>((double)iy, (double)ix, -1, cent, g);
+    atomicAdd(&sums[3 * (int64_t)bestj + 0], 1ull);
+    atomicAdd(&sums[3 * (int64_t)bestj + 1], (unsigned long long)(long long)iy);
+    atomicAdd(&sums[3 * (int64_t)bestj + 2], (unsigned long long)(long long)ix);
+}
+
+__global__ void __launch_bounds__(256)
+km_batch_closest_kernel(const double *__restrict__ cent, const int32_t *__restrict__ cwin,
+                        const WinDesc *__restrict__ batch, int64_t n_total, int32_t *head, int32_t *next,
+                        int32_t *__restrict__ closest)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_total) return;
+    const WinDesc &d = batch[cwin[k]];
+    const KmGrid g = km_grid_of(d, head, next);
+    const int j = km_nearest<true>(cent[2 * k], cent[2 * k + 1], (int)k, cent, g);
+    closest[k] = (j == 0x7fffffff) ? d.c0 : j;   // n == 1: argmin of [[inf]] is 0
+}
+
+// `steps = np.abs(centroids - centroids[closest]).mean(0)` (row-sequential float64 sums), `step = max(steps)`,
+// the spatial weight `1.0 / step ** 2` as slic.cu derives it; a window whose step is not positive is dropped
+// (the reference raises ValueError there: an "empty tile").  One thread per window.
+__global__ void __launch_bounds__(128)
+km_batch_steps_kernel(const double *__restrict__ cent, const int32_t *__restrict__ closest, WinDesc *batch, int64_t B)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= B) return;
+    WinDesc &d = batch[w];
+    if (!d.valid) return;
+    double sy = 0.0, sx = 0.0;
+    for (int i = 0; i < d.n; ++i) {
+        const int64_t k = (int64_t)d.c0 + i, j = closest[k];
+        sy = __dadd_rn(sy, fabs(__dsub_rn(cent[2 * k], cent[2 * j])));
+        sx = __dadd_rn(sx, fabs(__dsub_rn(cent[2 * k + 1], cent[2 * j + 1])));
+    }
+    sy = __ddiv_rn(sy, (double)d.n);
+    sx = __ddiv_rn(sx, (double)d.n);
+    const float step = (float)fmax(0.0, fmax(sy, sx));
+    if (!(step > 0.0f)) {
+        d.valid = 0;
+        return;
+    }
+    const float step_sq = __fmul_rn(step, step);
+    d.sw = (float)(1.0 / (double)step_sq);
+    d.inv_w = __fdiv_rn(1.0f, d.sw);
+}
+
+// SLIC centre table rows (cy, cx, 0 ...) from the float64 centroids
+__global__ void __launch_bounds__(256)
+km_batch_centres_kernel(const double *__restrict__ cent, int64_t n_total, int Cf, float *__restrict__ centres)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_total) return;
+    float *c = centres + k * (2 + Cf);
+    c[0] = (float)cent[2 * k];
+    c[1] = (float)cent[2 * k + 1];
+    for (int f = 0; f < Cf; ++f) c[2 + f] = 0.0f;
+}
+
 }  // namespace obia
 
 using namespace obia;
@@ -238,6 +349,62 @@ extern "C" int obia_b200_nearest_centroid(const double *centroids_yx, int64_t n,
     km_bin_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(centroids_yx, (int)n, g);
     OBIA_LAUNCH_CHECK();
     km_closest_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(centroids_yx, (int)n, g, closest);
+    OBIA_LAUNCH_CHECK();
+    return OBIA_B200_OK;
+}
+
+// ---- batched maskSLIC initialisation ------------------------------------------------------------------------
+extern "C" int64_t obia_b200_mask_kmeans_batch_workspace_bytes(int64_t n_total, int64_t km_cells_total)
+{
+    if (n_total <= 0 || km_cells_total <= 0) return -1;
+    return round_up(n_total * 3 * 8, 256) + round_up(km_cells_total * 4, 256) + round_up(n_total * 4, 256) +
+           round_up(n_total * 4, 256);
+}
+
+// k-means (`iters` sweeps from the seed pixels), nearest-other-centroid steps and the SLIC centre rows for
+// every window of a slab.  descs (device, batch.cuh) supply n / c0 / km grid per window and receive sw, inv_w
+// and valid = 0 for degenerate windows; centroids: (n_total, 2) float64 scratch, kept as the result.
+extern "C" int obia_b200_mask_kmeans_batch(const int32_t *points_pos, int64_t m_total, const int32_t *seed_pos,
+                                           const int32_t *cwin, void *descs, int64_t B, int64_t n_total,
+                                           int64_t km_cells_total, int32_t slab_w, int32_t win_rows, int32_t iters,
+                                           int32_t Cf, double *centroids, float *centres, void *workspace,
+                                           void *stream)
+{
+    if (!points_pos || !seed_pos || !cwin || !descs || !centroids || !centres || !workspace || m_total <= 0 || B <= 0 ||
+        n_total <= 0 || km_cells_total <= 0 || slab_w <= 0 || win_rows <= 0 || iters < 0 || Cf <= 0)
+        return set_err(OBIA_B200_ERR_ARG, "mask_kmeans_batch: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *p = (char *)workspace;
+    unsigned long long *sums = (unsigned long long *)p;
+    p += round_up(n_total * 3 * 8, 256);
+    int32_t *head = (int32_t *)p;
+    p += round_up(km_cells_total * 4, 256);
+    int32_t *next = (int32_t *)p;
+    p += round_up(n_total * 4, 256);
+    int32_t *closest = (int32_t *)p;
+    WinDesc *batch = (WinDesc *)descs;
+    const unsigned gn = (unsigned)ceil_div(n_total, 256);
+    km_batch_seed_kernel<<<gn, 256, 0, st>>>(seed_pos, cwin, batch, n_total, slab_w, centroids);
+    OBIA_LAUNCH_CHECK();
+    OBIA_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)n_total * 3 * 8, st));
+    for (int it = 0; it < iters; ++it) {
+        OBIA_CUDA_CHECK(cudaMemsetAsync(head, 0xff, (size_t)km_cells_total * 4, st));
+        km_batch_bin_kernel<<<gn, 256, 0, st>>>(centroids, cwin, batch, n_total, head, next);
+        OBIA_LAUNCH_CHECK();
+        km_batch_assign_kernel<<<(unsigned)ceil_div(m_total, 256), 256, 0, st>>>(points_pos, m_total, centroids, batch,
+                                                                                slab_w, win_rows, head, next, sums);
+        OBIA_LAUNCH_CHECK();
+        kmeans_update_kernel<<<gn, 256, 0, st>>>(centroids, sums, (int)n_total);
+        OBIA_LAUNCH_CHECK();
+    }
+    OBIA_CUDA_CHECK(cudaMemsetAsync(head, 0xff, (size_t)km_cells_total * 4, st));
+    km_batch_bin_kernel<<<gn, 256, 0, st>>>(centroids, cwin, batch, n_total, head, next);
+    OBIA_LAUNCH_CHECK();
+    km_batch_closest_kernel<<<gn, 256, 0, st>>>(centroids, cwin, batch, n_total, head, next, closest);
+    OBIA_LAUNCH_CHECK();
+    km_batch_steps_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, st>>>(centroids, closest, batch, B);
+    OBIA_LAUNCH_CHECK();
+    km_batch_centres_kernel<<<gn, 256, 0, st>>>(centroids, n_total, Cf, centres);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
 }

@@ -100,12 +100,17 @@ extern "C" int obia_b200_mask_sample_indices(int64_t n_coord, int64_t n_segments
     const int64_t k1 = std::min(n_segments, n_coord);
     const int64_t k2 = std::min((int64_t)100 * n_segments, n_coord);
     MT19937 rng(123u);
+    // the second draw selects every pixel when 100 * n_segments >= n_coord: sorted, that is 0 .. n_coord-1
+    // whatever the permutation was (the generator is not used afterwards)
+    const bool dense_all = k2 == n_coord;
+    if (dense_all)
+        for (int64_t i = 0; i < n_coord; ++i) idx_dense[i] = i;
     if (n_coord <= 0x7fffffffLL) {
         choice_sorted<int32_t>(rng, n_coord, k1, idx);
-        choice_sorted<int32_t>(rng, n_coord, k2, idx_dense);
+        if (!dense_all) choice_sorted<int32_t>(rng, n_coord, k2, idx_dense);
     } else {
         choice_sorted<int64_t>(rng, n_coord, k1, idx);
-        choice_sorted<int64_t>(rng, n_coord, k2, idx_dense);
+        if (!dense_all) choice_sorted<int64_t>(rng, n_coord, k2, idx_dense);
     }
     return OBIA_B200_OK;
 }

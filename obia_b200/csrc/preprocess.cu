@@ -5,6 +5,7 @@
 // has to be re-indexed per band.
 #include <math.h>
 
+#include "batch.cuh"
 #include "common.cuh"
 
 namespace obia {
@@ -367,6 +368,147 @@ gaussian_tiled_kernel(const float *__restrict__ in, float *__restrict__ out, int
     }
 }
 
+// ---------------------------------------------------------------- batched windows (tiled driver) --
+// Every window of a slab at once (batch.cuh): blockIdx.y = window.  `raw` is the source raster (H, Wl, C)
+// interleaved; a window's pixel (y, x) is raw[((y0 + y) * Wl + x0 + x) * C + band].
+__global__ void win_stats_init_kernel(uint32_t *keys, int32_t *flags, int32_t *counts, int64_t B, int C)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * C) {
+        keys[i * 4 + 0] = 0xffffffffu;
+        keys[i * 4 + 1] = 0u;
+        keys[i * 4 + 2] = 0xffffffffu;
+        keys[i * 4 + 3] = 0u;
+        flags[i] = 0;
+    }
+    if (i < B) counts[i] = 0;
+}
+
+constexpr int kWinStatRows = 16;
+
+// per window and band: min / max over the window, min / max over its mask pixels, NaN / inf flags (the
+// quantities obia_b200_band_minmax gives for one raster), plus the number of mask pixels.  The first
+// (256 / C) * C threads work, so a thread always sees the same band.
+__global__ void __launch_bounds__(256)
+win_stats_kernel(const float *__restrict__ raw, int64_t Wl, int C, const WinDesc *__restrict__ batch,
+                 const uint8_t *__restrict__ mask_slab, int slab_w, uint32_t *keys, int32_t *flags, int32_t *counts)
+{
+    const WinDesc &d = batch[blockIdx.y];
+    const int r0 = blockIdx.x * kWinStatRows;
+    if (r0 >= d.h) return;
+    const int r1 = min(d.h, r0 + kWinStatRows);
+    const int nt = (256 / C) * C;
+    const int t = threadIdx.x;
+    const float INF = __int_as_float(0x7f800000);
+    float mn = INF, mx = -INF, mmn = INF, mmx = -INF;
+    int fl = 0, cnt = 0;
+    if (t < nt) {
+        const int c = t % C;
+        const int ne = d.w * C;
+        for (int r = r0; r < r1; ++r) {
+            const float *row = raw + ((int64_t)(d.y0 + r) * Wl + d.x0) * C;
+            const uint8_t *mrow = mask_slab ? mask_slab + (int64_t)(d.row0 + r) * slab_w : nullptr;
+            for (int e = t; e < ne; e += nt) {
+                const float v = row[e];
+                fl |= classify_nonfinite(v);
+                mn = fminf(mn, v);
+                mx = fmaxf(mx, v);
+                if (mrow) {
+                    if (mrow[e / C]) {
+                        mmn = fminf(mmn, v);
+                        mmx = fmaxf(mmx, v);
+                        if (c == 0) ++cnt;
+                    }
+                }
+            }
+        }
+        uint32_t *k = keys + ((int64_t)blockIdx.y * C + c) * 4;
+        if (mn <= mx) {
+            atomicMin(k + 0, float_to_key(mn));
+            atomicMax(k + 1, float_to_key(mx));
+        }
+        if (mask_slab && mmn <= mmx) {
+            atomicMin(k + 2, float_to_key(mmn));
+            atomicMax(k + 3, float_to_key(mmx));
+        }
+        if (fl) atomicOr(flags + (int64_t)blockIdx.y * C + c, fl);
+        if (cnt) atomicAdd(counts + blockIdx.y, cnt);
+    }
+}
+
+__global__ void win_stats_finish_kernel(uint32_t *keys, int64_t n, int has_mask)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    float *out = reinterpret_cast<float *>(keys);
+    const float NANF = __int_as_float(0x7fc00000);
+    const uint32_t k0 = keys[c * 4 + 0], k1 = keys[c * 4 + 1], k2 = keys[c * 4 + 2], k3 = keys[c * 4 + 3];
+    const bool none = k0 == 0xffffffffu && k1 == 0u;
+    const float mn = none ? NANF : key_to_float(k0), mx = none ? NANF : key_to_float(k1);
+    float mmn, mmx;
+    if (!has_mask) {
+        mmn = mn; mmx = mx;
+    } else if (k2 == 0xffffffffu && k3 == 0u) {
+        mmn = NANF; mmx = NANF;
+    } else {
+        mmn = key_to_float(k2); mmx = key_to_float(k3);
+    }
+    out[c * 4 + 0] = mn; out[c * 4 + 1] = mx; out[c * 4 + 2] = mmn; out[c * 4 + 3] = mmx;
+}
+
+// window of a (H, Wm) mask raster -> slab rows (black tiles with a user mask)
+__global__ void __launch_bounds__(256)
+win_mask_copy_kernel(const uint8_t *__restrict__ mask, int64_t Wm, const WinDesc *__restrict__ batch,
+                     uint8_t *__restrict__ mask_slab, int slab_w, int hw_max)
+{
+    const WinDesc &d = batch[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.h * d.w || i >= hw_max) return;
+    const int y = i / d.w, x = i - y * d.w;
+    mask_slab[(int64_t)(d.row0 + y) * slab_w + x] = mask[(int64_t)(d.y0 + y) * Wm + d.x0 + x] != 0;
+}
+
+// features_kernel per window: same float32 operation order; band ranges per window in bmin / bdiff [B][Cs]
+__global__ void __launch_bounds__(256)
+win_features_kernel(const float *__restrict__ raw, int64_t Wl, int C, int Cs, const int32_t *__restrict__ bands,
+                    const float *__restrict__ bmin, const float *__restrict__ bdiff, const WinDesc *__restrict__ batch,
+                    int to_lab, float ratio, float *__restrict__ feat, int64_t pitch, int64_t plane, int hw_max)
+{
+    const WinDesc &d = batch[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!d.valid || i >= d.h * d.w || i >= hw_max) return;
+    const int y = i / d.w, x = i - y * d.w;
+    const float *src = raw + ((int64_t)(d.y0 + y) * Wl + d.x0 + x) * C;
+    const float *mn = bmin + (int64_t)blockIdx.y * Cs, *df = bdiff + (int64_t)blockIdx.y * Cs;
+    float *dst = feat + (int64_t)(d.row0 + y) * pitch + x;
+    const float imin = d.imin, idiff = d.idiff;
+    const int rescale = d.rescale;
+    if (to_lab) {
+        float v[3];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            float r = src[bands[s]];
+            r = __fdiv_rn(__fsub_rn(r, mn[s]), df[s]);
+            r = __fsub_rn(r, imin);
+            if (rescale) r = __fdiv_rn(r, idiff);
+            v[s] = r;
+        }
+        float L, A, B;
+        rgb2lab_f32(v[0], v[1], v[2], L, A, B);
+        dst[0] = __fmul_rn(L, ratio);
+        dst[plane] = __fmul_rn(A, ratio);
+        dst[2 * plane] = __fmul_rn(B, ratio);
+    } else {
+        for (int s = 0; s < Cs; ++s) {
+            float r = src[bands[s]];
+            r = __fdiv_rn(__fsub_rn(r, mn[s]), df[s]);
+            r = __fsub_rn(r, imin);
+            if (rescale) r = __fdiv_rn(r, idiff);
+            dst[(int64_t)s * plane] = __fmul_rn(r, ratio);
+        }
+    }
+}
+
 }  // namespace obia
 
 using namespace obia;
@@ -514,6 +656,59 @@ extern "C" int obia_b200_gaussian_planar(const float *in, float *tmp, float *out
     gaussian_pass_kernel<0><<<grid, 256, 0, st>>>(in, tmp, H, W, pitch, radius_y, 1.0f, 0);
     OBIA_LAUNCH_CHECK();
     gaussian_pass_kernel<1><<<grid, 256, 0, st>>>(tmp, out, H, W, pitch, radius_x, ratio, 1);
+    OBIA_LAUNCH_CHECK();
+    return OBIA_B200_OK;
+}
+
+// ---- batched windows (tiled driver) -----------------------------------------------------------------------
+// out: (B, C, 4) float32 = min, max, masked min, masked max; nonfinite: (B, C); mask_counts: (B) mask pixels.
+extern "C" int obia_b200_window_stats(const float *raw, int64_t Wl, int32_t C, const void *descs, int64_t B,
+                                      int32_t hmax, const uint8_t *mask_slab, int32_t slab_w, float *out,
+                                      int32_t *nonfinite, int32_t *mask_counts, void *stream)
+{
+    if (!raw || !descs || !out || !nonfinite || !mask_counts || Wl <= 0 || C <= 0 || C > 256 || B <= 0 || hmax <= 0 ||
+        B > 65535)
+        return set_err(OBIA_B200_ERR_ARG, "window_stats: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *keys = reinterpret_cast<uint32_t *>(out);
+    win_stats_init_kernel<<<(unsigned)ceil_div(B * C, 256), 256, 0, st>>>(keys, nonfinite, mask_counts, B, C);
+    OBIA_LAUNCH_CHECK();
+    dim3 grid((unsigned)ceil_div(hmax, kWinStatRows), (unsigned)B);
+    win_stats_kernel<<<grid, 256, 0, st>>>(raw, Wl, C, (const WinDesc *)descs, mask_slab, slab_w, keys, nonfinite,
+                                           mask_counts);
+    OBIA_LAUNCH_CHECK();
+    win_stats_finish_kernel<<<(unsigned)ceil_div(B * C, 256), 256, 0, st>>>(keys, B * C, mask_slab ? 1 : 0);
+    OBIA_LAUNCH_CHECK();
+    return OBIA_B200_OK;
+}
+
+extern "C" int obia_b200_window_mask_copy(const uint8_t *mask, int64_t Wm, const void *descs, int64_t B, int32_t hmax,
+                                          int32_t wmax, uint8_t *mask_slab, int32_t slab_w, void *stream)
+{
+    if (!mask || !descs || !mask_slab || Wm <= 0 || B <= 0 || B > 65535 || hmax <= 0 || wmax <= 0 || slab_w < wmax)
+        return set_err(OBIA_B200_ERR_ARG, "window_mask_copy: bad argument");
+    dim3 grid((unsigned)ceil_div((int64_t)hmax * wmax, 256), (unsigned)B);
+    win_mask_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mask, Wm, (const WinDesc *)descs, mask_slab, slab_w,
+                                                                  hmax * wmax);
+    OBIA_LAUNCH_CHECK();
+    return OBIA_B200_OK;
+}
+
+// features: (Cf, slab_rows, pitch) planar; bands (device, [Cs]); band_min / band_diff (device, [B][Cs]);
+// imin / idiff / rescale per window come from the descriptors.
+extern "C" int obia_b200_window_features(const float *raw, int64_t Wl, int32_t C, const int32_t *bands, int32_t Cs,
+                                         const float *band_min, const float *band_diff, const void *descs, int64_t B,
+                                         int32_t hmax, int32_t wmax, int32_t to_lab, float ratio, float *features,
+                                         int64_t slab_rows, int64_t pitch, void *stream)
+{
+    if (!raw || !bands || !band_min || !band_diff || !descs || !features || Wl <= 0 || C <= 0 || Cs <= 0 || B <= 0 ||
+        B > 65535 || hmax <= 0 || wmax <= 0 || pitch < wmax || slab_rows <= 0)
+        return set_err(OBIA_B200_ERR_ARG, "window_features: bad argument");
+    if (to_lab && Cs != 3) return set_err(OBIA_B200_ERR_ARG, "window_features: Lab needs 3 bands");
+    dim3 grid((unsigned)ceil_div((int64_t)hmax * wmax, 256), (unsigned)B);
+    win_features_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, Wl, C, Cs, bands, band_min, band_diff,
+                                                                 (const WinDesc *)descs, to_lab, ratio, features, pitch,
+                                                                 slab_rows * pitch, hmax * wmax);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
 }

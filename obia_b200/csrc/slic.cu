@@ -17,6 +17,7 @@
 //     fixed point and added with one coalesced RED.64 per field, so sums are
 //     independent of scheduling.
 // Features are band-planar so each lane streams 128-bit loads (4 pixels).
+#include "batch.cuh"
 #include "slic_common.cuh"
 
 namespace obia {
@@ -57,6 +58,45 @@ slic_centres_kernel(float *centres, unsigned long long *acc, int32_t *head, int3
     gy = max((int64_t)0, min(ncy - 1, gy));
     gx = max((int64_t)0, min(ncx - 1, gx));
     next[k] = atomicExch(&head[gy * ncx + gx], (int32_t)k);
+}
+
+// batched form (tiled driver): centre k belongs to window cwin[k]; its cell grid, fixed-point scale and
+// first centre come from the window descriptor, `next` holds window-local indices.
+__global__ void __launch_bounds__(256)
+slic_centres_batch_kernel(float *centres, unsigned long long *acc, int32_t *head, int32_t *next, int64_t n,
+                          int Cf, int from_acc, const int32_t *__restrict__ cwin, const WinDesc *__restrict__ batch)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const WinDesc *d = batch + cwin[k];
+    if (!d->valid) return;
+    const int rec = 2 + Cf;
+    float *c = centres + k * rec;
+    if (from_acc) {
+        unsigned long long *a = acc + k * (3 + Cf);
+        const long long cnt = (long long)a[0];
+        if (cnt > 0) {
+            const double dc = (double)cnt;
+            const double inv_fix = 1.0 / d->fix_scale;
+            c[0] = (float)((double)(long long)a[1] / dc);
+            c[1] = (float)((double)(long long)a[2] / dc);
+            for (int f = 0; f < Cf; ++f) c[2 + f] = (float)((double)(long long)a[3 + f] * inv_fix / dc);
+        } else {
+            const float NANF = __int_as_float(0x7fc00000);
+            for (int f = 0; f < rec; ++f) c[f] = NANF;
+        }
+        for (int f = 0; f < 3 + Cf; ++f) a[f] = 0ull;
+    }
+    const float cy = c[0], cx = c[1];
+    if (!(cy == cy) || !(cx == cx)) {
+        next[k] = -1;
+        return;
+    }
+    int64_t gy = (int64_t)floorf(cy / (float)d->step_y);
+    int64_t gx = (int64_t)floorf(cx / (float)d->step_x);
+    gy = max((int64_t)0, min((int64_t)d->ncy - 1, gy));
+    gx = max((int64_t)0, min((int64_t)d->ncx - 1, gx));
+    next[k] = atomicExch(&head[d->cell0 + gy * d->ncx + gx], (int32_t)(k - d->c0));
 }
 
 // ---- packed fp32x2 arithmetic (sm_100a FADD2 / FFMA2): two pixels per instruction ------
@@ -689,6 +729,11 @@ namespace obia {
 int launch_assign_fast(const float *feat, const uint8_t *mask, const float *centres, const SlicWs &w, int32_t *labels,
                        int64_t H, int64_t W, int64_t pitch, int Cf, float sw, int step_y, int step_x, int start_label,
                        int ignore_color, double fix_scale, int32_t *status, int y_off, int64_t Hg, cudaStream_t st);
+int launch_assign_fast_batch(const float *feat, const uint8_t *mask, const float *centres, const int32_t *head,
+                             const int32_t *next, unsigned long long *acc, int32_t *labels, const WinDesc *batch,
+                             int64_t B, int hmax, int wmax, int64_t slab_rows, int LW, int64_t pitch, int Cf,
+                             int start_label, int ignore_color, int32_t *status, cudaStream_t st);
+void fast_batch_fix_params(WinDesc *descs_host, int64_t B, int Cf);
 }
 
 using namespace obia;
@@ -888,4 +933,68 @@ extern "C" int obia_b200_slic_iterate_fast(const float *features, const uint8_t 
 {
     return slic_iterate_impl(features, mask, centres, labels, workspace, H, W, pitch, Cf, n, step, step_y, step_x,
                              max_num_iter, start_label, ignore_color, slic_zero, fix_scale, status, stream, 1);
+}
+
+// ---- batched iterations (tiled driver; batch.cuh) ---------------------------------------------------
+extern "C" int64_t obia_b200_slic_batch_workspace_bytes(int64_t n_total, int64_t cells_total, int32_t Cf)
+{
+    if (n_total <= 0 || cells_total <= 0 || Cf <= 0) return -1;
+    return round_up(n_total * (3 + Cf) * 8, 256) + round_up(cells_total * 4, 256) + round_up(n_total * 4, 256);
+}
+
+// fills the kernel-variant dependent fixed-point fields of HOST descriptors (before they are uploaded)
+extern "C" int obia_b200_slic_batch_prepare(void *descs_host, int64_t B, int32_t Cf)
+{
+    if (!descs_host || B <= 0 || Cf <= 0 || Cf > 64) return set_err(OBIA_B200_ERR_ARG, "slic_batch_prepare: bad argument");
+    fast_batch_fix_params((WinDesc *)descs_host, B, Cf);
+    return OBIA_B200_OK;
+}
+
+// `max_num_iter` sweeps (tolerance-mode kernel) over every window of the slab: the batched equivalent of
+// obia_b200_slic_iterate_fast called once per window.  labels: (slab_rows, slab_w) int32, filled with
+// start_label - 1 here; features: (Cf, slab_rows, pitch); centres: (n_total, 2 + Cf); descs / cwin on the device.
+extern "C" int obia_b200_slic_iterate_batch(const float *features, const uint8_t *mask, float *centres, int32_t *labels,
+                                            void *workspace, const void *descs, const int32_t *cwin, int64_t B,
+                                            int64_t n_total, int64_t cells_total, int32_t hmax, int32_t wmax,
+                                            int64_t slab_rows, int32_t slab_w, int64_t pitch, int32_t Cf,
+                                            int32_t max_num_iter, int32_t start_label, int32_t ignore_color,
+                                            int32_t *status, void *stream)
+{
+    if (!features || !centres || !labels || !workspace || !descs || !cwin || !status || B <= 0 || n_total <= 0 ||
+        cells_total <= 0 || hmax <= 0 || wmax <= 0 || slab_rows <= 0 || slab_w < wmax || pitch < wmax || (pitch & 3) ||
+        Cf <= 0 || Cf > 64 || max_num_iter < 0)
+        return set_err(OBIA_B200_ERR_ARG, "slic_iterate_batch: bad argument");
+    if (slab_rows * (int64_t)slab_w >= 0x7fffffffLL)
+        return set_err(OBIA_B200_ERR_UNSUPPORTED, "slic_iterate_batch: slab exceeds int32 pixels");
+    if ((reinterpret_cast<uintptr_t>(features) & 15) || (reinterpret_cast<uintptr_t>(labels) & 15) ||
+        (reinterpret_cast<uintptr_t>(workspace) & 15))
+        return set_err(OBIA_B200_ERR_ARG, "slic_iterate_batch: features, labels and workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *p = (char *)workspace;
+    unsigned long long *acc = (unsigned long long *)p;
+    p += round_up(n_total * (3 + Cf) * 8, 256);
+    int32_t *head = (int32_t *)p;
+    p += round_up(cells_total * 4, 256);
+    int32_t *next = (int32_t *)p;
+    const WinDesc *batch = (const WinDesc *)descs;
+    OBIA_CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t)(4 + B) * sizeof(int32_t), st));   // [4 + i]: window i overflowed
+    OBIA_CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)n_total * (3 + Cf) * 8, st));
+    fill_i32_kernel<<<kNumSMs * 4, 256, 0, st>>>(labels, slab_rows * slab_w, start_label - 1);
+    OBIA_LAUNCH_CHECK();
+    int rc = OBIA_B200_OK;
+    for (int it = 0; it < max_num_iter && !rc; ++it) {
+        OBIA_CUDA_CHECK(cudaMemsetAsync(head, 0xff, (size_t)cells_total * 4, st));
+        slic_centres_batch_kernel<<<(unsigned)ceil_div(n_total, 256), 256, 0, st>>>(centres, acc, head, next, n_total, Cf, 0,
+                                                                                   cwin, batch);
+        OBIA_LAUNCH_CHECK();
+        rc = launch_assign_fast_batch(features, mask, centres, head, next, acc, labels, batch, B, hmax, wmax, slab_rows,
+                                      slab_w, pitch, Cf, start_label, ignore_color, status, st);
+        if (rc) break;
+        // the reference updates the centres after every sweep, the last one included
+        OBIA_CUDA_CHECK(cudaMemsetAsync(head, 0xff, (size_t)cells_total * 4, st));
+        slic_centres_batch_kernel<<<(unsigned)ceil_div(n_total, 256), 256, 0, st>>>(centres, acc, head, next, n_total, Cf, 1,
+                                                                                   cwin, batch);
+        OBIA_LAUNCH_CHECK();
+    }
+    return rc;
 }

@@ -21,6 +21,7 @@
 // (pixels half-way between two centres) go to the lowest centre index exactly as in the reference.
 // Results differ from the exact kernel only where two candidates are within float32 rounding of
 // each other (tests: >= 99.9 % agreement per sweep, ARI reported).
+#include "batch.cuh"
 #include "slic_common.cuh"
 
 namespace obia {
@@ -74,7 +75,10 @@ __device__ __forceinline__ void eval_fast(const float (&pf)[PX][CP], float yr, f
 //   word 0 = count | (sum of tile-local rows << 13)     (tile <= 4096 pixels, <= 128 rows: 13 + 19 bits, unsigned)
 //   word 1 = sum of tile-local columns                 (records carry their slot in bits 16..)
 //   word 2 + c = 32-bit fixed-point sum of (f_c - o_c)
-template <int CP, int PX, int NS, int NW>
+// BATCH: one launch over all windows of a slab (batch.cuh): blockIdx.z selects the window, whose
+// descriptor replaces the scalar parameters; its rows, centres, cells and sums sit at the descriptor's
+// offsets inside the batch-wide arrays.  `LW` = row stride of labels / mask (W, or the slab width).
+template <int CP, int PX, int NS, int NW, bool BATCH>
 __global__ void __launch_bounds__(NW * 32, (CP <= 16) ? (24 / NW) : 1)
 slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restrict__ mask,
                         const float *__restrict__ centres, const int32_t *__restrict__ head,
@@ -82,9 +86,39 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
                         unsigned long long *__restrict__ acc, int H, int W, int64_t pitch, int Cf,
                         float spatial_weight, float inv_weight, int step_y, int step_x, int ncy, int ncx,
                         int start_label, int ignore_color, double fix_scale, float fix_scale32,
-                        long long fix_ratio, int32_t *status, int y_off, int Hg, int dbg)
+                        long long fix_ratio, int32_t *status, int y_off, int Hg, int dbg,
+                        const WinDesc *__restrict__ batch, int LW, int64_t plane)
 {
     using T = FastTraits<CP, NW>;
+    if constexpr (BATCH) {
+        const WinDesc *d = batch + blockIdx.z;
+        H = d->h;
+        W = d->w;
+        if (!d->valid || (int)blockIdx.x * 32 >= W) return;
+        {
+            constexpr int tile_rows = (NW / 2) * (32 / (16 / PX)) * NS;
+            if ((int)blockIdx.y * tile_rows >= H) return;
+        }
+        const int64_t r0 = d->row0, c0 = d->c0;
+        feat += r0 * pitch;
+        labels += r0 * LW;
+        if (mask) mask += r0 * LW;
+        centres += c0 * (2 + Cf);
+        next += c0;
+        head += d->cell0;
+        acc += c0 * (3 + Cf);
+        spatial_weight = d->sw;
+        inv_weight = d->inv_w;
+        step_y = d->step_y;
+        step_x = d->step_x;
+        ncy = d->ncy;
+        ncx = d->ncx;
+        fix_scale = d->fix_scale;
+        fix_scale32 = d->fix_scale32;
+        fix_ratio = d->fix_ratio;
+        y_off = 0;
+        Hg = H;
+    }
     static_assert(PX == T::PX, "pixels per lane");
     constexpr int LPR = 16 / PX;         // lanes per strip row
     constexpr int RW = 32 / LPR;         // rows per warp strip
@@ -139,7 +173,7 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
     __syncthreads();
     int nids = s_nids;
     if (nids > kIds) {
-        if (tid == 0) atomicExch(&status[0], 1);
+        if (tid == 0) atomicExch(&status[BATCH ? blockIdx.z : 0], 1);   // (batch: one word per window)
         nids = kIds;
     }
     for (int i = tid; i < nids; i += NT) {
@@ -159,7 +193,6 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
 
     const bool single_chunk = nids <= kChk;
     const float INF = __int_as_float(0x7f800000);
-    const int64_t plane = (int64_t)H * pitch;
     for (int sp = 0; sp < NS; ++sp) {
         // ---- this lane's pixels ------------------------------------------------------------
         const int sx0 = tx0 + (warp & 1) * 16, sy0 = ty0 + sp * TH + (warp >> 1) * RW;
@@ -171,7 +204,7 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
             bool v = ld_ok && (xb + j) < W;
-            if (v && mask) v = mask[(int64_t)y * W + xb + j] != 0;
+            if (v && mask) v = mask[(int64_t)y * LW + xb + j] != 0;
             vmask |= (v ? 1u : 0u) << j;
         }
         {
@@ -376,14 +409,14 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
             kk[j] = (v && bests[j] >= 0) ? s_sorted[bests[j]] : -1;
             all_found = all_found && v && bests[j] >= 0;
         }
-        if (PX == 4 && all_found && (W & 3) == 0) {
-            *reinterpret_cast<int4 *>(labels + (int64_t)y * W + xb) =
+        if (PX == 4 && all_found && (LW & 3) == 0) {
+            *reinterpret_cast<int4 *>(labels + (int64_t)y * LW + xb) =
                 make_int4(kk[0] + start_label, kk[1 % PX] + start_label, kk[2 % PX] + start_label,
                           kk[3 % PX] + start_label);
         } else {
 #pragma unroll
             for (int j = 0; j < PX; ++j)
-                if (kk[j] >= 0) labels[(int64_t)y * W + xb + j] = kk[j] + start_label;
+                if (kk[j] >= 0) labels[(int64_t)y * LW + xb + j] = kk[j] + start_label;
         }
 
         // ---- fused centre update -----------------------------------------------------------------
@@ -460,7 +493,7 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
                 ++rbase;
             } else {
                 int kcur = kk[j];
-                if (kcur < 0) kcur = labels[(int64_t)y * W + xb + j] - start_label;   // kept its previous centre
+                if (kcur < 0) kcur = labels[(int64_t)y * LW + xb + j] - start_label;   // kept its previous centre
                 if (kcur < 0) continue;
                 float fs[CP];
 #pragma unroll
@@ -513,6 +546,21 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
 static int g_fast_warps = 8;   // tuning knob (obia_b200_slic_fast_variant): warps per CTA, 8 or 4
 static int g_fast_dbg = 0;     // ablation switches (bits 8.. of the same call): 2 one candidate per chunk, 4 no seed
 
+// 32-bit fixed point for the per-tile sums: same derivation as the exact kernel (slic.cu), with
+// one more bit of head-room because |f - o| can reach twice the feature range
+static void fast_fix_params(int64_t Hg, int64_t W, int step_y, int step_x, double fix_scale, int strips32,
+                            float &fix_scale32, long long &fix_ratio)
+{
+    const int64_t reach = std::min<int64_t>(Hg * W, (int64_t)(4 * step_y + 1) * (4 * step_x + 1));
+    int bits_px = 1;
+    while ((1LL << bits_px) < reach + 1) ++bits_px;
+    int lg_ns = 0;
+    while ((1 << lg_ns) < strips32) ++lg_ns;
+    lg_ns += 1;
+    fix_scale32 = (float)ldexp(fix_scale, bits_px - 42 - lg_ns);
+    fix_ratio = 1LL << (42 - bits_px + lg_ns);
+}
+
 template <int CP, int PX, int NS, int NW>
 static int launch_fast_t(const float *feat, const uint8_t *mask, const float *centres, const SlicWs &w, int32_t *labels,
                          int64_t H, int64_t W, int64_t pitch, int Cf, float sw, int step_y, int step_x, int start_label,
@@ -520,24 +568,18 @@ static int launch_fast_t(const float *feat, const uint8_t *mask, const float *ce
 {
     using T = FastTraits<CP, NW>;
     constexpr int RW = 32 / (16 / PX), TH = (NW / 2) * RW;
-    // 32-bit fixed point for the per-tile sums: same derivation as the exact kernel (slic.cu), with
-    // one more bit of head-room because |f - o| can reach twice the feature range
-    const int64_t reach = std::min<int64_t>(Hg * W, (int64_t)(4 * step_y + 1) * (4 * step_x + 1));
-    int bits_px = 1;
-    while ((1LL << bits_px) < reach + 1) ++bits_px;
-    int lg_ns = 0;
-    while ((1 << lg_ns) < NS * TH / 32) ++lg_ns;
-    lg_ns += 1;
-    const float fix_scale32 = (float)ldexp(fix_scale, bits_px - 42 - lg_ns);
-    const long long fix_ratio = 1LL << (42 - bits_px + lg_ns);
+    float fix_scale32;
+    long long fix_ratio;
+    fast_fix_params(Hg, W, step_y, step_x, fix_scale, NS * TH / 32, fix_scale32, fix_ratio);
     dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, NS * TH));
     constexpr size_t dyn = T::kDyn;
-    auto kern = slic_assign_fast_kernel<CP, PX, NS, NW>;
+    auto kern = slic_assign_fast_kernel<CP, PX, NS, NW, false>;
     OBIA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     prof_begin(st);
     kern<<<grid, NW * 32, dyn, st>>>(feat, mask, centres, w.head, w.next, labels, w.acc, (int)H, (int)W, pitch, Cf, sw,
                                      1.0f / sw, step_y, step_x, (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale,
-                                     fix_scale32, fix_ratio, status, y_off, (int)Hg, g_fast_dbg);
+                                     fix_scale32, fix_ratio, status, y_off, (int)Hg, g_fast_dbg, nullptr, (int)W,
+                                     H * pitch);
     prof_end(st);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
@@ -560,6 +602,69 @@ int launch_assign_fast(const float *feat, const uint8_t *mask, const float *cent
     if (Cf <= 16) return launch_fast_t<16, 2, 2, 8>(OBIA_FAST_ARGS);
     if (Cf <= 32) return launch_fast_t<32, 2, 2, 8>(OBIA_FAST_ARGS);
     return launch_fast_t<64, 2, 2, 8>(OBIA_FAST_ARGS);
+#undef OBIA_FAST_ARGS
+}
+
+// ---- batched launch (tiled driver): every window of a slab in one grid -------------------------------
+// strips of 32 lanes per CTA tile and phase count of the variant that serves Cf channels
+static void fast_variant_geometry(int Cf, int &tile_rows, int &strips32)
+{
+    if (Cf <= 8) {            // <CP, 4, 4, 8>: 8 rows per warp strip, 32 rows per phase, 4 phases
+        tile_rows = 128;
+        strips32 = 4;
+    } else {                  // <CP, 2, 2, 8>: 4 rows per warp strip, 16 rows per phase, 2 phases
+        tile_rows = 32;
+        strips32 = 1;
+    }
+}
+
+void fast_batch_fix_params(WinDesc *descs_host, int64_t B, int Cf)
+{
+    int tile_rows, strips32;
+    fast_variant_geometry(Cf, tile_rows, strips32);
+    for (int64_t i = 0; i < B; ++i) {
+        WinDesc &d = descs_host[i];
+        if (!d.valid) continue;
+        long long ratio;
+        fast_fix_params(d.h, d.w, d.step_y, d.step_x, d.fix_scale, strips32, d.fix_scale32, ratio);
+        d.fix_ratio = ratio;
+    }
+}
+
+template <int CP, int PX, int NS, int NW>
+static int launch_fast_batch_t(const float *feat, const uint8_t *mask, const float *centres, const int32_t *head,
+                               const int32_t *next, unsigned long long *acc, int32_t *labels, const WinDesc *batch,
+                               int64_t B, int hmax, int wmax, int64_t slab_rows, int LW, int64_t pitch, int Cf,
+                               int start_label, int ignore_color, int32_t *status, cudaStream_t st)
+{
+    using T = FastTraits<CP, NW>;
+    constexpr int RW = 32 / (16 / PX), TH = (NW / 2) * RW;
+    constexpr size_t dyn = T::kDyn;
+    auto kern = slic_assign_fast_kernel<CP, PX, NS, NW, true>;
+    OBIA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    for (int64_t z0 = 0; z0 < B; z0 += 65535) {
+        const int64_t nz = std::min<int64_t>(65535, B - z0);
+        dim3 grid((unsigned)ceil_div(wmax, 32), (unsigned)ceil_div(hmax, NS * TH), (unsigned)nz);
+        kern<<<grid, NW * 32, dyn, st>>>(feat, mask, centres, head, next, labels, acc, 0, 0, pitch, Cf, 0.0f, 0.0f, 1, 1, 1, 1,
+                                         start_label, ignore_color, 1.0, 1.0f, 1, status + 4 + z0, 0, 0, 0, batch + z0, LW,
+                                         slab_rows * pitch);
+        OBIA_LAUNCH_CHECK();
+    }
+    return OBIA_B200_OK;
+}
+
+int launch_assign_fast_batch(const float *feat, const uint8_t *mask, const float *centres, const int32_t *head,
+                             const int32_t *next, unsigned long long *acc, int32_t *labels, const WinDesc *batch,
+                             int64_t B, int hmax, int wmax, int64_t slab_rows, int LW, int64_t pitch, int Cf,
+                             int start_label, int ignore_color, int32_t *status, cudaStream_t st)
+{
+#define OBIA_FAST_ARGS feat, mask, centres, head, next, acc, labels, batch, B, hmax, wmax, slab_rows, LW, pitch, Cf, \
+                       start_label, ignore_color, status, st
+    if (Cf <= 4) return launch_fast_batch_t<4, 4, 4, 8>(OBIA_FAST_ARGS);
+    if (Cf <= 8) return launch_fast_batch_t<8, 4, 4, 8>(OBIA_FAST_ARGS);
+    if (Cf <= 16) return launch_fast_batch_t<16, 2, 2, 8>(OBIA_FAST_ARGS);
+    if (Cf <= 32) return launch_fast_batch_t<32, 2, 2, 8>(OBIA_FAST_ARGS);
+    return launch_fast_batch_t<64, 2, 2, 8>(OBIA_FAST_ARGS);
 #undef OBIA_FAST_ARGS
 }
 

@@ -364,6 +364,286 @@ class TiledSegmenter:
         return final, int(allk.numel()), (x0, x1)
 
 
+class BatchedTiledSegmenter:
+    """The same two passes with every stage batched over windows (obia_b200/batch.py, csrc/tiled.cu): all black
+    tiles of a chunk, then all white windows of one tile-row, per launch.  Segments are int32 HANDLES into
+    per-rank tables (pixel count, live flag, creation key); G holds handles.  Results are identical to
+    `TiledSegmenter` (tests/test_tiling_batched.py)."""
+
+    def __init__(self, raw, mask, tile_size, buffer, crown_radius, pixel_area, slic_kwargs,
+                 rank=0, world=1, dist=None, verbose=False, x_origin=0, width_total=None):
+        from .. import _lib
+        self.lib = _lib.load()
+        self.raw = raw.contiguous()
+        self.xo = int(x_origin)
+        self.Wl = int(raw.shape[1])
+        self.H, self.W = int(raw.shape[0]), int(width_total if width_total is not None else raw.shape[1])
+        self.T, self.buffer, self.crown_radius, self.pixel_area = int(tile_size), int(buffer), crown_radius, pixel_area
+        self.kw = dict(slic_kwargs)
+        self.n_segments_fixed = self.kw.pop("n_segments", None)      # deviation 1
+        self.start_label = int(self.kw.get("start_label", 1))
+        self.rank, self.world, self.dist = rank, world, dist
+        self.verbose = verbose
+        self.device = raw.device
+        self.mask = None if mask is None else (mask != 0).to(torch.uint8).contiguous()
+        self.n_tile_cols = (self.W + self.T - 1) // self.T
+        self.n_tile_rows = (self.H + self.T - 1) // self.T
+        self.col_lo, self.col_hi = block_columns(self.W, self.T, world)
+        if self.T <= 2 * self.buffer:
+            raise ValueError("batched tiling needs tile_size > 2 * buffer")
+        self.G = torch.full((self.H, self.Wl), -1, dtype=torch.int32, device=self.device)
+        self.cap = 0
+        self.n_handles = 0
+        self.sizes = self.live = self.keys = self.cnt = None
+        self._grow(1 << 16)
+        self.h_of_key = {}      # seam segments: creation key -> handle on this rank
+        self.black, self.white = plan_tiles(self.H, self.W, self.T, self.buffer)
+        c = self.buffer / 2.0
+        self.corner = max(0, int(math.ceil(c - 0.5))) if c > 0 else 0     # window_polygon_mask
+
+    # ------------------------------------------------------------------ tables
+    def _grow(self, need):
+        if need <= self.cap:
+            return
+        cap = max(need, 2 * self.cap)
+        dev = self.device
+        sizes = torch.zeros((cap,), dtype=torch.int32, device=dev)
+        live = torch.zeros((cap,), dtype=torch.uint8, device=dev)
+        keys = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+        if self.cap:
+            sizes[:self.cap] = self.sizes
+            live[:self.cap] = self.live
+            keys[:self.cap] = self.keys
+        self.sizes, self.live, self.keys = sizes, live, keys
+        self.cnt = torch.zeros((2 * cap,), dtype=torch.int32, device=dev)     # all zero between calls
+        self.cap = cap
+
+    def owns(self, tile):
+        return self.col_lo[self.rank] <= tile["col"] < self.col_hi[self.rank]
+
+    def _windows(self, tiles):
+        return np.array([[t["y0"], t["x0"] - self.xo, t["h"], t["w"]] for t in tiles], dtype=np.int64)
+
+    def _chunks(self, tiles):
+        from .. import batch
+        if not tiles:
+            return
+        hmax = max(t["h"] for t in tiles) + 1
+        wmax = (max(t["w"] for t in tiles) + 3) // 4 * 4
+        per = max(1, min(batch.MAX_BATCH, batch.MAX_SLAB_PIXELS // (hmax * wmax)))
+        for i in range(0, len(tiles), per):
+            yield tiles[i:i + per]
+
+    # ------------------------------------------------------------------ one batch
+    def _segment_batch(self, tiles, wb, pass_idx):
+        """Run the window batch and paint its segments into G with fresh handles and creation keys."""
+        from .. import _lib
+        from ..batch import _p, _stream
+        try:
+            wb.segment(n_segments=self.n_segments_fixed, pixel_area=self.pixel_area, crown_radius=self.crown_radius,
+                       **self.kw)
+        except ValueError:
+            if self.verbose:
+                print(f"empty tiles: pass {pass_idx}, {len(tiles)} windows")
+            return
+        if self.verbose:
+            for t, ok in zip(tiles, wb.usable):
+                if not ok:
+                    print(f"empty tile: ({t['y0']}) ({t['x0']})")          # :149-150, :283-284
+        if wb.labels is None or not wb.usable.any():
+            return
+        B, N, sl = wb.B, wb.n_labels, self.start_label
+        hbase, hzero = self.n_handles, self.n_handles + N
+        self._grow(hzero + B)
+        dev = self.device
+        usable = torch.from_numpy(wb.usable.astype(np.uint8)).to(dev)
+        # labels are numbered window by window: the running maximum per window delimits each window's range
+        wmax = wb.labels.view(B, -1).amax(dim=1).clamp_(min=sl - 1).to(torch.int64)
+        cm = torch.cummax(wmax, 0).values
+        prev = torch.cat([torch.full((1,), sl - 1, dtype=torch.int64, device=dev), cm[:-1]])
+        first_label = torch.where(cm > prev, prev + 1, torch.full_like(prev, -1)).to(torch.int32)
+        _lib.check(self.lib.obia_b200_tiled_paint(
+            _p(wb.labels), _p(wb.mask_slab), wb.slab_w, _p(wb.desc_dev), _p(usable), _p(first_label), B, wb.hmax, wb.wmax,
+            sl, hbase, hzero, _p(self.G), self.Wl, _p(self.sizes), _stream()), "tiled_paint")
+        base_key = torch.tensor([creation_key(pass_idx, t["row"], t["col"]) for t in tiles], dtype=torch.int64,
+                                device=dev)
+        if N > 0:
+            lab = torch.arange(sl, sl + N, dtype=torch.int64, device=dev)
+            win = torch.searchsorted(cm, lab)
+            self.keys[hbase:hzero] = base_key[win] + (lab - prev[win] + (sl - 1))
+        self.keys[hzero:hzero + B] = base_key          # the leftover label 0 of a window (start_label 1)
+        self.live[hbase:hzero + B] = (self.sizes[hbase:hzero + B] > 0).to(torch.uint8)
+        self.n_handles = hzero + B
+
+    # ------------------------------------------------------------------ passes
+    def run_black(self):
+        from ..batch import WindowBatch
+        owned = [t for t in self.black if self.owns(t)]
+        for tiles in self._chunks(owned):
+            wb = WindowBatch(self.raw, self._windows(tiles))
+            if self.mask is not None:
+                wb.mask_from(self.mask)
+            self._segment_batch(tiles, wb, 0)
+        self._exchange(None)
+
+    def run_white(self):
+        from .. import _lib
+        from ..batch import WindowBatch, _p, _stream
+        rows = sorted({t["row"] for t in self.white})
+        by_row = {r: [t for t in self.white if t["row"] == r] for r in rows}
+        dev = self.device
+        for r in rows:
+            owned = [t for t in by_row[r] if self.owns(t)]
+            for tiles in self._chunks(owned):
+                wb = WindowBatch(self.raw, self._windows(tiles))
+                wb.new_mask_slab()
+                parity = torch.tensor([(t["col"] >> 1) & 1 for t in tiles], dtype=torch.uint8, device=dev)
+                any_seg = torch.zeros((wb.B,), dtype=torch.int32, device=dev)
+                _lib.check(self.lib.obia_b200_tiled_white_prepare(
+                    _p(self.G), self.Wl, _p(wb.desc_dev), _p(parity), wb.B, wb.hmax, wb.wmax, self.corner, _p(self.cnt),
+                    self.cap, _p(self.sizes), _p(self.live), _p(any_seg), _p(self.mask), self.Wl, _p(wb.mask_slab),
+                    wb.slab_w, _stream()), "tiled_white_prepare")
+                if self.mask is None:
+                    # a window without any earlier segment keeps `mask = None` in the reference: unmasked SLIC
+                    untouched = any_seg.cpu().numpy() == 0
+                    if untouched.any():
+                        if self.verbose:
+                            for t in (t for t, u in zip(tiles, untouched) if u):
+                                print(f"No overlapping black segments found for tile ({t['x0']}, {t['y0']}).")
+                        plain = [t for t, u in zip(tiles, untouched) if u]
+                        self._segment_batch(plain, WindowBatch(self.raw, self._windows(plain)), 1)
+                        keep = [i for i, u in enumerate(untouched) if not u]
+                        if not keep:
+                            continue
+                        tiles = [tiles[i] for i in keep]
+                        wb2 = WindowBatch(self.raw, self._windows(tiles))
+                        wb2.new_mask_slab()
+                        for j, i in enumerate(keep):
+                            h, w = tiles[j]["h"], tiles[j]["w"]
+                            wb2.mask_slab[j * wb2.win_rows:j * wb2.win_rows + h, :w] = \
+                                wb.mask_slab[i * wb.win_rows:i * wb.win_rows + h, :w]
+                        wb = wb2
+                self._segment_batch(tiles, wb, 1)
+            self._exchange(r)
+
+    # ------------------------------------------------------------------ seam exchange
+    def _exchange(self, white_row):
+        """As TiledSegmenter._exchange; the band travels as creation keys, each side keeps its own handles."""
+        if self.world == 1:
+            return
+        b, T, dev = self.buffer, self.T, self.device
+        if white_row is None:
+            ya, yb = 0, self.H
+        else:
+            ya, yb = max(0, white_row * T - b), min(self.H, (white_row + 1) * T + b)
+        sends, recvs = [], []
+        for nb, side in ((self.rank - 1, "left"), (self.rank + 1, "right")):
+            if nb < 0 or nb >= self.world:
+                continue
+            c_edge = self.col_lo[self.rank] if side == "left" else self.col_hi[self.rank]
+            if c_edge <= 0 or c_edge >= self.n_tile_cols or self.col_lo[nb] == self.col_hi[nb]:
+                continue
+            xb = c_edge * T
+            xa_, xb_ = max(0, xb - b), min(self.W, xb + b)
+            if white_row is None:
+                sx0, sx1 = (xb, xb_) if side == "left" else (xa_, xb)
+                rx0, rx1 = (xa_, xb) if side == "left" else (xb, xb_)
+                i_send = i_recv = True
+            else:
+                left_tile_white = ((white_row + c_edge - 1) % 2) == 1
+                i_send = left_tile_white == (side == "right")
+                i_recv = not i_send
+                sx0, sx1 = rx0, rx1 = xa_, xb_
+            if i_send:
+                band = self.G[ya:yb, sx0 - self.xo:sx1 - self.xo]
+                hs = torch.unique(band[band >= 0]).to(torch.int64)
+                table = torch.stack([self.keys[hs], self.sizes[hs].to(torch.int64)], dim=1).contiguous()
+                kband = torch.where(band >= 0, self.keys[band.clamp(min=0).to(torch.int64)],
+                                    torch.full((), -1, dtype=torch.int64, device=dev)).contiguous()
+                for k, h in zip(table[:, 0].tolist(), hs.tolist()):
+                    self.h_of_key[k] = h
+                meta = torch.tensor([table.shape[0]], dtype=torch.int64, device=dev)
+                sends.append((nb, meta, kband, table))
+            if i_recv:
+                recvs.append((nb, ya, yb, rx0, rx1))
+
+        def do_sends():
+            for nb, meta, kband, table in sends:
+                self.dist.send(meta, nb)
+                self.dist.send(kband, nb)
+                if table.shape[0]:
+                    self.dist.send(table, nb)
+
+        def do_recvs():
+            for nb, ra, rb, rx0, rx1 in recvs:
+                meta = torch.zeros(1, dtype=torch.int64, device=dev)
+                self.dist.recv(meta, nb)
+                kband = torch.empty((rb - ra, rx1 - rx0), dtype=torch.int64, device=dev)
+                self.dist.recv(kband, nb)
+                n = int(meta.item())
+                old = self.G[ra:rb, rx0 - self.xo:rx1 - self.xo]
+                gone = torch.unique(old[old >= 0]).to(torch.int64)
+                new_band = torch.full(kband.shape, -1, dtype=torch.int32, device=dev)
+                if n:
+                    table = torch.empty((n, 2), dtype=torch.int64, device=dev)
+                    self.dist.recv(table, nb)
+                    rows = table.tolist()
+                    fresh = [k for k, _ in rows if k not in self.h_of_key]
+                    self._grow(self.n_handles + len(fresh))
+                    for k in fresh:
+                        self.h_of_key[k] = self.n_handles
+                        self.n_handles += 1
+                    hs = torch.tensor([self.h_of_key[k] for k, _ in rows], dtype=torch.int64, device=dev)
+                    self.keys[hs] = table[:, 0]
+                    self.sizes[hs] = table[:, 1].to(torch.int32)
+                    order = torch.argsort(table[:, 0])
+                    skeys = table[order, 0].contiguous()
+                    pos = torch.searchsorted(skeys, kband.clamp(min=0)).clamp_(max=n - 1)
+                    new_band = torch.where(kband >= 0, hs[order][pos].to(torch.int32), new_band)
+                    if white_row is not None and gone.numel():
+                        # segments that vanished from the band were deleted by the neighbour
+                        self.live[gone] = 0
+                    self.live[hs] = 1
+                elif white_row is not None and gone.numel():
+                    self.live[gone] = 0
+                self.G[ra:rb, rx0 - self.xo:rx1 - self.xo] = new_band
+
+        if self.rank % 2 == 0:
+            do_sends()
+            do_recvs()
+        else:
+            do_recvs()
+            do_sends()
+
+    # ------------------------------------------------------------------ result
+    def finalize(self):
+        """Final 1..N numbering: the rank of the creation key among all live segments (:289-290)."""
+        x0 = min(self.W, self.col_lo[self.rank] * self.T)
+        x1 = max(x0, min(self.W, self.col_hi[self.rank] * self.T))
+        own = self.G[:, x0 - self.xo:x1 - self.xo] if x1 > x0 else self.G[:, :0]
+        dev = self.device
+        nh = self.n_handles
+        alive = torch.nonzero(self.live[:nh]).reshape(-1)
+        keys = self.keys[alive]
+        if self.world > 1:
+            n_loc = torch.tensor([keys.numel()], dtype=torch.int64, device=dev)
+            counts = [torch.zeros_like(n_loc) for _ in range(self.world)]
+            self.dist.all_gather(counts, n_loc)
+            nmax = max(1, int(max(c.item() for c in counts)))
+            pad = torch.full((nmax,), -1, dtype=torch.int64, device=dev)
+            pad[:keys.numel()] = keys
+            gathered = [torch.empty_like(pad) for _ in range(self.world)]
+            self.dist.all_gather(gathered, pad)
+            allk = torch.unique(torch.cat([g[:int(c.item())] for g, c in zip(gathered, counts)]))
+        else:
+            allk = torch.sort(keys).values
+        lut = torch.full((nh + 1,), -1, dtype=torch.int32, device=dev)      # entry 0: handle -1 (no segment)
+        if alive.numel():
+            lut[alive + 1] = (torch.searchsorted(allk, keys) + 1).to(torch.int32)
+        final = lut.index_select(0, (own + 1).reshape(-1)).reshape(own.shape)
+        return final, int(allk.numel()), (x0, x1)
+
+
 def _as_device_raster(input_raster, device, columns=None):
     """(raw (H, W_local, C) float32 tensor, pixel_area, Image-or-None, total width) from a path / Image /
     array.  `columns(width) -> (xa, xb)`: only those pixel columns are uploaded (multi-GPU: a rank
@@ -431,7 +711,7 @@ def _write_segments(output_dir, labels, n, image):
 def create_tiled_segments(input_raster, output_dir, input_mask=None,
                           method="slic", tile_size=200, buffer=30, crown_radius=5,
                           *, device=None, segment_tile=None, distributed=None, verbose=False,
-                          return_labels=False, polygons=True, save_labels=False, **kwargs):
+                          return_labels=False, polygons=True, save_labels=False, batched=None, **kwargs):
     """
     Same call and result as the reference (tiling.py:62-291): returns None and writes
     `<output_dir>/segments.gpkg` (`geometry`, `segment_id`) -- `segments.geojson` when geopandas /
@@ -443,6 +723,8 @@ def create_tiled_segments(input_raster, output_dir, input_mask=None,
     :param input_mask: path (`.npy`, or a raster file when rasterio is installed) / array (H, W); non-zero = segment here.
     :param method: only 'slic' (ValueError otherwise, tiling.py:76-77).
     :param polygons: False skips the host polygonisation and the vector file (label-raster users).
+    :param batched: None = one launch per stage over all windows of a pass / tile-row when the options allow
+        it (BatchedTiledSegmenter), False = one pipeline call per tile (TiledSegmenter); same result.
     :param save_labels: also write `segments_labels[.rankN].npy` (this rank's block of the label raster).
     :param return_labels: return (labels (H, W_block) int32 with ids 1..N and -1 elsewhere, N, (x0, x1)
         owned columns) instead of None.
@@ -471,9 +753,17 @@ def create_tiled_segments(input_raster, output_dir, input_mask=None,
             raise ValueError("image and mask should have the same shape.")
         mask = (m[:, xa:xa + int(raw.shape[1])] != 0).to(device).contiguous()
 
-    seg = TiledSegmenter(raw, mask, tile_size, buffer, crown_radius, pixel_area, kwargs,
-                         segment_tile=segment_tile, rank=rank, world=world, dist=dist, verbose=verbose,
-                         x_origin=xa, width_total=width)
+    from .. import batch as _batch
+    if batched is None:
+        batched = (segment_tile is None and raw.is_cuda and int(tile_size) > 2 * int(buffer) and
+                   _batch.supports({k: v for k, v in kwargs.items() if k != "n_segments"}))
+    if batched:
+        seg = BatchedTiledSegmenter(raw, mask, tile_size, buffer, crown_radius, pixel_area, kwargs,
+                                    rank=rank, world=world, dist=dist, verbose=verbose, x_origin=xa, width_total=width)
+    else:
+        seg = TiledSegmenter(raw, mask, tile_size, buffer, crown_radius, pixel_area, kwargs,
+                             segment_tile=segment_tile, rank=rank, world=world, dist=dist, verbose=verbose,
+                             x_origin=xa, width_total=width)
     seg.run_black()
     seg.run_white()
     labels, n, cols = seg.finalize()
