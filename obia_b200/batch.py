@@ -62,6 +62,24 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+TIMINGS = None      # set to a dict (section -> seconds) to collect synchronised per-stage times (debugging aid)
+
+
+_T_LAST = [0.0]
+
+
+def _tick(name):
+    """Attribute the (synchronised) time since the previous tick to `name` when TIMINGS is a dict."""
+    if TIMINGS is None:
+        return
+    import time
+    torch.cuda.synchronize()
+    now = time.perf_counter()
+    if name is not None:
+        TIMINGS[name] = TIMINGS.get(name, 0.0) + now - _T_LAST[0]
+    _T_LAST[0] = now
+
+
 @functools.lru_cache(maxsize=65536)
 def _geometry(h, w, n):
     """(step_y, step_x) of the +-2*step windows for n centres on an h x w window."""
@@ -137,8 +155,15 @@ class WindowBatch:
                    "window_mask_copy")
 
     # ------------------------------------------------------------------ the path
-    def segment(self, *, n_segments=None, pixel_area=1.0, crown_radius=5, segmentation_bands=None, compactness=10.0,
-                max_num_iter=10, convert2lab=None, min_size_factor=0.5, max_size_factor=3, start_label=1, **_ignored):
+    def segment(self, **kw):
+        return self.begin(**kw).finish()
+
+    def begin(self, *, n_segments=None, pixel_area=1.0, crown_radius=5, segmentation_bands=None, compactness=10.0,
+              max_num_iter=10, convert2lab=None, min_size_factor=0.5, max_size_factor=3, start_label=1, **_ignored):
+        """First half: per-window band ranges and mask counts (one read-back), the per-window parameters, and the
+        start of the host-side sample draws (background threads) -- nothing here waits for earlier device work
+        that was queued after the caller's last synchronisation."""
+        self._st = None
         lib, dev, B, C = self.lib, self.dev, self.B, self.C
         d = self.desc
         masked = self.mask_slab is not None
@@ -155,6 +180,7 @@ class WindowBatch:
         Cf = 3 if to_lab else Cs
         f32 = np.float32
 
+        _tick(None)
         # ---- K1a per window: band ranges, mask counts (one read-back) ---------------------------------
         stats = torch.empty((B, C, 4), dtype=torch.float32, device=dev)
         flags = torch.empty((B, C), dtype=torch.int32, device=dev)
@@ -170,6 +196,7 @@ class WindowBatch:
         hw = d["h"].astype(np.int64) * d["w"].astype(np.int64)
         n_coord = n_mask if masked else hw
 
+        _tick("stats + read-back")
         # ---- per-window parameters (what slic_labels derives on the host, vectorised) ------------------
         if n_segments is not None:
             n_seg = np.full(B, int(n_segments), dtype=np.int64)
@@ -245,12 +272,33 @@ class WindowBatch:
             return self
         _lib.check(lib.obia_b200_slic_batch_prepare(d.ctypes.data_as(ctypes.c_void_p), B, Cf), "slic_batch_prepare")
 
+        if masked:
+            # the RandomState(123) draws of the maskSLIC initialisation start now, on host threads
+            slic_host.prefetch_mask_samples([(int(n_coord[i]), int(n_seg[i])) for i in np.nonzero(valid)[0]])
+        _tick("host parameters")
+        self._st = dict(masked=masked, bands=bands, Cs=Cs, Cf=Cf, to_lab=to_lab, ratio=ratio, valid=valid, n=n, c0=c0,
+                        n_coord=n_coord, n_seg=n_seg, n_mask=n_mask, grids=grids, mn=mn, dd=dd, n_total=n_total,
+                        cells_total=cells_total, km_cells_total=km_cells_total, max_num_iter=max_num_iter,
+                        start_label=start_label)
+        return self
+
+    def finish(self):
+        """Second half of `segment`: centre initialisation, features, sweeps, connectivity."""
+        st = getattr(self, "_st", None)
+        if st is None:
+            return self
+        self._st = None
+        lib, dev, B, C, d = self.lib, self.dev, self.B, self.C, self.desc
+        masked, bands, Cs, Cf, to_lab, ratio, valid, n, c0 = (st[k] for k in (
+            "masked", "bands", "Cs", "Cf", "to_lab", "ratio", "valid", "n", "c0"))
+        n_coord, n_seg, n_mask, grids, mn, dd = (st[k] for k in ("n_coord", "n_seg", "n_mask", "grids", "mn", "dd"))
+        n_total, cells_total, km_cells_total = st["n_total"], st["cells_total"], st["km_cells_total"]
+        max_num_iter, start_label = st["max_num_iter"], st["start_label"]
+        _tick(None)
         cwin = torch.from_numpy(np.repeat(np.arange(B, dtype=np.int32), n)).to(dev)
         centres = torch.empty((n_total, 2 + Cf), dtype=torch.float32, device=dev)
         if masked:
-            # ---- maskSLIC initialisation: RandomState(123) draws on host threads, k-means on the device ------
-            keys = [(int(n_coord[i]), int(n_seg[i])) for i in np.nonzero(valid)[0]]
-            slic_host.prefetch_mask_samples(keys)
+            # ---- maskSLIC initialisation: RandomState(123) draws (host threads), k-means on the device ------
             pos_all = torch.nonzero(self.mask_slab.reshape(-1)).reshape(-1).to(torch.int32)
             base = np.concatenate([[0], np.cumsum(n_mask)[:-1]])
             seeds, dense, p0, m = [], [], np.zeros(B, dtype=np.int64), np.zeros(B, dtype=np.int64)
@@ -260,7 +308,7 @@ class WindowBatch:
                 idx, idx_dense = slic_host.mask_sample_indices(int(n_coord[i]), int(n_seg[i]))
                 draws[i] = idx_dense
                 seeds.append(idx + base[i])
-                if len(idx_dense) != n_coord[i]:
+                if idx_dense is not None:
                     all_dense = False
             if all_dense:
                 # coord[idx_dense] is every mask pixel of the window: the points are the slab's mask pixels
@@ -269,9 +317,10 @@ class WindowBatch:
             else:
                 off = 0
                 for i in np.nonzero(valid)[0]:
-                    dense.append(draws[i] + base[i])
-                    p0[i], m[i] = off, len(draws[i])
-                    off += len(draws[i])
+                    di = np.arange(n_coord[i], dtype=np.int64) if draws[i] is None else draws[i]
+                    dense.append(di + base[i])
+                    p0[i], m[i] = off, len(di)
+                    off += len(di)
                 pts = pos_all[torch.from_numpy(np.concatenate(dense)).to(dev)]
             d["p0"], d["m"] = np.where(valid, p0, 0), np.where(valid, m, 0)
             self.upload()
@@ -294,6 +343,7 @@ class WindowBatch:
                 rows[k0:k0 + n[i], 1] = np.tile(xs, len(ys))
             centres.copy_(torch.from_numpy(rows))
 
+        _tick("centre initialisation (draws + k-means)")
         # ---- K1b per window ---------------------------------------------------------------------------
         feats = torch.empty((Cf, self.slab_rows, self.pitch), dtype=torch.float32, device=dev)
         bands_dev = torch.tensor(bands, dtype=torch.int32, device=dev)
@@ -303,6 +353,7 @@ class WindowBatch:
             _p(self.raw), self.Wl, C, _p(bands_dev), Cs, _p(bmin), _p(bdiff), _p(self.desc_dev), B, self.hmax,
             self.wmax, int(to_lab), float(ratio), _p(feats), self.slab_rows, self.pitch, _stream()), "window_features")
 
+        _tick("features")
         # ---- K2 per window ----------------------------------------------------------------------------
         ws = torch.empty((lib.obia_b200_slic_batch_workspace_bytes(n_total, cells_total, Cf),), dtype=torch.uint8,
                          device=dev)
@@ -322,6 +373,7 @@ class WindowBatch:
         run(False)
         del ws, feats
 
+        _tick("slic sweeps")
         # ---- K3 on the slab, sizes per window -------------------------------------------------------------
         wsizes = np.ones((B, 2), dtype=np.int32)
         wsizes[valid, 0] = d["min_size"][valid]
@@ -335,11 +387,13 @@ class WindowBatch:
             _p(labels), _p(out), _p(cc_ws), self.slab_rows, self.slab_w, _p(wsizes_dev), self.win_rows,
             int(start_label), ctypes.byref(nl), _stream()), "enforce_connectivity_windows")
         del cc_ws, labels
+        _tick("connectivity")
         if masked:
             out.masked_fill_(self.mask_slab == 0, -1)       # segment_boundaries.py:55-57
         # windows dropped on the device (degenerate step) or that overflowed the candidate staging
         dev_valid = self.desc_dev.view(torch.int32).reshape(B, WIN_DESC.itemsize // 4)[:, 5]
         back = torch.stack([dev_valid, overflow]).cpu().numpy()
+        _tick("final read-back")
         self.usable = valid & (back[0] != 0) & (back[1] == 0)
         self.labels = out
         self.n_labels = int(nl.value)

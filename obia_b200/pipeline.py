@@ -132,7 +132,10 @@ def mask_centroids_device(mask_dev, n_segments):
         raise ValueError("n_segments must be positive")
     idx, idx_dense = slic_host.mask_sample_indices(n_coord, n_segments)
     dev = mask_dev.device
-    pts = coord.index_select(0, torch.from_numpy(idx_dense).to(dev)).to(torch.int32).contiguous()
+    if idx_dense is None:      # coord[idx_dense] is every mask pixel
+        pts = coord.to(torch.int32).contiguous()
+    else:
+        pts = coord.index_select(0, torch.from_numpy(idx_dense).to(dev)).to(torch.int32).contiguous()
     cent = coord.index_select(0, torch.from_numpy(idx).to(dev)).to(torch.float64).contiguous()
     n = int(cent.shape[0])
     H, W = (int(v) for v in mask_dev.shape)

@@ -113,10 +113,12 @@ def _draw_mask_samples(n_coord, n_segments):
     from . import _lib
     lib = _lib.load()
     idx = np.empty(min(n_segments, n_coord), dtype=np.int64)
-    idx_dense = np.empty(min(100 * n_segments, n_coord), dtype=np.int64)
+    # 100 * n_segments >= n_coord: the second draw is every pixel (returned as None, nothing to compute)
+    idx_dense = None if 100 * n_segments >= n_coord else np.empty(100 * n_segments, dtype=np.int64)
     _lib.check(lib.obia_b200_mask_sample_indices(int(n_coord), int(n_segments),
                                                  idx.ctypes.data_as(ctypes.c_void_p),
-                                                 idx_dense.ctypes.data_as(ctypes.c_void_p)), "mask_sample_indices")
+                                                 None if idx_dense is None else idx_dense.ctypes.data_as(ctypes.c_void_p)),
+               "mask_sample_indices")
     return idx, idx_dense
 
 
@@ -131,7 +133,7 @@ def prefetch_mask_samples(keys):
     if _CHOICE_POOL is None:
         # one process per GPU under torchrun: share the host cores between the local ranks
         local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1))
-        workers = max(1, min(8, ((os.cpu_count() or 2) - 1) // local))
+        workers = max(1, min(32, ((os.cpu_count() or 2) - 1) // local))
         _CHOICE_POOL = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="obia_b200_rng")
     for n_coord, n_segments in keys:
         key = (int(n_coord), int(n_segments))
@@ -143,7 +145,8 @@ def prefetch_mask_samples(keys):
 
 
 def mask_sample_indices(n_coord, n_segments):
-    """(idx, idx_dense) of `_get_mask_centroids`: two draws from RandomState(123).
+    """(idx, idx_dense) of `_get_mask_centroids`: two draws from RandomState(123); idx_dense is None when it
+    is every pixel (100 * n_segments >= n_coord).
 
     They depend only on the number of mask pixels and n_segments, so tiles with equal counts
     share them (cached; the legacy permutation is O(n_coord) on the host).

@@ -435,17 +435,27 @@ class BatchedTiledSegmenter:
             yield tiles[i:i + per]
 
     # ------------------------------------------------------------------ one batch
+    def _begin_batch(self, wb):
+        """Band ranges / mask counts / parameters of the batch and the start of its host-side sample draws."""
+        wb.begun, wb.failed = True, False
+        try:
+            wb.begin(n_segments=self.n_segments_fixed, pixel_area=self.pixel_area, crown_radius=self.crown_radius,
+                     **self.kw)
+        except ValueError:
+            wb.failed = True
+        return True
+
     def _segment_batch(self, tiles, wb, pass_idx):
         """Run the window batch and paint its segments into G with fresh handles and creation keys."""
         from .. import _lib
         from ..batch import _p, _stream
-        try:
-            wb.segment(n_segments=self.n_segments_fixed, pixel_area=self.pixel_area, crown_radius=self.crown_radius,
-                       **self.kw)
-        except ValueError:
+        if not getattr(wb, "begun", False) and not self._begin_batch(wb):
+            return
+        if wb.failed:
             if self.verbose:
                 print(f"empty tiles: pass {pass_idx}, {len(tiles)} windows")
             return
+        wb.finish()
         if self.verbose:
             for t, ok in zip(tiles, wb.usable):
                 if not ok:
@@ -479,11 +489,19 @@ class BatchedTiledSegmenter:
     def run_black(self):
         from ..batch import WindowBatch
         owned = [t for t in self.black if self.owns(t)]
+        pending = None
         for tiles in self._chunks(owned):
+            # the next chunk's statistics and sample draws are started before the current chunk's device work is
+            # queued: the draws (host threads) then overlap it
             wb = WindowBatch(self.raw, self._windows(tiles))
             if self.mask is not None:
                 wb.mask_from(self.mask)
-            self._segment_batch(tiles, wb, 0)
+            self._begin_batch(wb)
+            if pending is not None:
+                self._segment_batch(pending[0], pending[1], 0)
+            pending = (tiles, wb)
+        if pending is not None:
+            self._segment_batch(pending[0], pending[1], 0)
         self._exchange(None)
 
     def run_white(self):

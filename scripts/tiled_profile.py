@@ -15,3 +15,14 @@ create_tiled_segments(raw, None, mask, return_labels=True, polygons=False, **kw)
 torch.cuda.synchronize()
 pr.disable()
 s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(45); print(s.getvalue()[:9000])
+# stage split (synchronised: slower than the real run, shares only)
+from obia_b200 import batch
+batch.TIMINGS = {}
+t0 = time.perf_counter()
+create_tiled_segments(raw, None, mask, return_labels=True, polygons=False, **kw)
+torch.cuda.synchronize()
+tot = time.perf_counter() - t0
+print("synchronised total %.3f s" % tot)
+for k, v in sorted(batch.TIMINGS.items(), key=lambda kv: -kv[1]):
+    print("  %-45s %.3f s" % (k, v))
+print("  %-45s %.3f s" % ("outside WindowBatch.segment", tot - sum(batch.TIMINGS.values())))

@@ -117,7 +117,7 @@ def test_mask_sample_indices_equals_numpy_legacy_choice():
     rejection, backward Fisher-Yates) is bit-identical to numpy, also through the background prefetch."""
     from obia_b200 import slic_host
     cases = [(1, 1), (2, 1), (3, 5), (10, 3), (400, 4), (1000, 7), (40000, 199), (65536, 10), (65537, 700),
-             (123457, 1000)]
+             (123457, 1000), (623, 2), (624, 3), (625, 6), (67600, 100), (67600, 860), (250000, 40)]
     slic_host._CHOICE_CACHE.clear()
     slic_host.prefetch_mask_samples(cases[::2] + [(0, 3), (5, 0)])        # half of them in the background
     for n, k in cases:
@@ -127,5 +127,9 @@ def test_mask_sample_indices_equals_numpy_legacy_choice():
                 np.sort(rng.choice(full, min(100 * k, n), replace=False)))
         got = slic_host.mask_sample_indices(n, k)
         np.testing.assert_array_equal(got[0], want[0])
-        np.testing.assert_array_equal(got[1], want[1])
+        if 100 * k >= n:
+            assert got[1] is None                      # every pixel: nothing drawn (sorted = arange)
+            np.testing.assert_array_equal(want[1], np.arange(n))
+        else:
+            np.testing.assert_array_equal(got[1], want[1])
         assert slic_host.mask_sample_indices(n, k) is got                  # cached
