@@ -429,16 +429,19 @@ int obia_b200_window_features(const float *raw, int64_t Wl, int32_t C, const int
                               int32_t hmax, int32_t wmax, int32_t to_lab, float ratio, float *features,
                               int64_t slab_rows, int64_t pitch, void *stream);
 /* maskSLIC initialisation per window (obia_b200_mask_kmeans + obia_b200_nearest_centroid + the `steps` mean):
- * points_pos / seed_pos = slab pixel positions of coord[idx_dense] / coord[idx]; cwin (n_total) = window of
- * every centroid.  Writes centroids (n_total, 2) float64, the SLIC centre rows (n_total, 2 + Cf) and, into the
+ * points_pos / seed_pos = slab pixel positions of coord[idx_dense] / coord[idx] (dense_mask_slab != NULL instead
+ * of points_pos: the points of every window are all of its mask pixels, assigned tile by tile); cwin (n_total) =
+ * window of every centroid.  Writes centroids (n_total, 2) float64, the SLIC centre rows (n_total, 2 + Cf) and, into the
  * descriptors, sw / inv_w (valid = 0 where the step is not positive: the reference's ValueError). */
 int64_t obia_b200_mask_kmeans_batch_workspace_bytes(int64_t n_total, int64_t km_cells_total);
-int obia_b200_mask_kmeans_batch(const int32_t *points_pos, int64_t m_total, const int32_t *seed_pos,
-                                const int32_t *cwin, void *descs, int64_t B, int64_t n_total,
-                                int64_t km_cells_total, int32_t slab_w, int32_t win_rows, int32_t iters, int32_t Cf,
-                                double *centroids, float *centres, void *workspace, void *stream);
+int obia_b200_mask_kmeans_batch(const int32_t *points_pos, int64_t m_total, const uint8_t *dense_mask_slab,
+                                int32_t hmax, int32_t wmax, const int32_t *seed_pos, const int32_t *cwin, void *descs,
+                                int64_t B, int64_t n_total, int64_t km_cells_total, int32_t slab_w, int32_t win_rows,
+                                int32_t iters, int32_t Cf, double *centroids, float *centres, void *workspace,
+                                void *stream);
 /* obia_b200_slic_iterate_fast per window.  `prepare` fills the kernel-variant dependent fixed-point fields of
- * HOST descriptors before upload; status: (4 + B) int32, status[4 + i] != 0 = window i overflowed the
+ * HOST descriptors before upload (`pad` = strip phases of the tile variant that serves the window; `variants` =
+ * OR of it over the usable windows); status: (4 + B) int32, status[4 + i] != 0 = window i overflowed the
  * candidate staging (CandidateOverflowError of the single-raster path). */
 int64_t obia_b200_slic_batch_workspace_bytes(int64_t n_total, int64_t cells_total, int32_t Cf);
 int obia_b200_slic_batch_prepare(void *descs_host, int64_t B, int32_t Cf);
@@ -446,7 +449,8 @@ int obia_b200_slic_iterate_batch(const float *features, const uint8_t *mask, flo
                                  void *workspace, const void *descs, const int32_t *cwin, int64_t B,
                                  int64_t n_total, int64_t cells_total, int32_t hmax, int32_t wmax,
                                  int64_t slab_rows, int32_t slab_w, int64_t pitch, int32_t Cf, int32_t max_num_iter,
-                                 int32_t start_label, int32_t ignore_color, int32_t *status, void *stream);
+                                 int32_t start_label, int32_t ignore_color, int32_t variants, int32_t *status,
+                                 void *stream);
 /* obia_b200_enforce_connectivity on the slab with (min_size, max_size) per window (device int32 pairs);
  * kept pieces are numbered start_label.. in slab raster order, i.e. window by window.
  * workspace: obia_b200_connectivity_workspace_bytes(H, W). */

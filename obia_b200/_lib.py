@@ -70,12 +70,12 @@ SIGNATURES = {
     "obia_b200_window_features": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32,
                                                  _f32, _vp, _i64, _i64, _vp]),
     "obia_b200_mask_kmeans_batch_workspace_bytes": (_i64, [_i64, _i64]),
-    "obia_b200_mask_kmeans_batch": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32,
-                                                   _i32, _vp, _vp, _vp, _vp]),
+    "obia_b200_mask_kmeans_batch": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i32,
+                                                   _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "obia_b200_slic_batch_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "obia_b200_slic_batch_prepare": (ctypes.c_int, [_vp, _i64, _i32]),
     "obia_b200_slic_iterate_batch": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32,
-                                                    _i64, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+                                                    _i64, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "obia_b200_enforce_connectivity_windows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _vp]),
     "obia_b200_tiled_paint": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp,
                                              _i64, _vp, _vp]),

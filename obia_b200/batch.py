@@ -271,6 +271,7 @@ class WindowBatch:
         if n_total == 0:
             return self
         _lib.check(lib.obia_b200_slic_batch_prepare(d.ctypes.data_as(ctypes.c_void_p), B, Cf), "slic_batch_prepare")
+        variants = int(np.bitwise_or.reduce(d["pad"][valid])) if valid.any() else 0
 
         if masked:
             # the RandomState(123) draws of the maskSLIC initialisation start now, on host threads
@@ -279,7 +280,7 @@ class WindowBatch:
         self._st = dict(masked=masked, bands=bands, Cs=Cs, Cf=Cf, to_lab=to_lab, ratio=ratio, valid=valid, n=n, c0=c0,
                         n_coord=n_coord, n_seg=n_seg, n_mask=n_mask, grids=grids, mn=mn, dd=dd, n_total=n_total,
                         cells_total=cells_total, km_cells_total=km_cells_total, max_num_iter=max_num_iter,
-                        start_label=start_label)
+                        start_label=start_label, variants=variants)
         return self
 
     def finish(self):
@@ -329,8 +330,9 @@ class WindowBatch:
             km_ws = torch.empty((lib.obia_b200_mask_kmeans_batch_workspace_bytes(n_total, km_cells_total),),
                                 dtype=torch.uint8, device=dev)
             _lib.check(lib.obia_b200_mask_kmeans_batch(
-                _p(pts), int(pts.numel()), _p(seed_pos), _p(cwin), _p(self.desc_dev), B, n_total, km_cells_total,
-                self.slab_w, self.win_rows, 5, Cf, _p(cent), _p(centres), _p(km_ws), _stream()), "mask_kmeans_batch")
+                _p(pts), int(pts.numel()), _p(self.mask_slab) if all_dense else None, self.hmax, self.wmax, _p(seed_pos),
+                _p(cwin), _p(self.desc_dev), B, n_total, km_cells_total, self.slab_w, self.win_rows, 5, Cf, _p(cent),
+                _p(centres), _p(km_ws), _stream()), "mask_kmeans_batch")
             del km_ws, pts, pos_all
         else:
             self.upload()
@@ -365,7 +367,7 @@ class WindowBatch:
             _lib.check(lib.obia_b200_slic_iterate_batch(
                 _p(feats), _p(self.mask_slab), _p(centres), _p(labels), _p(ws), _p(self.desc_dev), _p(cwin), B, n_total,
                 cells_total, self.hmax, self.wmax, self.slab_rows, self.slab_w, self.pitch, Cf, int(max_num_iter),
-                int(start_label), int(ignore_color), _p(status), _stream()), "slic_iterate_batch")
+                int(start_label), int(ignore_color), st["variants"], _p(status), _stream()), "slic_iterate_batch")
             overflow.bitwise_or_(status[4:])
 
         if masked:

@@ -243,6 +243,99 @@ km_batch_assign_kernel(const int32_t *__restrict__ pts_pos, int64_t m_total, con
     atomicAdd(&sums[3 * (int64_t)bestj + 2], (unsigned long long)(long long)ix);
 }
 
+// The same assignment for DENSE windows (coord[idx_dense] = every mask pixel, the usual case: 100 * n_segments
+// >= mask pixels): one CTA per 16 x 16 pixel tile of a window.  The centroids of the cells around the tile are
+// staged in shared memory once and every pixel searches them by brute force; the result is accepted only when
+// the best distance is strictly inside the staged block (the bound km_nearest uses ring by ring), otherwise the
+// pixel falls back to km_nearest -- both give the exact nearest centroid with the lowest-index tie rule.
+// Sums are folded per tile in shared memory (integers) before they reach the global table.
+constexpr int kKmTile = 16, kKmStage = 192;
+
+__global__ void __launch_bounds__(256)
+km_batch_assign_tile_kernel(const uint8_t *__restrict__ mask_slab, int slab_w, const double *__restrict__ cent,
+                            const WinDesc *__restrict__ batch, int tiles_x, int32_t *head, int32_t *next,
+                            unsigned long long *__restrict__ sums)
+{
+    __shared__ double s_cy[kKmStage], s_cx[kKmStage];
+    __shared__ int s_k[kKmStage];
+    __shared__ int s_sum[kKmStage][3];
+    __shared__ int s_n;
+    const WinDesc &d = batch[blockIdx.y];
+    const int ty0 = (blockIdx.x / tiles_x) * kKmTile, tx0 = (blockIdx.x % tiles_x) * kKmTile;
+    if (!d.valid || d.n <= 0 || ty0 >= d.h || tx0 >= d.w) return;
+    const KmGrid g = km_grid_of(d, head, next);
+    const int ty1 = min(ty0 + kKmTile, d.h) - 1, tx1 = min(tx0 + kKmTile, d.w) - 1;
+    const int cy0 = max(0, km_cell((double)ty0, g.cs, g.ncy) - 1), cy1 = min(g.ncy - 1, km_cell((double)ty1, g.cs, g.ncy) + 1);
+    const int cx0 = max(0, km_cell((double)tx0, g.cs, g.ncx) - 1), cx1 = min(g.ncx - 1, km_cell((double)tx1, g.cs, g.ncx) + 1);
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int ncell = (cy1 - cy0 + 1) * (cx1 - cx0 + 1), cw = cx1 - cx0 + 1;
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+        const int cy = cy0 + c / cw, cx = cx0 + c % cw;
+        for (int k = g.head[cy * g.ncx + cx]; k >= 0; k = g.next[k]) {
+            const int slot = atomicAdd(&s_n, 1);
+            if (slot < kKmStage) {
+                s_k[slot] = k;
+                s_cy[slot] = cent[2 * k];
+                s_cx[slot] = cent[2 * k + 1];
+                s_sum[slot][0] = s_sum[slot][1] = s_sum[slot][2] = 0;
+            }
+        }
+    }
+    __syncthreads();
+    const int ns = s_n;
+    const int iy = ty0 + (int)threadIdx.x / kKmTile, ix = tx0 + (int)threadIdx.x % kKmTile;
+    if (iy < d.h && ix < d.w && mask_slab[(int64_t)(d.row0 + iy) * slab_w + ix]) {
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        const double py = (double)iy, px = (double)ix;
+        int bestk = 0x7fffffff, bests = -1;
+        bool exact = false;
+        if (ns <= kKmStage) {
+            double best = INF;
+            for (int j = 0; j < ns; ++j) {
+                const double dy = __dsub_rn(py, s_cy[j]);
+                const double dx = __dsub_rn(px, s_cx[j]);
+                const double d2 = __dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dx, dx));
+                const int k = s_k[j];
+                if (d2 < best || (d2 == best && k < bestk)) {
+                    best = d2;
+                    bestk = k;
+                    bests = j;
+                }
+            }
+            double lb = INF;
+            if (cy0 > 0) lb = fmin(lb, py - (double)cy0 * g.cs);
+            if (cy1 < g.ncy - 1) lb = fmin(lb, (double)(cy1 + 1) * g.cs - py);
+            if (cx0 > 0) lb = fmin(lb, px - (double)cx0 * g.cs);
+            if (cx1 < g.ncx - 1) lb = fmin(lb, (double)(cx1 + 1) * g.cs - px);
+            if (lb == INF) {
+                exact = bests >= 0;                    // the whole grid was staged
+            } else {
+                lb -= 1e-6;
+                exact = bests >= 0 && lb > 0.0 && best < lb * lb * (1.0 - 1e-9);
+            }
+        }
+        if (exact) {
+            atomicAdd(&s_sum[bests][0], 1);
+            atomicAdd(&s_sum[bests][1], iy);
+            atomicAdd(&s_sum[bests][2], ix);
+        } else {
+            const int k = km_nearest<false>(py, px, -1, cent, g);
+            atomicAdd(&sums[3 * (int64_t)k + 0], 1ull);
+            atomicAdd(&sums[3 * (int64_t)k + 1], (unsigned long long)(long long)iy);
+            atomicAdd(&sums[3 * (int64_t)k + 2], (unsigned long long)(long long)ix);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < min(ns, kKmStage); j += blockDim.x) {
+        if (s_sum[j][0] == 0) continue;
+        const int64_t k = s_k[j];
+        atomicAdd(&sums[3 * k + 0], (unsigned long long)s_sum[j][0]);
+        atomicAdd(&sums[3 * k + 1], (unsigned long long)s_sum[j][1]);
+        atomicAdd(&sums[3 * k + 2], (unsigned long long)s_sum[j][2]);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 km_batch_closest_kernel(const double *__restrict__ cent, const int32_t *__restrict__ cwin,
                         const WinDesc *__restrict__ batch, int64_t n_total, int32_t *head, int32_t *next,
@@ -364,13 +457,14 @@ extern "C" int64_t obia_b200_mask_kmeans_batch_workspace_bytes(int64_t n_total, 
 // k-means (`iters` sweeps from the seed pixels), nearest-other-centroid steps and the SLIC centre rows for
 // every window of a slab.  descs (device, batch.cuh) supply n / c0 / km grid per window and receive sw, inv_w
 // and valid = 0 for degenerate windows; centroids: (n_total, 2) float64 scratch, kept as the result.
-extern "C" int obia_b200_mask_kmeans_batch(const int32_t *points_pos, int64_t m_total, const int32_t *seed_pos,
-                                           const int32_t *cwin, void *descs, int64_t B, int64_t n_total,
-                                           int64_t km_cells_total, int32_t slab_w, int32_t win_rows, int32_t iters,
-                                           int32_t Cf, double *centroids, float *centres, void *workspace,
-                                           void *stream)
+extern "C" int obia_b200_mask_kmeans_batch(const int32_t *points_pos, int64_t m_total, const uint8_t *dense_mask_slab,
+                                           int32_t hmax, int32_t wmax, const int32_t *seed_pos, const int32_t *cwin,
+                                           void *descs, int64_t B, int64_t n_total, int64_t km_cells_total,
+                                           int32_t slab_w, int32_t win_rows, int32_t iters, int32_t Cf,
+                                           double *centroids, float *centres, void *workspace, void *stream)
 {
-    if (!points_pos || !seed_pos || !cwin || !descs || !centroids || !centres || !workspace || m_total <= 0 || B <= 0 ||
+    if ((!points_pos && !dense_mask_slab) || (dense_mask_slab && (hmax <= 0 || wmax <= 0 || B > 65535)) ||
+        (!dense_mask_slab && m_total <= 0) || !seed_pos || !cwin || !descs || !centroids || !centres || !workspace || B <= 0 ||
         n_total <= 0 || km_cells_total <= 0 || slab_w <= 0 || win_rows <= 0 || iters < 0 || Cf <= 0)
         return set_err(OBIA_B200_ERR_ARG, "mask_kmeans_batch: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
@@ -391,8 +485,15 @@ extern "C" int obia_b200_mask_kmeans_batch(const int32_t *points_pos, int64_t m_
         OBIA_CUDA_CHECK(cudaMemsetAsync(head, 0xff, (size_t)km_cells_total * 4, st));
         km_batch_bin_kernel<<<gn, 256, 0, st>>>(centroids, cwin, batch, n_total, head, next);
         OBIA_LAUNCH_CHECK();
-        km_batch_assign_kernel<<<(unsigned)ceil_div(m_total, 256), 256, 0, st>>>(points_pos, m_total, centroids, batch,
-                                                                                slab_w, win_rows, head, next, sums);
+        if (dense_mask_slab) {      // the points of every window are all of its mask pixels
+            const int tiles_x = (int)ceil_div(wmax, kKmTile);
+            dim3 grid((unsigned)(tiles_x * ceil_div(hmax, kKmTile)), (unsigned)B);
+            km_batch_assign_tile_kernel<<<grid, 256, 0, st>>>(dense_mask_slab, slab_w, centroids, batch, tiles_x, head,
+                                                              next, sums);
+        } else {
+            km_batch_assign_kernel<<<(unsigned)ceil_div(m_total, 256), 256, 0, st>>>(points_pos, m_total, centroids, batch,
+                                                                                    slab_w, win_rows, head, next, sums);
+        }
         OBIA_LAUNCH_CHECK();
         kmeans_update_kernel<<<gn, 256, 0, st>>>(centroids, sums, (int)n_total);
         OBIA_LAUNCH_CHECK();

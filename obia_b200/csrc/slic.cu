@@ -732,7 +732,7 @@ int launch_assign_fast(const float *feat, const uint8_t *mask, const float *cent
 int launch_assign_fast_batch(const float *feat, const uint8_t *mask, const float *centres, const int32_t *head,
                              const int32_t *next, unsigned long long *acc, int32_t *labels, const WinDesc *batch,
                              int64_t B, int hmax, int wmax, int64_t slab_rows, int LW, int64_t pitch, int Cf,
-                             int start_label, int ignore_color, int32_t *status, cudaStream_t st);
+                             int start_label, int ignore_color, int32_t *status, int ns_mask, cudaStream_t st);
 void fast_batch_fix_params(WinDesc *descs_host, int64_t B, int Cf);
 }
 
@@ -952,13 +952,14 @@ extern "C" int obia_b200_slic_batch_prepare(void *descs_host, int64_t B, int32_t
 
 // `max_num_iter` sweeps (tolerance-mode kernel) over every window of the slab: the batched equivalent of
 // obia_b200_slic_iterate_fast called once per window.  labels: (slab_rows, slab_w) int32, filled with
-// start_label - 1 here; features: (Cf, slab_rows, pitch); centres: (n_total, 2 + Cf); descs / cwin on the device.
+// start_label - 1 here; features: (Cf, slab_rows, pitch); centres: (n_total, 2 + Cf); descs / cwin on the device;
+// variants = OR over the usable windows of the `pad` field obia_b200_slic_batch_prepare wrote (tile variants present).
 extern "C" int obia_b200_slic_iterate_batch(const float *features, const uint8_t *mask, float *centres, int32_t *labels,
                                             void *workspace, const void *descs, const int32_t *cwin, int64_t B,
                                             int64_t n_total, int64_t cells_total, int32_t hmax, int32_t wmax,
                                             int64_t slab_rows, int32_t slab_w, int64_t pitch, int32_t Cf,
                                             int32_t max_num_iter, int32_t start_label, int32_t ignore_color,
-                                            int32_t *status, void *stream)
+                                            int32_t variants, int32_t *status, void *stream)
 {
     if (!features || !centres || !labels || !workspace || !descs || !cwin || !status || B <= 0 || n_total <= 0 ||
         cells_total <= 0 || hmax <= 0 || wmax <= 0 || slab_rows <= 0 || slab_w < wmax || pitch < wmax || (pitch & 3) ||
@@ -988,7 +989,7 @@ extern "C" int obia_b200_slic_iterate_batch(const float *features, const uint8_t
                                                                                    cwin, batch);
         OBIA_LAUNCH_CHECK();
         rc = launch_assign_fast_batch(features, mask, centres, head, next, acc, labels, batch, B, hmax, wmax, slab_rows,
-                                      slab_w, pitch, Cf, start_label, ignore_color, status, st);
+                                      slab_w, pitch, Cf, start_label, ignore_color, status, variants, st);
         if (rc) break;
         // the reference updates the centres after every sweep, the last one included
         OBIA_CUDA_CHECK(cudaMemsetAsync(head, 0xff, (size_t)cells_total * 4, st));

@@ -95,6 +95,7 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
         H = d->h;
         W = d->w;
         if (!d->valid || (int)blockIdx.x * 32 >= W) return;
+        if (CP <= 8 && d->pad != NS) return;      // (the window is served by the variant with d->pad strip phases)
         {
             constexpr int tile_rows = (NW / 2) * (32 / (16 / PX)) * NS;
             if ((int)blockIdx.y * tile_rows >= H) return;
@@ -546,6 +547,17 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
 static int g_fast_warps = 8;   // tuning knob (obia_b200_slic_fast_variant): warps per CTA, 8 or 4
 static int g_fast_dbg = 0;     // ablation switches (bits 8.. of the same call): 2 one candidate per chunk, 4 no seed
 
+// Strip phases per CTA tile (32 columns x 32 * NS rows for up to 8 channels).  A tile stages the centres within
+// 2 * step of it; with small steps a tall tile collects more than the 128 records that are resident at once and
+// would rebuild them per phase, so the tile height follows the grid step.  (The fixed-point scale of the per-tile
+// sums depends on the tile size: the choice is a function of (Cf, step) only, so every path -- whole raster, row
+// strips, window batches -- quantises identically.)
+int fast_pick_ns(int Cf, int step_y)
+{
+    if (Cf > 8) return 2;
+    return step_y >= 14 ? 4 : (step_y >= 7 ? 2 : 1);
+}
+
 // 32-bit fixed point for the per-tile sums: same derivation as the exact kernel (slic.cu), with
 // one more bit of head-room because |f - o| can reach twice the feature range
 static void fast_fix_params(int64_t Hg, int64_t W, int step_y, int step_x, double fix_scale, int strips32,
@@ -591,11 +603,16 @@ int launch_assign_fast(const float *feat, const uint8_t *mask, const float *cent
 {
 #define OBIA_FAST_ARGS feat, mask, centres, w, labels, H, W, pitch, Cf, sw, step_y, step_x, start_label, ignore_color, \
                        fix_scale, status, y_off, Hg, st
+    const int ns = fast_pick_ns(Cf, step_y);
     if (Cf <= 4) {
+        if (ns == 1) return launch_fast_t<4, 4, 1, 8>(OBIA_FAST_ARGS);
+        if (ns == 2) return launch_fast_t<4, 4, 2, 8>(OBIA_FAST_ARGS);
         if (g_fast_warps == 4) return launch_fast_t<4, 4, 4, 4>(OBIA_FAST_ARGS);
         return launch_fast_t<4, 4, 4, 8>(OBIA_FAST_ARGS);
     }
     if (Cf <= 8) {
+        if (ns == 1) return launch_fast_t<8, 4, 1, 8>(OBIA_FAST_ARGS);
+        if (ns == 2) return launch_fast_t<8, 4, 2, 8>(OBIA_FAST_ARGS);
         if (g_fast_warps == 4) return launch_fast_t<8, 4, 4, 4>(OBIA_FAST_ARGS);
         return launch_fast_t<8, 4, 4, 8>(OBIA_FAST_ARGS);
     }
@@ -606,12 +623,12 @@ int launch_assign_fast(const float *feat, const uint8_t *mask, const float *cent
 }
 
 // ---- batched launch (tiled driver): every window of a slab in one grid -------------------------------
-// strips of 32 lanes per CTA tile and phase count of the variant that serves Cf channels
-static void fast_variant_geometry(int Cf, int &tile_rows, int &strips32)
+// rows of a CTA tile and its number of 32-row strips for the variant that serves (Cf, ns)
+static void fast_variant_geometry(int Cf, int ns, int &tile_rows, int &strips32)
 {
-    if (Cf <= 8) {            // <CP, 4, 4, 8>: 8 rows per warp strip, 32 rows per phase, 4 phases
-        tile_rows = 128;
-        strips32 = 4;
+    if (Cf <= 8) {            // <CP, 4, ns, 8>: 8 rows per warp strip, 32 rows per phase
+        tile_rows = 32 * ns;
+        strips32 = ns;
     } else {                  // <CP, 2, 2, 8>: 4 rows per warp strip, 16 rows per phase, 2 phases
         tile_rows = 32;
         strips32 = 1;
@@ -620,11 +637,12 @@ static void fast_variant_geometry(int Cf, int &tile_rows, int &strips32)
 
 void fast_batch_fix_params(WinDesc *descs_host, int64_t B, int Cf)
 {
-    int tile_rows, strips32;
-    fast_variant_geometry(Cf, tile_rows, strips32);
     for (int64_t i = 0; i < B; ++i) {
         WinDesc &d = descs_host[i];
         if (!d.valid) continue;
+        int tile_rows, strips32;
+        d.pad = fast_pick_ns(Cf, d.step_y);
+        fast_variant_geometry(Cf, d.pad, tile_rows, strips32);
         long long ratio;
         fast_fix_params(d.h, d.w, d.step_y, d.step_x, d.fix_scale, strips32, d.fix_scale32, ratio);
         d.fix_ratio = ratio;
@@ -656,12 +674,23 @@ static int launch_fast_batch_t(const float *feat, const uint8_t *mask, const flo
 int launch_assign_fast_batch(const float *feat, const uint8_t *mask, const float *centres, const int32_t *head,
                              const int32_t *next, unsigned long long *acc, int32_t *labels, const WinDesc *batch,
                              int64_t B, int hmax, int wmax, int64_t slab_rows, int LW, int64_t pitch, int Cf,
-                             int start_label, int ignore_color, int32_t *status, cudaStream_t st)
+                             int start_label, int ignore_color, int32_t *status, int ns_mask, cudaStream_t st)
 {
 #define OBIA_FAST_ARGS feat, mask, centres, head, next, acc, labels, batch, B, hmax, wmax, slab_rows, LW, pitch, Cf, \
                        start_label, ignore_color, status, st
-    if (Cf <= 4) return launch_fast_batch_t<4, 4, 4, 8>(OBIA_FAST_ARGS);
-    if (Cf <= 8) return launch_fast_batch_t<8, 4, 4, 8>(OBIA_FAST_ARGS);
+    if (Cf <= 8) {      // one launch per tile variant present in the batch (windows of the others leave at once)
+        int rc = OBIA_B200_OK;
+        if (Cf <= 4) {
+            if (!rc && (ns_mask & 1)) rc = launch_fast_batch_t<4, 4, 1, 8>(OBIA_FAST_ARGS);
+            if (!rc && (ns_mask & 2)) rc = launch_fast_batch_t<4, 4, 2, 8>(OBIA_FAST_ARGS);
+            if (!rc && (ns_mask & 4)) rc = launch_fast_batch_t<4, 4, 4, 8>(OBIA_FAST_ARGS);
+        } else {
+            if (!rc && (ns_mask & 1)) rc = launch_fast_batch_t<8, 4, 1, 8>(OBIA_FAST_ARGS);
+            if (!rc && (ns_mask & 2)) rc = launch_fast_batch_t<8, 4, 2, 8>(OBIA_FAST_ARGS);
+            if (!rc && (ns_mask & 4)) rc = launch_fast_batch_t<8, 4, 4, 8>(OBIA_FAST_ARGS);
+        }
+        return rc;
+    }
     if (Cf <= 16) return launch_fast_batch_t<16, 2, 2, 8>(OBIA_FAST_ARGS);
     if (Cf <= 32) return launch_fast_batch_t<32, 2, 2, 8>(OBIA_FAST_ARGS);
     return launch_fast_batch_t<64, 2, 2, 8>(OBIA_FAST_ARGS);
