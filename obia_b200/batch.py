@@ -273,14 +273,15 @@ class WindowBatch:
         _lib.check(lib.obia_b200_slic_batch_prepare(d.ctypes.data_as(ctypes.c_void_p), B, Cf), "slic_batch_prepare")
         variants = int(np.bitwise_or.reduce(d["pad"][valid])) if valid.any() else 0
 
+        draws = None
         if masked:
             # the RandomState(123) draws of the maskSLIC initialisation start now, on host threads
-            slic_host.prefetch_mask_samples([(int(n_coord[i]), int(n_seg[i])) for i in np.nonzero(valid)[0]])
+            draws = slic_host.submit_mask_samples([(int(n_coord[i]), int(n_seg[i])) for i in np.nonzero(valid)[0]])
         _tick("host parameters")
         self._st = dict(masked=masked, bands=bands, Cs=Cs, Cf=Cf, to_lab=to_lab, ratio=ratio, valid=valid, n=n, c0=c0,
                         n_coord=n_coord, n_seg=n_seg, n_mask=n_mask, grids=grids, mn=mn, dd=dd, n_total=n_total,
                         cells_total=cells_total, km_cells_total=km_cells_total, max_num_iter=max_num_iter,
-                        start_label=start_label, variants=variants)
+                        start_label=start_label, variants=variants, draws=draws)
         return self
 
     def finish(self):
@@ -301,12 +302,14 @@ class WindowBatch:
         if masked:
             # ---- maskSLIC initialisation: RandomState(123) draws (host threads), k-means on the device ------
             pos_all = torch.nonzero(self.mask_slab.reshape(-1)).reshape(-1).to(torch.int32)
+            _tick("centre init: nonzero")
             base = np.concatenate([[0], np.cumsum(n_mask)[:-1]])
             seeds, dense, p0, m = [], [], np.zeros(B, dtype=np.int64), np.zeros(B, dtype=np.int64)
             all_dense = True
-            draws = {}
+            draws, futures = {}, st["draws"]
             for i in np.nonzero(valid)[0]:
-                idx, idx_dense = slic_host.mask_sample_indices(int(n_coord[i]), int(n_seg[i]))
+                got = futures[(int(n_coord[i]), int(n_seg[i]))]
+                idx, idx_dense = got if isinstance(got, tuple) else got.result()
                 draws[i] = idx_dense
                 seeds.append(idx + base[i])
                 if idx_dense is not None:
@@ -323,9 +326,11 @@ class WindowBatch:
                     p0[i], m[i] = off, len(di)
                     off += len(di)
                 pts = pos_all[torch.from_numpy(np.concatenate(dense)).to(dev)]
+            _tick("centre init: sample draws (host)")
             d["p0"], d["m"] = np.where(valid, p0, 0), np.where(valid, m, 0)
             self.upload()
             seed_pos = pos_all[torch.from_numpy(np.concatenate(seeds)).to(dev)]
+            _tick("centre init: seed upload")
             cent = torch.empty((n_total, 2), dtype=torch.float64, device=dev)
             km_ws = torch.empty((lib.obia_b200_mask_kmeans_batch_workspace_bytes(n_total, km_cells_total),),
                                 dtype=torch.uint8, device=dev)
@@ -345,7 +350,7 @@ class WindowBatch:
                 rows[k0:k0 + n[i], 1] = np.tile(xs, len(ys))
             centres.copy_(torch.from_numpy(rows))
 
-        _tick("centre initialisation (draws + k-means)")
+        _tick("centre init: k-means kernels")
         # ---- K1b per window ---------------------------------------------------------------------------
         feats = torch.empty((Cf, self.slab_rows, self.pitch), dtype=torch.float32, device=dev)
         bands_dev = torch.tensor(bands, dtype=torch.int32, device=dev)

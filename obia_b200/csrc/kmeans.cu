@@ -351,20 +351,31 @@ km_batch_closest_kernel(const double *__restrict__ cent, const int32_t *__restri
 
 // `steps = np.abs(centroids - centroids[closest]).mean(0)` (row-sequential float64 sums), `step = max(steps)`,
 // the spatial weight `1.0 / step ** 2` as slic.cu derives it; a window whose step is not positive is dropped
-// (the reference raises ValueError there: an "empty tile").  One thread per window.
+// (the reference raises ValueError there: an "empty tile").  One WARP per window: the lanes fetch 32 terms at a
+// time, the sum itself runs in index order (every lane adds the same sequence, so the rounding is numpy's).
 __global__ void __launch_bounds__(128)
 km_batch_steps_kernel(const double *__restrict__ cent, const int32_t *__restrict__ closest, WinDesc *batch, int64_t B)
 {
-    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (w >= B) return;
     WinDesc &d = batch[w];
     if (!d.valid) return;
     double sy = 0.0, sx = 0.0;
-    for (int i = 0; i < d.n; ++i) {
-        const int64_t k = (int64_t)d.c0 + i, j = closest[k];
-        sy = __dadd_rn(sy, fabs(__dsub_rn(cent[2 * k], cent[2 * j])));
-        sx = __dadd_rn(sx, fabs(__dsub_rn(cent[2 * k + 1], cent[2 * j + 1])));
+    for (int i0 = 0; i0 < d.n; i0 += 32) {
+        double ay = 0.0, ax = 0.0;
+        if (i0 + lane < d.n) {
+            const int64_t k = (int64_t)d.c0 + i0 + lane, j = closest[k];
+            ay = fabs(__dsub_rn(cent[2 * k], cent[2 * j]));
+            ax = fabs(__dsub_rn(cent[2 * k + 1], cent[2 * j + 1]));
+        }
+        const int cnt = min(32, d.n - i0);
+        for (int l = 0; l < cnt; ++l) {
+            sy = __dadd_rn(sy, __shfl_sync(0xffffffffu, ay, l));
+            sx = __dadd_rn(sx, __shfl_sync(0xffffffffu, ax, l));
+        }
     }
+    if (lane != 0) return;
     sy = __ddiv_rn(sy, (double)d.n);
     sx = __ddiv_rn(sx, (double)d.n);
     const float step = (float)fmax(0.0, fmax(sy, sx));
@@ -503,7 +514,7 @@ extern "C" int obia_b200_mask_kmeans_batch(const int32_t *points_pos, int64_t m_
     OBIA_LAUNCH_CHECK();
     km_batch_closest_kernel<<<gn, 256, 0, st>>>(centroids, cwin, batch, n_total, head, next, closest);
     OBIA_LAUNCH_CHECK();
-    km_batch_steps_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, st>>>(centroids, closest, batch, B);
+    km_batch_steps_kernel<<<(unsigned)ceil_div(B * 32, 128), 128, 0, st>>>(centroids, closest, batch, B);
     OBIA_LAUNCH_CHECK();
     km_batch_centres_kernel<<<gn, 256, 0, st>>>(centroids, n_total, Cf, centres);
     OBIA_LAUNCH_CHECK();

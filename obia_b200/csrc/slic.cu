@@ -984,10 +984,12 @@ extern "C" int obia_b200_slic_iterate_batch(const float *features, const uint8_t
     OBIA_LAUNCH_CHECK();
     int rc = OBIA_B200_OK;
     for (int it = 0; it < max_num_iter && !rc; ++it) {
-        OBIA_CUDA_CHECK(cudaMemsetAsync(head, 0xff, (size_t)cells_total * 4, st));
-        slic_centres_batch_kernel<<<(unsigned)ceil_div(n_total, 256), 256, 0, st>>>(centres, acc, head, next, n_total, Cf, 0,
-                                                                                   cwin, batch);
-        OBIA_LAUNCH_CHECK();
+        if (it == 0) {   // (later sweeps find the centres binned by the update at the end of the previous one)
+            OBIA_CUDA_CHECK(cudaMemsetAsync(head, 0xff, (size_t)cells_total * 4, st));
+            slic_centres_batch_kernel<<<(unsigned)ceil_div(n_total, 256), 256, 0, st>>>(centres, acc, head, next, n_total,
+                                                                                       Cf, 0, cwin, batch);
+            OBIA_LAUNCH_CHECK();
+        }
         rc = launch_assign_fast_batch(features, mask, centres, head, next, acc, labels, batch, B, hmax, wmax, slab_rows,
                                       slab_w, pitch, Cf, start_label, ignore_color, status, variants, st);
         if (rc) break;

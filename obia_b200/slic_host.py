@@ -144,6 +144,27 @@ def prefetch_mask_samples(keys):
         _CHOICE_CACHE[key] = _CHOICE_POOL.submit(_draw_mask_samples, *key)
 
 
+def submit_mask_samples(keys):
+    """Futures of the draws for `keys` (iterable of (n_coord, n_segments)), one per distinct key, owned by the
+    caller (the window batches of the tiled driver: tens of thousands of distinct keys per run, more than the
+    shared cache keeps)."""
+    global _CHOICE_POOL
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    if _CHOICE_POOL is None:
+        local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1))
+        workers = max(1, min(32, ((os.cpu_count() or 2) - 1) // local))
+        _CHOICE_POOL = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="obia_b200_rng")
+    out = {}
+    for n_coord, n_segments in keys:
+        key = (int(n_coord), int(n_segments))
+        if key[0] <= 0 or key[1] <= 0 or key in out:
+            continue
+        hit = _CHOICE_CACHE.get(key)
+        out[key] = hit if hit is not None else _CHOICE_POOL.submit(_draw_mask_samples, *key)
+    return out
+
+
 def mask_sample_indices(n_coord, n_segments):
     """(idx, idx_dense) of `_get_mask_centroids`: two draws from RandomState(123); idx_dense is None when it
     is every pixel (100 * n_segments >= n_coord).
