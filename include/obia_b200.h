@@ -474,6 +474,17 @@ int obia_b200_tiled_white_prepare(int32_t *G, int64_t GW, const void *descs, con
                                   const uint8_t *user_mask, int64_t Wm, uint8_t *mask_slab, int32_t slab_w,
                                   void *stream);
 
+/* Seam exchange of the column-block sharded driver: import a neighbour's version of a boundary band (three
+ * int64 planes per pixel: creation key or -1, segment size, home = owner rank << 32 | handle there) into the
+ * rows x cols block of G at G_band.  Segments homed on this rank keep their handle, neighbour segments are
+ * translated through `mirror` (neighbour handle -> local handle, -1 unknown; new ones take slots slot_base +
+ * [0, rows * cols), reserved by the caller).  retire != 0 (white rows): every handle in the band that does not
+ * come back is dead.  No host synchronisation. */
+int obia_b200_tiled_seam_import(int32_t *G_band, int64_t GW, int32_t rows, int32_t cols, const int64_t *planes,
+                                int32_t my_rank, int32_t retire, int32_t *mirror, int64_t mirror_cap,
+                                int32_t slot_base, int32_t *counter, int32_t *err, int64_t *keys, int32_t *sizes,
+                                uint8_t *live, int64_t *homes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

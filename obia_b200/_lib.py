@@ -79,6 +79,8 @@ SIGNATURES = {
     "obia_b200_enforce_connectivity_windows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _vp]),
     "obia_b200_tiled_paint": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp,
                                              _i64, _vp, _vp]),
+    "obia_b200_tiled_seam_import": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _vp,
+                                                   _vp, _vp, _vp, _vp]),
     "obia_b200_tiled_white_prepare": (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _vp,
                                                      _vp, _vp, _i64, _vp, _i32, _vp]),
     "obia_b200_texture_workspace_bytes": (_i64, [_i64]),

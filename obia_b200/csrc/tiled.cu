@@ -111,6 +111,68 @@ white_reset_kernel(int32_t *__restrict__ G, int64_t GW, const WinDesc *__restric
     cnt[(int64_t)parity[blockIdx.y] * cap + g] = 0;
 }
 
+// ---- seam exchange (multi-GPU: the raster is sharded into column blocks, obia_b200/utils/tiling.py) -------------
+// A neighbour's version of the 2*buffer-wide band on a block boundary replaces this rank's.  The band arrives as
+// three int64 planes per pixel: creation key (-1 = no segment), segment size, and the segment's home
+// (owner rank << 32 | handle on that rank).  Segments homed here keep their handle; segments homed on the
+// neighbour are looked up in `mirror` (neighbour handle -> local handle, -1 unknown) and get a fresh local handle
+// on first sight.  Three launches, no host round trip:
+//   retire  live = 0 for every handle currently in the band (white rows: what does not come back was deleted)
+//   claim   every pixel of an unknown neighbour segment draws a slot; one of them wins the mirror entry
+//   import  G, keys, sizes, live, home from the planes through the (now complete) mirror
+__global__ void __launch_bounds__(256)
+seam_retire_kernel(const int32_t *__restrict__ G, int64_t GW, int rows, int cols, uint8_t *live)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int32_t g = G[(int64_t)(i / cols) * GW + i % cols];
+    if (g >= 0) live[g] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+seam_claim_kernel(const long long *__restrict__ planes, int n, int me, int32_t *mirror, int64_t mirror_cap,
+                  int32_t slot_base, int32_t *counter, int32_t *err)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || planes[i] < 0) return;
+    const long long home = planes[2 * (int64_t)n + i];
+    if ((int)(home >> 32) == me) return;
+    const int64_t fh = home & 0xffffffffLL;
+    if (fh >= mirror_cap) {
+        *err = 1;
+        return;
+    }
+    if (mirror[fh] == -1) atomicCAS(mirror + fh, -1, slot_base + atomicAdd(counter, 1));
+}
+
+__global__ void __launch_bounds__(256)
+seam_import_kernel(const long long *__restrict__ planes, int rows, int cols, int me, const int32_t *__restrict__ mirror,
+                   int64_t mirror_cap, int32_t *__restrict__ G, int64_t GW, long long *keys, int32_t *sizes,
+                   uint8_t *live, long long *homes)
+{
+    const int n = rows * cols;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long key = planes[i];
+    int32_t h = -1;
+    if (key >= 0) {
+        const long long home = planes[2 * (int64_t)n + i];
+        const int64_t fh = home & 0xffffffffLL;
+        if ((int)(home >> 32) == me) {
+            h = (int32_t)fh;
+        } else if (fh < mirror_cap) {
+            h = mirror[fh];
+            if (h >= 0) {
+                keys[h] = key;
+                sizes[h] = (int32_t)planes[(int64_t)n + i];
+                homes[h] = home;
+            }
+        }
+        if (h >= 0) live[h] = 1;
+    }
+    G[(int64_t)(i / cols) * GW + i % cols] = h;
+}
+
 }  // namespace obia
 
 using namespace obia;
@@ -155,6 +217,35 @@ extern "C" int obia_b200_tiled_white_prepare(int32_t *G, int64_t GW, const void 
                                              user_mask, Wm, mask_slab, slab_w, hw);
     OBIA_LAUNCH_CHECK();
     white_reset_kernel<<<grid, 256, 0, st>>>(G, GW, batch, parity, counts, capacity, hw);
+    OBIA_LAUNCH_CHECK();
+    return OBIA_B200_OK;
+}
+
+// band: the rows x cols block of G at `G_band` (row stride GW); planes: (3, rows, cols) int64 as received;
+// mirror: (mirror_cap) int32 for this neighbour, -1 = unknown; new local handles are slot_base + [0, rows * cols):
+// the caller reserves that many table slots (counter: device int32, zeroed here; err: device int32, set to 1 when a
+// neighbour handle exceeds mirror_cap).  retire != 0: white-row exchange (segments that vanish were deleted).
+extern "C" int obia_b200_tiled_seam_import(int32_t *G_band, int64_t GW, int32_t rows, int32_t cols,
+                                           const int64_t *planes, int32_t my_rank, int32_t retire, int32_t *mirror,
+                                           int64_t mirror_cap, int32_t slot_base, int32_t *counter, int32_t *err,
+                                           int64_t *keys, int32_t *sizes, uint8_t *live, int64_t *homes, void *stream)
+{
+    if (!G_band || !planes || !mirror || !counter || !err || !keys || !sizes || !live || !homes || rows <= 0 ||
+        cols <= 0 || GW < cols || mirror_cap <= 0 || slot_base < 0)
+        return set_err(OBIA_B200_ERR_ARG, "tiled_seam_import: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = rows * cols;
+    const unsigned grid = (unsigned)ceil_div(n, 256);
+    OBIA_CUDA_CHECK(cudaMemsetAsync(counter, 0, 4, st));
+    if (retire) {
+        seam_retire_kernel<<<grid, 256, 0, st>>>(G_band, GW, rows, cols, live);
+        OBIA_LAUNCH_CHECK();
+    }
+    seam_claim_kernel<<<grid, 256, 0, st>>>((const long long *)planes, n, my_rank, mirror, mirror_cap, slot_base, counter,
+                                            err);
+    OBIA_LAUNCH_CHECK();
+    seam_import_kernel<<<grid, 256, 0, st>>>((const long long *)planes, rows, cols, my_rank, mirror, mirror_cap, G_band, GW,
+                                             (long long *)keys, sizes, live, (long long *)homes);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
 }

@@ -394,9 +394,12 @@ class BatchedTiledSegmenter:
         self.G = torch.full((self.H, self.Wl), -1, dtype=torch.int32, device=self.device)
         self.cap = 0
         self.n_handles = 0
-        self.sizes = self.live = self.keys = self.cnt = None
+        self.sizes = self.live = self.keys = self.homes = self.cnt = None
         self._grow(1 << 16)
-        self.h_of_key = {}      # seam segments: creation key -> handle on this rank
+        # seam exchange state (world > 1): neighbour handle -> local handle per side, claim counter, error flag
+        self.mirror = {}
+        self.mirror_cap = 1 << 26
+        self.seam_ctr = torch.zeros((2,), dtype=torch.int32, device=self.device)
         self.black, self.white = plan_tiles(self.H, self.W, self.T, self.buffer)
         c = self.buffer / 2.0
         self.corner = max(0, int(math.ceil(c - 0.5))) if c > 0 else 0     # window_polygon_mask
@@ -410,11 +413,13 @@ class BatchedTiledSegmenter:
         sizes = torch.zeros((cap,), dtype=torch.int32, device=dev)
         live = torch.zeros((cap,), dtype=torch.uint8, device=dev)
         keys = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+        homes = torch.full((cap,), -1, dtype=torch.int64, device=dev)     # owner rank << 32 | handle on that rank
         if self.cap:
             sizes[:self.cap] = self.sizes
             live[:self.cap] = self.live
             keys[:self.cap] = self.keys
-        self.sizes, self.live, self.keys = sizes, live, keys
+            homes[:self.cap] = self.homes
+        self.sizes, self.live, self.keys, self.homes = sizes, live, keys, homes
         self.cnt = torch.zeros((2 * cap,), dtype=torch.int32, device=dev)     # all zero between calls
         self.cap = cap
 
@@ -483,6 +488,8 @@ class BatchedTiledSegmenter:
             self.keys[hbase:hzero] = base_key[win] + (lab - prev[win] + (sl - 1))
         self.keys[hzero:hzero + B] = base_key          # the leftover label 0 of a window (start_label 1)
         self.live[hbase:hzero + B] = (self.sizes[hbase:hzero + B] > 0).to(torch.uint8)
+        if self.world > 1:
+            self.homes[hbase:hzero + B] = torch.arange(hbase, hzero + B, dtype=torch.int64, device=dev) + (self.rank << 32)
         self.n_handles = hzero + B
 
     # ------------------------------------------------------------------ passes
@@ -546,9 +553,13 @@ class BatchedTiledSegmenter:
 
     # ------------------------------------------------------------------ seam exchange
     def _exchange(self, white_row):
-        """As TiledSegmenter._exchange; the band travels as creation keys, each side keeps its own handles."""
+        """As TiledSegmenter._exchange, without host round trips: the band travels as three int64 planes per
+        pixel (creation key, size, home handle) in one message per boundary; the receiver translates the
+        neighbour's handles on the device (csrc/tiled.cu, seam import)."""
         if self.world == 1:
             return
+        from .. import _lib
+        from ..batch import _p, _stream
         b, T, dev = self.buffer, self.T, self.device
         if white_row is None:
             ya, yb = 0, self.H
@@ -574,57 +585,33 @@ class BatchedTiledSegmenter:
                 sx0, sx1 = rx0, rx1 = xa_, xb_
             if i_send:
                 band = self.G[ya:yb, sx0 - self.xo:sx1 - self.xo]
-                hs = torch.unique(band[band >= 0]).to(torch.int64)
-                table = torch.stack([self.keys[hs], self.sizes[hs].to(torch.int64)], dim=1).contiguous()
-                kband = torch.where(band >= 0, self.keys[band.clamp(min=0).to(torch.int64)],
-                                    torch.full((), -1, dtype=torch.int64, device=dev)).contiguous()
-                for k, h in zip(table[:, 0].tolist(), hs.tolist()):
-                    self.h_of_key[k] = h
-                meta = torch.tensor([table.shape[0]], dtype=torch.int64, device=dev)
-                sends.append((nb, meta, kband, table))
+                idx = band.clamp(min=0).to(torch.int64)
+                none = torch.full((), -1, dtype=torch.int64, device=dev)
+                planes = torch.stack([torch.where(band >= 0, self.keys[idx], none),
+                                      self.sizes[idx].to(torch.int64), self.homes[idx]]).contiguous()
+                sends.append((nb, planes))
             if i_recv:
-                recvs.append((nb, ya, yb, rx0, rx1))
+                recvs.append((nb, side, ya, yb, rx0, rx1))
 
         def do_sends():
-            for nb, meta, kband, table in sends:
-                self.dist.send(meta, nb)
-                self.dist.send(kband, nb)
-                if table.shape[0]:
-                    self.dist.send(table, nb)
+            for nb, planes in sends:
+                self.dist.send(planes, nb)
 
         def do_recvs():
-            for nb, ra, rb, rx0, rx1 in recvs:
-                meta = torch.zeros(1, dtype=torch.int64, device=dev)
-                self.dist.recv(meta, nb)
-                kband = torch.empty((rb - ra, rx1 - rx0), dtype=torch.int64, device=dev)
-                self.dist.recv(kband, nb)
-                n = int(meta.item())
-                old = self.G[ra:rb, rx0 - self.xo:rx1 - self.xo]
-                gone = torch.unique(old[old >= 0]).to(torch.int64)
-                new_band = torch.full(kband.shape, -1, dtype=torch.int32, device=dev)
-                if n:
-                    table = torch.empty((n, 2), dtype=torch.int64, device=dev)
-                    self.dist.recv(table, nb)
-                    rows = table.tolist()
-                    fresh = [k for k, _ in rows if k not in self.h_of_key]
-                    self._grow(self.n_handles + len(fresh))
-                    for k in fresh:
-                        self.h_of_key[k] = self.n_handles
-                        self.n_handles += 1
-                    hs = torch.tensor([self.h_of_key[k] for k, _ in rows], dtype=torch.int64, device=dev)
-                    self.keys[hs] = table[:, 0]
-                    self.sizes[hs] = table[:, 1].to(torch.int32)
-                    order = torch.argsort(table[:, 0])
-                    skeys = table[order, 0].contiguous()
-                    pos = torch.searchsorted(skeys, kband.clamp(min=0)).clamp_(max=n - 1)
-                    new_band = torch.where(kband >= 0, hs[order][pos].to(torch.int32), new_band)
-                    if white_row is not None and gone.numel():
-                        # segments that vanished from the band were deleted by the neighbour
-                        self.live[gone] = 0
-                    self.live[hs] = 1
-                elif white_row is not None and gone.numel():
-                    self.live[gone] = 0
-                self.G[ra:rb, rx0 - self.xo:rx1 - self.xo] = new_band
+            for nb, side, ra, rb, rx0, rx1 in recvs:
+                rows, cols = rb - ra, rx1 - rx0
+                planes = torch.empty((3, rows, cols), dtype=torch.int64, device=dev)
+                self.dist.recv(planes, nb)
+                if side not in self.mirror:
+                    self.mirror[side] = torch.full((self.mirror_cap,), -1, dtype=torch.int32, device=dev)
+                slot_base = self.n_handles
+                self._grow(slot_base + rows * cols)
+                self.n_handles = slot_base + rows * cols
+                band = self.G[ra:rb, rx0 - self.xo:rx1 - self.xo]
+                _lib.check(self.lib.obia_b200_tiled_seam_import(
+                    _p(band), self.Wl, rows, cols, _p(planes), self.rank, int(white_row is not None),
+                    _p(self.mirror[side]), self.mirror_cap, slot_base, _p(self.seam_ctr[0:1]), _p(self.seam_ctr[1:2]),
+                    _p(self.keys), _p(self.sizes), _p(self.live), _p(self.homes), _stream()), "tiled_seam_import")
 
         if self.rank % 2 == 0:
             do_sends()
@@ -641,6 +628,8 @@ class BatchedTiledSegmenter:
         own = self.G[:, x0 - self.xo:x1 - self.xo] if x1 > x0 else self.G[:, :0]
         dev = self.device
         nh = self.n_handles
+        if self.world > 1 and int(self.seam_ctr[1].item()) != 0:
+            raise RuntimeError("tiled seam exchange: a neighbour's segment handle exceeds the mirror table")
         alive = torch.nonzero(self.live[:nh]).reshape(-1)
         keys = self.keys[alive]
         if self.world > 1:
