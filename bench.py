@@ -258,6 +258,39 @@ def parity_block(size, seed=2):
     return out
 
 
+def tiled_c3_block(size, world, rank, dev, barrier):
+    """`create_tiled_segments` on c3 (size x size x 4 float32, tile 200, buffer 30, input mask + crown_radius 5 --
+    the one mode the reference runs), the raster sharded into column blocks over the ranks.  Synthetic raster and
+    mask generated on the device; the wall clock covers the whole call up to the final label raster (no polygons)."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from tiled_bench import synth
+    from obia_b200 import slic_host
+    from obia_b200.utils.tiling import create_tiled_segments
+    kw = dict(tile_size=200, buffer=30, crown_radius=5, compactness=0.2, return_labels=True, polygons=False)
+    raw, mask = synth(size, size, 4, dev)
+    create_tiled_segments(raw[:600, :600], None, mask[:600, :600], distributed=False, **kw)     # warm-up
+    slic_host._CHOICE_CACHE.clear()
+    torch.cuda.reset_peak_memory_stats()
+    barrier()
+    t0 = time.perf_counter()
+    labels, n, _ = create_tiled_segments(raw, None, mask, **kw)
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {"workload": f"c3: create_tiled_segments {size}x{size}x4 float32, tile 200, buffer 30, masked (crown_radius 5), "
+                       f"{(size // 200) ** 2} tiles, column blocks over {world} GPU(s)",
+           "seconds": float(t.item()), "value": size * size / 1e6 / float(t.item()), "unit": "MP/s", "segments": int(n),
+           "driver": "batched (one launch per stage over all windows of a pass / tile-row)",
+           "peak_mem_GB_rank0": torch.cuda.max_memory_allocated() / 2 ** 30}
+    del raw, mask, labels
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import ctypes
 
@@ -464,6 +497,11 @@ def run_ours(args):
                                            "note": "default segment() column set incl. GLCM texture"}
         del pristine, work
 
+    # ---- the tiled driver on c3 (BASELINE.json configs[2]): reported beside the headline, not part of it ----
+    tiled = None
+    if not args.no_tiled and not args.size:
+        tiled = tiled_c3_block(args.tiled_size, world, rank, dev, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -523,6 +561,8 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "cpu_baseline": cpu, "parity": parity, "split_ms": split, "also": alt,
     }
+    if tiled is not None:
+        line["tiled_c3"] = tiled
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -542,6 +582,8 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=768)
     ap.add_argument("--parity-size", type=int, default=768, help="crop side of the oracle-vs-CUDA parity block")
     ap.add_argument("--exact", action="store_true", help="time the exact-mode SLIC kernel instead of the tolerance mode")
+    ap.add_argument("--no-tiled", action="store_true", help="skip the create_tiled_segments (c3) block")
+    ap.add_argument("--tiled-size", type=int, default=40000, help="side of the c3 raster")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
