@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libobia_b200.so")
+LIB_PATH = os.environ.get("OBIA_B200_LIB") or os.path.join(_HERE, "_lib", "libobia_b200.so")   # (override: kernel experiments)
 
 _i32, _i64 = ctypes.c_int32, ctypes.c_int64
 _f32, _f64 = ctypes.c_float, ctypes.c_double

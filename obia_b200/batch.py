@@ -227,34 +227,51 @@ class WindowBatch:
         max_abs = float(ratio) * (256.0 if to_lab else 4.0)
         n = np.zeros(B, dtype=np.int64)
         grids = {}
-        for i in np.nonzero(valid)[0]:
-            h, w = int(d["h"][i]), int(d["w"][i])
-            if masked:
-                n[i] = min(int(n_seg[i]), int(n_coord[i]))
-            else:
-                ys, xs, step = _grid_init(h, w, int(n_seg[i]))
-                n[i] = len(ys) * len(xs)
-                grids[i] = (ys, xs, step)
-                if not step > 0 or n[i] == 0:
-                    valid[i] = False
-                    continue
-            sy, sx = _geometry(h, w, int(n[i]))
-            seg_size = float(n_coord[i]) / float(n[i])
-            mins, maxs = int(min_size_factor * seg_size), int(max_size_factor * seg_size)
-            if maxs < 1 or n[i] >= 2 ** 24:
-                valid[i] = False
-                continue
-            d["step_y"][i], d["step_x"][i] = sy, sx
-            d["min_size"][i], d["max_size"][i] = min(mins, 2 ** 31 - 1), min(maxs, 2 ** 31 - 1)
-            d["fix_scale"][i] = _fix_scale(max_abs, h, w, sy, sx)
-            d["ncy"][i], d["ncx"][i] = -(-h // sy), -(-w // sx)
-            cs = max(1.0, math.sqrt(float(h) * float(w) / float(n[i])))
-            d["km_cs"][i] = cs
-            d["km_ncy"][i], d["km_ncx"][i] = int(float(h) / cs) + 1, int(float(w) / cs) + 1
-            if not masked:
-                stepf = f32(step)
-                sw = f32(1.0 / float(f32(stepf * stepf)))
-                d["sw"][i], d["inv_w"][i] = sw, f32(f32(1.0) / sw)
+        # the derivation depends on (h, w, n_segments / n) only: once per distinct triple, broadcast to the windows
+        vi = np.nonzero(valid)[0]
+        hh, ww = d["h"][vi].astype(np.int64), d["w"][vi].astype(np.int64)
+        if masked:
+            nn = np.minimum(n_seg[vi], n_coord[vi])
+            step_u = None
+        else:
+            uk, inv = np.unique((hh << 44) | (ww << 24) | np.minimum(n_seg[vi], (1 << 24) - 1), return_inverse=True)
+            nn_u, step_u_ = np.zeros(len(uk), np.int64), np.zeros(len(uk), np.float64)
+            for u, k in enumerate(uk.tolist()):
+                ys, xs, step = _grid_init(k >> 44, (k >> 24) & 0xfffff, k & 0xffffff)
+                nn_u[u], step_u_[u] = len(ys) * len(xs), step
+            nn, step_u = nn_u[inv], step_u_[inv]
+            for i_, u in zip(vi.tolist(), inv.tolist()):
+                k = int(uk[u])
+                grids[i_] = _grid_init(k >> 44, (k >> 24) & 0xfffff, k & 0xffffff)
+        ok = (nn > 0) & (nn < 2 ** 24)
+        if step_u is not None:
+            ok &= step_u > 0
+        nn_safe = np.where(ok, nn, 1)
+        uk, inv = np.unique((hh << 44) | (ww << 24) | nn_safe, return_inverse=True)
+        cols = np.zeros((len(uk), 8), dtype=np.float64)     # sy, sx, fix_scale, ncy, ncx, km_cs, km_ncy, km_ncx
+        for u, k in enumerate(uk.tolist()):
+            h, w, nk = k >> 44, (k >> 24) & 0xfffff, k & 0xffffff
+            sy, sx = _geometry(h, w, nk)
+            cs = max(1.0, math.sqrt(float(h) * float(w) / float(nk)))
+            cols[u] = (sy, sx, _fix_scale(max_abs, h, w, sy, sx), -(-h // sy), -(-w // sx), cs,
+                       int(float(h) / cs) + 1, int(float(w) / cs) + 1)
+        cw = cols[inv]
+        seg_size = n_coord[vi].astype(np.float64) / nn_safe.astype(np.float64)
+        mins = np.minimum(np.trunc(min_size_factor * seg_size), 2 ** 31 - 1).astype(np.int64)
+        maxs = np.minimum(np.trunc(max_size_factor * seg_size), 2 ** 31 - 1).astype(np.int64)
+        ok &= maxs >= 1
+        valid[vi] = ok
+        n[vi] = np.where(ok, nn, 0)
+        for name, c in (("step_y", 0), ("step_x", 1), ("ncy", 3), ("ncx", 4), ("km_ncy", 6), ("km_ncx", 7)):
+            d[name][vi] = np.where(ok, cw[:, c], 0).astype(np.int32)
+        d["fix_scale"][vi] = np.where(ok, cw[:, 2], 0.0)
+        d["km_cs"][vi] = np.where(ok, cw[:, 5], 0.0)
+        d["min_size"][vi], d["max_size"][vi] = np.where(ok, mins, 0), np.where(ok, maxs, 0)
+        if step_u is not None:
+            stepf = step_u.astype(f32)
+            with np.errstate(divide="ignore"):
+                sw = (1.0 / (stepf * stepf).astype(f32).astype(np.float64)).astype(f32)
+                d["sw"][vi], d["inv_w"][vi] = np.where(ok, sw, 0), np.where(ok, (f32(1.0) / sw).astype(f32), 0)
         n = np.where(valid, n, 0)
         d["valid"] = valid.astype(np.int32)
         d["n"] = n
@@ -301,8 +318,14 @@ class WindowBatch:
         centres = torch.empty((n_total, 2 + Cf), dtype=torch.float32, device=dev)
         if masked:
             # ---- maskSLIC initialisation: RandomState(123) draws (host threads), k-means on the device ------
-            pos_all = torch.nonzero(self.mask_slab.reshape(-1)).reshape(-1).to(torch.int32)
-            _tick("centre init: nonzero")
+            # position of the r-th mask pixel of the slab = first index whose inclusive mask count reaches r + 1
+            # (np.nonzero order; no host round trip, unlike torch.nonzero)
+            mask_rank = torch.cumsum(self.mask_slab.reshape(-1), 0, dtype=torch.int32)
+
+            def positions(ranks):
+                want = torch.from_numpy(np.ascontiguousarray(ranks + 1, dtype=np.int32)).to(dev)
+                return torch.searchsorted(mask_rank, want).to(torch.int32)
+            _tick("centre init: mask ranks")
             base = np.concatenate([[0], np.cumsum(n_mask)[:-1]])
             seeds, dense, p0, m = [], [], np.zeros(B, dtype=np.int64), np.zeros(B, dtype=np.int64)
             all_dense = True
@@ -315,8 +338,8 @@ class WindowBatch:
                 if idx_dense is not None:
                     all_dense = False
             if all_dense:
-                # coord[idx_dense] is every mask pixel of the window: the points are the slab's mask pixels
-                pts = pos_all
+                # coord[idx_dense] is every mask pixel of the window: the k-means kernel walks the mask slab itself
+                pts = None
                 p0, m = base, n_mask
             else:
                 off = 0
@@ -325,20 +348,21 @@ class WindowBatch:
                     dense.append(di + base[i])
                     p0[i], m[i] = off, len(di)
                     off += len(di)
-                pts = pos_all[torch.from_numpy(np.concatenate(dense)).to(dev)]
+                pts = positions(np.concatenate(dense))
             _tick("centre init: sample draws (host)")
             d["p0"], d["m"] = np.where(valid, p0, 0), np.where(valid, m, 0)
             self.upload()
-            seed_pos = pos_all[torch.from_numpy(np.concatenate(seeds)).to(dev)]
+            seed_pos = positions(np.concatenate(seeds))
             _tick("centre init: seed upload")
             cent = torch.empty((n_total, 2), dtype=torch.float64, device=dev)
             km_ws = torch.empty((lib.obia_b200_mask_kmeans_batch_workspace_bytes(n_total, km_cells_total),),
                                 dtype=torch.uint8, device=dev)
             _lib.check(lib.obia_b200_mask_kmeans_batch(
-                _p(pts), int(pts.numel()), _p(self.mask_slab) if all_dense else None, self.hmax, self.wmax, _p(seed_pos),
+                _p(pts), 0 if pts is None else int(pts.numel()), _p(self.mask_slab) if all_dense else None, self.hmax,
+                self.wmax, _p(seed_pos),
                 _p(cwin), _p(self.desc_dev), B, n_total, km_cells_total, self.slab_w, self.win_rows, 5, Cf, _p(cent),
                 _p(centres), _p(km_ws), _stream()), "mask_kmeans_batch")
-            del km_ws, pts, pos_all
+            del km_ws, pts, mask_rank
         else:
             self.upload()
             rows = np.zeros((n_total, 2 + Cf), dtype=np.float32)

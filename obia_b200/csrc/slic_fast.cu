@@ -24,6 +24,13 @@
 #include "batch.cuh"
 #include "slic_common.cuh"
 
+#ifndef OBIA_K2_LOAD
+#define OBIA_K2_LOAD 1      // 1: one running pointer for the feature planes, mask test behind a uniform branch
+#endif
+#ifndef OBIA_K2_SKIP
+#define OBIA_K2_SKIP 0      // 1: groups of 32 candidate records beyond the chunk size are skipped
+#endif
+
 namespace obia {
 
 template <int CP, int NW> struct FastTraits {
@@ -202,25 +209,47 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
         const bool ld_ok = y < H && xb < W;
         float pf[PX][CP];
         unsigned vmask = 0;
+#if !OBIA_K2_LOAD
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
             bool v = ld_ok && (xb + j) < W;
             if (v && mask) v = mask[(int64_t)y * LW + xb + j] != 0;
             vmask |= (v ? 1u : 0u) << j;
         }
+#else
+        if (ld_ok) {
+            // columns of the lane that exist; then the mask (uniform branch: most runs have none)
+            vmask = (xb + PX <= W) ? ((1u << PX) - 1u) : ((1u << (W - xb)) - 1u);
+            if (mask) {
+                const uint8_t *mrow = mask + (int64_t)y * LW + xb;
+#pragma unroll
+                for (int j = 0; j < PX; ++j)
+                    if (((vmask >> j) & 1u) && mrow[j] == 0) vmask &= ~(1u << j);
+            }
+        }
+#endif
         {
+            // one pointer, advanced plane by plane (no 64-bit multiply per channel)
             const float *src = feat + (int64_t)y * pitch + xb;
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ld_ok && c < Cf) {
+#if OBIA_K2_LOAD
+                    const float *sc_ = src;
+#else
+                    const float *sc_ = src + c * plane;
+#endif
                     if constexpr (PX == 4) {
-                        v = ldg_stream_f4(reinterpret_cast<const float4 *>(src + c * plane));
+                        v = ldg_stream_f4(reinterpret_cast<const float4 *>(sc_));
                     } else {
-                        const float2 t = *reinterpret_cast<const float2 *>(src + c * plane);
+                        const float2 t = *reinterpret_cast<const float2 *>(sc_);
                         v.x = t.x; v.y = t.y;
                     }
                 }
+#if OBIA_K2_LOAD
+                src += plane;
+#endif
                 // raw features for now: the loads are in flight while the candidate records are built,
                 // the tile's colour origin is subtracted right after
                 pf[0][c] = v.x;
@@ -331,6 +360,10 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
                 const int sc = half * 32 + lane;
                 hit[half] = false;
                 lb[half] = INF;
+                fullbits[half] = 0u;
+#if OBIA_K2_SKIP
+                if (half * 32 >= nc) continue;      // (warp-uniform: no record in this group of 32)
+#endif
                 bool full = false;
                 if (sc < nc) {
                     const int4 w = s_win[sc];
@@ -380,6 +413,9 @@ slic_assign_fast_kernel(const float *__restrict__ feat, const uint8_t *__restric
             int wcnt = 0;
 #pragma unroll
             for (int half = 0; half < kChk / 32; ++half) {
+#if OBIA_K2_SKIP
+                if (half * 32 >= nc) continue;
+#endif
                 const unsigned m = __ballot_sync(0xffffffffu, hit[half] && lb[half] <= wbound);
                 if ((m >> lane) & 1u)
                     s_wl[warp][wcnt + __popc(m & ((1u << lane) - 1u))] =
