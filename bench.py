@@ -187,7 +187,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------ our arm ---
@@ -563,9 +563,31 @@ def run_ours(args):
     }
     if tiled is not None:
         line["tiled_c3"] = tiled
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else that native libraries (NCCL's version banner ...) or
+    Python write to file descriptor 1 during the run is sent to stderr; `emit` writes the line to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -585,6 +607,7 @@ def main():
     ap.add_argument("--no-tiled", action="store_true", help="skip the create_tiled_segments (c3) block")
     ap.add_argument("--tiled-size", type=int, default=40000, help="side of the c3 raster")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
