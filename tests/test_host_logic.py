@@ -133,3 +133,33 @@ def test_mask_sample_indices_equals_numpy_legacy_choice():
         else:
             np.testing.assert_array_equal(got[1], want[1])
         assert slic_host.mask_sample_indices(n, k) is got                  # cached
+
+
+def test_window_descriptor_layout_matches_the_cuda_header():
+    """obia_b200/batch.py::WIN_DESC mirrors struct WinDesc of csrc/batch.cuh field by field (names, order, types)."""
+    import os
+    import re
+    from obia_b200 import batch
+    src = open(os.path.join(os.path.dirname(batch.__file__), "csrc", "batch.cuh")).read()
+    body = src[src.index("struct WinDesc {"):src.index("};", src.index("struct WinDesc {"))]
+    ctype = {"int32_t": "<i4", "float": "<f4", "double": "<f8", "int64_t": "<i8"}
+    fields = []
+    for line in body.splitlines()[1:]:
+        line = line.split("//")[0].strip()
+        m = re.match(r"(int32_t|int64_t|float|double)\s+([^;]+);", line)
+        if m:
+            fields += [(name.strip(), ctype[m.group(1)]) for name in m.group(2).split(",")]
+    assert fields == [(n, batch.WIN_DESC.fields[n][0].str) for n in batch.WIN_DESC.names]
+    assert batch.WIN_DESC.itemsize == 136 and "sizeof(WinDesc) == 136" in src
+    offs = [batch.WIN_DESC.fields[n][1] for n in batch.WIN_DESC.names]
+    assert offs == sorted(offs) and batch.WIN_DESC.fields["fix_scale"][1] % 8 == 0      # packed, doubles aligned
+
+
+def test_batched_tiled_driver_option_gate():
+    """Which SLIC options the batched tiled driver reproduces (the others take the per-tile driver)."""
+    from obia_b200 import batch
+    assert batch.supports({})
+    assert batch.supports(dict(compactness=0.2, max_num_iter=5, start_label=0, convert2lab=False, sigma=0))
+    for kw in (dict(sigma=1.0), dict(sigma=(1, 1)), dict(slic_zero=True), dict(exact=True), dict(enforce_connectivity=False),
+               dict(spacing=(1, 2)), dict(start_label=2), dict(mask=None), dict(unknown_option=1)):
+        assert not batch.supports(kw)
