@@ -21,6 +21,13 @@
 
 #include "common.cuh"
 
+#ifndef OBIA_CC_ADJ_CTAS
+#define OBIA_CC_ADJ_CTAS 8      // CTAs per SM (128 threads) of the small-piece adjacency kernel
+#endif
+#ifndef OBIA_CC_FIN_CTAS
+#define OBIA_CC_FIN_CTAS 4      // CTAs per SM (256 threads) of the merge-chain kernel
+#endif
+
 namespace obia {
 
 constexpr int32_t kTInf = 0x7fffffff;
@@ -1002,7 +1009,7 @@ int cc_phase_a(CcRun &R, int top_open, int bottom_open, int64_t core_lo, int64_t
     cc_reset_round_kernel<<<1, 1, 0, st>>>(w.ctr, CTR_NDIRTY0);
     OBIA_LAUNCH_CHECK();
     P.optimistic = 1;
-    cc_small_adjacent_kernel<<<kNumSMs * 8, 128, 0, st>>>(A, P, w.dirty0);
+    cc_small_adjacent_kernel<<<kNumSMs * OBIA_CC_ADJ_CTAS, 128, 0, st>>>(A, P, w.dirty0);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
 }
@@ -1058,7 +1065,7 @@ int cc_phase_b(CcRun &R, int32_t label_base, int32_t *out, int64_t p_lo, int64_t
     // slab of windows with start_label 0: "label 0" is the first kept piece of the piece's own WINDOW, which the
     // caller resolves (marker -2); with start_label 1 it is the mask label 0 everywhere
     const int32_t leftover = (R.P.wsizes && R.P.start_label == 0) ? -2 : 0;
-    cc_small_final_kernel<<<kNumSMs * 4, 256, 0, R.st>>>(A, w.bits, R.fin, max_hops, leftover);
+    cc_small_final_kernel<<<kNumSMs * OBIA_CC_FIN_CTAS, 256, 0, R.st>>>(A, w.bits, R.fin, max_hops, leftover);
     OBIA_LAUNCH_CHECK();
     cc_resolve_kernel<<<(unsigned)ceil_div(p_hi - p_lo, 256), 256, 0, R.st>>>(
         w.T, w.bits, R.fin, R.strip ? w.flag : nullptr, out, w.ctr, p_lo, p_hi, R.P.mask_label);

@@ -377,10 +377,10 @@ extern "C" int obia_b200_texture_stats(const int32_t *labels, const float *raw, 
     }
     cudaStream_t st = (cudaStream_t)stream;
     ZonalWs w = zonal_ws_layout(workspace, max_label);
-    const int64_t n = max_label + 1, N = H * W;
+    const int64_t n = max_label + 1;
     zonal_init_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(w, n);
     OBIA_LAUNCH_CHECK();
-    zonal_bbox_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(labels, w, N, (int)W, max_label);
+    zonal_bbox_launch(labels, w, H, W, max_label, 0, 0, st);
     OBIA_LAUNCH_CHECK();
 
     int dev = 0, sms = 0;

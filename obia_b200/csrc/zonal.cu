@@ -435,7 +435,7 @@ static int zonal_stats_impl(const int32_t *labels, const float *raw, int64_t H, 
     const int32_t lo = (int32_t)label_lo;
     zonal_init_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(w, n);
     OBIA_LAUNCH_CHECK();
-    zonal_bbox_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(labels, w, N, (int)W, max_label, lo, zero_row);
+    zonal_bbox_launch(labels, w, H, W, max_label, lo, zero_row, st);
     OBIA_LAUNCH_CHECK();
     if (Cz >= 24) {
         // many bands: lanes across bands, one pass over the raster for all of them

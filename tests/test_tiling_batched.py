@@ -62,3 +62,26 @@ def test_batched_empty_and_degenerate_windows():
     b, nb = _run(raw, mask, False, tile_size=200, buffer=30, crown_radius=5, compactness=0.2, convert2lab=False)
     assert na == nb
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("with_mask", [False, True], ids=["no-mask", "user-mask"])
+def test_batched_white_windows_without_earlier_segments(with_mask):
+    """Every black tile fails (constant band inside the black tiles only -> the reference's swallowed ValueError), so
+    the white windows of the first tile-row meet no earlier segment: the reference leaves their mask untouched
+    (tiling.py:259-262: `None` without an input mask -> plain SLIC, no corner squares).  Later rows see the first
+    row's segments in the corner overlaps and take the usual path."""
+    H, W, T = 560, 600, 200
+    raw = _raster(H, W, 3, seed=9)
+    for j in range(0, H, T):
+        for i in range(0, W, T):
+            if (i // T + j // T) % 2 == 0:
+                raw[j:j + T, i:i + T, 2] = 0.5
+    mask = _mask(H, W) if with_mask else None
+    kw = dict(tile_size=T, buffer=30, compactness=0.3, convert2lab=False)
+    kw.update(dict(crown_radius=6) if with_mask else dict(n_segments=80))
+    a, na = _run(raw, mask, True, **kw)
+    b, nb = _run(raw, mask, False, **kw)
+    assert na == nb and na > 20
+    assert np.array_equal(a, b)
+    # the black tile stays empty outside the reach of its white neighbours' buffers; the white tile is segmented
+    assert (a[:T - 40, :T - 40] < 0).all() and (a[:T, T + 40:2 * T - 40] > 0).any()
