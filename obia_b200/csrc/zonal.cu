@@ -5,9 +5,10 @@
 //
 // Two kernels:
 //   zonal_bbox    one pass over the label raster (4 B/pixel): bounding box and
-//                 pixel count per label, one set of atomics per run of equal
-//                 labels inside a warp;
-//   zonal_gather  one warp per (label, chunk of 8 bands): walks the label's
+//                 pixel count per label; runs of equal labels are folded per CTA
+//                 tile in a shared-memory hash table, one set of global atomics
+//                 per distinct label of a tile (bbox.cuh);
+//   zonal_gather  one warp per (label, chunk of 4 or 8 bands): walks the label's
 //                 bounding box with coalesced label/raster loads, accumulates
 //                 pivot-shifted power sums in registers (float32 partials
 //                 folded into float64 every 16 pixels), reduces them with
@@ -34,23 +35,31 @@ __device__ __forceinline__ double warp_sum_d(double v)
 
 // stats layout per (label, band): count, mean, variance, min, max, skewness, kurtosis, sum
 //
-// VEC: the 8 bands of this pass are contiguous and 16-byte aligned in the pixel record, so a
-// pixel is fetched with two 128-bit loads.  Rows are processed four at a time so that a warp
-// has four label loads and then up to eight raster loads in flight instead of a chain of
-// dependent round trips per row.
-template <bool VEC>
-__global__ void __launch_bounds__(256, 2)
+// VEC: the ZB bands of this pass are contiguous and 16-byte aligned in the pixel record, so a
+// pixel is fetched with ZB/4 128-bit loads.  Rows are processed four at a time so that a warp
+// has four label loads and then up to four pixel loads in flight instead of a chain of
+// dependent round trips per row.  The kernel waits on those loads (ncu: long-scoreboard stalls, 22 % of
+// the warp slots filled at 128 registers), so the vector path runs FOUR bands per warp: 64 registers,
+// twice the resident warps (c2: 3.1 -> 2.7 ms although every label's box is read once per band group).
+#ifndef OBIA_ZG_ROWS
+#define OBIA_ZG_ROWS 4        // rows per trip
+#endif
+#ifndef OBIA_ZG_BANDS
+#define OBIA_ZG_BANDS 4       // bands per warp on the vector path (4: half the registers, twice the label reads, twice the warps in flight)
+#endif
+template <bool VEC, int ZB>
+__global__ void __launch_bounds__(256, ZB == 4 ? 4 : 2)
 zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw, ZonalWs w, int W,
                     int C, ZBands zb, int Cz, int64_t max_label, double resolution,
                     double *__restrict__ stats, int32_t label_lo, int32_t zero_row)
 {
-    constexpr int R = 4;
+    constexpr int R = OBIA_ZG_ROWS;
     const int lane = threadIdx.x & 31;
     const int64_t L = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // table row
     if (L > max_label) return;
     const int32_t LV = (zero_row && L == 0) ? 0 : (int32_t)L + label_lo - zero_row;   // label value
-    const int b0 = blockIdx.y * kZB;
-    const int nb = min(kZB, Cz - b0);
+    const int b0 = blockIdx.y * ZB;
+    const int nb = min(ZB, Cz - b0);
     double *out = stats + (L * Cz + b0) * 8;
     const int cnt_total = w.count[L];
     const double NAND = __longlong_as_double(0x7ff8000000000000LL);
@@ -59,42 +68,43 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
         return;
     }
     const int x0 = w.xmin[L], x1 = w.xmax[L], y0 = w.ymin[L], y1 = w.ymax[L];
-    int bidx[kZB];
+    int bidx[ZB];
 #pragma unroll
-    for (int b = 0; b < kZB; ++b) bidx[b] = zb.band[min(b0 + b, Cz - 1)];
+    for (int b = 0; b < ZB; ++b) bidx[b] = zb.band[min(b0 + b, Cz - 1)];
 
-    auto load_px = [&](int64_t pix, float (&v)[kZB]) {
+    auto load_px = [&](int64_t pix, float (&v)[ZB]) {
         const float *p = raw + pix * C;
         if (VEC) {
-            const float4 a = *reinterpret_cast<const float4 *>(p + bidx[0]);
-            const float4 c = *reinterpret_cast<const float4 *>(p + bidx[0] + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-            v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+#pragma unroll
+            for (int q = 0; q < ZB / 4; ++q) {
+                const float4 a = *reinterpret_cast<const float4 *>(p + bidx[0] + 4 * q);
+                v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+            }
         } else {
 #pragma unroll
-            for (int b = 0; b < kZB; ++b) v[b] = p[bidx[b]];
+            for (int b = 0; b < ZB; ++b) v[b] = p[bidx[b]];
         }
     };
 
     // pivot per band = the first VALID (non-NaN) sample among the segment's pixels of the first 32-column
     // chunk of its first row that holds one (row y0 holds a pixel by construction); 0 when they are
     // all NaN in that band.  The pivot only conditions the power sums, any finite value is correct.
-    float pivot[kZB];
+    float pivot[ZB];
     {
         bool found = false;
 #pragma unroll
-        for (int b = 0; b < kZB; ++b) pivot[b] = 0.0f;
+        for (int b = 0; b < ZB; ++b) pivot[b] = 0.0f;
         for (int xs = x0; xs <= x1 && !found; xs += 32) {
             const int x = xs + lane;
             const bool hit = (x <= x1) && (labels[(int64_t)y0 * W + x] == LV);
             if (__ballot_sync(0xffffffffu, hit)) {
                 found = true;
-                float v[kZB];
+                float v[ZB];
 #pragma unroll
-                for (int b = 0; b < kZB; ++b) v[b] = 0.0f;
+                for (int b = 0; b < ZB; ++b) v[b] = 0.0f;
                 if (hit) load_px((int64_t)y0 * W + x, v);
 #pragma unroll
-                for (int b = 0; b < kZB; ++b) {
+                for (int b = 0; b < ZB; ++b) {
                     const unsigned m = __ballot_sync(0xffffffffu, hit && v[b] == v[b]);
                     const float pv = __shfl_sync(0xffffffffu, v[b], m ? (__ffs(m) - 1) : 0);
                     pivot[b] = m ? pv : 0.0f;
@@ -106,13 +116,13 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
     const float INF = __int_as_float(0x7f800000);
     // ps[m*8 + b] = float32 partial of the (m+1)-th pivot-shifted power sum of band b (this lane's
     // pixels since the last fold); `tot` = float64 running total of ps[lane] over the whole warp.
-    float ps[4 * kZB], mn[kZB], mx[kZB];
-    int nvalid[kZB];   // NaN samples are dropped per band (segment_statistics.py:144-147)
+    float ps[4 * ZB], mn[ZB], mx[ZB];
+    int nvalid[ZB];   // NaN samples are dropped per band (segment_statistics.py:144-147)
     double tot = 0.0;
 #pragma unroll
-    for (int i = 0; i < 4 * kZB; ++i) ps[i] = 0.0f;
+    for (int i = 0; i < 4 * ZB; ++i) ps[i] = 0.0f;
 #pragma unroll
-    for (int b = 0; b < kZB; ++b) {
+    for (int b = 0; b < ZB; ++b) {
         mn[b] = INF;
         mx[b] = -INF;
         nvalid[b] = 0;
@@ -121,23 +131,25 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
     // its lane bit and adds the partner's copy of that half, so after 5 steps lane l holds the
     // warp total of element l (31 shuffles instead of 32 x 5).  Sums continue in float64.
     auto fold = [&]() {
-        double h16[16];
-        {
-            const bool up = lane & 16;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float send = up ? ps[i] : ps[i + 16];
-                const float keep = up ? ps[i + 16] : ps[i];
-                h16[i] = (double)keep + (double)__shfl_xor_sync(0xffffffffu, send, 16);
-            }
-        }
+        // (the first two steps are taken element by element: at most eight float64 partials are live)
         double h8[8];
         {
-            const bool up = lane & 8;
+            const bool up16 = lane & 16, up8 = lane & 8;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const double send = up ? h16[i] : h16[i + 8];
-                const double keep = up ? h16[i + 8] : h16[i];
+                double lo8, hi8;      // elements i and i + 8 of the 16-vector after the offset-16 step
+                if constexpr (ZB == 8) {
+                    const float s0 = up16 ? ps[i] : ps[i + 16], k0 = up16 ? ps[i + 16] : ps[i];
+                    const float s1 = up16 ? ps[i + 8] : ps[i + 24], k1 = up16 ? ps[i + 24] : ps[i + 8];
+                    lo8 = (double)k0 + (double)__shfl_xor_sync(0xffffffffu, s0, 16);
+                    hi8 = (double)k1 + (double)__shfl_xor_sync(0xffffffffu, s1, 16);
+                } else {
+                    // 16 sums: both half-warps end with all of them, lane l with element l & 15
+                    lo8 = (double)ps[i] + (double)__shfl_xor_sync(0xffffffffu, ps[i], 16);
+                    hi8 = (double)ps[i + 8] + (double)__shfl_xor_sync(0xffffffffu, ps[i + 8], 16);
+                }
+                const double send = up8 ? lo8 : hi8;
+                const double keep = up8 ? hi8 : lo8;
                 h8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
             }
         }
@@ -168,7 +180,7 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
             tot += keep + __shfl_xor_sync(0xffffffffu, send, 1);
         }
 #pragma unroll
-        for (int i = 0; i < 4 * kZB; ++i) ps[i] = 0.0f;
+        for (int i = 0; i < 4 * ZB; ++i) ps[i] = 0.0f;
     };
 
     int since_fold = 0;
@@ -181,7 +193,7 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
                 const int y = yb + r;
                 hit[r] = (x <= x1) && (y <= y1) && (labels[(int64_t)y * W + x] == LV);
             }
-            float v[R][kZB];
+            float v[R][ZB];
 #pragma unroll
             for (int r = 0; r < R; ++r)
                 if (hit[r]) load_px((int64_t)(yb + r) * W + x, v[r]);
@@ -189,21 +201,21 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
             for (int r = 0; r < R; ++r) {
                 if (!hit[r]) continue;
 #pragma unroll
-                for (int b = 0; b < kZB; ++b) {
+                for (int b = 0; b < ZB; ++b) {
                     const bool ok = v[r][b] == v[r][b];
                     const float d = ok ? v[r][b] - pivot[b] : 0.0f;
                     const float dd = d * d;
                     nvalid[b] += ok;
                     ps[b] += d;
-                    ps[kZB + b] += dd;
-                    ps[2 * kZB + b] = fmaf(dd, d, ps[2 * kZB + b]);
-                    ps[3 * kZB + b] = fmaf(dd, dd, ps[3 * kZB + b]);
+                    ps[ZB + b] += dd;
+                    ps[2 * ZB + b] = fmaf(dd, d, ps[2 * ZB + b]);
+                    ps[3 * ZB + b] = fmaf(dd, dd, ps[3 * ZB + b]);
                     mn[b] = fminf(mn[b], v[r][b]);   // fminf / fmaxf return the non-NaN operand
                     mx[b] = fmaxf(mx[b], v[r][b]);
                 }
             }
             // warp-uniform: at most R pixels per lane per iteration -> <= 32 float32 terms per fold
-            if (++since_fold == 8) {
+            if (++since_fold == 32 / R) {
                 since_fold = 0;
                 fold();
             }
@@ -211,7 +223,7 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
     }
     fold();
 #pragma unroll
-    for (int b = 0; b < kZB; ++b) {
+    for (int b = 0; b < ZB; ++b) {
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
             mn[b] = fminf(mn[b], __shfl_xor_sync(0xffffffffu, mn[b], o));
@@ -219,15 +231,15 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
         }
         nvalid[b] = __reduce_add_sync(0xffffffffu, nvalid[b]);
     }
-    // lane m*8 + b holds the m-th power sum of band b: hand the four sums of band b to lane b
-    const int bsel = lane & (kZB - 1);
+    // lane m*ZB + b holds the m-th power sum of band b: hand the four sums of band b to lane b
+    const int bsel = lane & (ZB - 1);
     const double S1 = __shfl_sync(0xffffffffu, tot, bsel);
-    const double S2 = __shfl_sync(0xffffffffu, tot, kZB + bsel);
-    const double S3 = __shfl_sync(0xffffffffu, tot, 2 * kZB + bsel);
-    const double S4 = __shfl_sync(0xffffffffu, tot, 3 * kZB + bsel);
+    const double S2 = __shfl_sync(0xffffffffu, tot, ZB + bsel);
+    const double S3 = __shfl_sync(0xffffffffu, tot, 2 * ZB + bsel);
+    const double S4 = __shfl_sync(0xffffffffu, tot, 3 * ZB + bsel);
     // lane b finishes band b
 #pragma unroll
-    for (int b = 0; b < kZB; ++b) {
+    for (int b = 0; b < ZB; ++b) {
         if (lane == b && b < nb) {
             double *o = out + b * 8;
             if (nvalid[b] == 0) {   // every sample of the band is NaN: the reference returns NaN statistics
@@ -431,7 +443,6 @@ static int zonal_stats_impl(const int32_t *labels, const float *raw, int64_t H, 
     cudaStream_t st = (cudaStream_t)stream;
     ZonalWs w = zonal_ws_layout(workspace, max_label);
     const int64_t n = max_label + 1;
-    const int64_t N = H * W;
     const int32_t lo = (int32_t)label_lo;
     zonal_init_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(w, n);
     OBIA_LAUNCH_CHECK();
@@ -447,17 +458,29 @@ static int zonal_stats_impl(const int32_t *labels, const float *raw, int64_t H, 
         OBIA_LAUNCH_CHECK();
         return OBIA_B200_OK;
     }
+    // vector path: every pass reads its kZB contiguous, 16-byte aligned floats of the pixel record
+    auto vec_ok = [&](int zbn) {
+        bool vec = (C % 4 == 0) && (Cz % zbn == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
+        for (int b = 0; b < Cz && vec; ++b)
+            vec = (b % zbn == 0) ? (zb.band[b] % 4 == 0) : (zb.band[b] == zb.band[b - 1] + 1);
+        return vec;
+    };
+#if OBIA_ZG_BANDS == 4
+    if (vec_ok(4)) {
+        dim3 grid4((unsigned)ceil_div(n, 8), (unsigned)ceil_div(Cz, 4));
+        zonal_gather_kernel<true, 4><<<grid4, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label, resolution,
+                                                            stats, lo, zero_row);
+        OBIA_LAUNCH_CHECK();
+        return OBIA_B200_OK;
+    }
+#endif
     dim3 grid((unsigned)ceil_div(n, 8), (unsigned)ceil_div(Cz, kZB));
-    // vector path: every 8-band pass reads 8 contiguous, 16-byte aligned floats of the pixel record
-    bool vec = (C % 4 == 0) && (Cz % kZB == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
-    for (int b = 0; b < Cz && vec; ++b)
-        vec = (b % kZB == 0) ? (zb.band[b] % 4 == 0) : (zb.band[b] == zb.band[b - 1] + 1);
-    if (vec)
-        zonal_gather_kernel<true><<<grid, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label,
-                                                        resolution, stats, lo, zero_row);
+    if (vec_ok(kZB))
+        zonal_gather_kernel<true, kZB><<<grid, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label,
+                                                             resolution, stats, lo, zero_row);
     else
-        zonal_gather_kernel<false><<<grid, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label,
-                                                         resolution, stats, lo, zero_row);
+        zonal_gather_kernel<false, kZB><<<grid, 256, 0, st>>>(labels, raw, w, (int)W, C, zb, Cz, max_label,
+                                                              resolution, stats, lo, zero_row);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
 }
