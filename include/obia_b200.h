@@ -189,6 +189,18 @@ int obia_b200_slic_iterate(const float *features, const uint8_t *mask,
                            int32_t start_label, int32_t ignore_color,
                            int32_t slic_zero, double fix_scale, int32_t *status,
                            void *stream);
+/* obia_b200_slic_iterate with skimage's `spacing=(spacing_y, spacing_x)` (obia forwards **kwargs to
+ * skimage.segmentation.slic, segment_boundaries.py:51): the spatial term of `_slic_cython` becomes
+ * ((sy * (cy - y))^2 + (sx * (cx - x))^2) / step^2; windows, grid and connectivity stay in pixel units.
+ * Exact kernel only; (1, 1) is bit-identical to obia_b200_slic_iterate. */
+int obia_b200_slic_iterate_spacing(const float *features, const uint8_t *mask,
+                                   float *centres, int32_t *labels, void *workspace,
+                                   int64_t H, int64_t W, int64_t pitch, int32_t Cf,
+                                   int64_t n, float step, int32_t step_y,
+                                   int32_t step_x, int32_t max_num_iter,
+                                   int32_t start_label, int32_t ignore_color,
+                                   int32_t slic_zero, double fix_scale, float spacing_y,
+                                   float spacing_x, int32_t *status, void *stream);
 
 /* The same iteration, one sweep at a time, for a raster sharded by ROW STRIPS across GPUs (global
  * multi-GPU SLIC): `features`/`mask`/`labels` hold the strip [y_offset, y_offset + H) of a raster with

@@ -37,6 +37,8 @@ SIGNATURES = {
     "obia_b200_slic_workspace_bytes": (_i64, [_i64, _i64, _i32, _i64, _i32, _i32]),
     "obia_b200_slic_iterate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i64, _f32,
                                               _i32, _i32, _i32, _i32, _i32, _i32, _f64, _vp, _vp]),
+    "obia_b200_slic_iterate_spacing": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i64, _f32,
+                                                      _i32, _i32, _i32, _i32, _i32, _i32, _f64, _f32, _f32, _vp, _vp]),
     "obia_b200_slic_iterate_fast": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i64, _f32,
                                                    _i32, _i32, _i32, _i32, _i32, _i32, _f64, _vp, _vp]),
     "obia_b200_slic_sweep_fast": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i64, _f32, _i32,

@@ -136,7 +136,7 @@ __device__ __forceinline__ void eval_candidate(const u64 (&px2)[(PX + 1) / 2][CP
                                                const u64 (&nx2)[(PX + 1) / 2], float nx1, float fy,
                                                float cy, float cx, const int4 w,
                                                const float *__restrict__ nf, float mdc, float spatial_weight,
-                                               int ignore_color, int y, int xb, int slot,
+                                               float sp_y, float sp_x, int ignore_color, int y, int xb, int slot,
                                                float (&best)[PX], int (&bests)[PX])
 {
     int lo = 0, span = PX;
@@ -144,7 +144,8 @@ __device__ __forceinline__ void eval_candidate(const u64 (&px2)[(PX + 1) / 2][CP
         lo = w.z - xb;
         span = (y >= w.x && y < w.y) ? (w.w - w.z) : 0;  // row outside the window: nothing valid
     }
-    const float ty = __fsub_rn(cy, fy);
+    // skimage: dy = (sy * (cy - y)) ** 2 with the `spacing` of the call (a product with 1.0f is exact)
+    const float ty = __fmul_rn(sp_y, __fsub_rn(cy, fy));
     const float dy = __fmul_rn(ty, ty);
     if constexpr (PX >= 2) {
 #pragma unroll
@@ -152,6 +153,8 @@ __device__ __forceinline__ void eval_candidate(const u64 (&px2)[(PX + 1) / 2][CP
             const u64 tx2 = add2(nx2[p], pack2(cx, cx));  // cx - x  ==  cx + (-x)
             float tx0, tx1;
             unpack2(tx2, tx0, tx1);
+            tx0 = __fmul_rn(sp_x, tx0);
+            tx1 = __fmul_rn(sp_x, tx1);
             const u64 s2 = add2(pack2(dy, dy), pack2(__fmul_rn(tx0, tx0), __fmul_rn(tx1, tx1)));
             float s0, s1;
             unpack2(s2, s0, s1);
@@ -184,7 +187,7 @@ __device__ __forceinline__ void eval_candidate(const u64 (&px2)[(PX + 1) / 2][CP
             }
         }
     } else {
-        const float tx = __fadd_rn(cx, nx1);
+        const float tx = __fmul_rn(sp_x, __fadd_rn(cx, nx1));
         float d = __fmul_rn(__fadd_rn(dy, __fmul_rn(tx, tx)), spatial_weight);
         if (!ignore_color) {
             float acc = 0.0f;
@@ -227,7 +230,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
                           unsigned long long *__restrict__ acc, int H, int W, int64_t pitch, int Cf,
                           float spatial_weight, int step_y, int step_x, int ncy, int ncx,
                           int start_label, int ignore_color, double fix_scale, float fix_scale32,
-                          long long fix_ratio, int32_t *status, int y_off, int Hg)
+                          long long fix_ratio, int32_t *status, int y_off, int Hg, float sp_y, float sp_x)
 {
     // (H, W) is the strip resident on this GPU; it is rows [y_off, y_off + H) of a raster with Hg
     // rows.  Memory is addressed with strip-local rows, the arithmetic (centre windows, spatial
@@ -420,7 +423,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
                     const float ddy = fmaxf(0.0f, fmaxf((float)wy0 - c.x, c.x - (float)wy1));
                     const float ddx = fmaxf(0.0f, fmaxf((float)wx0 - c.y, c.y - (float)wx1));
                     hit[half] = true;
-                    lb[half] = (ddy * ddy + ddx * ddx) * spatial_weight * 0.9999f;
+                    lb[half] = (sp_y * sp_y * (ddy * ddy) + sp_x * sp_x * (ddx * ddx)) * spatial_weight * 0.9999f;
                     seedkey = min(seedkey, (__float_as_uint(lb[half]) & ~63u) | (unsigned)sc);
                 }
             }
@@ -440,7 +443,7 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
             }
             const float2 c = s_cyx[s];
             eval_candidate<CP, PX, true, SZ>(px2, px1, nx2, nx1, fy, c.x, c.y, s_win[s], s_nf[s],
-                                             SZ ? s_mdc[s] : 1.0f, spatial_weight, ignore_color, yg, xb, 0, tb, ts);
+                                             SZ ? s_mdc[s] : 1.0f, spatial_weight, sp_y, sp_x, ignore_color, yg, xb, 0, tb, ts);
             float m = tb[0];
 #pragma unroll
             for (int j = 1; j < PX; ++j) m = fmaxf(m, tb[j]);
@@ -461,10 +464,10 @@ slic_assign_update_kernel(const float *__restrict__ feat, const uint8_t *__restr
                 const float mdc = SZ ? s_mdc[s] : 1.0f;
                 if (full)
                     eval_candidate<CP, PX, false, SZ>(px2, px1, nx2, nx1, fy, c.x, c.y, w, s_nf[s], mdc,
-                                                      spatial_weight, ignore_color, yg, xb, c0 + s, best, bests);
+                                                      spatial_weight, sp_y, sp_x, ignore_color, yg, xb, c0 + s, best, bests);
                 else
                     eval_candidate<CP, PX, true, SZ>(px2, px1, nx2, nx1, fy, c.x, c.y, w, s_nf[s], mdc,
-                                                     spatial_weight, ignore_color, yg, xb, c0 + s, best, bests);
+                                                     spatial_weight, sp_y, sp_x, ignore_color, yg, xb, c0 + s, best, bests);
             }
         }
     }
@@ -657,11 +660,13 @@ static int launch_assign(const float *feat, const uint8_t *mask, const float *ce
     if (slic_zero)
         slic_assign_update_kernel<CP, PX, NS, true><<<grid, kWarps * 32, dyn, st>>>(
             feat, mask, centres, w.maxdc, w.head, w.next, labels, w.acc, (int)H, (int)W, pitch, Cf, sw, step_y, step_x,
-            (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, fix_scale32, fix_ratio, status, y_off, (int)Hg);
+            (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, fix_scale32, fix_ratio, status, y_off, (int)Hg,
+            w.sp_y, w.sp_x);
     else
         slic_assign_update_kernel<CP, PX, NS, false><<<grid, kWarps * 32, dyn, st>>>(
             feat, mask, centres, w.maxdc, w.head, w.next, labels, w.acc, (int)H, (int)W, pitch, Cf, sw, step_y, step_x,
-            (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, fix_scale32, fix_ratio, status, y_off, (int)Hg);
+            (int)w.ncy, (int)w.ncx, start_label, ignore_color, fix_scale, fix_scale32, fix_ratio, status, y_off, (int)Hg,
+            w.sp_y, w.sp_x);
     prof_end(st);
     OBIA_LAUNCH_CHECK();
     return OBIA_B200_OK;
@@ -785,7 +790,7 @@ static int slic_sweep_impl(const float *features, const uint8_t *mask, const flo
                            int32_t Cf, int64_t n, float step, int32_t step_y, int32_t step_x,
                            int32_t start_label, int32_t ignore_color, int32_t slic_zero,
                            double fix_scale, int64_t y_offset, int64_t H_total, int32_t *status,
-                           void *stream, int fast)
+                           void *stream, int fast, float sp_y = 1.0f, float sp_x = 1.0f)
 {
     int rc = slic_check_args(features, centres, labels, workspace, status, H, W, pitch, Cf, n, step, step_y, step_x,
                              start_label, fix_scale);
@@ -793,6 +798,12 @@ static int slic_sweep_impl(const float *features, const uint8_t *mask, const flo
     if (y_offset < 0 || y_offset + H > H_total) return set_err(OBIA_B200_ERR_ARG, "slic_sweep: strip outside the raster");
     cudaStream_t st = (cudaStream_t)stream;
     SlicWs w = slic_ws_layout(workspace, H_total, W, Cf, n, step_y, step_x);
+    if (!(sp_y > 0.0f) || !(sp_x > 0.0f) || sp_y == INFINITY || sp_x == INFINITY)
+        return set_err(OBIA_B200_ERR_ARG, "slic_sweep: spacing must be positive and finite");
+    if ((sp_y != 1.0f || sp_x != 1.0f) && fast && !slic_zero)
+        return set_err(OBIA_B200_ERR_UNSUPPORTED, "slic_sweep: anisotropic spacing runs on the exact kernel only");
+    w.sp_y = sp_y;
+    w.sp_x = sp_x;
     // `1.0 / (step * step)`: float product, double division, float store
     const float step_sq = step * step;
     const float sw = (float)(1.0 / (double)step_sq);
@@ -894,7 +905,7 @@ static int slic_iterate_impl(const float *features, const uint8_t *mask, float *
                              int64_t pitch, int32_t Cf, int64_t n, float step, int32_t step_y,
                              int32_t step_x, int32_t max_num_iter, int32_t start_label,
                              int32_t ignore_color, int32_t slic_zero, double fix_scale,
-                             int32_t *status, void *stream, int fast)
+                             int32_t *status, void *stream, int fast, float sp_y = 1.0f, float sp_x = 1.0f)
 {
     int rc = slic_check_args(features, centres, labels, workspace, status, H, W, pitch, Cf, n, step, step_y, step_x,
                              start_label, fix_scale);
@@ -903,7 +914,7 @@ static int slic_iterate_impl(const float *features, const uint8_t *mask, float *
     rc = obia_b200_slic_begin(labels, workspace, H, W, H, Cf, n, step_y, step_x, start_label, status, stream);
     for (int it = 0; it < max_num_iter && !rc; ++it) {
         rc = slic_sweep_impl(features, mask, centres, labels, workspace, H, W, pitch, Cf, n, step, step_y,
-                             step_x, start_label, ignore_color, slic_zero, fix_scale, 0, H, status, stream, fast);
+                             step_x, start_label, ignore_color, slic_zero, fix_scale, 0, H, status, stream, fast, sp_y, sp_x);
         // the reference updates the centres after every sweep, the last one included
         if (!rc) rc = obia_b200_slic_finish_sweep(centres, workspace, H, W, Cf, n, step_y, step_x, fix_scale, stream);
         if (!rc && slic_zero)
@@ -922,6 +933,18 @@ extern "C" int obia_b200_slic_iterate(const float *features, const uint8_t *mask
 {
     return slic_iterate_impl(features, mask, centres, labels, workspace, H, W, pitch, Cf, n, step, step_y, step_x,
                              max_num_iter, start_label, ignore_color, slic_zero, fix_scale, status, stream, 0);
+}
+
+extern "C" int obia_b200_slic_iterate_spacing(const float *features, const uint8_t *mask, float *centres,
+                                              int32_t *labels, void *workspace, int64_t H, int64_t W,
+                                              int64_t pitch, int32_t Cf, int64_t n, float step, int32_t step_y,
+                                              int32_t step_x, int32_t max_num_iter, int32_t start_label,
+                                              int32_t ignore_color, int32_t slic_zero, double fix_scale,
+                                              float spacing_y, float spacing_x, int32_t *status, void *stream)
+{
+    return slic_iterate_impl(features, mask, centres, labels, workspace, H, W, pitch, Cf, n, step, step_y, step_x,
+                             max_num_iter, start_label, ignore_color, slic_zero, fix_scale, status, stream, 0,
+                             spacing_y, spacing_x);
 }
 
 extern "C" int obia_b200_slic_iterate_fast(const float *features, const uint8_t *mask, float *centres,

@@ -18,11 +18,13 @@ struct SlicWs {
     float *maxdc;             // [n] SLICO: largest colour distance seen per centre (slic_zero)
     int64_t ncy, ncx;
     int64_t bytes;
+    float sp_y, sp_x;         // voxel spacing of skimage's `spacing=(sy, sx)` (1, 1 unless the caller says otherwise)
 };
 
 static SlicWs slic_ws_layout(void *base, int64_t H, int64_t W, int Cf, int64_t n, int step_y, int step_x)
 {
     SlicWs w;
+    w.sp_y = w.sp_x = 1.0f;
     w.ncy = ceil_div(H, step_y);
     w.ncx = ceil_div(W, step_x);
     char *p = (char *)base;

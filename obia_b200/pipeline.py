@@ -184,6 +184,7 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
 
     kwargs are skimage.segmentation.slic's (obia forwards **kwargs verbatim).
 
+    `spacing=(sy, sx)` other than (1, 1) runs the exact kernel whatever `exact` says.
     `exact=False` (default) runs the tolerance-mode assignment kernel (one FMA per channel, see
     csrc/slic_fast.cu: north_star's ">= 99.5 % label agreement" bar); `exact=True` the kernel that
     reproduces `_slic_cython`'s float32 operation order bit for bit given the centres.
@@ -195,8 +196,20 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
     raw = _aligned(raw)
     if channel_axis not in (-1, 2):
         raise NotImplementedError("only channel_axis=-1 (obia always passes H, W, C)")
-    if spacing is not None and tuple(float(s) for s in np.ravel(spacing)) not in ((1.0, 1.0), (1.0, 1.0, 1.0)):
-        raise NotImplementedError("anisotropic `spacing` is not implemented on the B200 path")
+    # skimage's `spacing` (voxel size per spatial axis): scales the spatial term of the distance and divides
+    # sigma; grid, windows and connectivity stay in pixel units.  float32 like the image (slic: `dtype`).
+    if spacing is None:
+        sp_y = sp_x = np.float32(1.0)
+    else:
+        if isinstance(spacing, (str, bytes)) or not hasattr(spacing, "__iter__"):
+            raise TypeError("spacing must be None or iterable.")
+        sp = np.asarray(list(spacing), dtype=np.float32).ravel()
+        if sp.size not in (2, 3):
+            raise ValueError(f"Input image is 2D, but spacing has {sp.size} elements (expected 2).")
+        sp_y, sp_x = sp[-2], sp[-1]
+        if not (np.isfinite(sp_y) and np.isfinite(sp_x) and sp_y > 0 and sp_x > 0):
+            raise ValueError("spacing must be positive and finite")
+    anisotropic = bool(sp_y != 1.0 or sp_x != 1.0)
     if start_label not in (0, 1):
         raise ValueError("start_label should be 0 or 1.")
     H, W, C = (int(s) for s in raw.shape)
@@ -282,6 +295,7 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
         sig_y, sig_x = (f32(s) for s in np.ravel(sigma)[-2:])
     else:
         sig_y = sig_x = sig
+    sig_y, sig_x = f32(sig_y / sp_y), f32(sig_x / sp_x)     # slic: `sigma /= spacing`
     smooth = bool(sig_y > 0 or sig_x > 0)
     pitch = (W + 31) // 32 * 32
     feats = torch.empty((Cf, H, pitch), dtype=torch.float32, device=dev)
@@ -319,11 +333,18 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
     status = torch.zeros((4,), dtype=torch.int32, device=dev)
 
     def run(ignore_color):
-        iterate = lib.obia_b200_slic_iterate if exact else lib.obia_b200_slic_iterate_fast
-        _lib.check(iterate(
-            _p(feats), _p(mask_dev), _p(centres), _p(labels), _p(ws), H, W, pitch, Cf, n, step,
-            step_y, step_x, int(max_num_iter), int(start_label), int(ignore_color), int(bool(slic_zero)),
-            fix_scale, _p(status), _stream_ptr()), "slic_iterate")
+        if anisotropic:
+            # the spacing factors sit inside the squared spatial term: exact kernel only (see the header)
+            _lib.check(lib.obia_b200_slic_iterate_spacing(
+                _p(feats), _p(mask_dev), _p(centres), _p(labels), _p(ws), H, W, pitch, Cf, n, step,
+                step_y, step_x, int(max_num_iter), int(start_label), int(ignore_color), int(bool(slic_zero)),
+                fix_scale, float(sp_y), float(sp_x), _p(status), _stream_ptr()), "slic_iterate_spacing")
+        else:
+            iterate = lib.obia_b200_slic_iterate if exact else lib.obia_b200_slic_iterate_fast
+            _lib.check(iterate(
+                _p(feats), _p(mask_dev), _p(centres), _p(labels), _p(ws), H, W, pitch, Cf, n, step,
+                step_y, step_x, int(max_num_iter), int(start_label), int(ignore_color), int(bool(slic_zero)),
+                fix_scale, _p(status), _stream_ptr()), "slic_iterate")
         if int(status[0].item()) != 0:
             raise _lib.CandidateOverflowError(
                 "slic_iterate: a 32 x 64 pixel tile collected more than 1024 candidate centres -- the centre "

@@ -266,6 +266,9 @@ MODES = pytest.mark.parametrize("exact", [False, True], ids=["fast", "exact"])
     (120, 160, 3, 60, 5.0, dict(sigma=1.0)),
     (200, 260, 5, 130, 0.5, dict(slic_zero=True)),                      # SLICO
     (160, 160, 3, 70, 10.0, dict(slic_zero=True, max_num_iter=6)),      # SLICO on the Lab path
+    (200, 300, 4, 150, 0.1, dict(spacing=(1, 2))),                      # anisotropic spacing (exact kernel)
+    (160, 200, 3, 90, 10.0, dict(spacing=(0.5, 1.5), sigma=1.0)),       # ... with sigma / spacing, Lab path
+    (150, 170, 5, 60, 0.3, dict(spacing=(2.0, 1.0), slic_zero=True)),
 ])
 @MODES
 def test_slic_full_agreement(H, W, C, n, compactness, kw, exact):
@@ -283,6 +286,29 @@ def test_slic_full_agreement(H, W, C, n, compactness, kw, exact):
         finally:
             so.USE_FMA = False
         _check_labels(got, want, exact, f"fma={fma} labels gpu={res.n_labels} oracle={want.max()}")
+
+
+def test_spacing_known_answer_and_argument_errors():
+    """skimage test_slic.py::test_spacing (recalled, tests/test_oracle_slic.py) through the CUDA path, and the
+    argument errors of slic's `spacing` handling."""
+    from obia_b200 import pipeline
+    img = np.array([[1, 1, 1, 0, 0], [1, 1, 0, 0, 0]], float)
+    img = img + 0.1 * np.random.RandomState(0).normal(size=img.shape)
+    raw = np.ascontiguousarray(img[:, :, None], dtype=np.float32)
+    kw = dict(n_segments=2, sigma=0, compactness=1.0, start_label=0, convert2lab=False)
+    for exact in (False, True):
+        plain = pipeline.slic_labels(_cuda(raw), None, exact=exact, **kw).labels.cpu().numpy()
+        spaced = pipeline.slic_labels(_cuda(raw), None, exact=exact, spacing=[500, 1], **kw).labels.cpu().numpy()
+        np.testing.assert_array_equal(plain, [[0, 0, 0, 1, 1], [0, 0, 1, 1, 1]])
+        np.testing.assert_array_equal(spaced, [[0, 0, 0, 0, 0], [1, 1, 1, 1, 1]])
+        same = pipeline.slic_labels(_cuda(raw), None, exact=exact, spacing=(1, 1, 1), **kw).labels.cpu().numpy()
+        np.testing.assert_array_equal(same, plain)
+    with pytest.raises(TypeError):
+        pipeline.slic_labels(_cuda(raw), None, spacing=2.0, **kw)
+    with pytest.raises(ValueError):
+        pipeline.slic_labels(_cuda(raw), None, spacing=(1, 2, 3, 4), **kw)
+    with pytest.raises(ValueError):
+        pipeline.slic_labels(_cuda(raw), None, spacing=(0, 1), **kw)
 
 
 def test_skimage_known_answers_through_the_cuda_path():
