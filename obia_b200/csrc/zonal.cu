@@ -37,18 +37,22 @@ __device__ __forceinline__ double warp_sum_d(double v)
 //
 // VEC: the ZB bands of this pass are contiguous and 16-byte aligned in the pixel record, so a
 // pixel is fetched with ZB/4 128-bit loads.  Rows are processed four at a time so that a warp
-// has four label loads and then up to four pixel loads in flight instead of a chain of
-// dependent round trips per row.  The kernel waits on those loads (ncu: long-scoreboard stalls, 22 % of
-// the warp slots filled at 128 registers), so the vector path runs FOUR bands per warp: 64 registers,
-// twice the resident warps (c2: 3.1 -> 2.7 ms although every label's box is read once per band group).
+// has four label loads and then up to eight pixel loads in flight instead of a chain of
+// dependent round trips per row, and the trips are software-pipelined (labels of the next trip
+// requested under the pixel loads of this one).  The kernel waits on those loads (ncu: long-scoreboard
+// stalls, 22 % of the warp slots filled at 128 registers).  Measured on c2 (K4 = boxes + gather):
+// 8 bands per warp 3.7 ms, 4 bands per warp at 64 registers 3.3 ms, pipelined 2.9 ms / 8 bands pipelined 2.8 ms.
 #ifndef OBIA_ZG_ROWS
 #define OBIA_ZG_ROWS 4        // rows per trip
 #endif
 #ifndef OBIA_ZG_BANDS
-#define OBIA_ZG_BANDS 4       // bands per warp on the vector path (4: half the registers, twice the label reads, twice the warps in flight)
+#define OBIA_ZG_BANDS 8       // bands per warp on the vector path (4: half the registers, twice the label reads)
 #endif
 template <bool VEC, int ZB>
-__global__ void __launch_bounds__(256, ZB == 4 ? 4 : 2)
+#ifndef OBIA_ZG_CTAS8
+#define OBIA_ZG_CTAS8 2
+#endif
+__global__ void __launch_bounds__(256, ZB == 4 ? 4 : OBIA_ZG_CTAS8)
 zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw, ZonalWs w, int W,
                     int C, ZBands zb, int Cz, int64_t max_label, double resolution,
                     double *__restrict__ stats, int32_t label_lo, int32_t zero_row)
@@ -184,42 +188,61 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
     };
 
     int since_fold = 0;
-    for (int yb = y0; yb <= y1; yb += R) {
-        for (int xs = x0; xs <= x1; xs += 32) {
-            const int x = xs + lane;
-            bool hit[R];
+    // Software pipeline over the trips (32 columns x R rows each, row-major over the box): the labels of trip
+    // t + 1 are requested while the pixel loads of trip t are in flight, so a trip waits for one memory round
+    // trip instead of two dependent ones.
+    auto load_hits = [&](int yb, int xs, bool (&h)[R]) {
+        const int x = xs + lane;
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int y = yb + r;
-                hit[r] = (x <= x1) && (y <= y1) && (labels[(int64_t)y * W + x] == LV);
-            }
-            float v[R][ZB];
+        for (int r = 0; r < R; ++r) {
+            const int y = yb + r;
+            h[r] = (x <= x1) && (y <= y1) && (labels[(int64_t)y * W + x] == LV);
+        }
+    };
+    int yb = y0, xs = x0;
+    bool hit[R];
+    load_hits(yb, xs, hit);
+    while (yb <= y1) {
+        const int x = xs + lane;
+        float v[R][ZB];
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                if (hit[r]) load_px((int64_t)(yb + r) * W + x, v[r]);
+        for (int r = 0; r < R; ++r)
+            if (hit[r]) load_px((int64_t)(yb + r) * W + x, v[r]);
+        int nxs = xs + 32, nyb = yb;
+        if (nxs > x1) {
+            nxs = x0;
+            nyb = yb + R;
+        }
+        bool hnext[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (!hit[r]) continue;
+        for (int r = 0; r < R; ++r) hnext[r] = false;
+        if (nyb <= y1) load_hits(nyb, nxs, hnext);
 #pragma unroll
-                for (int b = 0; b < ZB; ++b) {
-                    const bool ok = v[r][b] == v[r][b];
-                    const float d = ok ? v[r][b] - pivot[b] : 0.0f;
-                    const float dd = d * d;
-                    nvalid[b] += ok;
-                    ps[b] += d;
-                    ps[ZB + b] += dd;
-                    ps[2 * ZB + b] = fmaf(dd, d, ps[2 * ZB + b]);
-                    ps[3 * ZB + b] = fmaf(dd, dd, ps[3 * ZB + b]);
-                    mn[b] = fminf(mn[b], v[r][b]);   // fminf / fmaxf return the non-NaN operand
-                    mx[b] = fmaxf(mx[b], v[r][b]);
-                }
-            }
-            // warp-uniform: at most R pixels per lane per iteration -> <= 32 float32 terms per fold
-            if (++since_fold == 32 / R) {
-                since_fold = 0;
-                fold();
+        for (int r = 0; r < R; ++r) {
+            if (!hit[r]) continue;
+#pragma unroll
+            for (int b = 0; b < ZB; ++b) {
+                const bool ok = v[r][b] == v[r][b];
+                const float d = ok ? v[r][b] - pivot[b] : 0.0f;
+                const float dd = d * d;
+                nvalid[b] += ok;
+                ps[b] += d;
+                ps[ZB + b] += dd;
+                ps[2 * ZB + b] = fmaf(dd, d, ps[2 * ZB + b]);
+                ps[3 * ZB + b] = fmaf(dd, dd, ps[3 * ZB + b]);
+                mn[b] = fminf(mn[b], v[r][b]);   // fminf / fmaxf return the non-NaN operand
+                mx[b] = fmaxf(mx[b], v[r][b]);
             }
         }
+        // warp-uniform: at most R pixels per lane per trip -> <= 32 float32 terms per fold
+        if (++since_fold == 32 / R) {
+            since_fold = 0;
+            fold();
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) hit[r] = hnext[r];
+        yb = nyb;
+        xs = nxs;
     }
     fold();
 #pragma unroll
