@@ -12,14 +12,18 @@ dev = torch.device("cuda", 0)
 raw = bench.synth_raster_cuda(10000, 10000, 8, 2, dev)
 
 
-def ev_time(fn, reps=5):
+def ev_time(fn, reps=7):
+    """median of per-call CUDA-event times (K3 has host read-backs: single calls jitter)"""
     fn(); torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
+    ts = []
     for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
         out = fn()
-    b.record(); torch.cuda.synchronize()
-    return a.elapsed_time(b) / reps, out
+        b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], out
 
 
 for comp in (0.1, 10.0):
