@@ -298,8 +298,11 @@ zonal_gather_kernel(const int32_t *__restrict__ labels, const float *__restrict_
 // segment are fetched with one coalesced load, then the warp visits only the matching pixels and
 // every lane reads and accumulates its own BPL bands of that pixel (a 64-band pixel is one 256-byte
 // coalesced request).  No shuffles: each lane owns its bands' sums from start to finish.
+#ifndef OBIA_ZB_CTAS
+#define OBIA_ZB_CTAS 3
+#endif
 template <int BPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, OBIA_ZB_CTAS)
 zonal_gather_bands_kernel(const int32_t *__restrict__ labels, const float *__restrict__ raw, ZonalWs w, int W,
                           int C, ZBands zb, int Cz, int64_t max_label, double resolution,
                           double *__restrict__ stats, int32_t label_lo, int32_t zero_row)
@@ -340,15 +343,27 @@ zonal_gather_bands_kernel(const int32_t *__restrict__ labels, const float *__res
         have_pivot[k] = false;
     }
     int pending = 0;
-    for (int y = y0; y <= y1; ++y) {
-        const int64_t row = (int64_t)y * W;
-        for (int xs = x0; xs <= x1; xs += 32) {
-            const int x = xs + lane;
-            const bool hit = (x <= x1) && (labels[row + x] == LV);
+#ifndef OBIA_ZB_U
+#define OBIA_ZB_U 4           // matching pixels per trip (c4: 4 at 3 CTAs per SM 11.2 ms, 8 at 2 CTAs 11.7 ms)
+#endif
+    // chunks of 32 columns, row-major over the box; the labels of the next chunk are requested before the
+    // pixel trips of this one (software pipeline, as in zonal_gather_kernel)
+    auto load_hit = [&](int y, int xs) { return (xs + lane <= x1) && (labels[(int64_t)y * W + xs + lane] == LV); };
+    int y = y0, xs = x0;
+    bool hit = load_hit(y, xs);
+    while (y <= y1) {
+        {
+            const int64_t row = (int64_t)y * W;
             unsigned m = __ballot_sync(0xffffffffu, hit);
+            int nxs = xs + 32, ny = y;
+            if (nxs > x1) {
+                nxs = x0;
+                ny = y + 1;
+            }
+            const bool hnext = (ny <= y1) ? load_hit(ny, nxs) : false;
             while (m) {
-                // up to four matching pixels per trip: all their loads are issued before any is used
-                constexpr int U = 4;
+                // up to U matching pixels per trip: all their loads are issued before any is used
+                constexpr int U = OBIA_ZB_U;
                 int bpos[U];
                 int nu = 0;
 #pragma unroll
@@ -400,6 +415,9 @@ zonal_gather_bands_kernel(const int32_t *__restrict__ labels, const float *__res
                     }
                 }
             }
+            hit = hnext;
+            y = ny;
+            xs = nxs;
         }
     }
 #pragma unroll
