@@ -487,9 +487,9 @@ struct CcArrays {
 // a label >= 0), at `tfix` for start_label 1 (label 0 == mask label until a later re-scan).
 // Strip mode: `unk` is raised when that time is not known inside the strip (the neighbour's component
 // is cut by the strip edge, or it is a merged piece whose own re-scan time is unknown).
-__device__ __forceinline__ int32_t label_time(const CcArrays &A, const CcParams &P, int32_t q, int32_t t, bool &unk)
+__device__ __forceinline__ int32_t label_time_of(const CcArrays &A, const CcParams &P, int32_t tq, int32_t t, bool &unk)
 {
-    const int32_t tq = A.T[q];       // -1 on masked pixels
+    // tq = T[q]: -1 on masked pixels
     if (tq < 0 || tq == t) return kTInf;
     if (A.flag) {
         const uint8_t f = A.flag[tq];
@@ -500,6 +500,10 @@ __device__ __forceinline__ int32_t label_time(const CcArrays &A, const CcParams 
     if ((int64_t)A.psize[tq] >= min_size_at(P, tq)) return tq;
     if (P.start_label == 0) return tq;
     return __ldcg(A.aux + tq);
+}
+__device__ __forceinline__ int32_t label_time(const CcArrays &A, const CcParams &P, int32_t q, int32_t t, bool &unk)
+{
+    return label_time_of(A, P, A.T[q], t, unk);
 }
 
 // replay of the reference BFS restricted to piece t, started at pixel s.  `unk_any`: some examined
@@ -516,11 +520,25 @@ __device__ int bfs_piece(const CcArrays &A, int32_t *qu, const CcParams &P, int3
     A.visit[s] = 1;
     while (head < cnt && (int64_t)cnt < max_size) {
         const int32_t p = qu[head];
-        const int py = p / P.W, px = p % P.W;
+        const int py = p / P.W, px = p - py * P.W;
+        // the four T loads of a pixel do not depend on each other: request them together (the walk is a chain of
+        // memory round trips, one thread per piece)
+        int32_t qs[4], tqs[4];
+#pragma unroll
         for (int d = 0; d < 4; ++d) {
+            qs[d] = -1;
+            tqs[d] = -1;
             int32_t q;
-            if (!nbr(d, py, px, P.H, P.W, q)) continue;
-            const bool same = A.T[q] == t;   // a piece is a set of equal-label pixels: T alone identifies it
+            if (nbr(d, py, px, P.H, P.W, q)) {
+                qs[d] = q;
+                tqs[d] = A.T[q];
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int32_t q = qs[d];
+            if (q < 0) continue;
+            const bool same = tqs[d] == t;   // a piece is a set of equal-label pixels: T alone identifies it
             if (same) {
                 if (!A.visit[q]) {
                     A.visit[q] = 1;
@@ -529,7 +547,7 @@ __device__ int bfs_piece(const CcArrays &A, int32_t *qu, const CcParams &P, int3
                 }
             } else {
                 bool unk = false;
-                const int32_t lt = label_time(A, P, q, t, unk);
+                const int32_t lt = label_time_of(A, P, tqs[d], t, unk);
                 if (unk) unk_any = true;
                 tmin = min(tmin, lt);
                 if (lt < s) {
@@ -575,14 +593,25 @@ __device__ bool small_piece_adjacent(const CcArrays &A, const CcParams &P, int32
     const int64_t max_size = max_size_at(P, t);
     const int32_t *members = qu;   // pixels of the first BFS
     if (n == 1) {
-        const int py = t / P.W, px = t % P.W;
+        const int py = t / P.W, px = t - py * P.W;
         // (with max_size <= 1 the reference's BFS loop never runs: no neighbour is looked at)
-        for (int d = 0; d < 4 && max_size > 1; ++d) {
+        int32_t qs[4], tqs[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {       // four independent loads, in flight together
+            qs[d] = -1;
+            tqs[d] = -1;
             int32_t q;
-            if (!nbr(d, py, px, P.H, P.W, q)) continue;
+            if (max_size > 1 && nbr(d, py, px, P.H, P.W, q)) {
+                qs[d] = q;
+                tqs[d] = A.T[q];
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            if (qs[d] < 0) continue;
             bool unk = false;
-            if (label_time(A, P, q, t, unk) < t) {
-                a = q;
+            if (label_time_of(A, P, tqs[d], t, unk) < t) {
+                a = qs[d];
                 if (!unk) known_before = true;
             }
             if (unk) unk_any = true;

@@ -30,10 +30,18 @@ def main(path):
         t = f(r, "gpu__time_duration.sum")
         unit = rows[1][col["gpu__time_duration.sum"]]
         ms = t / 1e6 if unit in ("ns", "nsecond") else t / 1e3 if unit in ("us", "usecond") else t
-        rd, wr = f(r, "dram__bytes_read.sum"), f(r, "dram__bytes_write.sum")
         scale = {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}
-        rd *= scale.get(rows[1][col["dram__bytes_read.sum"]], 1e-9)
-        wr *= scale.get(rows[1][col["dram__bytes_write.sum"]], 1e-9)
+        if "dram__bytes_read.sum" in col:
+            rd, wr = f(r, "dram__bytes_read.sum"), f(r, "dram__bytes_write.sum")
+            rd *= scale.get(rows[1][col["dram__bytes_read.sum"]], 1e-9)
+            wr *= scale.get(rows[1][col["dram__bytes_write.sum"]], 1e-9)
+        else:
+            # section-only captures carry the rate, not the byte counts: total traffic goes in the "read" column
+            u = rows[1][col["dram__bytes.sum.per_second"]]
+            rate = f(r, "dram__bytes.sum.per_second") * {"Tbyte/s": 1e3, "Gbyte/s": 1.0, "Mbyte/s": 1e-3,
+                                                         "Tbyte/second": 1e3, "Gbyte/second": 1.0,
+                                                         "Mbyte/second": 1e-3}.get(u, 1e-9)
+            rd, wr = rate * ms / 1e3, 0.0
         print(f"{short[:44]:44s} {len(rs):4d} {ms:9.4f} {f(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):6.1f} "
               f"{(rd + wr) / (ms / 1e3) / 1e3 if ms else 0:6.2f} "
               f"{f(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'):7.1f} {int(f(r, 'launch__registers_per_thread')):5d} "
