@@ -487,23 +487,27 @@ struct CcArrays {
 // a label >= 0), at `tfix` for start_label 1 (label 0 == mask label until a later re-scan).
 // Strip mode: `unk` is raised when that time is not known inside the strip (the neighbour's component
 // is cut by the strip edge, or it is a merged piece whose own re-scan time is unknown).
-__device__ __forceinline__ int32_t label_time_of(const CcArrays &A, const CcParams &P, int32_t tq, int32_t t, bool &unk)
+// (tq = T[q], -1 on masked pixels.)  The neighbour's flag byte and piece size are loaded by nb_prefetch for the four
+// neighbours of a pixel together instead of one dependent round trip after the other.
+__device__ __forceinline__ void nb_prefetch(const CcArrays &A, const CcParams &P, int32_t tq, int32_t t, uint8_t &f,
+                                            int32_t &ps)
 {
-    // tq = T[q]: -1 on masked pixels
+    f = 0;
+    ps = 0;
+    if (tq < 0 || tq == t) return;
+    if (A.flag) f = A.flag[tq];
+    if (!P.optimistic) ps = A.psize[tq];
+}
+__device__ __forceinline__ int32_t label_time_pre(const CcArrays &A, const CcParams &P, int32_t tq, int32_t t, uint8_t f,
+                                                  int32_t ps, bool &unk)
+{
     if (tq < 0 || tq == t) return kTInf;
-    if (A.flag) {
-        const uint8_t f = A.flag[tq];
-        if (f & FLAG_CUT) unk = true;
-        else if ((f & FLAG_TFIX_UNKNOWN) && P.start_label == 1) unk = true;
-    }
-    if (P.optimistic) return tq;     // round 1: merged pieces count as labelled from their start
-    if ((int64_t)A.psize[tq] >= min_size_at(P, tq)) return tq;
+    if (f & FLAG_CUT) unk = true;
+    else if ((f & FLAG_TFIX_UNKNOWN) && P.start_label == 1) unk = true;
+    if (P.optimistic) return tq;
+    if ((int64_t)ps >= min_size_at(P, tq)) return tq;
     if (P.start_label == 0) return tq;
     return __ldcg(A.aux + tq);
-}
-__device__ __forceinline__ int32_t label_time(const CcArrays &A, const CcParams &P, int32_t q, int32_t t, bool &unk)
-{
-    return label_time_of(A, P, A.T[q], t, unk);
 }
 
 // replay of the reference BFS restricted to piece t, started at pixel s.  `unk_any`: some examined
@@ -534,6 +538,10 @@ __device__ int bfs_piece(const CcArrays &A, int32_t *qu, const CcParams &P, int3
                 tqs[d] = A.T[q];
             }
         }
+        uint8_t nf[4];
+        int32_t nps[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) nb_prefetch(A, P, tqs[d], t, nf[d], nps[d]);
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
             const int32_t q = qs[d];
@@ -547,7 +555,7 @@ __device__ int bfs_piece(const CcArrays &A, int32_t *qu, const CcParams &P, int3
                 }
             } else {
                 bool unk = false;
-                const int32_t lt = label_time_of(A, P, tqs[d], t, unk);
+                const int32_t lt = label_time_pre(A, P, tqs[d], t, nf[d], nps[d], unk);
                 if (unk) unk_any = true;
                 tmin = min(tmin, lt);
                 if (lt < s) {
@@ -606,11 +614,15 @@ __device__ bool small_piece_adjacent(const CcArrays &A, const CcParams &P, int32
                 tqs[d] = A.T[q];
             }
         }
+        uint8_t nf[4];
+        int32_t nps[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) nb_prefetch(A, P, tqs[d], t, nf[d], nps[d]);
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
             if (qs[d] < 0) continue;
             bool unk = false;
-            if (label_time_of(A, P, tqs[d], t, unk) < t) {
+            if (label_time_pre(A, P, tqs[d], t, nf[d], nps[d], unk) < t) {
                 a = qs[d];
                 if (!unk) known_before = true;
             }
