@@ -322,41 +322,62 @@ cc_classify_kernel(const int32_t *__restrict__ roots, const int32_t *__restrict_
 {
     const int n_roots = ctr[CTR_NROOTS];
     const int lane = threadIdx.x & 31;
-    const int stride = gridDim.x * blockDim.x;
-    // warp-uniform trip count: one append per warp to the small list
-    for (int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); e0 < n_roots; e0 += stride) {
-        const int e = e0 + lane;
-        int32_t i = -1;
-        int64_t sz = 0;
-        if (e < n_roots) {
-            i = roots[e];
-            sz = psize[i];
-            if (wsizes) {   // slab of windows (tiled driver): the sizes of the window the component lies in
-                const int2 ws = wsizes[i / win_px];
-                min_size = ws.x;
-                max_size = ws.y;
+    // Four roots per lane and trip: the kernel is a chain of dependent loads (root -> size / flag -> scattered
+    // stores), so the loads of the four are requested together.  Warp-uniform trip count: one append per warp
+    // and group of 32 roots to the small list.
+    constexpr int U = 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
+    for (int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * U; e0 < n_roots; e0 += stride) {
+        int32_t iu[U];
+        int64_t szu[U], mnu[U], mxu[U];
+        uint8_t fu[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t e = e0 + u * 32 + lane;
+            iu[u] = (e < n_roots) ? roots[e] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            szu[u] = 0;
+            fu[u] = 0;
+            mnu[u] = min_size;
+            mxu[u] = max_size;
+            if (iu[u] >= 0) {
+                szu[u] = psize[iu[u]];
+                if (flag) fu[u] = flag[iu[u]];
+                if (wsizes) {   // slab of windows (tiled driver): the sizes of the window the component lies in
+                    const int2 ws = wsizes[iu[u] / win_px];
+                    mnu[u] = ws.x;
+                    mxu[u] = ws.y;
+                }
             }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int32_t i = iu[u];
+            int64_t sz = szu[u];
+            const int64_t mn = mnu[u], mx = mxu[u];
             // Strip mode: a component cut by an open strip edge is unknown anyway (FLAG_CUT: every result
             // that depends on it is reported incomplete).  It is booked as ONE kept piece -- the fragments
             // along an edge row would otherwise form long chains of "small pieces without an earlier
             // neighbour" whose fixed point needs hundreds of rounds.
-            if (flag && (flag[i] & FLAG_CUT)) sz = min_size > max_size ? max_size : min_size;
-        }
-        const bool small = i >= 0 && sz <= max_size && sz < min_size;   // (oversized components are split first)
-        const unsigned m = __ballot_sync(0xffffffffu, small);
-        int base = 0;
-        if (lane == 0 && m) base = atomicAdd(ctr + CTR_NSMALL, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (i < 0) continue;
-        if (sz > max_size) {
-            list[N - 1 - atomicAdd(ctr + CTR_NOVER, 1)] = i;
-        } else if (small) {
-            list[base + __popc(m & ((1u << lane) - 1u))] = i;
-            adj[i] = -1;
-            aux[i] = i;  // tfix: optimistic "labelled at its own time"
-            stamp[i] = 0;
-        } else {
-            atomicOr(bits + (i >> 5), 1u << (i & 31));
+            if (i >= 0 && (fu[u] & FLAG_CUT)) sz = mn > mx ? mx : mn;
+            const bool small = i >= 0 && sz <= mx && sz < mn;   // (oversized components are split first)
+            const unsigned m = __ballot_sync(0xffffffffu, small);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(ctr + CTR_NSMALL, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (i < 0) continue;
+            if (sz > mx) {
+                list[N - 1 - atomicAdd(ctr + CTR_NOVER, 1)] = i;
+            } else if (small) {
+                list[base + __popc(m & ((1u << lane) - 1u))] = i;
+                adj[i] = -1;
+                aux[i] = i;  // tfix: optimistic "labelled at its own time"
+                stamp[i] = 0;
+            } else {
+                atomicOr(bits + (i >> 5), 1u << (i & 31));
+            }
         }
     }
 }
@@ -899,30 +920,72 @@ __global__ void __launch_bounds__(256)
 cc_small_final_kernel(CcArrays A, const uint32_t *__restrict__ bits, int32_t *fin, int max_hops, int32_t leftover)
 {
     const int n_small = A.ctr[CTR_NSMALL];
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_small; e += gridDim.x * blockDim.x) {
-        const int32_t t0 = A.list[e];
-        int32_t t = t0, r = 0;
-        bool unk = false, done = false;
-        for (int hop = 0; hop < max_hops && !done; ++hop) {   // chains are short; never spin
-            if ((bits[t >> 5] >> (t & 31)) & 1u) {
-                r = fin[t];
-                if (A.flag && ((A.flag[t] & FLAG_CUT) || t >= A.ctr[CTR_CUTMIN])) unk = true;
-                done = true;
-            } else {
-                if (A.flag && (A.flag[t] & (FLAG_CUT | FLAG_ADJ_UNKNOWN))) unk = true;
-                const int32_t a = A.adj[t];
-                if (a < 0) {
-                    r = leftover;  // `adjacent` initial value: label 0 (of the window, see the windows entry)
-                    done = true;
-                    A.ctr[CTR_HASZERO] = 1;   // a leftover piece carries label 0 (benign race: same value)
+    // Four pieces per thread, hop by hop: every hop is a chain of dependent loads (kept bit -> adjacent or
+    // label -> piece start of the adjacent pixel), so the loads of the four pieces are requested together.
+    constexpr int U = 4;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int32_t cutmin = A.flag ? A.ctr[CTR_CUTMIN] : kTInf;
+    for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < n_small; e0 += nthreads * U) {
+        int32_t t0[U], t[U], r[U];
+        bool unk[U], done[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t e = e0 + u * nthreads;
+            t0[u] = (e < n_small) ? A.list[e] : -1;
+            t[u] = t0[u];
+            r[u] = 0;
+            unk[u] = false;
+            done[u] = t0[u] < 0;
+        }
+        for (int hop = 0; hop < max_hops; ++hop) {   // chains are short; never spin
+            if (done[0] && done[1] && done[2] && done[3]) break;
+            uint32_t bw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) bw[u] = done[u] ? 0u : bits[t[u] >> 5];
+            int32_t val[U];
+            uint8_t fl[U];
+            bool kept[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                kept[u] = false;
+                val[u] = -1;
+                fl[u] = 0;
+                if (done[u]) continue;
+                kept[u] = (bw[u] >> (t[u] & 31)) & 1u;
+                val[u] = kept[u] ? fin[t[u]] : A.adj[t[u]];
+                if (A.flag) fl[u] = A.flag[t[u]];
+            }
+            int32_t nxt[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                nxt[u] = -1;
+                if (done[u]) continue;
+                if (kept[u]) {
+                    r[u] = val[u];
+                    if (A.flag && ((fl[u] & FLAG_CUT) || t[u] >= cutmin)) unk[u] = true;
+                    done[u] = true;
                 } else {
-                    t = A.T[a];
+                    if (fl[u] & (FLAG_CUT | FLAG_ADJ_UNKNOWN)) unk[u] = true;
+                    if (val[u] < 0) {
+                        r[u] = leftover;  // `adjacent` initial value: label 0 (of the window, see the windows entry)
+                        done[u] = true;
+                        A.ctr[CTR_HASZERO] = 1;   // a leftover piece carries label 0 (benign race: same value)
+                    } else {
+                        nxt[u] = val[u];
+                    }
                 }
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (nxt[u] >= 0) t[u] = A.T[nxt[u]];
         }
-        if (!done) atomicExch(A.ctr + CTR_ERR, 2);
-        fin[t0] = r;            // kept and merged piece starts are disjoint: one table for both
-        if (unk) A.flag[t0] |= FLAG_LABEL_UNKNOWN;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (t0[u] < 0) continue;
+            if (!done[u]) atomicExch(A.ctr + CTR_ERR, 2);
+            fin[t0[u]] = r[u];            // kept and merged piece starts are disjoint: one table for both
+            if (unk[u]) A.flag[t0[u]] |= FLAG_LABEL_UNKNOWN;
+        }
     }
 }
 
