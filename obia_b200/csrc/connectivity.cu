@@ -271,21 +271,53 @@ cc_flatten_kernel(int32_t *T, int32_t *psize, int32_t *roots, int32_t *ctr, int6
     const int64_t base = (int64_t)blockIdx.x * (256 * PER);
     bool is_root[PER];
     int nroot = 0;
+    {
+        // the four pixels of a thread walk their parent chains in lock step: the loads of one step are
+        // requested together (the kernel waits on memory: one dependent round trip per chain link)
+        int32_t par[PER], x[PER], mine[PER];
+        bool act[PER], fin[PER];
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int64_t i = base + k * 256 + threadIdx.x;
-        is_root[k] = false;
-        if (i < N) {
-            const int32_t p = __ldcg(T + i);
-            if (p >= 0) {
-                const int32_t root = uf_find(T, p);
-                if (root != p) T[i] = root;
-                const int32_t mine = psize[i];
-                if (mine > 0 && root != (int32_t)i) atomicAdd(psize + root, mine);
-                is_root[k] = root == (int32_t)i;
+        for (int k = 0; k < PER; ++k) {
+            const int64_t i = base + k * 256 + threadIdx.x;
+            par[k] = (i < N) ? __ldcg(T + i) : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int64_t i = base + k * 256 + threadIdx.x;
+            act[k] = par[k] >= 0;
+            mine[k] = act[k] ? psize[i] : 0;
+            x[k] = par[k];
+            fin[k] = !act[k];
+        }
+        bool go = true;
+        while (go) {
+            go = false;
+            int32_t nx[PER];
+#pragma unroll
+            for (int k = 0; k < PER; ++k) nx[k] = fin[k] ? x[k] : __ldcg(T + x[k]);
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                if (fin[k]) continue;
+                if (nx[k] == x[k]) {
+                    fin[k] = true;
+                } else {
+                    x[k] = nx[k];
+                    go = true;
+                }
             }
         }
-        nroot += is_root[k];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int64_t i = base + k * 256 + threadIdx.x;
+            is_root[k] = false;
+            if (act[k]) {
+                const int32_t root = x[k];
+                if (root != par[k]) T[i] = root;
+                if (mine[k] > 0 && root != (int32_t)i) atomicAdd(psize + root, mine[k]);
+                is_root[k] = root == (int32_t)i;
+            }
+            nroot += is_root[k];
+        }
     }
     int incl = nroot;
 #pragma unroll
