@@ -640,6 +640,33 @@ __device__ __forceinline__ void push_dependents(const CcArrays &A, const CcParam
     }
 }
 
+// Books the result of one small piece (start pixel t): `adjacent`, the strip-mode flags and the re-scan time
+// `fix` (aux_old = the value stored so far); queues the small neighbours when the re-scan time changed.
+__device__ __forceinline__ bool piece_commit(const CcArrays &A, const CcParams &P, int32_t t, int32_t a, int32_t fix,
+                                             int32_t aux_old, int cnt, const int32_t *members, bool unk_any,
+                                             bool known_before, int round_id, int32_t *dirty_next, int32_t *n_next)
+{
+    A.adj[t] = a;
+    bool flag_changed = false;
+    if (A.flag && unk_any) {
+        // conservative: any unknown neighbour makes `adjacent` unknown; the re-scan time stays known
+        // when a KNOWN neighbour is labelled before the piece's own start (then tfix == start)
+        uint8_t f = A.flag[t];
+        uint8_t nf = f | FLAG_ADJ_UNKNOWN;
+        if (!known_before && P.start_label == 1) nf |= FLAG_TFIX_UNKNOWN;
+        if (nf != f) {
+            A.flag[t] = nf;
+            flag_changed = ((nf ^ f) & FLAG_TFIX_UNKNOWN) != 0;
+        }
+    }
+    if (aux_old == fix && !flag_changed) return false;
+    A.aux[t] = fix;
+    if (P.start_label == 0) return true;   // no label-0 ambiguity: nobody depends on tfix
+    // tell later small neighbours of the piece to look again
+    for (int i = 0; i < cnt; ++i) push_dependents(A, P, members[i], t, round_id, dirty_next, n_next);
+    return true;
+}
+
 // `adjacent` of one small piece (start pixel t) under the current knowledge of its earlier
 // neighbours; `qu` = queue space for max(psize[t], 1) pixels (+ psize[t] more for the re-scan copy,
 // claimed from the global cursor on demand).  Returns true when the piece's tfix changed.
@@ -733,45 +760,40 @@ __device__ bool small_piece_adjacent(const CcArrays &A, const CcParams &P, int32
             }
         }
     }
-    A.adj[t] = a;
-    bool flag_changed = false;
-    if (A.flag && unk_any) {
-        // conservative: any unknown neighbour makes `adjacent` unknown; the re-scan time stays known
-        // when a KNOWN neighbour is labelled before the piece's own start (then tfix == start)
-        uint8_t f = A.flag[t];
-        uint8_t nf = f | FLAG_ADJ_UNKNOWN;
-        if (!known_before && P.start_label == 1) nf |= FLAG_TFIX_UNKNOWN;
-        if (nf != f) {
-            A.flag[t] = nf;
-            flag_changed = ((nf ^ f) & FLAG_TFIX_UNKNOWN) != 0;
-        }
-    }
-    if (A.aux[t] == fix && !flag_changed) return false;
-    A.aux[t] = fix;
-    if (P.start_label == 0) return true;   // no label-0 ambiguity: nobody depends on tfix
-    // tell later small neighbours of the piece to look again
-    for (int i = 0; i < cnt; ++i) push_dependents(A, P, members[i], t, round_id, dirty_next, n_next);
-    return true;
+    return piece_commit(A, P, t, a, fix, A.aux[t], cnt, members, unk_any, known_before, round_id, dirty_next, n_next);
 }
 
 // round 1: every small piece, in parallel (optimistic: every merged neighbour counts as labelled
 // from its own start time).  Pieces whose tfix turns out different queue their dependents.
+#ifndef OBIA_CC_ADJ_U
+#define OBIA_CC_ADJ_U 4       // list entries per lane and trip
+#endif
+// One thread per piece is a chain of dependent loads (list -> size -> piece starts of the neighbours -> flags),
+// and most small pieces of a fragmented raster are single pixels: a lane takes OBIA_CC_ADJ_U list entries per
+// trip, walks their one-pixel pieces in lock step (the loads of every step requested together) and then replays
+// the larger ones one after the other.
 __global__ void __launch_bounds__(128)
 cc_small_adjacent_kernel(CcArrays A, CcParams P, int32_t *dirty_next)
 {
+    constexpr int U = OBIA_CC_ADJ_U;
     const int n_small = A.ctr[CTR_NSMALL];
     const int lane = threadIdx.x & 31;
-    const int stride = gridDim.x * blockDim.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
     // warp-uniform trip count: the queue space of a warp's pieces is claimed with one atomic
-    for (int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); e0 < n_small; e0 += stride) {
-        const int e = e0 + lane;
-        const bool active = e < n_small;
-        int32_t t = 0, n = 0;
-        if (active) {
-            t = A.list[e];
-            n = A.psize[t];
+    for (int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * U; e0 < n_small; e0 += stride) {
+        int32_t t[U], n[U], auxv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t e = e0 + u * 32 + lane;
+            t[u] = (e < n_small) ? A.list[e] : -1;
         }
-        const int need = active ? n : 0;
+        int need = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            n[u] = (t[u] >= 0) ? A.psize[t[u]] : 0;
+            auxv[u] = (t[u] >= 0) ? A.aux[t[u]] : 0;
+            need += n[u];
+        }
         int incl = need;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -782,8 +804,76 @@ cc_small_adjacent_kernel(CcArrays A, CcParams P, int32_t *dirty_next)
         int base = 0;
         if (lane == 0 && total > 0) base = atomicAdd(A.ctr + CTR_CURSOR, total);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (!active) continue;
-        small_piece_adjacent(A, P, t, A.queue + base + incl - need, 1, dirty_next, A.ctr + CTR_NDIRTY0);
+        int32_t *qu = A.queue + base + incl - need;     // this lane's queue space, entry after entry
+
+        // ---- one-pixel pieces, in lock step (this is round 1: P.optimistic, a neighbour piece counts as
+        //      labelled from its own start) --------------------------------------------------------------
+        int32_t tq[U][4];
+        unsigned have[U];      // bit d: neighbour d exists and is looked at
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            have[u] = 0;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) tq[u][d] = -1;
+            // (with max_size <= 1 the reference's BFS loop never runs: no neighbour is looked at)
+            if (n[u] == 1 && max_size_at(P, t[u]) > 1) {
+                const int py = t[u] / P.W, px = t[u] - py * P.W;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    int32_t q;
+                    if (nbr(d, py, px, P.H, P.W, q)) {
+                        have[u] |= 1u << d;
+                        tq[u][d] = A.T[q];
+                    }
+                }
+            }
+        }
+        uint8_t nf[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                nf[u][d] = (A.flag && tq[u][d] >= 0 && tq[u][d] != t[u]) ? A.flag[tq[u][d]] : (uint8_t)0;
+        int off = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (n[u] == 1) {
+                int32_t a = -1;
+                bool unk_any = false, known_before = false;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {     // reference neighbour order: x+1, x-1, y+1, y-1
+                    const int32_t v = tq[u][d];
+                    if (!((have[u] >> d) & 1u) || v < 0 || v == t[u]) continue;
+                    const bool unk = (nf[u][d] & FLAG_CUT) || ((nf[u][d] & FLAG_TFIX_UNKNOWN) && P.start_label == 1);
+                    if (v < t[u]) {
+                        a = t[u] + (d == 0 ? 1 : d == 1 ? -1 : d == 2 ? P.W : -P.W);
+                        if (!unk) known_before = true;
+                    }
+                    if (unk) unk_any = true;
+                }
+                const int32_t fix = (a < 0 && P.start_label == 1) ? kTInf : t[u];   // stays label 0: no later pixel
+                qu[off] = t[u];
+                piece_commit(A, P, t[u], a, fix, auxv[u], 1, qu + off, unk_any, known_before, 1, dirty_next,
+                             A.ctr + CTR_NDIRTY0);
+            }
+            off += n[u];
+        }
+        // ---- larger pieces: the BFS replay, one after the other ---------------------------------------------
+        // (ONE call site: U inlined copies of the replay do not fit the instruction cache -- 6.2 -> 13 ms)
+        int32_t mt[U], mo[U];
+        int nm = 0;
+        off = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (n[u] > 1) {
+                mt[nm] = t[u];
+                mo[nm] = off;
+                ++nm;
+            }
+            off += n[u];
+        }
+#pragma unroll 1
+        for (int i = 0; i < nm; ++i) small_piece_adjacent(A, P, mt[i], qu + mo[i], 1, dirty_next, A.ctr + CTR_NDIRTY0);
     }
 }
 
