@@ -887,10 +887,17 @@ cc_small_round_kernel(CcArrays A, CcParams P, const int32_t *__restrict__ cur, i
     const int n = A.ctr[cur_ctr];
     if (blockIdx.x == 0 && threadIdx.x == 0) A.ctr[CTR_ROUNDS] = round_id;
     const int lane = threadIdx.x & 31;
-    const int stride = gridDim.x * blockDim.x;
-    for (int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); e0 < n; e0 += stride) {
-        const int e = e0 + lane;
-        const bool active = e < n;
+    // A short list (the usual case: the tail of a strip's unknown-flag propagation is a few dozen pieces per
+    // round) is spread ONE PIECE PER WARP: 32 different BFS replays inside one warp take turns at its issue
+    // slot, and the round lasts as long as its slowest warp.
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const bool sparse = n <= nwarps;
+    const int stride = sparse ? nwarps : gridDim.x * blockDim.x;
+    const int first = sparse ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)
+                             : blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+    for (int e0 = first; e0 < n; e0 += stride) {
+        const int e = sparse ? e0 : e0 + lane;
+        const bool active = sparse ? (lane == 0) : (e < n);
         int32_t t = 0, need = 0;
         if (active) {
             t = cur[e];

@@ -48,6 +48,35 @@ def _aligned(t):
     return t if t.data_ptr() % 16 == 0 else t.clone()
 
 
+# Scratch memory kept by this module instead of being handed back to torch's caching allocator after every call.
+# The connectivity workspace is one 41 B/pixel block (4.4 GB on c2); once it is back in the allocator's pool the next
+# 0.4 GB request is carved out of it and the following step pays a fresh cudaMalloc of several GB (6 - 100 ms,
+# measured on the strip path) while the reserved pool keeps growing.  One buffer per (device, tag), grow-only.
+_SCRATCH = {}
+_SCRATCH_MAX_FRACTION = 0.2      # blocks beyond this share of the device memory are not kept
+
+
+def scratch(device, nbytes, tag):
+    """uint8 device buffer of `nbytes` for the duration of one call (one stream per process, as everywhere in this
+    package: two concurrent calls with the same tag would share it).  `release_scratch()` frees them."""
+    device = torch.device(device)
+    nbytes = int(nbytes)
+    if nbytes > _SCRATCH_MAX_FRACTION * torch.cuda.get_device_properties(device).total_memory:
+        return torch.empty((nbytes,), dtype=torch.uint8, device=device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _SCRATCH.pop(key, None)
+        buf = None                      # the smaller block goes back before the larger one is requested
+        buf = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        _SCRATCH[key] = buf
+    return buf[:nbytes]
+
+
+def release_scratch():
+    _SCRATCH.clear()
+
+
 def _i32_array(values):
     arr = (ctypes.c_int32 * len(values))(*[int(v) for v in values])
     return arr
@@ -367,8 +396,7 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
         max_size = int(max_size_factor * segment_size)
         if max_size < 1:
             raise ValueError("max_size_factor too small: connectivity needs max_size >= 1")
-        cc_bytes = lib.obia_b200_connectivity_workspace_bytes(H, W)
-        cc_ws = torch.empty((cc_bytes,), dtype=torch.uint8, device=dev)
+        cc_ws = scratch(dev, lib.obia_b200_connectivity_workspace_bytes(H, W), "connectivity")
         out = torch.empty_like(labels)
         nl = ctypes.c_int64(0)
         _lib.check(lib.obia_b200_enforce_connectivity(
@@ -446,8 +474,7 @@ def enforce_connectivity(labels, min_size, max_size, start_label=1):
     lib = _lib.load()
     labels = _aligned(_require_cuda(labels, "labels", torch.int32))
     H, W = (int(s) for s in labels.shape)
-    ws = torch.empty((lib.obia_b200_connectivity_workspace_bytes(H, W),), dtype=torch.uint8,
-                     device=labels.device)
+    ws = scratch(labels.device, lib.obia_b200_connectivity_workspace_bytes(H, W), "connectivity")
     out = torch.empty_like(labels)
     nl = ctypes.c_int64(0)
     _lib.check(lib.obia_b200_enforce_connectivity(_p(labels), _p(out), _p(ws), H, W, int(min_size),

@@ -341,8 +341,10 @@ class ShardedSlic:
         self.ext = torch.cat(parts, dim=0).contiguous() if len(parts) > 1 else self.labels
         self.core_row0 = 0 if halo_up is None else int(halo_up.shape[0])
         H_ext = int(self.ext.shape[0])
-        self.cc_ws = torch.empty((self.lib.obia_b200_connectivity_workspace_bytes(H_ext, self.W),),
-                                 dtype=torch.uint8, device=self.dev)
+        # (kept per strip: the workspace lives from strip_begin to strip_finish, and strips emulated in one process
+        #  must not share it)
+        self.cc_ws = pipeline.scratch(self.dev, self.lib.obia_b200_connectivity_workspace_bytes(H_ext, self.W),
+                                      ("connectivity-strip", self.row0))
         counts = (ctypes.c_int64 * 5)()
         min_size, max_size = self.sizes()
         _lib.check(self.lib.obia_b200_connectivity_strip_begin(

@@ -494,6 +494,25 @@ def _random_label_cases():
     return cases
 
 
+def test_scratch_buffers_are_kept_and_grow():
+    """pipeline.scratch: one persistent block per (device, tag) -- the connectivity workspace must not go back to
+    the caching allocator between steps (a fresh multi-GB cudaMalloc per step otherwise)."""
+    from obia_b200 import pipeline
+    pipeline.release_scratch()
+    a = pipeline.scratch("cuda:0", 1 << 20, "t")
+    b = pipeline.scratch("cuda:0", 1 << 19, "t")
+    assert a.data_ptr() == b.data_ptr() and b.numel() == 1 << 19
+    c = pipeline.scratch("cuda:0", 1 << 21, "t")
+    assert c.numel() == 1 << 21
+    assert pipeline.scratch("cuda:0", 1 << 20, "other").data_ptr() != c.data_ptr()
+    lab = torch.randint(1, 50, (300, 400), dtype=torch.int32, device="cuda")
+    o1, n1 = pipeline.enforce_connectivity(lab, 5, 200, 1)
+    o2, n2 = pipeline.enforce_connectivity(lab, 5, 200, 1)      # second call on the kept (dirty) workspace
+    assert n1 == n2 and torch.equal(o1, o2)
+    pipeline.release_scratch()
+    assert not pipeline._SCRATCH
+
+
 def test_connectivity_exact_random():
     """Exact equality with the sequential reference algorithm on adversarial label rasters."""
     import slic_oracle as so
