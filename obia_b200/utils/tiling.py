@@ -749,6 +749,9 @@ def create_tiled_segments(input_raster, output_dir, input_mask=None,
         dist, rank, world = tdist, tdist.get_rank(), tdist.get_world_size()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    if torch.cuda.is_available():
+        from .. import pipeline as _pipeline
+        _pipeline.release_scratch()      # whole-raster workspaces of earlier calls: the tiled driver sizes its own
     raw, pixel_area, image, width, xa = _as_device_raster(
         input_raster, device, columns=lambda w: local_columns(w, int(tile_size), int(buffer), world, rank))
     mask = None
