@@ -48,8 +48,9 @@ constexpr int kBoxSlots = 512;
 
 static __global__ void __launch_bounds__(256)
 zonal_bbox_kernel(const int32_t *__restrict__ labels, ZonalWs w, int H, int W, int64_t max_label,
-                  int32_t label_lo = 0, int32_t zero_row = 0)
+                  int32_t label_lo = 0, int32_t zero_row = 0, int y_base = 0)
 {
+    // (`labels` / H = the rows [y_base, y_base + H) of the raster: a grid has at most 65535 rows of tiles)
     // table row = label - label_lo (label_lo != 0: the rank-local label range of a sharded raster);
     // with zero_row the table starts with one extra row for label 0: row = label - label_lo + 1
     __shared__ int32_t s_key[kBoxSlots], s_x0[kBoxSlots], s_x1[kBoxSlots], s_y0[kBoxSlots], s_y1[kBoxSlots],
@@ -81,7 +82,7 @@ zonal_bbox_kernel(const int32_t *__restrict__ labels, ZonalWs w, int H, int W, i
     int32_t last_l = -1, last_slot = -1;
 #pragma unroll
     for (int r = 0; r < kBoxRows; ++r) {
-        const int y = yb + r;
+        const int y = y_base + yb + r;
         const int32_t l = lab[r];
         const int32_t prev = __shfl_up_sync(0xffffffffu, l, 1);
         const bool is_head = (lane == 0) || (prev != l);
@@ -137,9 +138,13 @@ zonal_bbox_kernel(const int32_t *__restrict__ labels, ZonalWs w, int H, int W, i
 static inline void zonal_bbox_launch(const int32_t *labels, const ZonalWs &w, int64_t H, int64_t W, int64_t max_label,
                                      int32_t label_lo, int32_t zero_row, cudaStream_t st)
 {
-    // (grid.y <= 65535 rows of tiles: 1 M raster rows; H * W < 2^31 is checked by the callers)
-    dim3 grid((unsigned)ceil_div(W, 256), (unsigned)ceil_div(H, kBoxRows));
-    zonal_bbox_kernel<<<grid, 256, 0, st>>>(labels, w, (int)H, (int)W, max_label, label_lo, zero_row);
+    // (H * W < 2^31 is checked by the callers; rasters taller than 65535 tiles go in several launches)
+    const int64_t rows_per_launch = (int64_t)65535 * kBoxRows;
+    for (int64_t y0 = 0; y0 < H; y0 += rows_per_launch) {
+        const int64_t h = std::min<int64_t>(rows_per_launch, H - y0);
+        dim3 grid((unsigned)ceil_div(W, 256), (unsigned)ceil_div(h, kBoxRows));
+        zonal_bbox_kernel<<<grid, 256, 0, st>>>(labels + y0 * W, w, (int)h, (int)W, max_label, label_lo, zero_row, (int)y0);
+    }
 }
 
 }  // namespace obia

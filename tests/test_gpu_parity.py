@@ -616,6 +616,25 @@ def test_zonal_stats_edge_cases():
     assert np.isnan(want[[0, 2], :, 4]).all()
 
 
+def test_zonal_stats_very_tall_raster():
+    """More rows than one grid of box tiles covers (65535 tiles of 16 rows): the box pass goes in several launches."""
+    from obia_b200 import pipeline
+    H, W = 65535 * 16 + 4099, 3
+    yy = np.arange(H, dtype=np.int64)[:, None]
+    labels = np.ascontiguousarray(np.broadcast_to((yy // 50000).astype(np.int32), (H, W)))
+    raw = np.ascontiguousarray(np.broadcast_to((yy % 977).astype(np.float32)[:, :, None], (H, W, 2)))
+    got = pipeline.zonal_stats(_cuda(labels), _cuda(raw), [0, 1]).cpu().numpy()
+    n_lab = int(labels.max()) + 1
+    assert got.shape == (n_lab, 2, 8)
+    counts = np.bincount(labels.ravel(), minlength=n_lab)
+    np.testing.assert_array_equal(got[:, 0, 0], counts)
+    for L in (0, n_lab // 2, n_lab - 2, n_lab - 1):      # the last labels lie in the second launch
+        v = raw[labels == L][:, 0].astype(np.float64)
+        np.testing.assert_allclose(got[L, :, 1], v.mean(), rtol=1e-6)
+        np.testing.assert_array_equal(got[L, :, 3], v.min())
+        np.testing.assert_array_equal(got[L, :, 4], v.max())
+
+
 @pytest.mark.parametrize("C,bands", [(8, None), (5, [4, 1, 2]), (40, None)])
 def test_zonal_stats_drop_nan_per_band(C, bands):
     """NaN nodata in a statistics band (not a segmentation band): the reference drops NaN samples per band
