@@ -227,17 +227,7 @@ def slic_labels(raw, segmentation_bands=None, *, n_segments=100, compactness=10.
         raise NotImplementedError("only channel_axis=-1 (obia always passes H, W, C)")
     # skimage's `spacing` (voxel size per spatial axis): scales the spatial term of the distance and divides
     # sigma; grid, windows and connectivity stay in pixel units.  float32 like the image (slic: `dtype`).
-    if spacing is None:
-        sp_y = sp_x = np.float32(1.0)
-    else:
-        if isinstance(spacing, (str, bytes)) or not hasattr(spacing, "__iter__"):
-            raise TypeError("spacing must be None or iterable.")
-        sp = np.asarray(list(spacing), dtype=np.float32).ravel()
-        if sp.size not in (2, 3):
-            raise ValueError(f"Input image is 2D, but spacing has {sp.size} elements (expected 2).")
-        sp_y, sp_x = sp[-2], sp[-1]
-        if not (np.isfinite(sp_y) and np.isfinite(sp_x) and sp_y > 0 and sp_x > 0):
-            raise ValueError("spacing must be positive and finite")
+    sp_y, sp_x = slic_host.parse_spacing(spacing)
     anisotropic = bool(sp_y != 1.0 or sp_x != 1.0)
     if start_label not in (0, 1):
         raise ValueError("start_label should be 0 or 1.")

@@ -222,3 +222,20 @@ def fixed_point_scale(max_abs_value, H, W, step_y, step_x):
     bits_val = math.ceil(math.log2(max(max_abs_value, 1e-30))) + 1
     shift = 62 - bits_px - bits_val
     return float(2.0 ** shift)
+
+
+def parse_spacing(spacing):
+    """(sy, sx) float32 of skimage.segmentation.slic's `spacing` argument for a 2-D image: None -> (1, 1); an
+    iterable of two values, or of three with the leading (z) one ignored as slic still accepts with a
+    FutureWarning; anything else raises like slic does."""
+    if spacing is None:
+        return np.float32(1.0), np.float32(1.0)
+    if isinstance(spacing, (str, bytes)) or not hasattr(spacing, "__iter__"):
+        raise TypeError("spacing must be None or iterable.")
+    sp = np.asarray(list(spacing), dtype=np.float32).ravel()
+    if sp.size not in (2, 3):
+        raise ValueError(f"Input image is 2D, but spacing has {sp.size} elements (expected 2).")
+    sp_y, sp_x = sp[-2], sp[-1]
+    if not (np.isfinite(sp_y) and np.isfinite(sp_x) and sp_y > 0 and sp_x > 0):
+        raise ValueError("spacing must be positive and finite")
+    return sp_y, sp_x

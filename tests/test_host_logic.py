@@ -163,3 +163,20 @@ def test_batched_tiled_driver_option_gate():
     for kw in (dict(sigma=1.0), dict(sigma=(1, 1)), dict(slic_zero=True), dict(exact=True), dict(enforce_connectivity=False),
                dict(spacing=(1, 2)), dict(start_label=2), dict(mask=None), dict(unknown_option=1)):
         assert not batch.supports(kw)
+
+
+def test_parse_spacing():
+    """slic's `spacing` handling for 2-D images (obia forwards **kwargs to skimage.segmentation.slic)."""
+    from obia_b200 import slic_host
+    assert slic_host.parse_spacing(None) == (1.0, 1.0)
+    assert slic_host.parse_spacing([500, 1]) == (500.0, 1.0)
+    assert slic_host.parse_spacing(np.array([0.5, 2.0])) == (0.5, 2.0)
+    assert slic_host.parse_spacing((7, 0.25, 3)) == (0.25, 3.0)          # (z, y, x): z ignored for a 2-D image
+    assert all(isinstance(v, np.float32) for v in slic_host.parse_spacing((1, 2)))
+    with pytest.raises(TypeError):
+        slic_host.parse_spacing(2.0)
+    with pytest.raises(TypeError):
+        slic_host.parse_spacing("12")
+    for bad in ((1,), (1, 2, 3, 4), (0, 1), (1, -2), (np.inf, 1), (np.nan, 1)):
+        with pytest.raises(ValueError):
+            slic_host.parse_spacing(bad)
